@@ -1,0 +1,107 @@
+"""Generate tests/golden/*.npz by running the REFERENCE'S OWN code.
+
+Run in the build container (needs oracle/_ref/libref_oracle.so, i.e. /root/reference):
+
+    python tests/golden/make_golden.py
+
+The reference ships no known-answer vectors for this path, so these files
+are outputs of the reference itself (oracle/ref_harness.cpp -> NTTProcessor, PolynomialRing,
+MultiLimbModularArithmetic, BootstrapEngine) on seeded inputs; keys come from the
+reference's own KeyManager / encrypt_ggsw / generate_key_switch_key (random_device-seeded,
+hence stored rather than regenerated).  They pin oracle/fhe_oracle.c on machines where
+the reference cannot be built (the GPU box) and are the fixed fixtures of the GPU parity tests.
+"""
+import os
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.dirname(HERE))
+from oracle_bindings import RefOracle, mt19937_64_coeffs  # noqa: E402
+
+Q27 = 132120577                 # cpp/tests/test_ntt_processor.cpp PRIME_1024
+Q62 = 4611686018326724609       # cpp/tests/test_harness.h:143-147
+QT = 1099511678977              # substitute for the composite tfhe-128-fast modulus
+
+
+def ntt_case(r, n, q, seed, polys):
+    h = r.ntt_create(n, q)
+    fwd, inv, psi, psi_inv, inv_n = r.ntt_tables(h, n)
+    x = mt19937_64_coeffs(seed, n * polys, q).reshape(polys, n)
+    y = r.ntt_forward(h, x)
+    z = r.ntt_inverse(h, x)  # inverse applied to the raw input as well (not only round trips)
+    ring = r.ring_create(n, q)
+    prod = r.ring_op(ring, "multiply", x[: polys // 2], x[polys // 2 : 2 * (polys // 2)])
+    r.ring_destroy(ring)
+    r.ntt_destroy(h)
+    return dict(n=n, q=np.uint64(q), seed=seed, psi=np.uint64(psi), psi_inv=np.uint64(psi_inv),
+                inv_n=np.uint64(inv_n), fwd_head=fwd[:8].copy(), inv_head=inv[:8].copy(),
+                x=x, forward=y, inverse=z, product=prod)
+
+
+def main():
+    r = RefOracle()
+    rng = np.random.default_rng(20261018)
+
+    # --- transforms + polymul (C1, C2 shapes and the reference's own small configs)
+    for n, q, seed, polys in [(8, 17, 42, 4), (8, 97, 42, 4), (16, 97, 42, 4), (1024, Q27, 42, 4),
+                              (1024, QT, 7, 2), (4096, Q62, 42, 2), (16384, Q62, 123, 2)]:
+        np.savez_compressed(os.path.join(HERE, f"ntt_n{n}_q{q}.npz"), **ntt_case(r, n, q, seed, polys))
+
+    # --- multi-limb (C3 modulus, cpp/tests/test_multi_limb.cpp:143)
+    ql = np.array([0xFFFFFFFFFFFFFF43, 1], np.uint64)
+    h = r.mlimb_create(ql)
+    q_inv, r1, r2 = r.mlimb_constants(h, 2)
+    qint = int(ql[0]) + (int(ql[1]) << 64)
+    vals = [int.from_bytes(rng.bytes(17), "little") % qint for _ in range(512)]
+    vals[:6] = [0, 1, qint - 1, qint - 2, (1 << 64) - 1, 1 << 64]
+    ab = np.array([[v & (2**64 - 1), v >> 64] for v in vals], np.uint64)
+    a, b = ab[:256], ab[256:]
+    np.savez_compressed(os.path.join(HERE, "mlimb_q65.npz"), q=ql, q_inv=np.uint64(q_inv), r_mod_q=r1, r2_mod_q=r2,
+                        a=a, b=b, montmul=r.mlimb_op(h, "montmul", a, b), add=r.mlimb_op(h, "add", a, b),
+                        sub=r.mlimb_op(h, "sub", a, b), to_mont=r.mlimb_op(h, "to_mont", a),
+                        from_mont=r.mlimb_op(h, "from_mont", a))
+    r.mlimb_destroy(h)
+
+    # --- bootstrap: two small shapes with keys drawn by the reference's own generators
+    for tag, (N, n, k, base_log, level, with_ksk) in {
+        "n128_l3": (128, 8, 1, 4, 3, True),          # engine defaults base_log 4 / level 3; n power of two -> KSK works
+        "tfhe_shape_small_n": (1024, 6, 1, 23, 1, False),  # tfhe-128-fast gadget (23,1) at N=1024, short LWE key
+    }.items():
+        h = r.boot_create(N, QT, n, k, base_log, level, 4)
+        sk = r.boot_keygen(h, with_ksk)
+        bsk = r.boot_export_bsk(h)
+        lwe = r.boot_encrypt_lwe(h, np.array([0, 1, 2, 3], np.uint64), sk)
+        lwe[3, 0] = 0            # exercises the rotation == 0 skip (bootstrap_engine.cpp:566)
+        lwe[2, 1] = QT - 1       # rotation == 2N (not skipped, identity rotation)
+        tp = r.boot_default_test_poly(h)
+        acc = r.boot_blind_rotate(h, lwe, tp)
+        glwe = rng.integers(0, QT, size=(k + 1, N), dtype=np.uint64)
+        out = dict(N=N, n=n, k=k, base_log=base_log, level=level, q=np.uint64(QT), t=4, lwe_sk=sk, bsk=bsk, lwe=lwe,
+                   test_poly=tp, blind_rotate=acc, glwe=glwe, external_product=r.boot_external_product(h, glwe, 1),
+                   cmux=r.boot_cmux(h, 2, glwe, acc[0]), sample_extract=r.boot_sample_extract(h, acc),
+                   decompose=r.boot_decompose(h, glwe[0], base_log, level), rotate_5=r.boot_rotate(h, glwe[0], 5),
+                   rotate_m3=r.boot_rotate(h, glwe[0], -3), rotate_big=r.boot_rotate(h, glwe[0], N + 7),
+                   lut_identity=r.boot_lut(h, 0, 4), lut_negation=r.boot_lut(h, 1, 4), lut_threshold=r.boot_lut(h, 2, 2, 4))
+        if with_ksk:
+            ksk = r.boot_export_ksk(h)
+            out.update(ksk=ksk, key_switch=r.boot_key_switch(h, r.boot_sample_extract(h, acc), n),
+                       bootstrap=r.boot_bootstrap(h, lwe, tp, n))
+        np.savez_compressed(os.path.join(HERE, f"boot_{tag}.npz"), **out)
+        r.boot_destroy(h)
+
+    # --- tally + tensor product (C5 shape scaled down)
+    for n, q, m in [(64, QT, 5), (1024, QT, 9)]:
+        ring = r.ring_create(n, q)
+        cts = rng.integers(0, q, size=(m, 2, n), dtype=np.uint64)
+        cts[1, 0, :4] = [q, q + 1, 2**64 - 1, 0]  # unreduced words: mod_add reduces inputs first
+        np.savez_compressed(os.path.join(HERE, f"tally_n{n}_m{m}.npz"), n=n, q=np.uint64(q), cts=cts,
+                            linear=r.tally(ring, cts), tree=r.tally(ring, cts, tree=True), single=r.tally(ring, cts[1:2]),
+                            tensor=r.tensor_multiply(ring, cts[0], cts[2]))
+        r.ring_destroy(ring)
+    print("golden vectors written to", HERE)
+
+
+if __name__ == "__main__":
+    main()
