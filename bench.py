@@ -1,0 +1,296 @@
+#!/usr/bin/env python
+"""Benchmark of the hot path (BASELINE.json metric: NTT coefficients/s at N=16384, batched).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--no-secondary]
+
+One step = the forward transform and the inverse transform of a batch of 1024 polynomials of
+degree 16384 over the 62-bit prime 4611686018326724609 (BASELINE config C2's shape); value =
+coefficient-transforms per second = 2 * batch * N * steps / time, aggregated over all ranks
+(weak scaling: every rank owns its own batch, no data-path collective).
+
+`value`   : inputs resident in HBM, CUDA-event timed, max over ranks.
+`e2e`     : the same step through the C ABI with pinned HOST buffers (H2D + kernels + D2H inside
+            the timed region).
+`roofline`: the forward-transform kernel, algorithmic bytes (16 B per coefficient) / live
+            CUDA-event time, against MEASURED_PEAKS.json's HBM copy bandwidth.
+`cpu_baseline`: the reference's own scalar C++ (oracle/_ref/libref_oracle.so when present, else
+            the C port) on a bounded sample, all host cores.
+`secondary`: polymul, multi-limb, bootstrap and tally throughput with their own rooflines.
+
+--impl reference times the reference's CPU implementation on the host cores (rank 0 only).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+N_DEG = 16384
+BATCH = 1024
+Q62 = 4611686018326724609
+QT = 1099511678977  # substitute prime for the tfhe-128-fast shape (preset modulus 2^40+1 is composite)
+METRIC = "ntt_coeffs_per_sec_n16384_batched"
+UNIT = "coeff/s"
+
+
+def measured_peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            p = json.load(f)
+        return float(p["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons while the timed region runs."""
+
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index, self.samples, self.proc = index, [], None
+
+    def __enter__(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+        return self
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.samples.append([s.strip() for s in line.split(",")])
+
+    def __exit__(self, *a):
+        if self.proc:
+            time.sleep(0.15)
+            self.proc.terminate()
+            self.t.join(timeout=2)
+
+    def summary(self):
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for s in self.samples:
+            try:
+                sm.append(float(s[0]))
+                mx.append(float(s[1]))
+                for nm, v in zip(names, s[2:6]):
+                    if v.lower().startswith("active"):
+                        reasons.add(nm)
+            except Exception:
+                pass
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        return {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------ CPU reference --
+def cpu_reference_ntt(polys: int, threads: int):
+    """Times forward+inverse transforms of `polys` polynomials (N=16384, Q62) with the reference's own
+    NTTProcessor (oracle/_ref) or the C port.  Returns (coeff/s, kind, seconds)."""
+    import numpy as np
+
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from oracle_bindings import Oracle, RefOracle, ref_available
+
+    rng = np.random.default_rng(0)
+    x = rng.integers(0, Q62, size=(polys, N_DEG), dtype=np.uint64)
+    if ref_available():
+        r = RefOracle()
+        h = r.ntt_create(N_DEG, Q62)
+        t0 = time.perf_counter()
+        y = r.ntt_forward(h, x, threads=threads)
+        z = r.ntt_inverse(h, y, threads=threads)
+        dt = time.perf_counter() - t0
+        r.ntt_destroy(h)
+        kind = "reference"
+    else:
+        o = Oracle()
+        fwd, inv, _, _, inv_n = o.twiddles(N_DEG, Q62)
+        threads = 1
+        t0 = time.perf_counter()
+        y = o.forward(x, Q62, fwd)
+        z = o.inverse(y, Q62, inv, inv_n)
+        dt = time.perf_counter() - t0
+        kind = "port"
+    assert np.array_equal(z, x)
+    return 2.0 * polys * N_DEG / dt, kind, dt, threads
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    polys = 8 * cores  # ~7 ms per transform per core: a fraction of a second per step
+    vals = []
+    for i in range(args.warmup + args.steps):
+        v, kind, dt, used = cpu_reference_ntt(polys, cores)
+        if i >= args.warmup:
+            vals.append((v, dt))
+    value = sum(2.0 * polys * N_DEG for _ in vals) / sum(dt for _, dt in vals)
+    ms = 1e3 * sum(dt for _, dt in vals) / len(vals)
+    sample = f"{polys} polynomials (of the batch of {BATCH}) forward+inverse per step, {used} threads"
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "u64", "data": "synthetic",
+        "config": {"workload": f"forward+inverse transform, N={N_DEG}, batch {BATCH}, q={Q62} (CPU: bounded sample)"},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": used, "kind": kind, "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+# -------------------------------------------------------------------------------- ours ---
+def run_ours(args):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    import fheb200
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    fheb200.initialize(local)
+    dev = torch.device("cuda", local)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(ms: float) -> float:
+        if world == 1:
+            return ms
+        t = torch.tensor([ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    ntt = fheb200.NTTProcessor(N_DEG, Q62)
+    gen = torch.Generator(device=dev).manual_seed(1234 + rank)
+    NSETS = 4  # rotate input sets: 4 x 134 MB in + 134 MB out never fit the 126 MB L2 together
+    xs = [torch.randint(0, Q62, (BATCH, N_DEG), dtype=torch.int64, device=dev, generator=gen) for _ in range(NSETS)]
+    y = torch.empty_like(xs[0])
+    z = torch.empty_like(xs[0])
+
+    def step(i):
+        ntt.forward_ntt(xs[i % NSETS], out=y)
+        ntt.inverse_ntt(y, out=z)
+
+    for i in range(args.warmup):
+        step(i)
+    torch.cuda.synchronize()
+    assert torch.equal(z, xs[(args.warmup - 1) % NSETS]) if args.warmup else True  # round trip is exact
+
+    fheb200.launch_count(reset=True)
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    fwd_ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    barrier()
+    with ClockSampler(local) as clk:
+        ev0.record()
+        for i in range(args.steps):
+            fwd_ev[i][0].record()
+            ntt.forward_ntt(xs[i % NSETS], out=y)
+            fwd_ev[i][1].record()
+            ntt.inverse_ntt(y, out=z)
+        ev1.record()
+        barrier()
+    launches = fheb200.launch_count()
+    ms_total = max_over_ranks(ev0.elapsed_time(ev1))
+    ms_step = ms_total / args.steps
+    value = world * 2.0 * BATCH * N_DEG * args.steps / (ms_total * 1e-3)
+    fwd_ms = statistics.mean(a.elapsed_time(b) for a, b in fwd_ev)
+    peak, peak_src = measured_peaks()
+    algo_bytes = 16.0 * BATCH * N_DEG
+    achieved = algo_bytes / (fwd_ms * 1e-3) / 1e9
+    roofline = {"bound": "hbm", "kernel": "ntt_forward_kernel<14>", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                "algorithmic_bytes_per_launch": algo_bytes, "avg_launch_ms": fwd_ms}
+
+    # ---- end to end: pinned host buffers through the C ABI, copies inside the timed region
+    hx = torch.empty((BATCH, N_DEG), dtype=torch.int64).pin_memory()
+    hx.copy_(xs[0])
+    hy = torch.empty_like(hx).pin_memory()
+    hz = torch.empty_like(hx).pin_memory()
+    hxn, hyn, hzn = (t.numpy().view(np.uint64) for t in (hx, hy, hz))
+    e2e_steps = max(2, min(args.steps, 5))
+    ntt.forward_ntt(hxn, out=hyn)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        ntt.forward_ntt(hxn, out=hyn)
+        ntt.inverse_ntt(hyn, out=hzn)
+    torch.cuda.synchronize()
+    e2e_ms = max_over_ranks((time.perf_counter() - t0) * 1e3)
+    assert np.array_equal(hzn, hxn)
+    e2e = {"value": world * 2.0 * BATCH * N_DEG * e2e_steps / (e2e_ms * 1e-3), "unit": UNIT,
+           "h2d_bytes_per_step": 2 * BATCH * N_DEG * 8, "d2h_bytes_per_step": 2 * BATCH * N_DEG * 8,
+           "steps": e2e_steps, "note": "forward then inverse, each call stages pinned host buffers in and out"}
+
+    secondary = {}
+    if not args.no_secondary:
+        try:
+            import bench_secondary
+
+            secondary = bench_secondary.run(fheb200, torch, dist, world, rank, dev, barrier, max_over_ranks, peak)
+        except Exception as exc:  # secondary numbers never take the headline down
+            secondary = {"error": repr(exc)}
+
+    cpu = None
+    if rank == 0:
+        cores = os.cpu_count() or 1
+        v, kind, dt, used = cpu_reference_ntt(8 * cores, cores)
+        cpu = {"value": v, "unit": UNIT, "cores": used, "kind": kind,
+               "sample": f"{8 * cores} polynomials forward+inverse ({dt:.2f} s), N={N_DEG}, same prime"}
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64",
+            "data": "synthetic",
+            "config": {"workload": f"forward+inverse transform, N={N_DEG}, batch {BATCH} per GPU, q={Q62}",
+                       "l2": f"{NSETS} rotating input sets of 134 MB + 2 output buffers: larger than the 126 MB L2",
+                       "sharding": "batch split across ranks, no collective"},
+            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches),
+            "clocks": clk.summary(), "secondary": secondary,
+        }
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-secondary", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,91 @@
+"""Secondary workloads of bench.py: the other BASELINE.json configs, each with its own roofline.
+
+Every entry: {"value", "unit", "ms", "roofline": {...}} measured with CUDA events on torch's
+current stream (the stream the library launches on), inputs resident in HBM and larger than L2
+(or rotated) between timed iterations.
+"""
+from __future__ import annotations
+
+import statistics
+
+import numpy as np
+
+Q62 = 4611686018326724609
+QT = 1099511678977
+Q27 = 132120577
+
+
+def _time(torch, fn, iters, warm=3):
+    for i in range(warm):
+        fn(i)
+    torch.cuda.synchronize()
+    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(iters)]
+    for i, (a, b) in enumerate(evs):
+        a.record()
+        fn(i)
+        b.record()
+    torch.cuda.synchronize()
+    return statistics.mean(a.elapsed_time(b) for a, b in evs)
+
+
+def _hbm(peak, algo_bytes, ms):
+    ach = algo_bytes / (ms * 1e-3) / 1e9
+    return {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak}
+
+
+def run(fhe, torch, dist, world, rank, dev, barrier, max_over_ranks, peak):
+    out = {}
+    gen = torch.Generator(device=dev).manual_seed(99 + rank)
+
+    # ---- C2: fused polynomial multiplication, batch 1024
+    for n in (4096, 16384):
+        ring = fhe.PolynomialRing(n, Q62)
+        sets = 3 if n == 16384 else 8
+        a = [torch.randint(0, Q62, (1024, n), dtype=torch.int64, device=dev, generator=gen) for _ in range(sets)]
+        b = [torch.randint(0, Q62, (1024, n), dtype=torch.int64, device=dev, generator=gen) for _ in range(sets)]
+        c = torch.empty_like(a[0])
+        ms = _time(torch, lambda i: ring.multiply(a[i % sets], b[i % sets], out=c), 10)
+        out[f"polymul_n{n}_b1024"] = {"value": 1024 / (ms * 1e-3), "unit": "polymul/s", "ms": ms,
+                                       "roofline": _hbm(peak, 24.0 * n * 1024, ms)}
+        del a, b, c
+
+    # ---- C3: two-limb Montgomery products (n = 65536 is launch-bound; 2^24 shows the bandwidth)
+    ml = fhe.MultiLimbModularArithmetic([0xFFFFFFFFFFFFFF43, 1])
+    for cnt in (65536, 1 << 24):
+        a = torch.randint(0, 2**62, (cnt, 2), dtype=torch.int64, device=dev, generator=gen)
+        a[:, 1] &= 1
+        b = a.flip(0).contiguous()
+        r = torch.empty_like(a)
+        ms = _time(torch, lambda i: ml.montgomery_mul(a, b, out=r), 10)
+        out[f"mlimb2_montmul_n{cnt}"] = {"value": cnt / (ms * 1e-3), "unit": "montmul/s", "ms": ms,
+                                          "roofline": _hbm(peak, 48.0 * cnt, ms)}
+        del a, b, r
+
+    # ---- C5: ballot tally, sharded across ranks with one all-gather + the combine kernel
+    n = 1024
+    per_rank = 131072  # 2.1 GB per rank (>> L2); 1M ballots = 8 ranks x 131072
+    cts = torch.empty((per_rank, 2, n), dtype=torch.int64, device=dev)
+    fhe.synth_ballots(cts, rank * per_rank, per_rank, n, QT, 0xB200)
+    st = fhe.ShardedTally(n, QT)
+    res = [None]
+
+    def tally(i):
+        res[0] = st.tally(cts)
+
+    for i in range(3):
+        tally(i)
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    iters = 10
+    e0.record()
+    for i in range(iters):
+        tally(i)
+    e1.record()
+    barrier()
+    ms = max_over_ranks(e0.elapsed_time(e1)) / iters
+    out["tally_n1024"] = {"value": world * per_rank / (ms * 1e-3), "unit": "ballots/s", "ms": ms,
+                          "ballots": world * per_rank, "n_gpus": world,
+                          "roofline": _hbm(peak, 16384.0 * per_rank, ms),
+                          "checksum": int(res[0].view(-1)[:4].sum().item() & 0xFFFFFFFF)}
+    del cts
+    return out

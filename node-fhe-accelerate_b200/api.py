@@ -1,0 +1,432 @@
+"""Host-side mirror of the reference's C++ classes for the hot path, over the C ABI.
+
+Class and method names follow the reference (cpp/include/ntt_processor.h:49-303,
+polynomial_ring.h:312-513, modular_arithmetic.h:124-194, bootstrap_engine.h:176-508,
+encryption.h:192 tally slice) so that the parity tests read like the reference's own.
+Data are flat unsigned 64-bit words:
+
+* numpy ``uint64`` arrays  -> HOST buffers (staged through the device inside the call);
+* torch CUDA tensors of dtype int64/uint64 -> DEVICE buffers, used in place, asynchronous
+  on torch's current stream.
+
+torch is used only for device memory and streams.  All arithmetic runs in libfheb200.so.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional, Sequence
+
+import numpy as np
+
+from . import _cabi
+from ._cabi import BootParams, DeviceInfo, FheError, check, lib
+
+try:  # torch is plumbing only (device tensors / streams); numpy-only use works without it
+    import torch
+except Exception:  # pragma: no cover
+    torch = None
+
+
+# ------------------------------------------------------------------------------ buffers --
+def _is_torch(x) -> bool:
+    return torch is not None and isinstance(x, torch.Tensor)
+
+
+def _ptr(x) -> int:
+    if x is None:
+        return None
+    if _is_torch(x):
+        if not x.is_contiguous():
+            raise FheError(_cabi.INVALID_PARAMETERS, "tensor must be contiguous")
+        if x.element_size() != 8:
+            raise FheError(_cabi.INVALID_PARAMETERS, "tensor must hold 64-bit words (int64/uint64)")
+        return x.data_ptr()
+    if isinstance(x, np.ndarray):
+        if x.dtype != np.uint64 or not x.flags["C_CONTIGUOUS"]:
+            raise FheError(_cabi.INVALID_PARAMETERS, "array must be C-contiguous uint64")
+        return x.ctypes.data
+    raise FheError(_cabi.INVALID_PARAMETERS, f"unsupported buffer type {type(x)!r}")
+
+
+def _like(x, shape=None):
+    if _is_torch(x):
+        return torch.empty(x.shape if shape is None else shape, dtype=x.dtype, device=x.device)
+    return np.empty(x.shape if shape is None else shape, dtype=np.uint64)
+
+
+def _stream(*xs) -> Optional[int]:
+    for x in xs:
+        if _is_torch(x) and x.is_cuda:
+            return torch.cuda.current_stream(x.device).cuda_stream
+    return None
+
+
+def _words(x) -> int:
+    return int(x.numel()) if _is_torch(x) else int(x.size)
+
+
+def as_words(x):
+    """numpy uint64 view/copy of host data; torch tensors pass through."""
+    if _is_torch(x):
+        return x
+    return np.ascontiguousarray(x, dtype=np.uint64)
+
+
+# ------------------------------------------------------------------------------ library --
+def initialize(device: int = -1) -> None:
+    """initialize(): src/native/lib.rs:23-30."""
+    check(lib().fheb_init(device))
+
+
+def version() -> str:
+    return lib().fheb_version().decode()
+
+
+def detect_hardware() -> dict:
+    """detect_hardware(): src/native/lib.rs:32-42 (Apple fields truthfully false)."""
+    info = DeviceInfo()
+    check(lib().fheb_device_info_get(C.byref(info)))
+    return dict(has_sme=bool(info.has_sme), has_metal=bool(info.has_metal), has_neon=bool(info.has_neon),
+                has_amx=bool(info.has_amx), has_cuda=bool(info.has_cuda), compute_capability=(info.cc_major, info.cc_minor),
+                sm_count=info.sm_count, device_memory_bytes=info.device_memory_bytes, l2_bytes=info.l2_bytes,
+                smem_per_block_optin=info.smem_per_block_optin, name=info.name.decode())
+
+
+def launch_count(reset: bool = False) -> int:
+    return int(lib().fheb_launch_count(1 if reset else 0))
+
+
+def synchronize() -> None:
+    check(lib().fheb_synchronize(None))
+
+
+# ------------------------------------------------------------------------- NTTProcessor --
+class NTTProcessor:
+    """cpp/include/ntt_processor.h:49-303."""
+
+    def __init__(self, degree: int, modulus: int, fwd_table=None, inv_table=None, inv_n: int = 0):
+        self._h = C.c_void_p()
+        if fwd_table is None:
+            check(lib().fheb_ntt_plan_create(degree, modulus, C.byref(self._h)))
+        else:  # caller-supplied tables: fast_ntt_forward / MetalComputeContext::batch_ntt_forward shape
+            f, v = as_words(fwd_table), as_words(inv_table)
+            check(lib().fheb_ntt_plan_create_with_tables(degree, modulus, _ptr(f), _ptr(v), inv_n, C.byref(self._h)))
+        self.degree, self.modulus = degree, modulus
+
+    def __del__(self):
+        h, self._h = getattr(self, "_h", None), None
+        if h:
+            lib().fheb_ntt_plan_destroy(h)
+
+    def get_degree(self) -> int:
+        return int(lib().fheb_ntt_plan_degree(self._h))
+
+    def get_modulus(self) -> int:
+        return int(lib().fheb_ntt_plan_modulus(self._h))
+
+    def get_twiddles(self):
+        """TwiddleFactors: (forward[N], inverse[N], primitive_root, inv_primitive_root, inv_n)."""
+        f = np.empty(self.degree, np.uint64)
+        v = np.empty(self.degree, np.uint64)
+        s = np.empty(3, np.uint64)
+        check(lib().fheb_ntt_plan_get_tables(self._h, _ptr(f), _ptr(v), _ptr(s)))
+        return f, v, int(s[0]), int(s[1]), int(s[2])
+
+    def _run(self, fn, coeffs, out):
+        coeffs = as_words(coeffs)
+        if coeffs.shape[-1] != self.degree:
+            raise FheError(_cabi.INVALID_PARAMETERS, "Size must match polynomial degree")
+        out = _like(coeffs) if out is None else out
+        batch = _words(coeffs) // self.degree
+        check(fn(self._h, _ptr(coeffs), _ptr(out), batch, _stream(coeffs, out)))
+        return out
+
+    def forward_ntt(self, coeffs, out=None):
+        """forward_ntt / forward_ntt_batch (leading dimensions are the batch); out=coeffs is in place."""
+        return self._run(lib().fheb_ntt_forward_batch, coeffs, out)
+
+    def inverse_ntt(self, coeffs, out=None):
+        return self._run(lib().fheb_ntt_inverse_batch, coeffs, out)
+
+    def inverse_ntt_forward_network(self, coeffs, out=None):
+        """fast_ntt_inverse semantics: cpp/src/adaptive_dispatcher.cpp:171-205."""
+        return self._run(lib().fheb_ntt_inverse_fwdnet_batch, coeffs, out)
+
+    forward_ntt_batch = forward_ntt
+    inverse_ntt_batch = inverse_ntt
+
+
+# ----------------------------------------------------------------------- PolynomialRing --
+def _elementwise(fn, a, b, modulus, out):
+    a, b = as_words(a), as_words(b)
+    out = _like(a) if out is None else out
+    check(fn(_ptr(a), _ptr(b), _ptr(out), _words(a), modulus, _stream(a, b, out)))
+    return out
+
+
+def modadd_batch(a, b, modulus, out=None):
+    return _elementwise(lib().fheb_modadd_batch, a, b, modulus, out)
+
+
+def modsub_batch(a, b, modulus, out=None):
+    return _elementwise(lib().fheb_modsub_batch, a, b, modulus, out)
+
+
+def modmul_batch(a, b, modulus, out=None):
+    """fast_modmul_batch / MetalComputeContext::batch_modmul."""
+    return _elementwise(lib().fheb_modmul_batch, a, b, modulus, out)
+
+
+def modneg_batch(a, modulus, out=None):
+    a = as_words(a)
+    out = _like(a) if out is None else out
+    check(lib().fheb_modneg_batch(_ptr(a), _ptr(out), _words(a), modulus, _stream(a, out)))
+    return out
+
+
+def modmul_scalar_batch(a, scalar, modulus, out=None):
+    a = as_words(a)
+    out = _like(a) if out is None else out
+    check(lib().fheb_modmul_scalar_batch(_ptr(a), scalar, _ptr(out), _words(a), modulus, _stream(a, out)))
+    return out
+
+
+class PolynomialRing:
+    """cpp/include/polynomial_ring.h:312-513; polynomials are [..., N] word arrays."""
+
+    def __init__(self, degree: int, modulus: int):
+        self.ntt = NTTProcessor(degree, modulus)
+        self.degree, self.modulus = degree, modulus
+
+    def add(self, a, b, out=None):
+        return modadd_batch(a, b, self.modulus, out)
+
+    def subtract(self, a, b, out=None):
+        return modsub_batch(a, b, self.modulus, out)
+
+    def negate(self, a, out=None):
+        return modneg_batch(a, self.modulus, out)
+
+    def multiply_scalar(self, a, scalar, out=None):
+        return modmul_scalar_batch(a, scalar, self.modulus, out)
+
+    def pointwise_multiply(self, a, b, out=None):
+        return modmul_batch(a, b, self.modulus, out)
+
+    def to_ntt(self, a, out=None):
+        return self.ntt.forward_ntt(a, out)
+
+    def from_ntt(self, a, out=None):
+        return self.ntt.inverse_ntt(a, out)
+
+    def multiply(self, a, b, out=None):
+        """PolynomialRing::multiply on coefficient-form operands (polynomial_ring.cpp:421-447)."""
+        a, b = as_words(a), as_words(b)
+        if a.shape[-1] != self.degree or _words(a) != _words(b):
+            raise FheError(_cabi.INVALID_PARAMETERS, "Polynomial degree mismatch")
+        out = _like(a) if out is None else out
+        check(lib().fheb_polymul_batch(self.ntt._h, _ptr(a), _ptr(b), _ptr(out), _words(a) // self.degree,
+                                       _stream(a, b, out)))
+        return out
+
+    def tensor_multiply(self, ct1, ct2, out=None):
+        """EncryptionEngine::multiply tensor product: [batch][2][N] x [batch][2][N] -> [batch][3][N]."""
+        ct1, ct2 = as_words(ct1), as_words(ct2)
+        batch = _words(ct1) // (2 * self.degree)
+        out = _like(ct1, tuple(ct1.shape[:-2]) + (3, self.degree)) if out is None else out
+        check(lib().fheb_tensor_multiply_batch(self.ntt._h, _ptr(ct1), _ptr(ct2), _ptr(out), batch, _stream(ct1, ct2, out)))
+        return out
+
+
+# ----------------------------------------------------------- MultiLimbModularArithmetic --
+class MultiLimbModularArithmetic:
+    """cpp/include/modular_arithmetic.h:124-194; integers are [count][limbs] little-endian words."""
+
+    def __init__(self, q_limbs: Sequence[int]):
+        self.q = np.ascontiguousarray(q_limbs, dtype=np.uint64)
+        self.limbs = int(self.q.size)
+        consts = np.zeros(1 + 2 * self.limbs, np.uint64)
+        check(lib().fheb_mlimb_constants(_ptr(self.q), self.limbs, _ptr(consts)))
+        self.q_inv = int(consts[0])
+        self.r_mod_q = consts[1:1 + self.limbs].copy()
+        self.r2_mod_q = consts[1 + self.limbs:].copy()
+
+    def _bin(self, which, a, b, out):
+        a, b = as_words(a), as_words(b)
+        out = _like(a) if out is None else out
+        count = _words(a) // self.limbs
+        L = lib()
+        if which == 0:
+            check(L.fheb_mlimb_montmul_batch(_ptr(a), _ptr(b), _ptr(out), count, self.limbs, _ptr(self.q), self.q_inv,
+                                             _stream(a, b, out)))
+        elif which == 1:
+            check(L.fheb_mlimb_add_batch(_ptr(a), _ptr(b), _ptr(out), count, self.limbs, _ptr(self.q), _stream(a, b, out)))
+        else:
+            check(L.fheb_mlimb_sub_batch(_ptr(a), _ptr(b), _ptr(out), count, self.limbs, _ptr(self.q), _stream(a, b, out)))
+        return out
+
+    def montgomery_mul(self, a, b, out=None):
+        return self._bin(0, a, b, out)
+
+    def mod_add(self, a, b, out=None):
+        return self._bin(1, a, b, out)
+
+    def mod_sub(self, a, b, out=None):
+        return self._bin(2, a, b, out)
+
+    def _const_like(self, a, row):
+        a = as_words(a)
+        count = _words(a) // self.limbs
+        tiled = np.ascontiguousarray(np.broadcast_to(row, (count, self.limbs)))
+        if _is_torch(a):
+            return torch.from_numpy(tiled.view(np.int64)).to(a.device).view(a.dtype)
+        return tiled
+
+    def to_montgomery(self, a, out=None):
+        """montgomery_mul(a, R^2 mod q): modular_arithmetic.cpp:673-683."""
+        return self._bin(0, a, self._const_like(a, self.r2_mod_q), out)
+
+    def from_montgomery(self, a, out=None):
+        """montgomery_mul(a, 1): modular_arithmetic.cpp:685-693."""
+        one = np.zeros(self.limbs, np.uint64)
+        one[0] = 1
+        return self._bin(0, a, self._const_like(a, one), out)
+
+    montgomery_mul_neon, mod_add_neon, mod_sub_neon = montgomery_mul, mod_add, mod_sub
+
+
+# ---------------------------------------------------------------------- BootstrapEngine --
+class BootstrapEngine:
+    """Deterministic part of cpp/include/bootstrap_engine.h:176-508 (key generation and
+    encryption stay with the reference: they are RNG-bound host code)."""
+
+    def __init__(self, poly_degree: int, modulus: int, lwe_dimension: int, glwe_dimension: int, decomp_base_log: int,
+                 decomp_level: int, bsk, plaintext_modulus: int = 4):
+        self.N, self.q, self.n, self.k = poly_degree, modulus, lwe_dimension, glwe_dimension
+        self.base_log, self.level, self.t = decomp_base_log, decomp_level, plaintext_modulus
+        self.ntt = NTTProcessor(poly_degree, modulus)
+        self._h = C.c_void_p()
+        bsk = as_words(bsk)
+        rows = (self.k + 1) * self.level
+        if _words(bsk) != self.n * rows * (self.k + 1) * self.N:
+            raise FheError(_cabi.INVALID_PARAMETERS, "bootstrap key has the wrong number of words")
+        params = BootParams(self.n, self.k, self.base_log, self.level)
+        check(lib().fheb_boot_key_create(self.ntt._h, C.byref(params), _ptr(bsk), C.byref(self._h)))
+        self.n_out = None
+
+    def __del__(self):
+        h, self._h = getattr(self, "_h", None), None
+        if h:
+            lib().fheb_boot_key_destroy(h)
+
+    def set_key_switch_key(self, ksk, n_out: int, base_log: int, level: int):
+        ksk = as_words(ksk)
+        entries = _words(ksk) // (n_out + 1)
+        check(lib().fheb_boot_key_set_ksk(self._h, _ptr(ksk), entries, n_out, base_log, level))
+        self.n_out = n_out
+
+    def _glwe_words(self):
+        return (self.k + 1) * self.N
+
+    def external_product(self, glwe, index: int, out=None):
+        glwe = as_words(glwe)
+        out = _like(glwe) if out is None else out
+        check(lib().fheb_external_product_batch(self._h, index, _ptr(glwe), _ptr(out), _words(glwe) // self._glwe_words(),
+                                                _stream(glwe, out)))
+        return out
+
+    def cmux(self, index: int, ct0, ct1, out=None):
+        ct0, ct1 = as_words(ct0), as_words(ct1)
+        out = _like(ct0) if out is None else out
+        check(lib().fheb_cmux_batch(self._h, index, _ptr(ct0), _ptr(ct1), _ptr(out), _words(ct0) // self._glwe_words(),
+                                    _stream(ct0, ct1, out)))
+        return out
+
+    def blind_rotate(self, lwe, test_poly, out=None):
+        """blind_rotate of acc = (0,..,0,test_poly): lwe [batch][n+1] -> [batch][k+1][N]."""
+        lwe, test_poly = as_words(lwe), as_words(test_poly)
+        batch = _words(lwe) // (self.n + 1)
+        out = _like(lwe, (batch, self.k + 1, self.N)) if out is None else out
+        check(lib().fheb_blind_rotate_batch(self._h, _ptr(lwe), _ptr(test_poly), _ptr(out), batch, _stream(lwe, out)))
+        return out
+
+    def sample_extract(self, glwe, out=None):
+        glwe = as_words(glwe)
+        batch = _words(glwe) // self._glwe_words()
+        out = _like(glwe, (batch, self.k * self.N + 1)) if out is None else out
+        check(lib().fheb_sample_extract_batch(self._h, _ptr(glwe), _ptr(out), batch, _stream(glwe, out)))
+        return out
+
+    def key_switch(self, lwe, out=None):
+        lwe = as_words(lwe)
+        batch = _words(lwe) // (self.k * self.N + 1)
+        out = _like(lwe, (batch, self.n_out + 1)) if out is None else out
+        check(lib().fheb_key_switch_batch(self._h, _ptr(lwe), _ptr(out), batch, _stream(lwe, out)))
+        return out
+
+    def bootstrap_with_test_poly(self, lwe, test_poly, out=None):
+        lwe, test_poly = as_words(lwe), as_words(test_poly)
+        batch = _words(lwe) // (self.n + 1)
+        width = (self.n_out + 1) if self.n_out is not None else (self.k * self.N + 1)
+        out = _like(lwe, (batch, width)) if out is None else out
+        check(lib().fheb_bootstrap_batch(self._h, _ptr(lwe), _ptr(test_poly), _ptr(out), batch, _stream(lwe, out)))
+        return out
+
+    bootstrap = bootstrap_with_test_poly
+
+    def _lut(self, kind, arg0, arg1=0):
+        out = np.empty(self.N, np.uint64)
+        check(lib().fheb_make_test_poly(self.ntt._h, kind, arg0, arg1, _ptr(out)))
+        return out
+
+    def get_default_test_poly(self):
+        return self._lut(3, self.t)
+
+    def create_identity_lut(self, modulus):
+        return self._lut(0, modulus)
+
+    def create_negation_lut(self, modulus):
+        return self._lut(1, modulus)
+
+    def create_threshold_lut(self, threshold, modulus):
+        return self._lut(2, threshold, modulus)
+
+
+# -------------------------------------------------------------------------------- tally --
+def tally_votes(cts, degree: int, modulus: int, out=None):
+    """EncryptionEngine::batch_add / batch_add_tree / tally_votes words: [count][2][N] -> [2][N]."""
+    cts = as_words(cts)
+    count = _words(cts) // (2 * degree)
+    if count == 0:
+        raise FheError(_cabi.INVALID_PARAMETERS, "Cannot add empty vector of ciphertexts")
+    out = _like(cts, (2, degree)) if out is None else out
+    check(lib().fheb_tally(_ptr(cts), count, degree, modulus, _ptr(out), _stream(cts, out)))
+    return out
+
+
+batch_add = tally_votes
+
+
+def tally_combine(partials, degree: int, modulus: int, out=None):
+    partials = as_words(partials)
+    parts = _words(partials) // (2 * degree)
+    out = _like(partials, (2, degree)) if out is None else out
+    check(lib().fheb_tally_combine(_ptr(partials), parts, degree, modulus, _ptr(out), _stream(partials, out)))
+    return out
+
+
+def synth_ballots(cts_device, first_ballot: int, count: int, degree: int, modulus: int, seed: int):
+    check(lib().fheb_synth_ballots(_ptr(cts_device), first_ballot, count, degree, modulus, seed, _stream(cts_device)))
+    return cts_device
+
+
+def tally_noise_budget(budgets: Sequence[float], variant: str = "linear") -> float:
+    """noise_budget metadata of the reference's tally variants (host-side):
+    linear = min - log2(count) (encryption.cpp:1359-1360); tree = min - 1 per level (:1413,1437)."""
+    import math
+    lo, count = min(budgets), len(budgets)
+    if count == 1:
+        return lo
+    if variant == "linear":
+        return lo - math.log2(count)
+    return lo - math.ceil(math.log2(count))

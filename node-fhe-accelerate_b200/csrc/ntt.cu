@@ -1,0 +1,350 @@
+// Batched forward / inverse transform and fused polynomial multiplication for sm_100a.
+//
+// One thread block owns PPC whole polynomials in shared memory and walks the pass plan of
+// ntt_core.cuh: the first pass reads coalesced from global memory straight into registers,
+// the middle passes exchange through bank-swizzled shared memory, the last pass stores
+// coalesced from registers (in the reference's bit-reversed order for the forward
+// transform).  Blocks are persistent (grid = SMs x resident blocks) and walk the batch with
+// a grid stride, prefetching their next polynomials into L2 with a bulk-async prefetch.
+//
+// C-ABI entry points here (include/fheb200.h): fheb_ntt_plan_*, fheb_ntt_forward_batch,
+// fheb_ntt_inverse_batch, fheb_ntt_inverse_fwdnet_batch, fheb_polymul_batch.
+#include "ntt_device.cuh"
+#include "ntt_plan.hpp"
+#include "plan.hpp"
+#include "runtime.hpp"
+
+namespace fheb {
+
+// ---- host-side plan maths (mirrors the reference's constructor) --------------------------
+static uint64_t h_mod_pow(uint64_t base, uint64_t exp, uint64_t mod) {  // ntt_processor.cpp:47-62
+    uint64_t result = 1;
+    base %= mod;
+    while (exp > 0) {
+        if (exp & 1) result = (uint64_t)(((u128)result * base) % mod);
+        base = (uint64_t)(((u128)base * base) % mod);
+        exp >>= 1;
+    }
+    return result;
+}
+
+static uint64_t h_mod_inverse(uint64_t a, uint64_t m) {  // ntt_processor.cpp:64-90 (signed Euclid)
+    if (m == 1) return 0;
+    int64_t m0 = (int64_t)m, x0 = 0, x1 = 1;
+    int64_t as = (int64_t)(a % m), ms = (int64_t)m;
+    while (as > 1) {
+        int64_t quo = as / ms, t = ms;
+        ms = as % ms;
+        as = t;
+        t = x0;
+        x0 = x1 - quo * x0;
+        x1 = t;
+    }
+    if (x1 < 0) x1 += m0;
+    return (uint64_t)x1;
+}
+
+static bool h_find_primitive_root(uint32_t degree, uint64_t q, uint64_t* root) {  // ntt_processor.cpp:92-128
+    const uint64_t two_n = (uint64_t)degree * 2;
+    if ((q - 1) % two_n != 0) return false;
+    const uint64_t exponent = (q - 1) / two_n;
+    // The reference scans every g < q; a composite modulus (e.g. the tfhe-128-fast preset's
+    // 2^40+1) makes that a ~10^12-step loop ending in the same exception, so the
+    // scan is capped far beyond where any prime modulus finds its root.
+    for (uint64_t g = 2; g < q && g < (1u << 20); g++) {
+        const uint64_t omega = h_mod_pow(g, exponent, q);
+        if (h_mod_pow(omega, two_n, q) == 1 && h_mod_pow(omega, degree, q) == q - 1) {
+            *root = omega;
+            return true;
+        }
+    }
+    return false;
+}
+
+static int validate_degree_modulus(uint32_t degree, uint64_t modulus) {
+    // messages follow NTTProcessor::NTTProcessor, cpp/src/ntt_processor.cpp:141-153
+    FHEB_REQUIRE(degree > 0 && (degree & (degree - 1)) == 0, "Polynomial degree must be a power of 2");
+    FHEB_REQUIRE(degree >= 4 && degree <= 65536, "Polynomial degree must be between 4 and 65536");
+    FHEB_REQUIRE((modulus & 1) != 0, "Modulus must be odd");
+    FHEB_REQUIRE(degree <= 16384, "degree %u is above this backend's limit of 16384", degree);
+    FHEB_REQUIRE(modulus > 2 && modulus < (1ULL << 62), "modulus must be below 2^62 on this backend");
+    return FHEB_OK;
+}
+
+static int upload_heap(const std::vector<Tw>& heap, Tw** out) {
+    FHEB_CUDA(cudaMalloc(out, heap.size() * sizeof(Tw)));
+    FHEB_CUDA(cudaMemcpy(*out, heap.data(), heap.size() * sizeof(Tw), cudaMemcpyHostToDevice));
+    return FHEB_OK;
+}
+
+static int plan_finish(NttPlan* p) {
+    const uint64_t q = p->modulus;
+    p->logn = log2_exact(p->degree);
+    p->mod = make_modq(q);
+    p->ninv = Tw{p->inv_n % q, shoup_companion(p->inv_n % q, q)};
+    p->unit_first = (p->fwd_table[0] % q == 1) && (p->inv_table[0] % q == 1);
+    FHEB_REQUIRE(p->unit_first, "twiddle tables must start with 1 (root^0)");
+    FHEB_TRY(upload_heap(build_heap_table(p->fwd_table.data(), p->logn, q), &p->d_fwd));
+    FHEB_TRY(upload_heap(build_heap_table(p->inv_table.data(), p->logn, q), &p->d_inv));
+    return FHEB_OK;
+}
+
+// ---- kernel dispatch --------------------------------------------------------------------
+template <int L>
+struct Geometry {  // threads per block, polynomials per block
+    static constexpr int PPC = (L <= 9) ? (1024 >> L) : (L == 10 ? 2 : 1);
+    static constexpr int THREADS = (L <= 11) ? 128 : (L == 12 ? 256 : 512);
+    static constexpr size_t SMEM = (Plan<L>::P > 1) ? (size_t)PPC * (1u << L) * 8 : 0;
+};
+
+template <class K>
+static int configure(K kernel, size_t smem, int threads, int* blocks_per_sm) {
+    static std::mutex mu;
+    std::lock_guard<std::mutex> lock(mu);
+    if (smem > 48 * 1024) FHEB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    FHEB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, kernel, threads, smem));
+    if (*blocks_per_sm < 1) return set_error(FHEB_ERR_NATIVE, "kernel does not fit on an SM (smem %zu)", smem);
+    return FHEB_OK;
+}
+
+static unsigned persistent_grid(size_t work_groups, int blocks_per_sm) {
+    const size_t resident = (size_t)ctx().sm_count * (size_t)blocks_per_sm;
+    return (unsigned)(work_groups < resident ? work_groups : resident);
+}
+
+enum { DIR_FWD = 0, DIR_INV = 1, DIR_INV_FWDNET = 2 };
+
+template <int L, bool LAZY>
+static int launch_transform(const NttPlan* p, int dir, const uint64_t* in, uint64_t* out, size_t batch, cudaStream_t s) {
+    using G = Geometry<L>;
+    const size_t groups = (batch + G::PPC - 1) / G::PPC;
+    int bps = 0;
+    if (dir == DIR_INV) {
+        auto k = ntt_inverse_kernel<L, LAZY, G::THREADS, G::PPC>;
+        FHEB_TRY(configure(k, G::SMEM, G::THREADS, &bps));
+        k<<<persistent_grid(groups, bps), G::THREADS, G::SMEM, s>>>(in, out, batch, p->d_inv, p->ninv, p->mod);
+    } else if (dir == DIR_FWD) {
+        auto k = ntt_forward_kernel<L, LAZY, G::THREADS, G::PPC, false>;
+        FHEB_TRY(configure(k, G::SMEM, G::THREADS, &bps));
+        k<<<persistent_grid(groups, bps), G::THREADS, G::SMEM, s>>>(in, out, batch, p->d_fwd, p->ninv, p->mod);
+    } else {
+        auto k = ntt_forward_kernel<L, LAZY, G::THREADS, G::PPC, true>;
+        FHEB_TRY(configure(k, G::SMEM, G::THREADS, &bps));
+        k<<<persistent_grid(groups, bps), G::THREADS, G::SMEM, s>>>(in, out, batch, p->d_inv, p->ninv, p->mod);
+    }
+    FHEB_CHECK_LAUNCH();
+    count_launch();
+    return FHEB_OK;
+}
+
+template <int L, bool LAZY>
+static int launch_polymul(const NttPlan* p, const uint64_t* a, const uint64_t* b, uint64_t* c, size_t batch,
+                          cudaStream_t s) {
+    using G = Geometry<L>;
+    constexpr bool STASH_GLOBAL = (L >= 14);  // two 128 KB operands do not fit in shared memory
+    constexpr size_t SMEM = STASH_GLOBAL ? G::SMEM : 2 * (size_t)G::PPC * (1u << L) * 8;
+    const size_t groups = (batch + G::PPC - 1) / G::PPC;
+    int bps = 0;
+    auto k = polymul_kernel<L, LAZY, G::THREADS, G::PPC, STASH_GLOBAL>;
+    FHEB_TRY(configure(k, SMEM, G::THREADS, &bps));
+    const unsigned grid = persistent_grid(groups, bps);
+    uint64_t* stash = nullptr;
+    if (STASH_GLOBAL) {
+        // per-block scratch for T(a); small enough to stay L2 resident (grid x 128 KB)
+        FHEB_CUDA(cudaMallocAsync(&stash, (size_t)grid * G::PPC * (1u << L) * 8, s));
+    }
+    k<<<grid, G::THREADS, SMEM, s>>>(a, b, c, batch, p->d_fwd, p->d_inv, p->ninv, p->mod, stash);
+    FHEB_CHECK_LAUNCH();
+    count_launch();
+    if (stash) FHEB_CUDA(cudaFreeAsync(stash, s));
+    return FHEB_OK;
+}
+
+#define FHEB_DISPATCH_L(FN, L_, ...)                                         \
+    case L_:                                                                 \
+        return lazy ? FN<L_, true>(__VA_ARGS__) : FN<L_, false>(__VA_ARGS__);
+
+static int dispatch_transform(const NttPlan* p, int dir, const uint64_t* in, uint64_t* out, size_t batch, cudaStream_t s) {
+    const bool lazy = p->mod.lazy != 0;
+    switch (p->logn) {
+        FHEB_DISPATCH_L(launch_transform, 2, p, dir, in, out, batch, s)
+        FHEB_DISPATCH_L(launch_transform, 3, p, dir, in, out, batch, s)
+        FHEB_DISPATCH_L(launch_transform, 4, p, dir, in, out, batch, s)
+        FHEB_DISPATCH_L(launch_transform, 5, p, dir, in, out, batch, s)
+        FHEB_DISPATCH_L(launch_transform, 6, p, dir, in, out, batch, s)
+        FHEB_DISPATCH_L(launch_transform, 7, p, dir, in, out, batch, s)
+        FHEB_DISPATCH_L(launch_transform, 8, p, dir, in, out, batch, s)
+        FHEB_DISPATCH_L(launch_transform, 9, p, dir, in, out, batch, s)
+        FHEB_DISPATCH_L(launch_transform, 10, p, dir, in, out, batch, s)
+        FHEB_DISPATCH_L(launch_transform, 11, p, dir, in, out, batch, s)
+        FHEB_DISPATCH_L(launch_transform, 12, p, dir, in, out, batch, s)
+        FHEB_DISPATCH_L(launch_transform, 13, p, dir, in, out, batch, s)
+        FHEB_DISPATCH_L(launch_transform, 14, p, dir, in, out, batch, s)
+    }
+    return set_error(FHEB_ERR_INVALID_PARAMETERS, "unsupported degree 2^%u", p->logn);
+}
+
+static int dispatch_polymul(const NttPlan* p, const uint64_t* a, const uint64_t* b, uint64_t* c, size_t batch, cudaStream_t s) {
+    const bool lazy = p->mod.lazy != 0;
+    switch (p->logn) {
+        FHEB_DISPATCH_L(launch_polymul, 2, p, a, b, c, batch, s)
+        FHEB_DISPATCH_L(launch_polymul, 3, p, a, b, c, batch, s)
+        FHEB_DISPATCH_L(launch_polymul, 4, p, a, b, c, batch, s)
+        FHEB_DISPATCH_L(launch_polymul, 5, p, a, b, c, batch, s)
+        FHEB_DISPATCH_L(launch_polymul, 6, p, a, b, c, batch, s)
+        FHEB_DISPATCH_L(launch_polymul, 7, p, a, b, c, batch, s)
+        FHEB_DISPATCH_L(launch_polymul, 8, p, a, b, c, batch, s)
+        FHEB_DISPATCH_L(launch_polymul, 9, p, a, b, c, batch, s)
+        FHEB_DISPATCH_L(launch_polymul, 10, p, a, b, c, batch, s)
+        FHEB_DISPATCH_L(launch_polymul, 11, p, a, b, c, batch, s)
+        FHEB_DISPATCH_L(launch_polymul, 12, p, a, b, c, batch, s)
+        FHEB_DISPATCH_L(launch_polymul, 13, p, a, b, c, batch, s)
+        FHEB_DISPATCH_L(launch_polymul, 14, p, a, b, c, batch, s)
+    }
+    return set_error(FHEB_ERR_INVALID_PARAMETERS, "unsupported degree 2^%u", p->logn);
+}
+
+// Device-pointer entry points used by other translation units (bootstrap, tally).
+int ntt_forward_device(const NttPlan* p, const uint64_t* in, uint64_t* out, size_t batch, cudaStream_t s) {
+    return batch ? dispatch_transform(p, DIR_FWD, in, out, batch, s) : FHEB_OK;
+}
+int ntt_inverse_device(const NttPlan* p, const uint64_t* in, uint64_t* out, size_t batch, cudaStream_t s) {
+    return batch ? dispatch_transform(p, DIR_INV, in, out, batch, s) : FHEB_OK;
+}
+
+static int transform_entry(const fheb_ntt_plan* plan, int dir, const uint64_t* in, uint64_t* out, size_t batch, void* stream) {
+    FHEB_TRY(ensure_ready());
+    FHEB_REQUIRE(plan != nullptr, "plan must not be null");
+    if (batch == 0) return FHEB_OK;
+    FHEB_REQUIRE(in != nullptr && out != nullptr, "coefficient pointers must not be null");
+    const NttPlan* p = reinterpret_cast<const NttPlan*>(plan);
+    cudaStream_t s = (cudaStream_t)stream;
+    const size_t bytes = batch * (size_t)p->degree * 8;
+    Staged sin, sout;
+    FHEB_TRY(sin.bind(in, bytes, true, false, s));
+    if (out == in) FHEB_TRY(sout.bind_alias(sin, true));
+    else FHEB_TRY(sout.bind(out, bytes, false, true, s));
+    FHEB_TRY(dispatch_transform(p, dir, sin.ptr<const uint64_t>(), sout.ptr<uint64_t>(), batch, s));
+    FHEB_TRY(sin.finish());
+    FHEB_TRY(sout.finish());
+    return sync_if_staged(s, {&sin, &sout});
+}
+
+}  // namespace fheb
+
+using namespace fheb;
+
+extern "C" {
+
+int fheb_ntt_plan_create(uint32_t degree, uint64_t modulus, fheb_ntt_plan** out) {
+    FHEB_REQUIRE(out != nullptr, "out must not be null");
+    *out = nullptr;
+    FHEB_TRY(ensure_ready());
+    FHEB_TRY(validate_degree_modulus(degree, modulus));
+    uint64_t psi = 0;
+    // messages follow find_primitive_root, cpp/src/ntt_processor.cpp:103-105,127
+    FHEB_REQUIRE((modulus - 1) % ((uint64_t)degree * 2) == 0, "Modulus is not NTT-friendly: q != 1 (mod 2N)");
+    FHEB_REQUIRE(h_find_primitive_root(degree, modulus, &psi), "Could not find primitive root for given parameters");
+    NttPlan* p = new NttPlan();
+    p->degree = degree;
+    p->modulus = modulus;
+    p->psi = psi;
+    p->psi_inv = h_mod_inverse(psi, modulus);
+    p->inv_n = h_mod_inverse(degree, modulus);
+    p->fwd_table.resize(degree);
+    p->inv_table.resize(degree);
+    p->fwd_table[0] = 1;
+    p->inv_table[0] = 1;
+    for (uint32_t i = 1; i < degree; i++) {  // cpp/src/ntt_processor.cpp:188-202
+        p->fwd_table[i] = (uint64_t)(((u128)p->fwd_table[i - 1] * psi) % modulus);
+        p->inv_table[i] = (uint64_t)(((u128)p->inv_table[i - 1] * p->psi_inv) % modulus);
+    }
+    int rc = plan_finish(p);
+    if (rc != FHEB_OK) {
+        fheb_ntt_plan_destroy(reinterpret_cast<fheb_ntt_plan*>(p));
+        return rc;
+    }
+    *out = reinterpret_cast<fheb_ntt_plan*>(p);
+    return FHEB_OK;
+}
+
+int fheb_ntt_plan_create_with_tables(uint32_t degree, uint64_t modulus, const uint64_t* fwd_table,
+                                     const uint64_t* inv_table, uint64_t inv_n, fheb_ntt_plan** out) {
+    FHEB_REQUIRE(out != nullptr, "out must not be null");
+    *out = nullptr;
+    FHEB_TRY(ensure_ready());
+    FHEB_TRY(validate_degree_modulus(degree, modulus));
+    FHEB_REQUIRE(fwd_table != nullptr && inv_table != nullptr, "twiddle tables must not be null");
+    NttPlan* p = new NttPlan();
+    p->degree = degree;
+    p->modulus = modulus;
+    p->inv_n = inv_n;
+    p->fwd_table.assign(fwd_table, fwd_table + degree);
+    p->inv_table.assign(inv_table, inv_table + degree);
+    int rc = plan_finish(p);
+    if (rc != FHEB_OK) {
+        fheb_ntt_plan_destroy(reinterpret_cast<fheb_ntt_plan*>(p));
+        return rc;
+    }
+    *out = reinterpret_cast<fheb_ntt_plan*>(p);
+    return FHEB_OK;
+}
+
+int fheb_ntt_plan_destroy(fheb_ntt_plan* plan) {
+    NttPlan* p = reinterpret_cast<NttPlan*>(plan);
+    if (!p) return FHEB_OK;
+    if (p->d_fwd) cudaFree(p->d_fwd);
+    if (p->d_inv) cudaFree(p->d_inv);
+    delete p;
+    return FHEB_OK;
+}
+
+int fheb_ntt_plan_get_tables(const fheb_ntt_plan* plan, uint64_t* fwd_table, uint64_t* inv_table, uint64_t scalars[3]) {
+    FHEB_REQUIRE(plan != nullptr, "plan must not be null");
+    const NttPlan* p = reinterpret_cast<const NttPlan*>(plan);
+    if (fwd_table) std::memcpy(fwd_table, p->fwd_table.data(), p->degree * 8);
+    if (inv_table) std::memcpy(inv_table, p->inv_table.data(), p->degree * 8);
+    if (scalars) {
+        scalars[0] = p->psi;
+        scalars[1] = p->psi_inv;
+        scalars[2] = p->inv_n;
+    }
+    return FHEB_OK;
+}
+
+uint32_t fheb_ntt_plan_degree(const fheb_ntt_plan* plan) { return plan ? reinterpret_cast<const NttPlan*>(plan)->degree : 0; }
+uint64_t fheb_ntt_plan_modulus(const fheb_ntt_plan* plan) { return plan ? reinterpret_cast<const NttPlan*>(plan)->modulus : 0; }
+
+int fheb_ntt_forward_batch(const fheb_ntt_plan* plan, const uint64_t* in, uint64_t* out, size_t batch, void* stream) {
+    return transform_entry(plan, DIR_FWD, in, out, batch, stream);
+}
+int fheb_ntt_inverse_batch(const fheb_ntt_plan* plan, const uint64_t* in, uint64_t* out, size_t batch, void* stream) {
+    return transform_entry(plan, DIR_INV, in, out, batch, stream);
+}
+int fheb_ntt_inverse_fwdnet_batch(const fheb_ntt_plan* plan, const uint64_t* in, uint64_t* out, size_t batch, void* stream) {
+    return transform_entry(plan, DIR_INV_FWDNET, in, out, batch, stream);
+}
+
+int fheb_polymul_batch(const fheb_ntt_plan* plan, const uint64_t* a, const uint64_t* b, uint64_t* c, size_t batch, void* stream) {
+    FHEB_TRY(ensure_ready());
+    FHEB_REQUIRE(plan != nullptr, "plan must not be null");
+    if (batch == 0) return FHEB_OK;
+    FHEB_REQUIRE(a != nullptr && b != nullptr && c != nullptr, "coefficient pointers must not be null");
+    const NttPlan* p = reinterpret_cast<const NttPlan*>(plan);
+    cudaStream_t s = (cudaStream_t)stream;
+    const size_t bytes = batch * (size_t)p->degree * 8;
+    Staged sa, sb, sc;
+    FHEB_TRY(sa.bind(a, bytes, true, false, s));
+    if (b == a) FHEB_TRY(sb.bind_alias(sa, false));
+    else FHEB_TRY(sb.bind(b, bytes, true, false, s));
+    if (c == a) FHEB_TRY(sc.bind_alias(sa, true));
+    else if (c == b) FHEB_TRY(sc.bind_alias(sb, true));
+    else FHEB_TRY(sc.bind(c, bytes, false, true, s));
+    FHEB_TRY(dispatch_polymul(p, sa.ptr<const uint64_t>(), sb.ptr<const uint64_t>(), sc.ptr<uint64_t>(), batch, s));
+    FHEB_TRY(sa.finish());
+    FHEB_TRY(sb.finish());
+    FHEB_TRY(sc.finish());
+    return sync_if_staged(s, {&sa, &sb, &sc});
+}
+
+}  // extern "C"

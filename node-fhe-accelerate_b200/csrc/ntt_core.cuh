@@ -1,0 +1,421 @@
+// Radix-2^R register passes of the reference's transform, in "position space".
+//
+// The reference's forward transform (cpp/src/ntt_processor.cpp:262-311) is: bit-reverse the
+// input, then for stage s = 0..L-1 (m = 2^s) do (A,B) <- (A + w*B, A - w*B) on entries
+// (k+j, k+j+m) of the PERMUTED array with w = table[j * N/(2m)].  Writing i = bitrev(p) for
+// the position of permuted entry p in the ORIGINAL array, stage s pairs original positions
+// that differ in bit (L-1-s), and its twiddle depends only on the TOP s bits of i:
+//     table index  j*N/(2m)  with  j = bitrev_s(i >> (L-s)).
+// So the network can run on the data where it lies (no permutation): distance N/2 first,
+// distance 1 last, one twiddle per contiguous block of N/2^s positions, and the result for
+// permuted entry p ends up at position bitrev(p).  The device twiddle table is therefore
+// stored block-ordered as a binary heap: entry (2^s + b) holds table[bitrev_s(b) << (L-1-s)],
+// and the children of the twiddle used at one stage are the two twiddles of the next.
+// The inverse (ntt_processor.cpp:325-380) is the same pairs walked backwards with
+// (A,B) <- (A + B, (A - B)*w), then the bit-reversal (which brings entry p back to position
+// bitrev(bitrev(i)) = i, i.e. nothing to move) and the scaling by N^-1.
+//
+// Values are kept lazily in [0, K*q) with K tracked at compile time (Harvey butterflies);
+// every function states the bound it needs and the bound it leaves.  Outputs handed back
+// to the caller are always canonical, so results are bit-identical to the reference's.
+#pragma once
+#include "modarith.cuh"
+
+namespace fheb {
+
+// Bank swizzle for 8-byte words in shared memory: XOR-fold the higher index nibbles into
+// the low nibble (16 word-banks).  Any 5 index bits that cover all residues mod 4 - which
+// holds for every access pattern of the passes below, including the bit-reversed one - hit
+// 16 distinct word-banks twice, i.e. the 2-wavefront minimum for a 256-byte warp access.
+FHEB_HD constexpr uint32_t swz(uint32_t i) { return i ^ ((i >> 4) & 15u) ^ ((i >> 8) & 15u) ^ ((i >> 12) & 15u); }
+
+FHEB_HD constexpr uint32_t bitrev_c(uint32_t x, int bits) {
+    uint32_t r = 0;
+    for (int i = 0; i < bits; ++i) r |= ((x >> i) & 1u) << (bits - 1 - i);
+    return r;
+}
+
+FHEB_HD uint32_t bitrev_rt(uint32_t x, int bits) {
+#if defined(__CUDA_ARCH__)
+    return bits ? (__brev(x) >> (32 - bits)) : 0u;
+#else
+    return bitrev_c(x, bits);
+#endif
+}
+
+constexpr int CAP_STRICT = 4;        // q < 2^62: 4q fits a word
+constexpr int CAP_LAZY = 1 << 18;    // q < 2^46: 2^18 q fits a word
+
+template <bool LAZY>
+constexpr int cap_of() { return LAZY ? CAP_LAZY : CAP_STRICT; }
+
+// ---- compile-time range tracking -----------------------------------------------------
+constexpr int fwd_next_k(int K, bool has_unit, bool has_nonunit, int cap) {
+    int kn = has_nonunit ? (((K + 2 > cap) ? 2 : K) + 2) : 0;
+    int ku = has_unit ? ((2 * K > cap) ? 4 : 2 * K) : 0;
+    return kn > ku ? kn : ku;
+}
+constexpr int fwd_pass_k(int K, int R, bool unit_first, int cap) {
+    for (int a = 0; a < R; ++a) K = fwd_next_k(K, unit_first, !(unit_first && a == 0), cap);
+    return K;
+}
+constexpr int inv_next_k(int K, int cap) { return (2 * K > cap / 2) ? 2 : 2 * K; }
+constexpr int inv_pass_k(int K, int R, int cap) {
+    for (int a = 0; a < R; ++a) K = inv_next_k(K, cap);
+    return K;
+}
+
+template <int K>
+FHEB_HD uint64_t kq(const ModQ& m) {
+    if constexpr (K == 1) return m.q;
+    else if constexpr (K == 2) return m.q2;
+    else return m.q * (uint64_t)K;
+}
+
+// Forward butterfly on values < K*q; leaves values < fwd_next_k(K)*q.
+template <int K, int CAP, bool UNIT>
+FHEB_HD void fwd_bfly(uint64_t& A, uint64_t& B, const Tw& w, const ModQ& m) {
+    if constexpr (UNIT) {  // twiddle == 1: no multiplication
+        constexpr bool red = (2 * K > CAP);
+        static_assert(!red || K <= 4, "conditional subtraction only halves [0,4q)");
+        uint64_t a = A, t = B;
+        if constexpr (red) {
+            a = csub(a, m.q2);
+            t = csub(t, m.q2);
+        }
+        constexpr int KT = red ? 2 : K;
+        A = a + t;
+        B = a - t + kq<KT>(m);
+    } else {
+        constexpr bool red = (K + 2 > CAP);
+        static_assert(!red || K <= 4, "conditional subtraction only halves [0,4q)");
+        uint64_t a = A;
+        if constexpr (red) a = csub(a, m.q2);
+        uint64_t t = shoup_lazy(B, w.w, w.wp, m.q);  // [0, 2q) for any B
+        A = a + t;
+        B = a - t + m.q2;
+    }
+}
+
+// Inverse (Gentleman-Sande) butterfly on values < K*q; leaves values < inv_next_k(K)*q.
+template <int K, int CAP, bool UNIT>
+FHEB_HD void inv_bfly(uint64_t& A, uint64_t& B, const Tw& w, const ModQ& m) {
+    static_assert(2 * K <= CAP, "sum would overflow the word");
+    constexpr bool red = (2 * K > CAP / 2);
+    static_assert(!red || 2 * K <= 4, "conditional subtraction only halves [0,4q)");
+    uint64_t s = A + B;
+    uint64_t d = A - B + kq<K>(m);
+    if constexpr (red) s = csub(s, m.q2);
+    A = s;
+    if constexpr (UNIT) {
+        if constexpr (red) d = csub(d, m.q2);
+        B = d;
+    } else {
+        B = shoup_lazy(d, w.w, w.wp, m.q);
+    }
+}
+
+FHEB_HD Tw load_tw(const Tw* __restrict__ tw, uint32_t idx) {
+#if defined(__CUDA_ARCH__)
+    const ulonglong2 v = __ldg(reinterpret_cast<const ulonglong2*>(tw) + idx);
+    Tw t;
+    t.w = v.x;
+    t.wp = v.y;
+    return t;
+#else
+    return tw[idx];
+#endif
+}
+
+// R forward stages on 2^R register-resident values; element bit (R-1) is the highest
+// position bit of the pass.  T0 = heap index of the first stage's twiddle for this block.
+template <int R, int K, int CAP, bool UNITFIRST, int A = 0>
+FHEB_HD void fwd_stages(uint64_t (&x)[1 << R], const Tw* __restrict__ tw, uint32_t T0, const ModQ& m) {
+    if constexpr (A < R) {
+        constexpr int half = 1 << (R - 1 - A);
+#pragma unroll
+        for (int g = 0; g < (1 << A); ++g) {
+            if (UNITFIRST && g == 0) {
+                Tw dummy{0, 0};
+#pragma unroll
+                for (int j = 0; j < half; ++j) fwd_bfly<K, CAP, true>(x[g * 2 * half + j], x[g * 2 * half + j + half], dummy, m);
+            } else {
+                const Tw w = load_tw(tw, (T0 << A) + g);
+#pragma unroll
+                for (int j = 0; j < half; ++j) fwd_bfly<K, CAP, false>(x[g * 2 * half + j], x[g * 2 * half + j + half], w, m);
+            }
+        }
+        fwd_stages<R, fwd_next_k(K, UNITFIRST, !(UNITFIRST && A == 0), CAP), CAP, UNITFIRST, A + 1>(x, tw, T0, m);
+    }
+}
+
+// R inverse stages, highest stage of the pass first (element bit 0 first).
+template <int R, int K, int CAP, bool UNITFIRST, int A = R - 1>
+FHEB_HD void inv_stages(uint64_t (&x)[1 << R], const Tw* __restrict__ tw, uint32_t T0, const ModQ& m) {
+    if constexpr (A >= 0) {
+        constexpr int half = 1 << (R - 1 - A);
+#pragma unroll
+        for (int g = 0; g < (1 << A); ++g) {
+            if (UNITFIRST && g == 0) {
+                Tw dummy{0, 0};
+#pragma unroll
+                for (int j = 0; j < half; ++j) inv_bfly<K, CAP, true>(x[g * 2 * half + j], x[g * 2 * half + j + half], dummy, m);
+            } else {
+                const Tw w = load_tw(tw, (T0 << A) + g);
+#pragma unroll
+                for (int j = 0; j < half; ++j) inv_bfly<K, CAP, false>(x[g * 2 * half + j], x[g * 2 * half + j + half], w, m);
+            }
+        }
+        inv_stages<R, inv_next_k(K, CAP), CAP, UNITFIRST, A - 1>(x, tw, T0, m);
+    }
+}
+
+// value < K*q  ->  canonical
+template <int K>
+FHEB_HD uint64_t canon_k(uint64_t x, const ModQ& m) {
+    if constexpr (K <= 1) return x;
+    else if constexpr (K == 2) return csub(x, m.q);
+    else if constexpr (K <= 4) return csub(csub(x, m.q2), m.q);
+    else return reduce64(x, m);
+}
+
+// ---- pass plans: how the L stages are split into register passes ----------------------
+// plan<L>::R[p] = stages in pass p (forward order); at most 4 passes, each of 1..4 stages.
+template <int L> struct Plan;
+#define FHEB_PLAN(L_, P_, ...)                         \
+    template <> struct Plan<L_> {                      \
+        static constexpr int P = P_;                   \
+        static constexpr int R[4] = {__VA_ARGS__};     \
+    };
+FHEB_PLAN(2, 1, 2, 0, 0, 0)
+FHEB_PLAN(3, 1, 3, 0, 0, 0)
+FHEB_PLAN(4, 1, 4, 0, 0, 0)
+FHEB_PLAN(5, 2, 3, 2, 0, 0)
+FHEB_PLAN(6, 2, 3, 3, 0, 0)
+FHEB_PLAN(7, 2, 4, 3, 0, 0)
+FHEB_PLAN(8, 2, 4, 4, 0, 0)
+FHEB_PLAN(9, 3, 3, 3, 3, 0)
+FHEB_PLAN(10, 3, 4, 3, 3, 0)
+FHEB_PLAN(11, 3, 4, 4, 3, 0)
+FHEB_PLAN(12, 3, 4, 4, 4, 0)
+FHEB_PLAN(13, 4, 4, 3, 3, 3)
+FHEB_PLAN(14, 4, 4, 4, 3, 3)
+#undef FHEB_PLAN
+
+template <int L, int PASS>
+constexpr int plan_s0() {  // first stage of pass PASS
+    int s = 0;
+    for (int p = 0; p < PASS; ++p) s += Plan<L>::R[p];
+    return s;
+}
+template <int L, bool LAZY, int PASS>
+constexpr int plan_fwd_kin() {  // bound on values entering forward pass PASS (inputs canonical)
+    int K = 1;
+    for (int p = 0; p < PASS; ++p) K = fwd_pass_k(K, Plan<L>::R[p], p == 0, cap_of<LAZY>());
+    return K;
+}
+template <int L, bool LAZY, int PASS>
+constexpr int plan_inv_kin() {  // bound entering inverse pass PASS (run order P-1 .. 0), inputs < kin0*q
+    int K = 1;
+    for (int p = Plan<L>::P - 1; p > PASS; --p) K = inv_pass_k(K, Plan<L>::R[p], cap_of<LAZY>());
+    return K;
+}
+
+// ---- one pass over `polys` polynomials held by one thread block ---------------------------
+// Work item U in [0, polys * N / 2^R); the block walks them with stride nthreads.
+// IO roles of a pass:
+//   IN_GLOBAL  : values come from global memory (first pass)    else from shared memory
+//   OUT_GLOBAL : values go to global memory (last pass)         else to shared memory
+// Shared memory holds `polys` polynomials of N words each, word index swizzled by swz().
+
+enum {
+    IO_SMEM = 0,          // the block's work buffer in shared memory (swizzled)
+    IO_GLOBAL = 1,        // caller memory
+    IO_STASH_SMEM = 2,    // second shared-memory buffer holding a finished transform (swizzled)
+    IO_STASH_GLOBAL = 3   // per-block global scratch holding a finished transform (natural index)
+};
+
+// Forward pass PASS of an L-stage transform.  `gin`/`gout` point at the block's first
+// polynomial.  The last pass stores in the reference's (bit-reversed) output order.
+//   SCALE      : multiply the outputs by `ninv` (fast_ntt_inverse semantics)
+// OUT == IO_STASH_*: the finished transform is parked (position order, no bit reversal) in
+// `gout` for the fused polynomial product; canonical unless LAZY (then < KOUT*q, small).
+template <int L, bool LAZY, int PASS, int IN, int OUT, bool BITREV_OUT = true, bool SCALE = false>
+FHEB_HD void fwd_pass(uint32_t tid, uint32_t nthreads, uint32_t polys, const uint64_t* gin, uint64_t* gout,
+                      uint64_t* smem, const Tw* __restrict__ tw, const ModQ& m, const Tw ninv = Tw{0, 0}) {
+    constexpr int R = Plan<L>::R[PASS];
+    constexpr int E = 1 << R;
+    constexpr int S0 = plan_s0<L, PASS>();
+    constexpr int EB = L - S0 - R;  // lowest position bit handled by this pass
+    constexpr int CAP = cap_of<LAZY>();
+    constexpr int KIN = plan_fwd_kin<L, LAZY, PASS>();
+    constexpr int KOUT = fwd_pass_k(KIN, R, PASS == 0, CAP);
+    constexpr bool LAST = (PASS == Plan<L>::P - 1);
+    constexpr uint32_t N = 1u << L;
+    constexpr uint32_t ITEMS = N >> R;  // per polynomial
+    static_assert(IN == IO_SMEM || PASS == 0, "only the first pass reads global memory");
+    static_assert(OUT == IO_SMEM || LAST, "only the last pass writes outside the work buffer");
+
+    for (uint32_t U = tid; U < polys * ITEMS; U += nthreads) {
+        const uint32_t poly = U >> (L - R);
+        uint32_t u = U & (ITEMS - 1);
+        // In the last pass consecutive threads take bit-reversed item indices so that the
+        // bit-reversed stores below are coalesced.
+        const uint32_t t = u;
+        if (OUT == IO_GLOBAL && BITREV_OUT) u = bitrev_rt(t, L - R);
+        const uint32_t base = ((u >> EB) << (EB + R)) | (u & ((1u << EB) - 1u));
+        uint64_t x[E];
+        if (IN == IO_GLOBAL) {
+            const uint64_t* src = gin + (size_t)poly * N;
+#pragma unroll
+            for (int c = 0; c < E; ++c) x[c] = canon_any(src[base | ((uint32_t)c << EB)], m);
+        } else {
+            const uint64_t* src = smem + (size_t)poly * N;
+            const uint32_t pb = swz(base);
+#pragma unroll
+            for (int c = 0; c < E; ++c) x[c] = src[pb ^ swz((uint32_t)c << EB)];
+        }
+        const uint32_t T0 = (1u << S0) + (base >> (L - S0));
+        fwd_stages<R, KIN, CAP, PASS == 0>(x, tw, T0, m);
+        if (OUT == IO_GLOBAL) {
+            uint64_t* dst = gout + (size_t)poly * N;
+#pragma unroll
+            for (int c = 0; c < E; ++c) {
+                const uint64_t v = SCALE ? csub(shoup_lazy(x[c], ninv.w, ninv.wp, m.q), m.q) : canon_k<KOUT>(x[c], m);
+                if (BITREV_OUT) dst[(bitrev_c((uint32_t)c, R) << (L - R)) | t] = v;
+                else dst[base | ((uint32_t)c << EB)] = v;
+            }
+        } else if (OUT == IO_STASH_GLOBAL) {
+            uint64_t* dst = gout + (size_t)poly * N;
+#pragma unroll
+            for (int c = 0; c < E; ++c) dst[base | ((uint32_t)c << EB)] = LAZY ? x[c] : canon_k<KOUT>(x[c], m);
+        } else {
+            uint64_t* dst = (OUT == IO_STASH_SMEM ? gout : smem) + (size_t)poly * N;
+            const uint32_t pb = swz(base);
+#pragma unroll
+            for (int c = 0; c < E; ++c)
+                dst[pb ^ swz((uint32_t)c << EB)] = (OUT == IO_STASH_SMEM && !LAZY) ? canon_k<KOUT>(x[c], m) : x[c];
+        }
+    }
+}
+
+// Fused middle of the polynomial product (reference PolynomialRing::multiply,
+// cpp/src/polynomial_ring.cpp:421-447): last forward pass of operand b, pointwise product
+// with the parked transform of operand a, and the first executed inverse pass - all on the
+// same 2^R register-resident positions, so neither bit-reversal ever happens.
+//   IN    : IO_GLOBAL when the plan has a single pass (b read from caller memory), else IO_SMEM
+//   OUT   : IO_GLOBAL when the plan has a single pass (scaled, canonical), else IO_SMEM
+//   STASH : IO_STASH_SMEM or IO_STASH_GLOBAL (where fwd_pass parked T(a))
+template <int L, bool LAZY, int IN, int OUT, int STASH>
+FHEB_HD void polymul_mid_pass(uint32_t tid, uint32_t nthreads, uint32_t polys, const uint64_t* gin, uint64_t* gout,
+                              uint64_t* smem, const uint64_t* stash, const Tw* __restrict__ twf,
+                              const Tw* __restrict__ twi, const Tw ninv, const ModQ& m) {
+    constexpr int PASS = Plan<L>::P - 1;
+    constexpr int R = Plan<L>::R[PASS];
+    constexpr int E = 1 << R;
+    constexpr int S0 = plan_s0<L, PASS>();
+    constexpr int EB = L - S0 - R;  // == 0
+    constexpr int CAP = cap_of<LAZY>();
+    constexpr int KIN = plan_fwd_kin<L, LAZY, PASS>();
+    constexpr int KOUT = fwd_pass_k(KIN, R, PASS == 0, CAP);
+    constexpr uint32_t N = 1u << L;
+    constexpr uint32_t ITEMS = N >> R;
+    static_assert(EB == 0, "the last forward pass covers the lowest position bits");
+    // lazy operands: (KOUT*q)^2 must stay below q*2^64 for reduce128
+    static_assert(!LAZY || (uint64_t)KOUT * KOUT < (1ull << 18), "lazy product bound");
+
+    for (uint32_t U = tid; U < polys * ITEMS; U += nthreads) {
+        const uint32_t poly = U >> (L - R);
+        const uint32_t u = U & (ITEMS - 1);
+        const uint32_t base = u << R;
+        const uint32_t pb = swz(base);
+        uint64_t x[E];
+        if (IN == IO_GLOBAL) {
+            const uint64_t* src = gin + (size_t)poly * N;
+#pragma unroll
+            for (int c = 0; c < E; ++c) x[c] = canon_any(src[base | (uint32_t)c], m);
+        } else {
+            const uint64_t* src = smem + (size_t)poly * N;
+#pragma unroll
+            for (int c = 0; c < E; ++c) x[c] = src[pb ^ swz((uint32_t)c)];
+        }
+        const uint32_t T0 = (1u << S0) + (base >> (L - S0));
+        fwd_stages<R, KIN, CAP, PASS == 0>(x, twf, T0, m);
+        const uint64_t* sa = stash + (size_t)poly * N;
+#pragma unroll
+        for (int c = 0; c < E; ++c) {
+            const uint64_t av = (STASH == IO_STASH_GLOBAL) ? sa[base | (uint32_t)c] : sa[pb ^ swz((uint32_t)c)];
+            const uint64_t bv = LAZY ? x[c] : canon_k<KOUT>(x[c], m);
+            x[c] = mulmod(av, bv, m);
+        }
+        inv_stages<R, 1, CAP, PASS == 0>(x, twi, T0, m);
+        if (OUT == IO_GLOBAL) {
+            uint64_t* dst = gout + (size_t)poly * N;
+#pragma unroll
+            for (int c = 0; c < E; ++c) dst[base | (uint32_t)c] = csub(shoup_lazy(x[c], ninv.w, ninv.wp, m.q), m.q);
+        } else {
+            uint64_t* dst = smem + (size_t)poly * N;
+#pragma unroll
+            for (int c = 0; c < E; ++c) dst[pb ^ swz((uint32_t)c)] = x[c];
+        }
+    }
+}
+
+// Inverse pass PASS (run in order P-1, P-2, .., 0).  The first one executed (PASS == P-1)
+// may read the reference's input order (bit-reversed positions) from global memory; the
+// last one executed (PASS == 0) multiplies by N^-1 (`ninv`, Shoup pair) and stores canonical
+// values in natural order.
+template <int L, bool LAZY, int PASS, int IN, int OUT, bool BITREV_IN = true>
+FHEB_HD void inv_pass(uint32_t tid, uint32_t nthreads, uint32_t polys, const uint64_t* gin, uint64_t* gout,
+                      uint64_t* smem, const Tw* __restrict__ tw, const Tw ninv, const ModQ& m) {
+    constexpr int R = Plan<L>::R[PASS];
+    constexpr int E = 1 << R;
+    constexpr int S0 = plan_s0<L, PASS>();
+    constexpr int EB = L - S0 - R;
+    constexpr int CAP = cap_of<LAZY>();
+    constexpr int KIN = plan_inv_kin<L, LAZY, PASS>();
+    constexpr bool FIRST = (PASS == Plan<L>::P - 1);
+    constexpr uint32_t N = 1u << L;
+    constexpr uint32_t ITEMS = N >> R;
+    static_assert(IN == IO_SMEM || FIRST, "only the first executed pass reads global memory");
+    static_assert(OUT == IO_SMEM || PASS == 0, "only the last executed pass writes global memory");
+
+    for (uint32_t U = tid; U < polys * ITEMS; U += nthreads) {
+        const uint32_t poly = U >> (L - R);
+        uint32_t u = U & (ITEMS - 1);
+        const uint32_t t = u;
+        if (FIRST && IN == IO_GLOBAL && BITREV_IN) u = bitrev_rt(t, L - R);
+        const uint32_t base = ((u >> EB) << (EB + R)) | (u & ((1u << EB) - 1u));
+        uint64_t x[E];
+        if (IN == IO_GLOBAL) {
+            const uint64_t* src = gin + (size_t)poly * N;
+            if (BITREV_IN) {
+#pragma unroll
+                for (int c = 0; c < E; ++c) x[c] = canon_any(src[(bitrev_c((uint32_t)c, R) << (L - R)) | t], m);
+            } else {
+#pragma unroll
+                for (int c = 0; c < E; ++c) x[c] = canon_any(src[base | ((uint32_t)c << EB)], m);
+            }
+        } else {
+            const uint64_t* src = smem + (size_t)poly * N;
+            const uint32_t pb = swz(base);
+#pragma unroll
+            for (int c = 0; c < E; ++c) x[c] = src[pb ^ swz((uint32_t)c << EB)];
+        }
+        const uint32_t T0 = (1u << S0) + (base >> (L - S0));
+        inv_stages<R, KIN, CAP, PASS == 0>(x, tw, T0, m);
+        if (OUT == IO_GLOBAL) {
+            uint64_t* dst = gout + (size_t)poly * N;
+#pragma unroll
+            for (int c = 0; c < E; ++c)
+                dst[base | ((uint32_t)c << EB)] = csub(shoup_lazy(x[c], ninv.w, ninv.wp, m.q), m.q);
+        } else {
+            uint64_t* dst = smem + (size_t)poly * N;
+            const uint32_t pb = swz(base);
+#pragma unroll
+            for (int c = 0; c < E; ++c) dst[pb ^ swz((uint32_t)c << EB)] = x[c];
+        }
+    }
+}
+
+}  // namespace fheb

@@ -1,0 +1,30 @@
+// The object behind fheb_ntt_plan: the reference's TwiddleFactors (host copies, natural
+// exponent order - cpp/include/ntt_processor.h:29-41) plus the device-side heap tables.
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstdint>
+#include <vector>
+
+#include "modarith.cuh"
+
+namespace fheb {
+
+struct NttPlan {
+    uint32_t degree = 0;
+    uint32_t logn = 0;
+    uint64_t modulus = 0;
+    uint64_t psi = 0, psi_inv = 0, inv_n = 0;
+    std::vector<uint64_t> fwd_table, inv_table;  // as the reference holds them
+    bool unit_first = false;
+    ModQ mod{};
+    Tw ninv{};
+    Tw* d_fwd = nullptr;  // heap-ordered (w, w') pairs, N entries
+    Tw* d_inv = nullptr;
+};
+
+// device-pointer entry points shared between translation units
+int ntt_forward_device(const NttPlan* p, const uint64_t* in, uint64_t* out, size_t batch, cudaStream_t s);
+int ntt_inverse_device(const NttPlan* p, const uint64_t* in, uint64_t* out, size_t batch, cudaStream_t s);
+
+}  // namespace fheb

@@ -1,0 +1,92 @@
+// Host runtime shared by the C-ABI translation units: status/error plumbing, the device
+// context, pointer classification and host-buffer staging.  No CPU compute path lives
+// here: without a usable sm_100 device every entry point fails.
+#pragma once
+#include <cuda_runtime.h>
+
+#include <atomic>
+#include <cstdarg>
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../../include/fheb200.h"
+
+namespace fheb {
+
+struct Context {
+    bool ready = false;
+    int device = -1;
+    cudaDeviceProp prop{};
+    int sm_count = 0;
+    cudaStream_t copy_in = nullptr;   // staging streams for host buffers
+    cudaStream_t copy_out = nullptr;
+    cudaStream_t work = nullptr;
+};
+
+Context& ctx();
+int set_error(int code, const char* fmt, ...);
+int ensure_ready();  // lazily initialises the context; FHEB_ERR_HARDWARE_UNAVAILABLE if no sm_100 GPU
+extern std::atomic<uint64_t> g_launches;
+
+inline void count_launch(uint64_t n = 1) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+
+#define FHEB_CUDA(expr)                                                                              \
+    do {                                                                                             \
+        cudaError_t _e = (expr);                                                                     \
+        if (_e != cudaSuccess)                                                                       \
+            return ::fheb::set_error(_e == cudaErrorMemoryAllocation ? FHEB_ERR_OUT_OF_MEMORY : FHEB_ERR_NATIVE, \
+                                     "%s failed: %s", #expr, cudaGetErrorString(_e));                \
+    } while (0)
+
+#define FHEB_CHECK_LAUNCH()                                                                          \
+    do {                                                                                             \
+        cudaError_t _e = cudaGetLastError();                                                         \
+        if (_e != cudaSuccess) return ::fheb::set_error(FHEB_ERR_NATIVE, "kernel launch failed: %s", cudaGetErrorString(_e)); \
+    } while (0)
+
+#define FHEB_REQUIRE(cond, ...)                                                                      \
+    do {                                                                                             \
+        if (!(cond)) return ::fheb::set_error(FHEB_ERR_INVALID_PARAMETERS, __VA_ARGS__);             \
+    } while (0)
+
+#define FHEB_TRY(expr)                 \
+    do {                               \
+        int _rc = (expr);              \
+        if (_rc != FHEB_OK) return _rc; \
+    } while (0)
+
+bool is_device_pointer(const void* p);
+
+// A view of caller memory on the device.  Device pointers are used in place; host pointers
+// get a device staging buffer, filled on `stream` when `copy_in` is set and written back by
+// finish().  finish() synchronises the stream only when something was staged from the host.
+class Staged {
+   public:
+    Staged() = default;
+    ~Staged();
+    Staged(const Staged&) = delete;
+    Staged& operator=(const Staged&) = delete;
+    int bind(const void* user, size_t bytes, bool copy_in, bool copy_out, cudaStream_t stream);
+    int bind_alias(Staged& other, bool copy_out);  // same user pointer as `other`: share its device buffer
+    template <class T>
+    T* ptr() const { return reinterpret_cast<T*>(dev_); }
+    int finish();  // copy back (if needed); caller syncs once at the end via sync_if_staged
+    bool staged() const { return owned_; }
+    const void* user() const { return user_; }
+
+   private:
+    void* dev_ = nullptr;
+    const void* user_ = nullptr;
+    size_t bytes_ = 0;
+    bool owned_ = false;
+    bool copy_out_ = false;
+    cudaStream_t stream_ = nullptr;
+};
+
+int sync_if_staged(cudaStream_t stream, std::initializer_list<const Staged*> bufs);
+
+}  // namespace fheb

@@ -1,0 +1,212 @@
+// Encrypted-ballot tally: column sums of [count][2][N] ciphertext words modulo q.
+//
+// The reference folds ballots with PolynomialRing::add_inplace (linear, cpp/src/encryption.cpp:
+// 1327-1364) or pairwise (tree, :1366-1458); both reduce every operand first and keep the
+// running sum canonical, so the result words are sum_i(x_i mod q) mod q = (sum_i x_i) mod q
+// for any grouping.  The kernel therefore accumulates the RAW words in a 128-bit counter per
+// column (exact for any count < 2^64) and reduces once.  HBM-bound: every ballot word is read
+// exactly once with 16-byte streaming loads, 8 independent loads in flight per thread.
+//
+// C-ABI entry points here (include/fheb200.h): fheb_tally, fheb_tally_combine,
+// fheb_tensor_multiply_batch, fheb_synth_ballots.
+#include "elementwise.hpp"
+#include "modarith.cuh"
+#include "plan.hpp"
+#include "runtime.hpp"
+
+namespace fheb {
+
+__device__ __forceinline__ void acc128(uint64_t& lo, uint64_t& hi, uint64_t v) {
+    lo += v;
+    hi += (lo < v) ? 1 : 0;
+}
+
+__device__ __forceinline__ uint64_t fold128(uint64_t hi, uint64_t lo, const ModQ& m) {
+    return reduce128(canon_any(hi, m), lo, m);  // hi reduced first so that (hi:lo) < q * 2^64
+}
+
+// grid = (column chunks, slabs).  Block: 256 threads x 2 columns.  Slab y sums ballots
+// [y*per_slab, min(count, (y+1)*per_slab)) and writes canonical partial sums to
+// partial[y][width].
+constexpr int TALLY_THREADS = 256;
+constexpr int TALLY_UNROLL = 8;
+
+__global__ void __launch_bounds__(TALLY_THREADS) tally_kernel(const uint64_t* __restrict__ cts, size_t count,
+                                                              size_t per_slab, uint32_t width /* 2N words */,
+                                                              uint64_t* __restrict__ partial, const ModQ m, int vec_ok) {
+    const uint32_t col = (blockIdx.x * TALLY_THREADS + threadIdx.x) * 2;
+    if (col >= width) return;
+    const size_t first = (size_t)blockIdx.y * per_slab;
+    size_t last = first + per_slab;
+    if (last > count) last = count;
+    uint64_t lo0 = 0, hi0 = 0, lo1 = 0, hi1 = 0;
+    const bool pair = (col + 1 < width);
+    if (vec_ok && pair) {
+        const ulonglong2* base = reinterpret_cast<const ulonglong2*>(cts + col);
+        const size_t row = width / 2;  // ulonglong2 per ballot
+        size_t i = first;
+        for (; i + TALLY_UNROLL <= last; i += TALLY_UNROLL) {
+            ulonglong2 v[TALLY_UNROLL];
+#pragma unroll
+            for (int u = 0; u < TALLY_UNROLL; ++u) v[u] = __ldcs(base + (i + u) * row);
+#pragma unroll
+            for (int u = 0; u < TALLY_UNROLL; ++u) {
+                acc128(lo0, hi0, v[u].x);
+                acc128(lo1, hi1, v[u].y);
+            }
+        }
+        for (; i < last; ++i) {
+            const ulonglong2 v = __ldcs(base + i * row);
+            acc128(lo0, hi0, v.x);
+            acc128(lo1, hi1, v.y);
+        }
+    } else {
+        for (size_t i = first; i < last; ++i) {
+            acc128(lo0, hi0, cts[i * width + col]);
+            if (pair) acc128(lo1, hi1, cts[i * width + col + 1]);
+        }
+    }
+    uint64_t* out = partial + (size_t)blockIdx.y * width + col;
+    out[0] = fold128(hi0, lo0, m);
+    if (pair) out[1] = fold128(hi1, lo1, m);
+}
+
+// splitmix64 (public-domain constants) - counter-based, reproducible on the CPU
+__device__ __forceinline__ uint64_t splitmix64(uint64_t x) {
+    x += 0x9E3779B97F4A7C15ULL;
+    x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ULL;
+    x = (x ^ (x >> 27)) * 0x94D049BB133111EBULL;
+    return x ^ (x >> 31);
+}
+
+__global__ void __launch_bounds__(256) synth_ballots_kernel(uint64_t* out, size_t first_word, size_t words, uint64_t seed,
+                                                            const ModQ m) {
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < words; i += stride)
+        out[i] = reduce64(splitmix64(seed + first_word + i), m);
+}
+
+// Sums `count` rows of `width` words; out = [width].  single_raw: a lone row is copied verbatim
+// (EncryptionEngine::batch_add returns the ciphertext untouched for size 1, encryption.cpp:1332-1334).
+static int tally_device(const uint64_t* cts, size_t count, uint32_t width, uint64_t q, uint64_t* out, bool single_raw,
+                        cudaStream_t s) {
+    if (count == 1 && single_raw) {
+        FHEB_CUDA(cudaMemcpyAsync(out, cts, (size_t)width * 8, cudaMemcpyDeviceToDevice, s));
+        return FHEB_OK;
+    }
+    const ModQ m = make_modq(q);
+    const unsigned chunks = (width + 2 * TALLY_THREADS - 1) / (2 * TALLY_THREADS);
+    // enough slabs to put ~4 blocks on every SM, but at least 64 ballots per slab
+    size_t slabs = ((size_t)ctx().sm_count * 4 + chunks - 1) / chunks;
+    const size_t max_slabs = (count + 63) / 64;
+    if (slabs > max_slabs) slabs = max_slabs;
+    if (slabs < 1) slabs = 1;
+    const size_t per_slab = (count + slabs - 1) / slabs;
+    slabs = (count + per_slab - 1) / per_slab;
+    const int vec_ok = ((reinterpret_cast<uintptr_t>(cts) & 15u) == 0) && (width % 2 == 0);
+    if (slabs == 1) {
+        tally_kernel<<<dim3(chunks, 1), TALLY_THREADS, 0, s>>>(cts, count, per_slab, width, out, m, vec_ok);
+        FHEB_CHECK_LAUNCH();
+        count_launch();
+        return FHEB_OK;
+    }
+    uint64_t* partial = nullptr;
+    FHEB_CUDA(cudaMallocAsync(&partial, slabs * (size_t)width * 8, s));
+    tally_kernel<<<dim3(chunks, (unsigned)slabs), TALLY_THREADS, 0, s>>>(cts, count, per_slab, width, partial, m, vec_ok);
+    FHEB_CHECK_LAUNCH();
+    tally_kernel<<<dim3(chunks, 1), TALLY_THREADS, 0, s>>>(partial, slabs, slabs, width, out, m, 1);
+    FHEB_CHECK_LAUNCH();
+    count_launch(2);
+    FHEB_CUDA(cudaFreeAsync(partial, s));
+    return FHEB_OK;
+}
+
+static int tally_entry(const uint64_t* cts, size_t count, uint32_t degree, uint64_t q, uint64_t* out, bool single_raw,
+                       void* stream) {
+    FHEB_TRY(ensure_ready());
+    // message follows EncryptionEngine::batch_add, cpp/src/encryption.cpp:1328-1330
+    FHEB_REQUIRE(count != 0, "Cannot add empty vector of ciphertexts");
+    FHEB_REQUIRE(degree > 0 && (degree & (degree - 1)) == 0, "Polynomial degree must be a power of 2");
+    FHEB_REQUIRE(q >= 2, "Modulus must be at least 2");
+    FHEB_REQUIRE(cts != nullptr && out != nullptr, "ciphertext pointers must not be null");
+    cudaStream_t s = (cudaStream_t)stream;
+    const uint32_t width = 2 * degree;
+    Staged sin, sout;
+    FHEB_TRY(sin.bind(cts, count * (size_t)width * 8, true, false, s));
+    FHEB_TRY(sout.bind(out, (size_t)width * 8, false, true, s));
+    FHEB_TRY(tally_device(sin.ptr<const uint64_t>(), count, width, q, sout.ptr<uint64_t>(), single_raw, s));
+    FHEB_TRY(sin.finish());
+    FHEB_TRY(sout.finish());
+    return sync_if_staged(s, {&sin, &sout});
+}
+
+}  // namespace fheb
+
+using namespace fheb;
+
+extern "C" {
+
+int fheb_tally(const uint64_t* cts, size_t count, uint32_t degree, uint64_t modulus, uint64_t* out, void* stream) {
+    return tally_entry(cts, count, degree, modulus, out, true, stream);
+}
+
+int fheb_tally_combine(const uint64_t* partials, size_t parts, uint32_t degree, uint64_t modulus, uint64_t* out,
+                       void* stream) {
+    return tally_entry(partials, parts, degree, modulus, out, true, stream);
+}
+
+int fheb_tensor_multiply_batch(const fheb_ntt_plan* plan, const uint64_t* ct1, const uint64_t* ct2, uint64_t* out,
+                               size_t batch, void* stream) {
+    // EncryptionEngine::multiply, cpp/src/encryption.cpp:737-798: T on the four operand
+    // polynomials, c0 = a0.b0, c1 = a0.b1 + a1.b0, c2 = a1.b1, T^-1 on the three results.
+    FHEB_TRY(ensure_ready());
+    FHEB_REQUIRE(plan != nullptr, "plan must not be null");
+    if (batch == 0) return FHEB_OK;
+    FHEB_REQUIRE(ct1 != nullptr && ct2 != nullptr && out != nullptr, "ciphertext pointers must not be null");
+    const NttPlan* p = reinterpret_cast<const NttPlan*>(plan);
+    const size_t N = p->degree;
+    const uint64_t q = p->modulus;
+    cudaStream_t s = (cudaStream_t)stream;
+    Staged s1, s2, so;
+    FHEB_TRY(s1.bind(ct1, batch * 2 * N * 8, true, false, s));
+    FHEB_TRY(s2.bind(ct2, batch * 2 * N * 8, true, false, s));
+    FHEB_TRY(so.bind(out, batch * 3 * N * 8, false, true, s));
+    uint64_t* work = nullptr;  // [batch][2][N] x 2 transformed operands + 2 product temporaries per ct
+    FHEB_CUDA(cudaMallocAsync(&work, batch * 6 * N * 8, s));
+    uint64_t* ta = work;                   // T(ct1): [batch][2][N]
+    uint64_t* tb = work + batch * 2 * N;   // T(ct2)
+    uint64_t* tmp = work + batch * 4 * N;  // [batch][2][N] scratch
+    int rc = ntt_forward_device(p, s1.ptr<const uint64_t>(), ta, batch * 2, s);
+    if (rc == FHEB_OK) rc = ntt_forward_device(p, s2.ptr<const uint64_t>(), tb, batch * 2, s);
+    uint64_t* o = so.ptr<uint64_t>();
+    for (size_t i = 0; i < batch && rc == FHEB_OK; ++i) {
+        const uint64_t *a0 = ta + i * 2 * N, *a1 = a0 + N, *b0 = tb + i * 2 * N, *b1 = b0 + N;
+        uint64_t *c0 = o + i * 3 * N, *c1 = c0 + N, *c2 = c1 + N, *x = tmp + i * 2 * N, *y = x + N;
+        rc = elementwise_device(2, a0, b0, 0, c0, N, q, s);
+        if (rc == FHEB_OK) rc = elementwise_device(2, a0, b1, 0, x, N, q, s);
+        if (rc == FHEB_OK) rc = elementwise_device(2, a1, b0, 0, y, N, q, s);
+        if (rc == FHEB_OK) rc = elementwise_device(0, x, y, 0, c1, N, q, s);
+        if (rc == FHEB_OK) rc = elementwise_device(2, a1, b1, 0, c2, N, q, s);
+    }
+    if (rc == FHEB_OK) rc = ntt_inverse_device(p, o, o, batch * 3, s);
+    cudaFreeAsync(work, s);
+    FHEB_TRY(rc);
+    FHEB_TRY(so.finish());
+    return sync_if_staged(s, {&s1, &s2, &so});
+}
+
+int fheb_synth_ballots(uint64_t* cts_device, size_t first_ballot, size_t count, uint32_t degree, uint64_t modulus,
+                       uint64_t seed, void* stream) {
+    FHEB_TRY(ensure_ready());
+    FHEB_REQUIRE(cts_device != nullptr && is_device_pointer(cts_device), "cts_device must be a device pointer");
+    FHEB_REQUIRE(modulus >= 2, "Modulus must be at least 2");
+    const size_t words = count * 2 * (size_t)degree;
+    if (words == 0) return FHEB_OK;
+    synth_ballots_kernel<<<stream_grid(words, 256, 8), 256, 0, (cudaStream_t)stream>>>(
+        cts_device, first_ballot * 2 * (size_t)degree, words, seed, make_modq(modulus));
+    FHEB_CHECK_LAUNCH();
+    count_launch();
+    return FHEB_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,147 @@
+// CPU emulation of the CUDA transform passes (no GPU needed).
+//
+// The device passes in node-fhe-accelerate_b200/csrc/ntt_core.cuh are written as
+// host/device functions of (thread id, thread count).  Passes are separated by block
+// barriers and every work item reads and writes only its own positions, so running the
+// items of one pass sequentially on the host is equivalent to the barrier-synchronised
+// device execution.  This program runs them that way for every supported degree and both
+// range-tracking modes and checks the results word-for-word against the C oracle
+// (oracle/fhe_oracle.c, which is pinned to the reference).  It validates index math,
+// twiddle ordering, swizzling, bit-reversed I/O and the lazy-range bookkeeping; it says
+// nothing about device-only code (launch geometry, PTX, memory spaces).
+//
+// Build + run: see tests/test_host_emulation.py.
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <random>
+#include <vector>
+
+#include "../../node-fhe-accelerate_b200/csrc/ntt_plan.hpp"
+#include "../../oracle/fhe_oracle.h"
+
+using namespace fheb;
+
+template <int L, bool LAZY, int PASS>
+static void run_fwd(uint32_t threads, uint32_t polys, const uint64_t* gin, uint64_t* gout, uint64_t* smem,
+                    const Tw* tw, const ModQ& m) {
+    constexpr int P = Plan<L>::P;
+    if constexpr (PASS < P) {
+        for (uint32_t tid = 0; tid < threads; ++tid) {
+            if constexpr (P == 1) fwd_pass<L, LAZY, PASS, IO_GLOBAL, IO_GLOBAL>(tid, threads, polys, gin, gout, smem, tw, m);
+            else if constexpr (PASS == 0) fwd_pass<L, LAZY, PASS, IO_GLOBAL, IO_SMEM>(tid, threads, polys, gin, gout, smem, tw, m);
+            else if constexpr (PASS == P - 1) fwd_pass<L, LAZY, PASS, IO_SMEM, IO_GLOBAL>(tid, threads, polys, gin, gout, smem, tw, m);
+            else fwd_pass<L, LAZY, PASS, IO_SMEM, IO_SMEM>(tid, threads, polys, gin, gout, smem, tw, m);
+        }
+        run_fwd<L, LAZY, PASS + 1>(threads, polys, gin, gout, smem, tw, m);
+    }
+}
+
+template <int L, bool LAZY, int PASS>
+static void run_inv(uint32_t threads, uint32_t polys, const uint64_t* gin, uint64_t* gout, uint64_t* smem,
+                    const Tw* tw, const Tw& ninv, const ModQ& m) {
+    constexpr int P = Plan<L>::P;
+    if constexpr (PASS >= 0) {
+        for (uint32_t tid = 0; tid < threads; ++tid) {
+            if constexpr (P == 1) inv_pass<L, LAZY, PASS, IO_GLOBAL, IO_GLOBAL>(tid, threads, polys, gin, gout, smem, tw, ninv, m);
+            else if constexpr (PASS == P - 1) inv_pass<L, LAZY, PASS, IO_GLOBAL, IO_SMEM>(tid, threads, polys, gin, gout, smem, tw, ninv, m);
+            else if constexpr (PASS == 0) inv_pass<L, LAZY, PASS, IO_SMEM, IO_GLOBAL>(tid, threads, polys, gin, gout, smem, tw, ninv, m);
+            else inv_pass<L, LAZY, PASS, IO_SMEM, IO_SMEM>(tid, threads, polys, gin, gout, smem, tw, ninv, m);
+        }
+        run_inv<L, LAZY, PASS - 1>(threads, polys, gin, gout, smem, tw, ninv, m);
+    }
+}
+
+static uint64_t pick_prime(int L, bool lazy) {
+    // q == 1 (mod 2N), coprime to 2^64-1 where possible
+    if (lazy) return (L <= 10) ? 1099511678977ULL /* 41 bit */ : 132120577ULL /* 27 bit, 2N | q-1 up to 2^20 */;
+    return 4611686018326724609ULL;  // 62 bit
+}
+
+template <int L, bool LAZY>
+static int check(uint32_t threads, uint32_t polys) {
+    const uint32_t N = 1u << L;
+    uint64_t q = pick_prime(L, LAZY);
+    if (L <= 3 && !LAZY) q = 4611686018326724609ULL;
+    std::vector<uint64_t> fwd(N), inv(N);
+    uint64_t sc[3];
+    if (orc_precompute_twiddles(N, q, fwd.data(), inv.data(), sc) != 0) {
+        std::printf("L=%d: prime %llu not NTT-friendly\n", L, (unsigned long long)q);
+        return 1;
+    }
+    ModQ m = make_modq(q);
+    if ((m.lazy != 0) != LAZY) {
+        std::printf("L=%d: mode mismatch\n", L);
+        return 1;
+    }
+    std::vector<Tw> hf = build_heap_table(fwd.data(), L, q), hi = build_heap_table(inv.data(), L, q);
+    Tw ninv{sc[2], shoup_companion(sc[2], q)};
+    std::mt19937_64 rng(1234 + L);
+    std::vector<uint64_t> x((size_t)polys * N), ref, got((size_t)polys * N), smem((size_t)polys * N);
+    int bad = 0;
+    for (int variant = 0; variant < 3; ++variant) {
+        for (auto& v : x) v = (variant == 0) ? rng() % q : (variant == 1 ? rng() : q - 1);  // canonical / unreduced / extreme
+        ref = x;
+        orc_forward_ntt_batch(ref.data(), polys, N, q, fwd.data());
+        std::fill(smem.begin(), smem.end(), 0xDEADBEEFDEADBEEFULL);
+        run_fwd<L, LAZY, 0>(threads, polys, x.data(), got.data(), smem.data(), hf.data(), m);
+        if (std::memcmp(ref.data(), got.data(), got.size() * 8) != 0) {
+            std::printf("L=%d lazy=%d variant=%d threads=%u polys=%u: FORWARD mismatch\n", L, LAZY, variant, threads, polys);
+            ++bad;
+        }
+        ref = x;
+        orc_inverse_ntt_batch(ref.data(), polys, N, q, inv.data(), sc[2]);
+        run_inv<L, LAZY, Plan<L>::P - 1>(threads, polys, x.data(), got.data(), smem.data(), hi.data(), ninv, m);
+        if (std::memcmp(ref.data(), got.data(), got.size() * 8) != 0) {
+            std::printf("L=%d lazy=%d variant=%d threads=%u polys=%u: INVERSE mismatch\n", L, LAZY, variant, threads, polys);
+            ++bad;
+        }
+    }
+    return bad;
+}
+
+template <int L>
+static int check_all() {
+    int bad = 0;
+    bad += check<L, false>(64, 1);
+    bad += check<L, true>(64, 1);
+    bad += check<L, false>(96, 3);  // thread count not dividing the work, several polynomials per block
+    bad += check<L, true>(32, 2);
+    if constexpr (L < 14) bad += check_all<L + 1>();
+    return bad;
+}
+
+static int check_arith() {
+    // reduce128 / mulmod / reduce64 against __int128 arithmetic on edge and random operands
+    std::mt19937_64 rng(99);
+    const uint64_t primes[] = {17ULL, 97ULL, 132120577ULL, 1099511678977ULL, 1125899906826241ULL,
+                               1152921504606584833ULL, 4611686018326724609ULL, 0xFFFFFFFFFFFFFFC5ULL, 0x8000000000000011ULL};
+    int bad = 0;
+    for (uint64_t q : primes) {
+        ModQ m = make_modq(q);
+        for (int i = 0; i < 200000; ++i) {
+            uint64_t a = rng(), b = rng();
+            if (i < 8) { a = (i & 1) ? q - 1 : 0; b = (i & 2) ? q - 1 : 1; if (i & 4) { a = ~0ULL; b = ~0ULL; } }
+            uint64_t e = (uint64_t)(((u128)a * b) % q);
+            if (mulmod_any(a, b, m) != e) { ++bad; break; }
+            if (reduce64(a, m) != a % q) { ++bad; break; }
+            if (q < (1ULL << 63)) {
+                uint64_t w = b % q, wp = shoup_companion(w, q);
+                uint64_t r = shoup_lazy(a, w, wp, q);
+                if (r >= 2 * q || r % q != (uint64_t)(((u128)a * w) % q)) { ++bad; break; }
+            }
+            uint64_t ac = a % q, bc = b % q;
+            if (addmod_canon(ac, bc, q) != (uint64_t)(((u128)ac + bc) % q)) { ++bad; break; }
+            if (submod_canon(ac, bc, q) != (uint64_t)(((u128)ac + q - bc) % q)) { ++bad; break; }
+        }
+    }
+    if (bad) std::printf("arithmetic primitive mismatch (%d moduli)\n", bad);
+    return bad;
+}
+
+int main() {
+    int bad = check_arith();
+    bad += check_all<2>();
+    if (bad == 0) std::printf("HOST EMULATION OK\n");
+    return bad ? 1 : 0;
+}

@@ -1,0 +1,140 @@
+"""CPU-side checks of the boundary and the host logic (no GPU needed, no compute calls):
+
+* libfheb200.so loads and exports every symbol include/fheb200.h declares, and the Python
+  binding table covers exactly those symbols;
+* without a GPU every compute entry point fails loudly (HARDWARE_UNAVAILABLE) - there is no
+  CPU fallback in the product;
+* shard partitioning, and the sharded tally's exchange step on a world_size-2 gloo group.
+"""
+import os
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HEADER = os.path.join(ROOT, "include", "fheb200.h")
+
+
+@pytest.fixture(scope="module")
+def fhe():
+    sys.path.insert(0, ROOT)
+    import __graft_entry__ as ge
+
+    if not os.path.exists(os.path.join(ROOT, "node-fhe-accelerate_b200", "libfheb200.so")):
+        ge.build()
+    import fheb200
+
+    return fheb200
+
+
+def declared_symbols():
+    text = open(HEADER).read()
+    return sorted(set(re.findall(r"FHEB_API\s+[^;(]*?\b(fheb_\w+)\s*\(", text)))
+
+
+def test_header_symbols_exported_and_bound(fhe):
+    syms = declared_symbols()
+    assert len(syms) >= 40
+    lib = fhe.lib()
+    for s in syms:
+        assert hasattr(lib, s), f"{s} declared in include/fheb200.h but not exported"
+    assert sorted(fhe.SIGNATURES) == syms
+    out = subprocess.run(["nm", "-D", "--defined-only", fhe.LIB_PATH], capture_output=True, text=True).stdout
+    exported = set(re.findall(r" T (fheb_\w+)", out))
+    assert exported == set(syms), exported ^ set(syms)
+
+
+def test_product_never_touches_the_oracle():
+    pkg = os.path.join(ROOT, "node-fhe-accelerate_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".hpp", ".h", ".cpp")):
+                text = open(os.path.join(dirpath, f)).read()
+                assert "libfhe_oracle" not in text and "oracle_bindings" not in text and "libref_oracle" not in text, f
+
+
+def test_no_cpu_fallback_without_gpu(fhe):
+    import torch
+
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    assert fhe.version().endswith("b200")
+    with pytest.raises(fhe.FheError) as e:
+        fhe.initialize()
+    assert e.value.code_name == "HARDWARE_UNAVAILABLE"
+    x = np.arange(8, dtype=np.uint64)
+    for call in (lambda: fhe.NTTProcessor(8, 97), lambda: fhe.modadd_batch(x, x, 97),
+                 lambda: fhe.tally_votes(np.zeros((2, 2, 8), np.uint64), 8, 97),
+                 lambda: fhe.MultiLimbModularArithmetic([0xFFFFFFFFFFFFFF43, 1]).mod_add(np.zeros((1, 2), np.uint64),
+                                                                                         np.zeros((1, 2), np.uint64))):
+        with pytest.raises(fhe.FheError) as e:
+            call()
+        assert e.value.code_name == "HARDWARE_UNAVAILABLE", e.value
+
+
+def test_multi_limb_constants_are_host_side(fhe, oracle):
+    for q in ([0xFFFFFFFFFFFFFF43, 1], [0xFFFFFFFFFFFFFFC5], [0x1D, 0, 1]):
+        ml = fhe.MultiLimbModularArithmetic(q)
+        q_inv, r1, r2 = oracle.mlimb_constants(np.array(q, np.uint64))
+        assert ml.q_inv == q_inv
+        assert np.array_equal(ml.r_mod_q, r1) and np.array_equal(ml.r2_mod_q, r2)
+    with pytest.raises(fhe.FheError):
+        fhe.MultiLimbModularArithmetic([2, 1])  # even modulus
+
+
+def test_shard_range_partitions(fhe):
+    for total in (0, 1, 7, 4096, 10**6):
+        for world in (1, 2, 3, 8):
+            spans = [fhe.shard_range(total, r, world) for r in range(world)]
+            assert spans[0][0] == 0 and spans[-1][1] == total
+            assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
+            sizes = [hi - lo for lo, hi in spans]
+            assert max(sizes) - min(sizes) <= 1
+    with pytest.raises(ValueError):
+        fhe.shard_range(10, 2, 2)
+
+
+def test_noise_budget_metadata(fhe):
+    assert fhe.tally_noise_budget([30.0] * 20000, "linear") == pytest.approx(30.0 - np.log2(20000))
+    assert fhe.tally_noise_budget([30.0] * 20000, "tree") == 15.0
+    assert fhe.tally_noise_budget([12.5], "tree") == 12.5
+
+
+_WORKER = r"""
+import os, sys
+import numpy as np, torch, torch.distributed as dist
+sys.path.insert(0, {root!r}); sys.path.insert(0, os.path.join({root!r}, "tests"))
+import fheb200
+from oracle_bindings import Oracle
+rank, world = int(sys.argv[1]), 2
+os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=sys.argv[2], RANK=str(rank), WORLD_SIZE=str(world))
+dist.init_process_group("gloo", rank=rank, world_size=world)
+orc = Oracle()
+n, q, total = 64, 1099511678977, 101
+cts = np.random.default_rng(3).integers(0, q, size=(total, 2, n), dtype=np.uint64)
+lo, hi = fheb200.shard_range(total, rank, world)
+# host logic under test: partition + all-gather + combine order.  The kernels are replaced by the
+# CPU checker here only because this test runs without a GPU; the product default is the CUDA path.
+to_t = lambda a: torch.from_numpy(np.ascontiguousarray(a).view(np.int64))
+to_n = lambda t: t.numpy().view(np.uint64)
+st = fheb200.ShardedTally(n, q, local_fn=lambda c: to_t(orc.tally(to_n(c), q)),
+                          combine_fn=lambda p: to_t(orc.tally(to_n(p), q)))
+got = to_n(st.tally(to_t(cts[lo:hi])))
+assert np.array_equal(got, orc.tally(cts, q)), "sharded tally differs"
+dist.destroy_process_group()
+print("ok", rank)
+"""
+
+
+def test_sharded_tally_exchange_gloo_world2(fhe, tmp_path):
+    script = tmp_path / "worker.py"
+    script.write_text(_WORKER.format(root=ROOT))
+    port = str(29500 + os.getpid() % 2000)
+    procs = [subprocess.Popen([sys.executable, str(script), str(r), port], stdout=subprocess.PIPE,
+                              stderr=subprocess.STDOUT, text=True) for r in range(2)]
+    outs = [p.communicate(timeout=180)[0] for p in procs]
+    for r, (p, o) in enumerate(zip(procs, outs)):
+        assert p.returncode == 0 and f"ok {r}" in o, o

@@ -1,0 +1,316 @@
+"""GPU parity tests (run on the B200 with `-m gpu`): the CUDA path, called through the C ABI
+(libfheb200.so via the host mirror in node-fhe-accelerate_b200/api.py), against
+
+* the golden vectors under tests/golden/ (outputs of the reference's own code), and
+* the CPU oracle (oracle/fhe_oracle.c, pinned to the reference) on fresh seeded inputs.
+
+Everything is integer work: comparisons are bit-exact.  Modelled on the reference's
+backend-equivalence tests (cpp/tests/test_metal_compute.cpp:109-181) and on
+cpp/tests/test_ntt_processor.cpp / test_polynomial_ring.cpp / test_multi_limb.cpp.
+"""
+import glob
+import os
+
+import numpy as np
+import pytest
+
+from oracle_bindings import mt19937_64_coeffs
+
+pytestmark = pytest.mark.gpu
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+Q27 = 132120577
+Q62 = 4611686018326724609
+QT = 1099511678977
+Q50 = 1125899906826241
+
+
+def eq(a, b):
+    a, b = np.asarray(a), np.asarray(b)
+    assert a.shape == b.shape, (a.shape, b.shape)
+    assert np.array_equal(a, b), f"{int((a != b).sum())} words differ; first at {np.argwhere(a != b)[:3].tolist()}"
+
+
+@pytest.fixture(scope="module")
+def fhe():
+    import fheb200
+
+    fheb200.initialize()
+    return fheb200
+
+
+@pytest.fixture(scope="module")
+def torch():
+    import torch
+
+    assert torch.cuda.is_available()
+    return torch
+
+
+def dev(torch, x):
+    """numpy uint64 -> CUDA int64 tensor holding the same words."""
+    return torch.from_numpy(np.ascontiguousarray(x).view(np.int64)).cuda()
+
+
+def host(t):
+    return t.cpu().numpy().view(np.uint64)
+
+
+# ------------------------------------------------------------------------------ library --
+def test_device_is_b200_and_library_loaded(fhe):
+    info = fhe.detect_hardware()
+    assert info["has_cuda"] and info["compute_capability"][0] == 10
+    assert not (info["has_metal"] or info["has_sme"] or info["has_neon"] or info["has_amx"])
+    assert info["sm_count"] > 0
+    with open("/proc/self/maps") as f:
+        assert "libfheb200.so" in f.read()
+
+
+# --------------------------------------------------------------------------- transforms --
+@pytest.mark.parametrize("path", sorted(glob.glob(os.path.join(GOLDEN, "ntt_*.npz"))), ids=os.path.basename)
+def test_golden_transforms(fhe, torch, path):
+    g = np.load(path)
+    n, q = int(g["n"]), int(g["q"])
+    ntt = fhe.NTTProcessor(n, q)
+    fwd, inv, psi, psi_inv, inv_n = ntt.get_twiddles()
+    assert (psi, psi_inv, inv_n) == (int(g["psi"]), int(g["psi_inv"]), int(g["inv_n"]))
+    eq(fwd[:8], g["fwd_head"])
+    eq(inv[:8], g["inv_head"])
+    x = g["x"]
+    # host buffers (staged inside the call)
+    eq(ntt.forward_ntt(x), g["forward"])
+    eq(ntt.inverse_ntt(x), g["inverse"])
+    eq(ntt.inverse_ntt(g["forward"]), x)
+    # device buffers, out of place and in place
+    xd = dev(torch, x)
+    eq(host(ntt.forward_ntt(xd)), g["forward"])
+    yd = xd.clone()
+    ntt.forward_ntt(yd, out=yd)
+    eq(host(yd), g["forward"])
+    ntt.inverse_ntt(yd, out=yd)
+    eq(host(yd), x)
+    ring = fhe.PolynomialRing(n, q)
+    h = x.shape[0] // 2
+    eq(ring.multiply(x[:h], x[h:2 * h]), g["product"])
+    eq(host(ring.multiply(dev(torch, x[:h]), dev(torch, x[h:2 * h]))), g["product"])
+
+
+def _prime_for(logn, lazy):
+    n = 1 << logn
+    if not lazy:
+        return Q62
+    return QT if n <= 1024 else Q27
+
+
+@pytest.mark.parametrize("lazy", [False, True], ids=["q62", "q<2^46"])
+@pytest.mark.parametrize("logn", range(2, 15))
+def test_transforms_match_oracle_all_degrees(fhe, torch, oracle, logn, lazy):
+    n, q = 1 << logn, _prime_for(logn, lazy)
+    ntt = fhe.NTTProcessor(n, q)
+    fwd, inv, psi, psi_inv, inv_n = oracle.twiddles(n, q)
+    gf, gi, gpsi, gpsi_inv, ginv_n = ntt.get_twiddles()
+    eq(gf, fwd)
+    eq(gi, inv)
+    assert (gpsi, gpsi_inv, ginv_n) == (psi, psi_inv, inv_n)
+    rng = np.random.default_rng(1000 + logn)
+    batch = 37 if logn <= 10 else 5  # ragged against every polys-per-block setting
+    cases = [rng.integers(0, q, size=(batch, n), dtype=np.uint64),
+             rng.integers(0, 2**64, size=(3, n), dtype=np.uint64),  # unreduced inputs are reduced first
+             np.zeros((1, n), np.uint64), np.full((2, n), q - 1, np.uint64)]
+    for x in cases:
+        xd = dev(torch, x)
+        eq(host(ntt.forward_ntt(xd)), oracle.forward(x, q, fwd))
+        eq(host(ntt.inverse_ntt(xd)), oracle.inverse(x, q, inv, inv_n))
+    x = cases[0]
+    eq(host(ntt.inverse_ntt_forward_network(dev(torch, x))), oracle.fast_inverse(x, q, inv))
+    ring = fhe.PolynomialRing(n, q)
+    a, b = cases[0], np.roll(cases[0], 1, axis=0)
+    eq(host(ring.multiply(dev(torch, a), dev(torch, b))), oracle.multiply(a, b, q, fwd, inv, inv_n))
+    au, bu = cases[1], cases[1][::-1].copy()
+    eq(host(ring.multiply(dev(torch, au), dev(torch, bu))), oracle.multiply(au, bu, q, fwd, inv, inv_n))
+    eq(ring.multiply(a[:2], a[:2]), oracle.multiply(a[:2], a[:2], q, fwd, inv, inv_n))  # aliased operands
+
+
+def test_reference_test_ntt_processor_configs(fhe, oracle):
+    """cpp/tests/test_ntt_processor.cpp:198-235,276-300: seeds 42/123, (8,17), (16,97), (1024,132120577)."""
+    for n, q, iters in [(8, 17, 100), (16, 97, 100), (1024, Q27, 20)]:
+        ntt = fhe.NTTProcessor(n, q)
+        fwd, inv, _, _, inv_n = oracle.twiddles(n, q)
+        for seed in (42, 123):
+            x = mt19937_64_coeffs(seed, n * iters, q).reshape(iters, n)
+            y = ntt.forward_ntt(x)
+            eq(y, oracle.forward(x, q, fwd))
+            eq(ntt.inverse_ntt(y), x)  # Property 1: round trip
+
+
+def test_caller_supplied_cyclic_tables(fhe, torch, oracle):
+    """fast_ntt_forward / benchmark backends feed an omega (N-th root) table through the same network."""
+    n, q = 1024, Q27
+    _, _, psi, psi_inv, inv_n = oracle.twiddles(n, q)
+    omega, omega_inv = pow(psi, 2, q), pow(psi_inv, 2, q)
+    fwd = np.array([pow(omega, i, q) for i in range(n)], np.uint64)
+    inv = np.array([pow(omega_inv, i, q) for i in range(n)], np.uint64)
+    ntt = fhe.NTTProcessor(n, q, fwd, inv, inv_n)
+    x = np.random.default_rng(5).integers(0, q, size=(6, n), dtype=np.uint64)
+    y = ntt.forward_ntt(x)
+    eq(y, oracle.forward(x, q, fwd))
+    eq(ntt.inverse_ntt_forward_network(y), oracle.fast_inverse(y, q, inv))
+    eq(ntt.inverse_ntt_forward_network(y), x)  # with a cyclic table that IS the inverse transform
+
+
+def test_plan_errors(fhe):
+    for args, msg in [((1000, Q27), "power of 2"), ((2, 17), "between 4 and 65536"), ((1024, Q27 + 1), "odd"),
+                      ((1024, 1099511627777 - 2), "NTT-friendly"), ((1024, 1099511627777), "primitive root")]:
+        with pytest.raises(fhe.FheError) as e:
+            fhe.NTTProcessor(*args)
+        assert msg in str(e.value), str(e.value)
+    ntt = fhe.NTTProcessor(8, 97)
+    with pytest.raises(fhe.FheError):
+        ntt.forward_ntt(np.zeros(7, np.uint64))
+    assert ntt.forward_ntt(np.zeros((0, 8), np.uint64)).shape == (0, 8)  # empty batch
+
+
+def test_full_size_properties(fhe, torch):
+    """BASELINE C2 sizes (N = 4096 / 16384, batch 1024): round trip, linearity, ring axioms."""
+    for n in (4096, 16384):
+        q = Q62
+        ring = fhe.PolynomialRing(n, q)
+        g = torch.Generator(device="cuda").manual_seed(n)
+        a = torch.randint(0, q, (1024, n), dtype=torch.int64, device="cuda", generator=g)
+        b = torch.randint(0, q, (1024, n), dtype=torch.int64, device="cuda", generator=g)
+        fa = ring.to_ntt(a)
+        assert torch.equal(ring.from_ntt(fa), a)
+        # T(a + b) == T(a) + T(b)
+        assert torch.equal(ring.to_ntt(ring.add(a, b)), ring.add(fa, ring.to_ntt(b)))
+        ab = ring.multiply(a, b)
+        assert torch.equal(ab, ring.multiply(b, a))
+        # fused product == unfused composition of the same library calls
+        assert torch.equal(ab, ring.from_ntt(ring.pointwise_multiply(fa, ring.to_ntt(b))))
+        one = torch.zeros_like(a)
+        one[:, 0] = 1
+        # multiply by T^-1(1,1,..,1) is the identity of this ring's product
+        ident = ring.from_ntt(torch.ones_like(a))
+        assert torch.equal(ring.multiply(a, ident), a)
+
+
+# -------------------------------------------------------------------------- elementwise --
+@pytest.mark.parametrize("q", [17, Q27, QT, Q62, (1 << 63) + 29, (1 << 64) - 59])
+def test_elementwise_matches_oracle(fhe, torch, oracle, q):
+    rng = np.random.default_rng(q % 1000)
+    for count in (1, 2, 3, 1023, 4096, 100001):
+        a = rng.integers(0, 2**64, size=count, dtype=np.uint64)
+        b = rng.integers(0, 2**64, size=count, dtype=np.uint64)
+        if count > 2:
+            a[:3] = [0, q - 1, q]
+            b[:3] = [q - 1, q - 1, 0]
+        ad, bd = dev(torch, a), dev(torch, b)
+        eq(host(fhe.modadd_batch(ad, bd, q)), oracle.add(a, b, q))
+        eq(host(fhe.modsub_batch(ad, bd, q)), oracle.sub(a, b, q))
+        eq(host(fhe.modmul_batch(ad, bd, q)), oracle.pointwise(a, b, q))
+        eq(host(fhe.modneg_batch(dev(torch, a % np.uint64(q)), q)), oracle.negate(a % np.uint64(q), q))
+        s = int(b[0])
+        eq(host(fhe.modmul_scalar_batch(ad, s, q)), oracle.scalar(a, s, q))
+    # host buffers, odd alignment (16-byte vector path must fall back) and aliasing r == a
+    a = rng.integers(0, 2**64, size=1001, dtype=np.uint64)
+    b = rng.integers(0, 2**64, size=1001, dtype=np.uint64)
+    eq(fhe.modmul_batch(a[1:], b[1:], q), oracle.pointwise(a[1:], b[1:], q))
+    ad = dev(torch, a)
+    exp = oracle.add(a, b, q)
+    fhe.modadd_batch(ad, dev(torch, b), q, out=ad)
+    eq(host(ad), exp)
+
+
+def test_golden_multi_limb(fhe, torch):
+    g = np.load(os.path.join(GOLDEN, "mlimb_q65.npz"))
+    ml = fhe.MultiLimbModularArithmetic(g["q"])
+    assert ml.q_inv == int(g["q_inv"])
+    eq(ml.r_mod_q, g["r_mod_q"])
+    eq(ml.r2_mod_q, g["r2_mod_q"])
+    a, b = g["a"], g["b"]
+    for buf in (lambda x: x, lambda x: dev(torch, x)):
+        out = lambda t: t if isinstance(t, np.ndarray) else host(t)
+        eq(out(ml.montgomery_mul(buf(a), buf(b))), g["montmul"])
+        eq(out(ml.mod_add(buf(a), buf(b))), g["add"])
+        eq(out(ml.mod_sub(buf(a), buf(b))), g["sub"])
+        eq(out(ml.to_montgomery(buf(a))), g["to_mont"])
+        eq(out(ml.from_montgomery(buf(a))), g["from_mont"])
+
+
+@pytest.mark.parametrize("q_limbs", [[0xFFFFFFFFFFFFFF43, 1], [0xFFFFFFFFFFFFFFC5], [0x1D, 0, 1],
+                                     [0xFFFFFFFFFFFFFF61, 0xFFFFFFFFFFFFFFFF], [0x2F, 5, 0, 9], [3, 0, 0, 0, 0, 0, 0, 1]])
+def test_multi_limb_matches_oracle(fhe, torch, oracle, q_limbs):
+    q = np.array(q_limbs, np.uint64)
+    l = q.size
+    qi = sum(int(v) << (64 * i) for i, v in enumerate(q))
+    q_inv, r1, r2 = oracle.mlimb_constants(q)
+    ml = fhe.MultiLimbModularArithmetic(q)
+    assert ml.q_inv == q_inv
+    eq(ml.r_mod_q, r1)
+    eq(ml.r2_mod_q, r2)
+    rng = np.random.default_rng(l)
+    count = 65536 if l == 2 else 3001  # BASELINE C3: n = 65536 two-limb elements
+    vals = [int.from_bytes(rng.bytes(8 * l + 1), "little") % qi for _ in range(2 * count)]
+    vals[:4] = [0, 1, qi - 1, qi - 2]
+    arr = np.array([[(v >> (64 * i)) & (2**64 - 1) for i in range(l)] for v in vals], np.uint64)
+    a, b = arr[:count], arr[count:]
+    ad, bd = dev(torch, a), dev(torch, b)
+    eq(host(ml.montgomery_mul(ad, bd)), oracle.mlimb_montmul(a, b, q, q_inv))
+    eq(host(ml.mod_add(ad, bd)), oracle.mlimb_add(a, b, q))
+    eq(host(ml.mod_sub(ad, bd)), oracle.mlimb_sub(a, b, q))
+    if l == 2:  # independent check with Python integers on a sample
+        got = host(ml.montgomery_mul(ad[:64], bd[:64]))
+        rinv = pow(1 << 128, -1, qi)
+        for i in range(64):
+            assert int(got[i, 0]) + (int(got[i, 1]) << 64) == vals[i] * vals[count + i] * rinv % qi
+
+
+# -------------------------------------------------------------------------------- tally --
+@pytest.mark.parametrize("name", ["tally_n64_m5.npz", "tally_n1024_m9.npz"])
+def test_golden_tally(fhe, torch, name):
+    g = np.load(os.path.join(GOLDEN, name))
+    n, q, cts = int(g["n"]), int(g["q"]), g["cts"]
+    eq(fhe.tally_votes(cts, n, q), g["linear"])
+    eq(host(fhe.tally_votes(dev(torch, cts), n, q)), g["tree"])
+    eq(fhe.tally_votes(cts[1:2], n, q), g["single"])  # one ballot: words returned untouched
+    with pytest.raises(fhe.FheError) as e:
+        fhe.tally_votes(cts[:0], n, q)
+    assert "Cannot add empty vector of ciphertexts" in str(e.value)
+    ring = fhe.PolynomialRing(n, q)
+    eq(ring.tensor_multiply(cts[0:1], cts[2:3])[0], g["tensor"])
+
+
+@pytest.mark.parametrize("count", [2, 3, 63, 64, 65, 1000, 20000])
+def test_tally_matches_oracle(fhe, torch, oracle, count):
+    n, q = 1024, QT
+    rng = np.random.default_rng(count)
+    cts = rng.integers(0, q, size=(count, 2, n), dtype=np.uint64)
+    if count == 3:
+        cts[1] = rng.integers(0, 2**64, size=(2, n), dtype=np.uint64)  # unreduced words are reduced by add
+    exp = oracle.tally(cts, q)
+    eq(host(fhe.tally_votes(dev(torch, cts), n, q)), exp)
+    if count >= 64:  # sharded shape: per-shard partials, then the combine kernel
+        parts = np.stack([host(fhe.tally_votes(dev(torch, cts[lo:hi]), n, q))
+                          for lo, hi in [fhe.shard_range(count, r, 4) for r in range(4)]])
+        eq(host(fhe.tally_combine(dev(torch, parts), n, q)), exp)
+
+
+def test_synthetic_ballots_reproducible_and_tally_checksum(fhe, torch, oracle):
+    """The on-device ballot generator is restated on the CPU; a 64k-ballot tally is checked through
+    a checksum of per-chunk oracle tallies (size-independent: the tally of tallies)."""
+    n, q, seed = 1024, QT, 0xB200
+    count = 1 << 16
+    cts = torch.empty((count, 2, n), dtype=torch.int64, device="cuda")
+    fhe.synth_ballots(cts, 0, count, n, q, seed)
+
+    def splitmix(idx):
+        x = (idx + np.uint64(0x9E3779B97F4A7C15)).astype(np.uint64)
+        x = (x ^ (x >> np.uint64(30))) * np.uint64(0xBF58476D1CE4E5B9)
+        x = (x ^ (x >> np.uint64(27))) * np.uint64(0x94D049BB133111EB)
+        return x ^ (x >> np.uint64(31))
+
+    with np.errstate(over="ignore"):
+        words = splitmix(np.uint64(seed) + np.arange(300 * 2 * n, dtype=np.uint64)) % np.uint64(q)
+    eq(host(cts[:300]).reshape(-1), words)
+    total = host(fhe.tally_votes(cts, n, q))
+    chunks = np.stack([oracle.tally(host(cts[i:i + 8192]), q) for i in range(0, count, 8192)])
+    eq(total, oracle.tally(chunks, q))
