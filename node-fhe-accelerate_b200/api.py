@@ -358,6 +358,8 @@ class BootstrapEngine:
         return out
 
     def key_switch(self, lwe, out=None):
+        if self.n_out is None:
+            raise FheError(_cabi.INVALID_PARAMETERS, "no key switching key has been set (set_key_switch_key)")
         lwe = as_words(lwe)
         batch = _words(lwe) // (self.k * self.N + 1)
         out = _like(lwe, (batch, self.n_out + 1)) if out is None else out

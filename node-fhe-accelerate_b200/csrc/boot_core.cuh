@@ -1,0 +1,230 @@
+// One CMux / external product of the TFHE blind rotation as a sequence of barrier-separated
+// phases over one thread block's shared memory (host/device code: the same functions are run
+// sequentially by tests/host_emulation to validate them without a GPU).
+//
+// Reference semantics (cpp/src/bootstrap_engine.cpp):
+//   cmux(ggsw, ct0, ct1) = ct0 + external_product(ct1 - ct0, ggsw)                    :520-540
+//   external_product     = sum over rows (c, l) of T^-1( T(digit_{c,l}) . T(ggsw[row][j]) ),
+//                          accumulated in the coefficient domain, j = output component    :431-518
+//   digit_{c,l}          = low-bit gadget digit of component c, centred without carry     :152-185
+//   blind-rotate step    : ct1 = X^rot * acc (rotate_polynomial :122-145), ct0 = acc      :562-576
+// T is Z_q-linear, so sum_rows T^-1(D_row . G_row,j) == T^-1(sum_rows D_row . G_row,j) exactly:
+// the GGSW is transformed ONCE at key upload (kept in HBM in position order with its Shoup
+// companions) and each step costs (k+1)*L forward and (k+1) inverse transforms instead of the
+// reference's 10*L.  The last forward pass, the multiply-accumulate against the GGSW and the
+// first inverse pass run on the same register-resident positions, so transformed digits
+// never touch memory and no bit-reversal happens anywhere.
+#pragma once
+#include "ntt_core.cuh"
+
+namespace fheb {
+
+struct BootStep {          // block-uniform description of one step
+    uint64_t* acc;         // smem [KP1][N], natural index: ct0 / running accumulator
+    uint64_t* work;        // smem [max(rows, KP1)][N], swizzled index
+    const uint64_t* diff;  // smem [KP1][N] natural index: precomputed ct1 - ct0 (or the GLWE itself); null = rotate acc
+    const Tw* ggsw;        // global [rows][KP1][N], position order, (value, Shoup companion)
+    uint64_t* gout;        // when non-null the final pass stores here ([KP1][N], global) instead of acc
+    uint32_t rot;          // normalised rotation in [0, 2N) (used when diff == null)
+    uint32_t levels;
+    uint32_t base_log;
+    uint32_t add_acc;      // 1: result = acc + product (cmux); 0: product only (external product)
+};
+
+// normalisation of rotate_polynomial (cpp/src/bootstrap_engine.cpp:127-128), int32 arithmetic as written
+FHEB_HD uint32_t normalise_rotation(int32_t rotation, uint32_t N) {
+    const int32_t two_n = 2 * (int32_t)N;
+    return (uint32_t)(((rotation % two_n) + two_n) % two_n);
+}
+
+// (X^rot * p)[j] for rot in [0, 2N): p[j - rot] or its negation `(q - v) % q` in u64 arithmetic (:131-143)
+FHEB_HD uint64_t rotated_at(const uint64_t* p, uint32_t j, uint32_t rot, uint32_t N, const ModQ& m) {
+    const uint32_t s = (j + 2u * N - rot) & (2u * N - 1u);
+    if (s < N) return p[s];
+    const uint64_t t = m.q - p[s - N];
+    return t >= m.q ? reduce64(t, m) : t;
+}
+
+// gadget digit l of coefficient c (decompose_polynomial, :165-178), as a canonical residue
+FHEB_HD uint64_t gadget_digit(uint64_t c, uint32_t shift, uint64_t mask, uint64_t base, const ModQ& m) {
+    const uint64_t d = (c >> shift) & mask;
+    const uint64_t v = (d > (base >> 1)) ? (m.q - (base - d)) : d;
+    return canon_any(v, m);
+}
+
+template <int L>
+constexpr int boot_phases() { return 2 * Plan<L>::P - 1; }
+
+// ---- phase 0: difference, decomposition and the first forward pass ------------------------
+template <int L, bool LAZY, int KP1>
+FHEB_HD void boot_first_pass(uint32_t tid, uint32_t nthreads, const BootStep& s, const Tw* __restrict__ tw,
+                             const ModQ& m) {
+    constexpr int R = Plan<L>::R[0];
+    constexpr int E = 1 << R;
+    constexpr int EB = L - R;
+    constexpr int CAP = cap_of<LAZY>();
+    constexpr uint32_t N = 1u << L;
+    constexpr uint32_t ITEMS = N >> R;
+    static_assert(Plan<L>::P >= 2, "bootstrap kernels need at least two passes (N >= 32)");
+    const uint64_t base = 1ull << s.base_log;
+    const uint64_t mask = base - 1;
+    for (uint32_t U = tid; U < (uint32_t)KP1 * ITEMS; U += nthreads) {
+        const uint32_t c = U >> (L - R);
+        const uint32_t u = U & (ITEMS - 1);
+        uint64_t d[E];
+        if (s.diff) {
+            const uint64_t* src = s.diff + (size_t)c * N;
+#pragma unroll
+            for (int e = 0; e < E; ++e) d[e] = src[u | ((uint32_t)e << EB)];
+        } else {
+            const uint64_t* a = s.acc + (size_t)c * N;
+#pragma unroll
+            for (int e = 0; e < E; ++e) {
+                const uint32_t pos = u | ((uint32_t)e << EB);
+                const uint64_t ct0 = canon_any(a[pos], m);
+                const uint64_t ct1 = canon_any(rotated_at(a, pos, s.rot, N, m), m);
+                d[e] = submod_canon(ct1, ct0, m.q);  // PolynomialRing::subtract(ct1, ct0), :527-530
+            }
+        }
+        const uint32_t pb = swz(u);
+        for (uint32_t l = 0; l < s.levels; ++l) {
+            const uint32_t shift = (s.levels - 1 - l) * s.base_log;
+            uint64_t x[E];
+#pragma unroll
+            for (int e = 0; e < E; ++e) x[e] = gadget_digit(d[e], shift, mask, base, m);
+            fwd_stages<R, 1, CAP, true>(x, tw, 1u, m);
+            uint64_t* dst = s.work + (size_t)(c * s.levels + l) * N;
+#pragma unroll
+            for (int e = 0; e < E; ++e) dst[pb ^ swz((uint32_t)e << EB)] = x[e];
+        }
+    }
+}
+
+// ---- phase P-1: last forward pass of every digit row, multiply-accumulate with the GGSW, first
+//      inverse pass of every output component -------------------------------------------------
+template <int L, bool LAZY, int KP1>
+FHEB_HD void boot_mid_pass(uint32_t tid, uint32_t nthreads, const BootStep& s, const Tw* __restrict__ twf,
+                           const Tw* __restrict__ twi, const ModQ& m) {
+    constexpr int PASS = Plan<L>::P - 1;
+    constexpr int R = Plan<L>::R[PASS];
+    constexpr int E = 1 << R;
+    constexpr int S0 = plan_s0<L, PASS>();
+    constexpr int CAP = cap_of<LAZY>();
+    constexpr int KIN = plan_fwd_kin<L, LAZY, PASS>();
+    constexpr uint32_t N = 1u << L;
+    constexpr uint32_t ITEMS = N >> R;
+    static_assert(L - S0 - R == 0, "the last forward pass covers the lowest position bits");
+    const uint32_t rows = (uint32_t)KP1 * s.levels;
+    for (uint32_t u = tid; u < ITEMS; u += nthreads) {
+        const uint32_t base = u << R;
+        const uint32_t pb = swz(base);
+        const uint32_t T0 = (1u << S0) + (base >> (L - S0));
+        uint64_t out[KP1][E];
+#pragma unroll
+        for (int j = 0; j < KP1; ++j)
+#pragma unroll
+            for (int e = 0; e < E; ++e) out[j][e] = 0;
+        for (uint32_t row = 0; row < rows; ++row) {
+            const uint64_t* src = s.work + (size_t)row * N;
+            uint64_t x[E];
+#pragma unroll
+            for (int e = 0; e < E; ++e) x[e] = src[pb ^ swz((uint32_t)e)];
+            fwd_stages<R, KIN, CAP, false>(x, twf, T0, m);
+            const Tw* g = s.ggsw + ((size_t)row * KP1) * N + base;
+#pragma unroll
+            for (int j = 0; j < KP1; ++j) {
+#pragma unroll
+                for (int e = 0; e < E; ++e) {
+                    const Tw w = load_tw(g, (uint32_t)j * N + (uint32_t)e);
+                    const uint64_t t = shoup_lazy(x[e], w.w, w.wp, m.q);  // [0, 2q) for any x
+                    // lazy moduli (q < 2^46): plain sums, 2q * rows stays far below 2^64;
+                    // otherwise keep the running sum in [0, 2q)
+                    out[j][e] = LAZY ? out[j][e] + t : csub(out[j][e] + t, m.q2);
+                }
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < KP1; ++j) {
+            if (LAZY) {
+#pragma unroll
+                for (int e = 0; e < E; ++e) out[j][e] = reduce64(out[j][e], m);
+            }
+            inv_stages<R, LAZY ? 1 : 2, CAP, false>(out[j], twi, T0, m);
+            uint64_t* dst = s.work + (size_t)j * N;
+#pragma unroll
+            for (int e = 0; e < E; ++e) dst[pb ^ swz((uint32_t)e)] = out[j][e];
+        }
+    }
+}
+
+// ---- last phase: final inverse pass, scaling by N^-1, `+ ct0` ------------------------------------
+template <int L, bool LAZY, int KP1>
+FHEB_HD void boot_final_pass(uint32_t tid, uint32_t nthreads, const BootStep& s, const Tw* __restrict__ twi,
+                             const Tw ninv, const ModQ& m) {
+    constexpr int R = Plan<L>::R[0];
+    constexpr int E = 1 << R;
+    constexpr int EB = L - R;
+    constexpr int CAP = cap_of<LAZY>();
+    constexpr int KIN = plan_inv_kin<L, LAZY, 0>();
+    constexpr uint32_t N = 1u << L;
+    constexpr uint32_t ITEMS = N >> R;
+    for (uint32_t U = tid; U < (uint32_t)KP1 * ITEMS; U += nthreads) {
+        const uint32_t c = U >> (L - R);
+        const uint32_t u = U & (ITEMS - 1);
+        const uint32_t pb = swz(u);
+        const uint64_t* src = s.work + (size_t)c * N;
+        uint64_t x[E];
+#pragma unroll
+        for (int e = 0; e < E; ++e) x[e] = src[pb ^ swz((uint32_t)e << EB)];
+        inv_stages<R, KIN, CAP, true>(x, twi, 1u, m);
+        const uint64_t* a = s.acc + (size_t)c * N;
+        uint64_t* dst = (s.gout ? s.gout : s.acc) + (size_t)c * N;
+#pragma unroll
+        for (int e = 0; e < E; ++e) {
+            const uint32_t pos = u | ((uint32_t)e << EB);
+            uint64_t v = csub(shoup_lazy(x[e], ninv.w, ninv.wp, m.q), m.q);
+            if (s.add_acc) v = addmod_canon(v, canon_any(a[pos], m), m.q);  // PolynomialRing::add(result, ct0), :533-537
+            dst[pos] = v;
+        }
+    }
+}
+
+// Phase PH of a step; the caller puts a block barrier after every phase.
+template <int L, bool LAZY, int KP1, int PH>
+FHEB_HD void boot_phase(uint32_t tid, uint32_t nthreads, const BootStep& s, const Tw* __restrict__ twf,
+                        const Tw* __restrict__ twi, const Tw ninv, const ModQ& m) {
+    constexpr int P = Plan<L>::P;
+    static_assert(PH >= 0 && PH < 2 * P - 1, "phase out of range");
+    if constexpr (PH == 0) {
+        boot_first_pass<L, LAZY, KP1>(tid, nthreads, s, twf, m);
+    } else if constexpr (PH < P - 1) {
+        fwd_pass<L, LAZY, PH, IO_SMEM, IO_SMEM>(tid, nthreads, (uint32_t)KP1 * s.levels, nullptr, nullptr, s.work, twf, m);
+    } else if constexpr (PH == P - 1) {
+        boot_mid_pass<L, LAZY, KP1>(tid, nthreads, s, twf, twi, m);
+    } else if constexpr (PH < 2 * P - 2) {
+        inv_pass<L, LAZY, 2 * P - 2 - PH, IO_SMEM, IO_SMEM>(tid, nthreads, (uint32_t)KP1, nullptr, nullptr, s.work, twi, ninv, m);
+    } else {
+        boot_final_pass<L, LAZY, KP1>(tid, nthreads, s, twi, ninv, m);
+    }
+}
+
+// Rotation amounts of blind_rotate (cpp/src/bootstrap_engine.cpp:558,564): wrapping u64 product,
+// truncation to int32, sign applied before the normalisation of rotate_polynomial.
+FHEB_HD uint32_t lwe_rotation(uint64_t word, bool negate, uint32_t N, uint64_t q) {
+    const uint64_t scaled = (word * 2ull * (uint64_t)N + q / 2) / q;
+    int32_t r = (int32_t)(uint32_t)scaled;
+    if (negate) r = (int32_t)(0u - (uint32_t)r);
+    return normalise_rotation(r, N);
+}
+
+// sample_extract (cpp/src/bootstrap_engine.cpp:594-624): word idx of the LWE [k*N + 1] extracted from glwe
+FHEB_HD uint64_t sample_extract_word(const uint64_t* glwe, uint32_t idx, uint32_t k, uint32_t N, const ModQ& m) {
+    if (idx == k * N) return glwe[(size_t)k * N];
+    const uint32_t i = idx / N, j = idx % N;
+    const uint64_t* mask = glwe + (size_t)i * N;
+    if (j == 0) return mask[0];
+    const uint64_t t = m.q - mask[N - j];
+    return t >= m.q ? reduce64(t, m) : t;  // (q - v) % q in u64 arithmetic
+}
+
+}  // namespace fheb

@@ -1,0 +1,164 @@
+// The persistent blind-rotation / CMux / external-product kernel (device-only part; the phase
+// bodies live in boot_core.cuh).  One thread block owns one ciphertext: its accumulator stays in
+// shared memory for all n CMux steps, the pre-transformed bootstrapping key streams in from
+// HBM/L2 (it is shared by every block of the batch), and nothing but the final GLWE goes back.
+#pragma once
+#include <cuda_runtime.h>
+
+#include "boot_core.cuh"
+#include "runtime.hpp"
+
+namespace fheb {
+
+enum { BOOT_BLIND = 0, BOOT_CMUX = 1, BOOT_EXT = 2 };
+
+struct BootLaunch {
+    const Tw* bsk;           // BLIND: all n GGSWs; CMUX/EXT: the selected GGSW
+    const uint64_t* in0;     // BLIND: lwe [batch][n+1]; CMUX: ct0 [batch][KP1][N]; EXT: glwe
+    const uint64_t* in1;     // BLIND: test polynomial [N]; CMUX: ct1
+    uint64_t* out;           // [batch][KP1][N]
+    size_t batch;
+    uint32_t n;              // LWE dimension (BLIND)
+    uint32_t levels, base_log;
+    int mode;
+    const Tw* twf;
+    const Tw* twi;
+    Tw ninv;
+    ModQ m;
+};
+
+template <int L>
+struct BootGeometry {
+    static constexpr int THREADS = (L <= 6) ? 32 : (L <= 8) ? 64 : (L <= 10) ? 128 : (L == 11) ? 256 : 512;
+};
+
+// shared-memory words: acc [KP1][N] | work [rows][N] | (CMUX/EXT) diff [KP1][N] | (BLIND) rotations [n] (u32)
+inline size_t boot_smem_bytes(int mode, uint32_t N, uint32_t kp1, uint32_t levels, uint32_t n) {
+    size_t words = (size_t)kp1 * N + (size_t)kp1 * levels * N;
+    if (mode != BOOT_BLIND) words += (size_t)kp1 * N;
+    size_t bytes = words * 8;
+    if (mode == BOOT_BLIND) bytes += ((size_t)n * 4 + 15) & ~(size_t)15;
+    return bytes;
+}
+
+template <int L, bool LAZY, int KP1, int PH = 0>
+__device__ __forceinline__ void boot_run_step(uint32_t tid, uint32_t nthreads, const BootStep& s, const BootLaunch& a) {
+    if constexpr (PH < boot_phases<L>()) {
+        boot_phase<L, LAZY, KP1, PH>(tid, nthreads, s, a.twf, a.twi, a.ninv, a.m);
+        __syncthreads();
+        boot_run_step<L, LAZY, KP1, PH + 1>(tid, nthreads, s, a);
+    }
+}
+
+template <int L, bool LAZY, int KP1>
+__global__ void __launch_bounds__(BootGeometry<L>::THREADS) boot_kernel(const BootLaunch a) {
+    extern __shared__ __align__(16) uint64_t smem[];
+    constexpr uint32_t N = 1u << L;
+    constexpr uint32_t THREADS = BootGeometry<L>::THREADS;
+    constexpr uint32_t GW = (uint32_t)KP1 * N;  // words per GLWE
+    const uint32_t tid = threadIdx.x;
+    const uint32_t rows = (uint32_t)KP1 * a.levels;
+    uint64_t* acc = smem;
+    uint64_t* work = acc + GW;
+    uint64_t* diff = work + (size_t)rows * N;                   // CMUX / EXT only
+    uint32_t* rots = reinterpret_cast<uint32_t*>(work + (size_t)rows * N);  // BLIND only
+    const size_t ggsw_words = (size_t)rows * KP1 * N;
+
+    for (size_t ct = blockIdx.x; ct < a.batch; ct += gridDim.x) {
+        BootStep s;
+        s.acc = acc;
+        s.work = work;
+        s.levels = a.levels;
+        s.base_log = a.base_log;
+        uint64_t* gout = a.out + ct * GW;
+        if (a.mode == BOOT_BLIND) {
+            const uint64_t* lwe = a.in0 + ct * ((size_t)a.n + 1);
+            for (uint32_t i = tid; i < a.n; i += THREADS) rots[i] = lwe_rotation(lwe[i], false, N, a.m.q);
+            // acc = X^(-round(b * 2N / q)) * (0, .., 0, test_poly): multiply_glwe_by_monomial, :558-559
+            const uint32_t rb = lwe_rotation(lwe[a.n], true, N, a.m.q);
+            for (uint32_t i = tid; i < GW; i += THREADS) {
+                const uint32_t c = i >> L, j = i & (N - 1);
+                acc[i] = (c == (uint32_t)KP1 - 1) ? rotated_at(a.in1, j, rb, N, a.m) : 0;
+            }
+            __syncthreads();
+            s.diff = nullptr;
+            s.add_acc = 1;
+            s.gout = nullptr;
+            for (uint32_t i = 0; i < a.n; ++i) {
+                const uint32_t rot = rots[i];
+                if (rot == 0) continue;  // :566 (block-uniform)
+                s.rot = rot;
+                s.ggsw = a.bsk + (size_t)i * ggsw_words;
+                boot_run_step<L, LAZY, KP1>(tid, THREADS, s, a);
+            }
+            for (uint32_t i = tid; i < GW; i += THREADS) gout[i] = acc[i];
+            __syncthreads();  // the next ciphertext overwrites acc / rots
+        } else {
+            const uint64_t* g0 = a.in0 + ct * GW;
+            if (a.mode == BOOT_CMUX) {
+                const uint64_t* g1 = a.in1 + ct * GW;
+                for (uint32_t i = tid; i < GW; i += THREADS) {
+                    const uint64_t c0 = g0[i];
+                    acc[i] = c0;
+                    diff[i] = submod_canon(canon_any(g1[i], a.m), canon_any(c0, a.m), a.m.q);
+                }
+            } else {
+                for (uint32_t i = tid; i < GW; i += THREADS) diff[i] = g0[i];
+            }
+            __syncthreads();
+            s.diff = diff;
+            s.add_acc = (a.mode == BOOT_CMUX) ? 1 : 0;
+            s.gout = gout;
+            s.rot = 0;
+            s.ggsw = a.bsk;
+            boot_run_step<L, LAZY, KP1>(tid, THREADS, s, a);
+        }
+    }
+}
+
+template <int L, bool LAZY, int KP1>
+int boot_launch_one(const BootLaunch& a, cudaStream_t stream) {
+    constexpr int THREADS = BootGeometry<L>::THREADS;
+    const size_t smem = boot_smem_bytes(a.mode, 1u << L, KP1, a.levels, a.n);
+    auto k = boot_kernel<L, LAZY, KP1>;
+    if (smem > (size_t)ctx().prop.sharedMemPerBlockOptin)
+        return set_error(FHEB_ERR_INVALID_PARAMETERS,
+                         "bootstrap working set (%zu bytes) exceeds the shared memory of one SM; reduce N, k or the level count",
+                         smem);
+    if (smem > 48 * 1024) FHEB_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int bps = 0;
+    FHEB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, k, THREADS, smem));
+    if (bps < 1) return set_error(FHEB_ERR_NATIVE, "bootstrap kernel does not fit on an SM");
+    const size_t resident = (size_t)ctx().sm_count * (size_t)bps;
+    const unsigned grid = (unsigned)(a.batch < resident ? a.batch : resident);
+    k<<<grid, THREADS, smem, stream>>>(a);
+    FHEB_CHECK_LAUNCH();
+    count_launch();
+    return FHEB_OK;
+}
+
+template <int KP1>
+int boot_launch_kp1(uint32_t logn, bool lazy, const BootLaunch& a, cudaStream_t stream) {
+#define FHEB_BOOT_CASE(L_) \
+    case L_:               \
+        return lazy ? boot_launch_one<L_, true, KP1>(a, stream) : boot_launch_one<L_, false, KP1>(a, stream);
+    switch (logn) {
+        FHEB_BOOT_CASE(5)
+        FHEB_BOOT_CASE(6)
+        FHEB_BOOT_CASE(7)
+        FHEB_BOOT_CASE(8)
+        FHEB_BOOT_CASE(9)
+        FHEB_BOOT_CASE(10)
+        FHEB_BOOT_CASE(11)
+        FHEB_BOOT_CASE(12)
+    }
+#undef FHEB_BOOT_CASE
+    return set_error(FHEB_ERR_INVALID_PARAMETERS, "bootstrap kernels support polynomial degrees 32..4096 (got 2^%u)", logn);
+}
+
+// one translation unit per GLWE dimension (parallel compilation)
+int boot_launch_k1(uint32_t logn, bool lazy, const BootLaunch& a, cudaStream_t stream);
+int boot_launch_k2(uint32_t logn, bool lazy, const BootLaunch& a, cudaStream_t stream);
+int boot_launch_k3(uint32_t logn, bool lazy, const BootLaunch& a, cudaStream_t stream);
+
+}  // namespace fheb

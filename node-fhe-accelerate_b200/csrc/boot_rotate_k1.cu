@@ -1,0 +1,8 @@
+// Blind-rotation kernel instantiations for GLWE dimension k = 1 (see boot_kernel.cuh).
+#include "boot_kernel.cuh"
+
+namespace fheb {
+int boot_launch_k1(uint32_t logn, bool lazy, const BootLaunch& a, cudaStream_t stream) {
+    return boot_launch_kp1<2>(logn, lazy, a, stream);
+}
+}  // namespace fheb

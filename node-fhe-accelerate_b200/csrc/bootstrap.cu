@@ -1,16 +1,402 @@
-// placeholder entry points (replaced by the real kernels)
-#include "runtime.hpp"
-using namespace fheb;
-#define NI return set_error(FHEB_ERR_NATIVE, "not implemented yet")
-extern "C" {
-int fheb_boot_key_create(const fheb_ntt_plan*, const fheb_boot_params*, const uint64_t*, fheb_boot_key**) { NI; }
-int fheb_boot_key_set_ksk(fheb_boot_key*, const uint64_t*, size_t, uint32_t, uint32_t, uint32_t) { NI; }
-int fheb_boot_key_destroy(fheb_boot_key*) { return 0; }
-int fheb_external_product_batch(const fheb_boot_key*, uint32_t, const uint64_t*, uint64_t*, size_t, void*) { NI; }
-int fheb_cmux_batch(const fheb_boot_key*, uint32_t, const uint64_t*, const uint64_t*, uint64_t*, size_t, void*) { NI; }
-int fheb_blind_rotate_batch(const fheb_boot_key*, const uint64_t*, const uint64_t*, uint64_t*, size_t, void*) { NI; }
-int fheb_sample_extract_batch(const fheb_boot_key*, const uint64_t*, uint64_t*, size_t, void*) { NI; }
-int fheb_key_switch_batch(const fheb_boot_key*, const uint64_t*, uint64_t*, size_t, void*) { NI; }
-int fheb_bootstrap_batch(const fheb_boot_key*, const uint64_t*, const uint64_t*, uint64_t*, size_t, void*) { NI; }
-int fheb_make_test_poly(const fheb_ntt_plan*, int, uint64_t, uint64_t, uint64_t*) { NI; }
+// TFHE bootstrap chain: device-resident keys, blind rotation (persistent fused kernel in
+// boot_kernel.cuh), sample extraction, key switching and the host-side LUT builders.
+//
+// C-ABI entry points here (include/fheb200.h): fheb_boot_key_create, fheb_boot_key_set_ksk,
+// fheb_boot_key_destroy, fheb_external_product_batch, fheb_cmux_batch, fheb_blind_rotate_batch,
+// fheb_sample_extract_batch, fheb_key_switch_batch, fheb_bootstrap_batch, fheb_make_test_poly.
+#include "boot_kernel.cuh"
+#include "elementwise.hpp"
+#include "plan.hpp"
+
+namespace fheb {
+
+struct BootKey {
+    const NttPlan* plan = nullptr;  // borrowed: the plan must outlive the key
+    uint32_t n = 0, k = 0, base_log = 0, levels = 0;
+    Tw* d_bsk = nullptr;            // [n][rows][k+1][N], transformed, position order, Shoup pairs
+    uint64_t* d_ksk = nullptr;      // [entries][n_out + 1] raw words
+    size_t ksk_entries = 0;
+    uint32_t ksk_n_out = 0, ksk_base_log = 0, ksk_levels = 0;
+};
+
+// ---- key preparation --------------------------------------------------------------------
+// in: transforms in the reference's output order (index p of the permuted array); out: the same
+// values in position order (index bitrev(p)) with their Shoup companions floor(w * 2^64 / q).
+__global__ void __launch_bounds__(256) bsk_pack_kernel(const uint64_t* __restrict__ y, Tw* __restrict__ g, size_t words,
+                                                       uint32_t logn, uint64_t q) {
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    const uint32_t nmask = (1u << logn) - 1u;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < words; i += stride) {
+        const uint32_t pos = (uint32_t)i & nmask;
+        const size_t src = (i - pos) + bitrev_rt(pos, (int)logn);
+        const uint64_t w = y[src];
+        Tw t;
+        t.w = w;
+        t.wp = (uint64_t)((((u128)w) << 64) / q);
+        g[i] = t;
+    }
 }
+
+// ---- sample extraction ---------------------------------------------------------------------
+__global__ void __launch_bounds__(256) sample_extract_kernel(const uint64_t* __restrict__ glwe, uint64_t* __restrict__ out,
+                                                             size_t batch, uint32_t k, uint32_t N, const ModQ m) {
+    const size_t width = (size_t)k * N + 1;
+    const size_t total = batch * width;
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+        const size_t ct = i / width;
+        const uint32_t idx = (uint32_t)(i - ct * width);
+        out[i] = sample_extract_word(glwe + ct * ((size_t)k + 1) * N, idx, k, N, m);
+    }
+}
+
+// ---- key switching (cpp/src/bootstrap_engine.cpp:626-669) -------------------------------------
+// out[j] = (0 - sum_idx t(idx, j)) mod q with t = ((digit_idx * ksk[idx][j]) mod 2^64) % q and
+// digit_idx the low-bit digit of input coefficient idx / levels; the reference's running
+// `(res + q - t) % q` is this sum in any order.  The b word starts from the input's b instead of 0.
+// Block: KS_COLS output columns x KS_CTS ciphertexts; digits of the block's ciphertexts are staged
+// in shared memory in chunks; every KSK word is read once per block and reused KS_CTS times.
+constexpr int KS_COLS = 128;
+constexpr int KS_CTS = 8;
+constexpr int KS_CHUNK = 512;
+
+__global__ void __launch_bounds__(KS_COLS) key_switch_kernel(const uint64_t* __restrict__ lwe, const uint64_t* __restrict__ ksk,
+                                                             uint64_t* __restrict__ out, size_t batch, uint32_t dim_in,
+                                                             uint32_t n_out, uint32_t base_log, uint32_t levels, const ModQ m) {
+    __shared__ uint64_t digits[KS_CTS][KS_CHUNK];
+    const uint32_t col = blockIdx.x * KS_COLS + threadIdx.x;
+    const size_t ct0 = (size_t)blockIdx.y * KS_CTS;
+    const uint32_t ncts = (uint32_t)((batch - ct0) < (size_t)KS_CTS ? (batch - ct0) : (size_t)KS_CTS);
+    const size_t in_w = (size_t)dim_in + 1, out_w = (size_t)n_out + 1;
+    const uint64_t mask = (base_log >= 64) ? ~0ull : ((1ull << base_log) - 1);
+    const size_t entries = (size_t)dim_in * levels;
+    uint64_t acc[KS_CTS];
+#pragma unroll
+    for (int c = 0; c < KS_CTS; ++c) acc[c] = 0;
+    for (size_t e0 = 0; e0 < entries; e0 += KS_CHUNK) {
+        const uint32_t chunk = (uint32_t)((entries - e0) < (size_t)KS_CHUNK ? (entries - e0) : (size_t)KS_CHUNK);
+        __syncthreads();
+        for (uint32_t t = threadIdx.x; t < KS_CTS * chunk; t += KS_COLS) {
+            const uint32_t c = t / chunk, e = t % chunk;
+            uint64_t d = 0;
+            if (c < ncts) {
+                const size_t idx = e0 + e;
+                const uint32_t i = (uint32_t)(idx / levels), l = (uint32_t)(idx % levels);
+                d = (lwe[(ct0 + c) * in_w + i] >> ((levels - 1 - l) * base_log)) & mask;
+            }
+            digits[c][e] = d;
+        }
+        __syncthreads();
+        if (col < out_w) {
+            const uint64_t* kp = ksk + e0 * out_w + col;
+#pragma unroll 4
+            for (uint32_t e = 0; e < chunk; ++e) {
+                const uint64_t kv = __ldg(kp + (size_t)e * out_w);
+#pragma unroll
+                for (int c = 0; c < KS_CTS; ++c) {
+                    const uint64_t d = digits[c][e];  // zero digits contribute nothing (:654-657)
+                    const uint64_t t = reduce64(d * kv, m);
+                    acc[c] = csub(acc[c] + t, m.q);
+                }
+            }
+        }
+    }
+    if (col < out_w) {
+        for (uint32_t c = 0; c < ncts; ++c) {
+            uint64_t start = 0;
+            if (col == n_out) start = canon_any(lwe[(ct0 + c) * in_w + dim_in], m);
+            out[(ct0 + c) * out_w + col] = submod_canon(start, acc[c], m.q);
+        }
+    }
+}
+
+static int boot_dispatch(const BootKey* key, const BootLaunch& a, cudaStream_t s) {
+    const bool lazy = key->plan->mod.lazy != 0;
+    switch (key->k) {
+        case 1: return boot_launch_k1(key->plan->logn, lazy, a, s);
+        case 2: return boot_launch_k2(key->plan->logn, lazy, a, s);
+        case 3: return boot_launch_k3(key->plan->logn, lazy, a, s);
+    }
+    return set_error(FHEB_ERR_INVALID_PARAMETERS, "glwe_dimension must be 1, 2 or 3 on this backend (got %u)", key->k);
+}
+
+static BootLaunch base_launch(const BootKey* key) {
+    BootLaunch a{};
+    a.n = key->n;
+    a.levels = key->levels;
+    a.base_log = key->base_log;
+    a.twf = key->plan->d_fwd;
+    a.twi = key->plan->d_inv;
+    a.ninv = key->plan->ninv;
+    a.m = key->plan->mod;
+    return a;
+}
+
+static size_t glwe_words(const BootKey* key) { return ((size_t)key->k + 1) * key->plan->degree; }
+static size_t ggsw_words(const BootKey* key) {
+    return ((size_t)key->k + 1) * key->levels * ((size_t)key->k + 1) * key->plan->degree;
+}
+
+// device-pointer stages of the chain
+static int blind_rotate_device(const BootKey* key, const uint64_t* lwe, const uint64_t* test_poly, uint64_t* out,
+                               size_t batch, cudaStream_t s) {
+    BootLaunch a = base_launch(key);
+    a.mode = BOOT_BLIND;
+    a.bsk = key->d_bsk;
+    a.in0 = lwe;
+    a.in1 = test_poly;
+    a.out = out;
+    a.batch = batch;
+    return boot_dispatch(key, a, s);
+}
+
+static int sample_extract_device(const BootKey* key, const uint64_t* glwe, uint64_t* out, size_t batch, cudaStream_t s) {
+    const size_t total = batch * ((size_t)key->k * key->plan->degree + 1);
+    sample_extract_kernel<<<stream_grid(total, 256, 8), 256, 0, s>>>(glwe, out, batch, key->k, key->plan->degree,
+                                                                     key->plan->mod);
+    FHEB_CHECK_LAUNCH();
+    count_launch();
+    return FHEB_OK;
+}
+
+static int key_switch_device(const BootKey* key, const uint64_t* lwe, uint64_t* out, size_t batch, cudaStream_t s) {
+    const uint32_t dim_in = key->k * key->plan->degree;
+    const dim3 grid((key->ksk_n_out + 1 + KS_COLS - 1) / KS_COLS, (unsigned)((batch + KS_CTS - 1) / KS_CTS));
+    key_switch_kernel<<<grid, KS_COLS, 0, s>>>(lwe, key->d_ksk, out, batch, dim_in, key->ksk_n_out, key->ksk_base_log,
+                                               key->ksk_levels, key->plan->mod);
+    FHEB_CHECK_LAUNCH();
+    count_launch();
+    return FHEB_OK;
+}
+
+static int check_key(const fheb_boot_key* key) {
+    FHEB_TRY(ensure_ready());
+    FHEB_REQUIRE(key != nullptr, "bootstrap key must not be null");
+    return FHEB_OK;
+}
+
+}  // namespace fheb
+
+using namespace fheb;
+
+extern "C" {
+
+int fheb_boot_key_create(const fheb_ntt_plan* plan, const fheb_boot_params* params, const uint64_t* bsk,
+                         fheb_boot_key** out) {
+    FHEB_REQUIRE(out != nullptr, "out must not be null");
+    *out = nullptr;
+    FHEB_TRY(ensure_ready());
+    FHEB_REQUIRE(plan != nullptr && params != nullptr && bsk != nullptr, "plan, params and bsk must not be null");
+    const NttPlan* p = reinterpret_cast<const NttPlan*>(plan);
+    FHEB_REQUIRE(params->glwe_dimension >= 1 && params->glwe_dimension <= 3, "glwe_dimension must be 1, 2 or 3 on this backend");
+    FHEB_REQUIRE(params->decomp_level >= 1 && params->decomp_base_log >= 1 &&
+                     (uint64_t)params->decomp_level * params->decomp_base_log <= 64 && params->decomp_base_log <= 63,
+                 "decomposition must satisfy 1 <= base_log <= 63 and level * base_log <= 64");
+    FHEB_REQUIRE(params->lwe_dimension >= 1, "lwe_dimension must be positive");
+    FHEB_REQUIRE(p->logn >= 5 && p->logn <= 12, "bootstrap kernels support polynomial degrees 32..4096");
+    BootKey* key = new BootKey();
+    key->plan = p;
+    key->n = params->lwe_dimension;
+    key->k = params->glwe_dimension;
+    key->base_log = params->decomp_base_log;
+    key->levels = params->decomp_level;
+    const size_t words = (size_t)key->n * ggsw_words(key);
+    const size_t polys = words / p->degree;
+    cudaStream_t s = nullptr;
+    int rc = FHEB_OK;
+    uint64_t* tmp = nullptr;
+    {
+        Staged in;
+        rc = in.bind(bsk, words * 8, true, false, s);
+        if (rc == FHEB_OK && cudaMalloc(&tmp, words * 8) != cudaSuccess) rc = set_error(FHEB_ERR_OUT_OF_MEMORY, "cudaMalloc of the key staging buffer failed");
+        if (rc == FHEB_OK && cudaMalloc(&key->d_bsk, words * sizeof(Tw)) != cudaSuccess) rc = set_error(FHEB_ERR_OUT_OF_MEMORY, "cudaMalloc of the device bootstrapping key failed");
+        // T(row polynomial) once, here, instead of on every external product (bootstrap_engine.cpp:478-487)
+        if (rc == FHEB_OK) rc = ntt_forward_device(p, in.ptr<const uint64_t>(), tmp, polys, s);
+        if (rc == FHEB_OK) {
+            bsk_pack_kernel<<<stream_grid(words, 256, 8), 256, 0, s>>>(tmp, key->d_bsk, words, p->logn, p->modulus);
+            if (cudaGetLastError() != cudaSuccess) rc = set_error(FHEB_ERR_NATIVE, "bsk_pack_kernel launch failed");
+            count_launch();
+        }
+        if (rc == FHEB_OK && cudaStreamSynchronize(s) != cudaSuccess) rc = set_error(FHEB_ERR_NATIVE, "bootstrapping key upload failed");
+    }
+    if (tmp) cudaFree(tmp);
+    if (rc != FHEB_OK) {
+        fheb_boot_key_destroy(reinterpret_cast<fheb_boot_key*>(key));
+        return rc;
+    }
+    *out = reinterpret_cast<fheb_boot_key*>(key);
+    return FHEB_OK;
+}
+
+int fheb_boot_key_set_ksk(fheb_boot_key* key_, const uint64_t* ksk, size_t entries, uint32_t n_out, uint32_t base_log,
+                          uint32_t level) {
+    FHEB_TRY(check_key(key_));
+    BootKey* key = reinterpret_cast<BootKey*>(key_);
+    FHEB_REQUIRE(ksk != nullptr, "ksk must not be null");
+    FHEB_REQUIRE(level >= 1 && base_log >= 1 && base_log <= 63 && (uint64_t)level * base_log <= 64,
+                 "decomposition must satisfy 1 <= base_log <= 63 and level * base_log <= 64");
+    FHEB_REQUIRE(entries == (size_t)key->k * key->plan->degree * level,
+                 "key switching key must hold k * N * level entries (got %zu)", entries);
+    FHEB_REQUIRE(n_out >= 1, "output dimension must be positive");
+    if (key->d_ksk) cudaFree(key->d_ksk);
+    key->d_ksk = nullptr;
+    const size_t bytes = entries * ((size_t)n_out + 1) * 8;
+    FHEB_CUDA(cudaMalloc(&key->d_ksk, bytes));
+    FHEB_CUDA(cudaMemcpy(key->d_ksk, ksk, bytes, cudaMemcpyDefault));
+    key->ksk_entries = entries;
+    key->ksk_n_out = n_out;
+    key->ksk_base_log = base_log;
+    key->ksk_levels = level;
+    return FHEB_OK;
+}
+
+int fheb_boot_key_destroy(fheb_boot_key* key_) {
+    BootKey* key = reinterpret_cast<BootKey*>(key_);
+    if (!key) return FHEB_OK;
+    if (key->d_bsk) cudaFree(key->d_bsk);
+    if (key->d_ksk) cudaFree(key->d_ksk);
+    delete key;
+    return FHEB_OK;
+}
+
+static int one_step_entry(const fheb_boot_key* key_, uint32_t index, int mode, const uint64_t* in0, const uint64_t* in1,
+                          uint64_t* out, size_t batch, void* stream) {
+    FHEB_TRY(check_key(key_));
+    const BootKey* key = reinterpret_cast<const BootKey*>(key_);
+    FHEB_REQUIRE(index < key->n, "bootstrapping key index %u out of range (n = %u)", index, key->n);
+    if (batch == 0) return FHEB_OK;
+    FHEB_REQUIRE(in0 != nullptr && out != nullptr && (mode != BOOT_CMUX || in1 != nullptr), "ciphertext pointers must not be null");
+    cudaStream_t s = (cudaStream_t)stream;
+    const size_t bytes = batch * glwe_words(key) * 8;
+    Staged s0, s1, so;
+    FHEB_TRY(s0.bind(in0, bytes, true, false, s));
+    if (mode == BOOT_CMUX) FHEB_TRY(s1.bind(in1, bytes, true, false, s));
+    FHEB_TRY(so.bind(out, bytes, false, true, s));
+    BootLaunch a = base_launch(key);
+    a.mode = mode;
+    a.bsk = key->d_bsk + (size_t)index * ggsw_words(key);
+    a.in0 = s0.ptr<const uint64_t>();
+    a.in1 = (mode == BOOT_CMUX) ? s1.ptr<const uint64_t>() : nullptr;
+    a.out = so.ptr<uint64_t>();
+    a.batch = batch;
+    FHEB_REQUIRE(a.out != a.in0 && a.out != a.in1, "out must not alias an input");
+    FHEB_TRY(boot_dispatch(key, a, s));
+    FHEB_TRY(so.finish());
+    return sync_if_staged(s, {&s0, &s1, &so});
+}
+
+int fheb_external_product_batch(const fheb_boot_key* key, uint32_t index, const uint64_t* glwe, uint64_t* out,
+                                size_t batch, void* stream) {
+    return one_step_entry(key, index, BOOT_EXT, glwe, nullptr, out, batch, stream);
+}
+
+int fheb_cmux_batch(const fheb_boot_key* key, uint32_t index, const uint64_t* ct0, const uint64_t* ct1, uint64_t* out,
+                    size_t batch, void* stream) {
+    return one_step_entry(key, index, BOOT_CMUX, ct0, ct1, out, batch, stream);
+}
+
+int fheb_blind_rotate_batch(const fheb_boot_key* key_, const uint64_t* lwe, const uint64_t* test_poly, uint64_t* out,
+                            size_t batch, void* stream) {
+    FHEB_TRY(check_key(key_));
+    const BootKey* key = reinterpret_cast<const BootKey*>(key_);
+    if (batch == 0) return FHEB_OK;
+    FHEB_REQUIRE(lwe != nullptr && test_poly != nullptr && out != nullptr, "ciphertext pointers must not be null");
+    cudaStream_t s = (cudaStream_t)stream;
+    Staged sl, st, so;
+    FHEB_TRY(sl.bind(lwe, batch * ((size_t)key->n + 1) * 8, true, false, s));
+    FHEB_TRY(st.bind(test_poly, (size_t)key->plan->degree * 8, true, false, s));
+    FHEB_TRY(so.bind(out, batch * glwe_words(key) * 8, false, true, s));
+    FHEB_TRY(blind_rotate_device(key, sl.ptr<const uint64_t>(), st.ptr<const uint64_t>(), so.ptr<uint64_t>(), batch, s));
+    FHEB_TRY(so.finish());
+    return sync_if_staged(s, {&sl, &st, &so});
+}
+
+int fheb_sample_extract_batch(const fheb_boot_key* key_, const uint64_t* glwe, uint64_t* out, size_t batch, void* stream) {
+    FHEB_TRY(check_key(key_));
+    const BootKey* key = reinterpret_cast<const BootKey*>(key_);
+    if (batch == 0) return FHEB_OK;
+    FHEB_REQUIRE(glwe != nullptr && out != nullptr, "ciphertext pointers must not be null");
+    cudaStream_t s = (cudaStream_t)stream;
+    Staged sg, so;
+    FHEB_TRY(sg.bind(glwe, batch * glwe_words(key) * 8, true, false, s));
+    FHEB_TRY(so.bind(out, batch * ((size_t)key->k * key->plan->degree + 1) * 8, false, true, s));
+    FHEB_TRY(sample_extract_device(key, sg.ptr<const uint64_t>(), so.ptr<uint64_t>(), batch, s));
+    FHEB_TRY(so.finish());
+    return sync_if_staged(s, {&sg, &so});
+}
+
+int fheb_key_switch_batch(const fheb_boot_key* key_, const uint64_t* lwe, uint64_t* out, size_t batch, void* stream) {
+    FHEB_TRY(check_key(key_));
+    const BootKey* key = reinterpret_cast<const BootKey*>(key_);
+    FHEB_REQUIRE(key->d_ksk != nullptr, "no key switching key has been set (fheb_boot_key_set_ksk)");
+    if (batch == 0) return FHEB_OK;
+    FHEB_REQUIRE(lwe != nullptr && out != nullptr, "ciphertext pointers must not be null");
+    cudaStream_t s = (cudaStream_t)stream;
+    Staged sl, so;
+    FHEB_TRY(sl.bind(lwe, batch * ((size_t)key->k * key->plan->degree + 1) * 8, true, false, s));
+    FHEB_TRY(so.bind(out, batch * ((size_t)key->ksk_n_out + 1) * 8, false, true, s));
+    FHEB_TRY(key_switch_device(key, sl.ptr<const uint64_t>(), so.ptr<uint64_t>(), batch, s));
+    FHEB_TRY(so.finish());
+    return sync_if_staged(s, {&sl, &so});
+}
+
+int fheb_bootstrap_batch(const fheb_boot_key* key_, const uint64_t* lwe, const uint64_t* test_poly, uint64_t* out,
+                         size_t batch, void* stream) {
+    FHEB_TRY(check_key(key_));
+    const BootKey* key = reinterpret_cast<const BootKey*>(key_);
+    if (batch == 0) return FHEB_OK;
+    FHEB_REQUIRE(lwe != nullptr && test_poly != nullptr && out != nullptr, "ciphertext pointers must not be null");
+    cudaStream_t s = (cudaStream_t)stream;
+    const size_t ext_w = (size_t)key->k * key->plan->degree + 1;
+    const size_t out_w = key->d_ksk ? (size_t)key->ksk_n_out + 1 : ext_w;
+    Staged sl, st, so;
+    FHEB_TRY(sl.bind(lwe, batch * ((size_t)key->n + 1) * 8, true, false, s));
+    FHEB_TRY(st.bind(test_poly, (size_t)key->plan->degree * 8, true, false, s));
+    FHEB_TRY(so.bind(out, batch * out_w * 8, false, true, s));
+    uint64_t* acc = nullptr;
+    uint64_t* ext = nullptr;
+    FHEB_CUDA(cudaMallocAsync(&acc, batch * glwe_words(key) * 8, s));
+    int rc = blind_rotate_device(key, sl.ptr<const uint64_t>(), st.ptr<const uint64_t>(), acc, batch, s);
+    if (rc == FHEB_OK && key->d_ksk) {
+        if (cudaMallocAsync(&ext, batch * ext_w * 8, s) != cudaSuccess) rc = set_error(FHEB_ERR_OUT_OF_MEMORY, "cudaMallocAsync failed");
+        if (rc == FHEB_OK) rc = sample_extract_device(key, acc, ext, batch, s);
+        if (rc == FHEB_OK) rc = key_switch_device(key, ext, so.ptr<uint64_t>(), batch, s);
+    } else if (rc == FHEB_OK) {
+        rc = sample_extract_device(key, acc, so.ptr<uint64_t>(), batch, s);
+    }
+    cudaFreeAsync(acc, s);
+    if (ext) cudaFreeAsync(ext, s);
+    FHEB_TRY(rc);
+    FHEB_TRY(so.finish());
+    return sync_if_staged(s, {&sl, &st, &so});
+}
+
+int fheb_make_test_poly(const fheb_ntt_plan* plan, int kind, uint64_t arg0, uint64_t arg1, uint64_t* out_host) {
+    // Host-side set-up, integer arithmetic exactly as written in cpp/src/bootstrap_engine.cpp:57-77
+    // (default test polynomial) and :725-779 (lookup tables); u64 products wrap as they do there.
+    FHEB_REQUIRE(plan != nullptr && out_host != nullptr, "plan and out must not be null");
+    const NttPlan* p = reinterpret_cast<const NttPlan*>(plan);
+    const uint64_t N = p->degree, q = p->modulus;
+    if (kind == 3) {
+        const uint64_t t = arg0 > 0 ? arg0 : 4;
+        const uint64_t delta = q / t;
+        for (uint64_t i = 0; i < N; ++i) out_host[i] = (((i * t) / (2 * N)) * delta) % q;
+        return FHEB_OK;
+    }
+    FHEB_REQUIRE(kind >= 0 && kind <= 2, "unknown lookup table kind %d", kind);
+    const uint64_t in_mod = (kind == 2) ? arg1 : arg0;
+    const uint64_t out_mod = (kind == 2) ? 2 : arg0;
+    FHEB_REQUIRE(in_mod != 0 && out_mod != 0, "lookup table moduli must be non-zero");
+    const uint64_t delta_out = q / out_mod;
+    for (uint64_t i = 0; i < N; ++i) {
+        uint64_t x = ((i * in_mod + N) / (2 * N)) % in_mod;
+        uint64_t y;
+        if (kind == 0) y = x;
+        else if (kind == 1) y = (arg0 - x) % arg0;
+        else y = (x >= arg0) ? 1 : 0;
+        out_host[i] = ((y % out_mod) * delta_out) % q;
+    }
+    return FHEB_OK;
+}
+
+}  // extern "C"
