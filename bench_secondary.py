@@ -88,4 +88,36 @@ def run(fhe, torch, dist, world, rank, dev, barrier, max_over_ranks, peak):
                           "roofline": _hbm(peak, 16384.0 * per_rank, ms),
                           "checksum": int(res[0].view(-1)[:4].sum().item() & 0xFFFFFFFF)}
     del cts
+    out["bootstrap_tfhe128fast_shape"] = run_bootstrap(fhe, torch, dist, world, rank, dev, barrier, max_over_ranks)
     return out
+
+
+def run_bootstrap(fhe, torch, dist, world, rank, dev, barrier, max_over_ranks, batch=4096, n=742, iters=2):
+    """C4: tfhe-128-fast SHAPE (N=1024, k=1, n=742, base_log=23, L=1) with the substitute prime
+    1099511678977 (the preset's 2^40+1 is composite) and a synthetic uniformly random key; each rank
+    bootstraps its own `batch` LWE ciphertexts (blind rotation + sample extraction), no collective."""
+    N, q, k, base_log, level = 1024, QT, 1, 23, 1
+    rng = np.random.default_rng(742)
+    bsk = rng.integers(0, q, size=(n, (k + 1) * level, k + 1, N), dtype=np.uint64)
+    eng = fhe.BootstrapEngine(N, q, n, k, base_log, level, bsk)
+    gen = torch.Generator(device=dev).manual_seed(7 + rank)
+    lwe = torch.randint(0, q, (batch, n + 1), dtype=torch.int64, device=dev, generator=gen)
+    tp = torch.from_numpy(eng.get_default_test_poly().view(np.int64)).to(dev)
+    out = torch.empty((batch, k * N + 1), dtype=torch.int64, device=dev)
+    eng.bootstrap(lwe[:256], tp, out=out[:256])  # warm-up
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(iters):
+        eng.bootstrap(lwe, tp, out=out)
+    e1.record()
+    barrier()
+    ms = max_over_ranks(e0.elapsed_time(e1)) / iters
+    # integer work actually executed per bootstrap: n steps x ((k+1)L forward + (k+1) inverse transforms of
+    # (N/2) log2 N butterflies + (k+1)^2 L N multiply-accumulates)
+    bfly = n * ((k + 1) * level + (k + 1)) * (N // 2) * 10
+    macs = n * (k + 1) * (k + 1) * level * N
+    return {"value": world * batch / (ms * 1e-3), "unit": "bootstraps/s", "ms": ms, "batch_per_gpu": batch, "n_gpus": world,
+            "shape": f"N={N} k={k} n={n} base_log={base_log} L={level} q={q}",
+            "modmul_per_bootstrap": bfly + macs,
+            "gmodmul_per_s_per_gpu": (bfly + macs) * batch / (ms * 1e-3) / 1e9}
