@@ -106,6 +106,7 @@ class NTTProcessor:
 
     def __init__(self, degree: int, modulus: int, fwd_table=None, inv_table=None, inv_n: int = 0):
         self._h = C.c_void_p()
+        self._destroy = lib().fheb_ntt_plan_destroy  # bound now: module globals are gone at interpreter exit
         if fwd_table is None:
             check(lib().fheb_ntt_plan_create(degree, modulus, C.byref(self._h)))
         else:  # caller-supplied tables: fast_ntt_forward / MetalComputeContext::batch_ntt_forward shape
@@ -115,8 +116,8 @@ class NTTProcessor:
 
     def __del__(self):
         h, self._h = getattr(self, "_h", None), None
-        if h:
-            lib().fheb_ntt_plan_destroy(h)
+        if h and self._destroy is not None:
+            self._destroy(h)
 
     def get_degree(self) -> int:
         return int(lib().fheb_ntt_plan_degree(self._h))
@@ -306,6 +307,7 @@ class BootstrapEngine:
         self.base_log, self.level, self.t = decomp_base_log, decomp_level, plaintext_modulus
         self.ntt = NTTProcessor(poly_degree, modulus)
         self._h = C.c_void_p()
+        self._destroy = lib().fheb_boot_key_destroy
         bsk = as_words(bsk)
         rows = (self.k + 1) * self.level
         if _words(bsk) != self.n * rows * (self.k + 1) * self.N:
@@ -316,8 +318,8 @@ class BootstrapEngine:
 
     def __del__(self):
         h, self._h = getattr(self, "_h", None), None
-        if h:
-            lib().fheb_boot_key_destroy(h)
+        if h and self._destroy is not None:
+            self._destroy(h)
 
     def set_key_switch_key(self, ksk, n_out: int, base_log: int, level: int):
         ksk = as_words(ksk)

@@ -30,6 +30,8 @@ struct BootLaunch {
 template <int L>
 struct BootGeometry {
     static constexpr int THREADS = (L <= 6) ? 32 : (L <= 8) ? 64 : (L <= 10) ? 128 : (L == 11) ? 256 : 512;
+    // resident blocks per SM the register allocation must allow: 512 threads per SM, i.e. <= 128 registers
+    static constexpr int MIN_BLOCKS = 512 / THREADS;
 };
 
 // shared-memory words: acc [KP1][N] | work [rows][N] | (CMUX/EXT) diff [KP1][N] | (BLIND) rotations [n] (u32)
@@ -51,7 +53,7 @@ __device__ __forceinline__ void boot_run_step(uint32_t tid, uint32_t nthreads, c
 }
 
 template <int L, bool LAZY, int KP1>
-__global__ void __launch_bounds__(BootGeometry<L>::THREADS) boot_kernel(const BootLaunch a) {
+__global__ void __launch_bounds__(BootGeometry<L>::THREADS, BootGeometry<L>::MIN_BLOCKS) boot_kernel(const BootLaunch a) {
     extern __shared__ __align__(16) uint64_t smem[];
     constexpr uint32_t N = 1u << L;
     constexpr uint32_t THREADS = BootGeometry<L>::THREADS;
@@ -70,7 +72,10 @@ __global__ void __launch_bounds__(BootGeometry<L>::THREADS) boot_kernel(const Bo
         s.work = work;
         s.levels = a.levels;
         s.base_log = a.base_log;
+        s.rot = 0;
+        s.ggsw = a.bsk;
         uint64_t* gout = a.out + ct * GW;
+        uint32_t nsteps = 1;
         if (a.mode == BOOT_BLIND) {
             const uint64_t* lwe = a.in0 + ct * ((size_t)a.n + 1);
             for (uint32_t i = tid; i < a.n; i += THREADS) rots[i] = lwe_rotation(lwe[i], false, N, a.m.q);
@@ -80,19 +85,10 @@ __global__ void __launch_bounds__(BootGeometry<L>::THREADS) boot_kernel(const Bo
                 const uint32_t c = i >> L, j = i & (N - 1);
                 acc[i] = (c == (uint32_t)KP1 - 1) ? rotated_at(a.in1, j, rb, N, a.m) : 0;
             }
-            __syncthreads();
             s.diff = nullptr;
             s.add_acc = 1;
             s.gout = nullptr;
-            for (uint32_t i = 0; i < a.n; ++i) {
-                const uint32_t rot = rots[i];
-                if (rot == 0) continue;  // :566 (block-uniform)
-                s.rot = rot;
-                s.ggsw = a.bsk + (size_t)i * ggsw_words;
-                boot_run_step<L, LAZY, KP1>(tid, THREADS, s, a);
-            }
-            for (uint32_t i = tid; i < GW; i += THREADS) gout[i] = acc[i];
-            __syncthreads();  // the next ciphertext overwrites acc / rots
+            nsteps = a.n;
         } else {
             const uint64_t* g0 = a.in0 + ct * GW;
             if (a.mode == BOOT_CMUX) {
@@ -105,14 +101,25 @@ __global__ void __launch_bounds__(BootGeometry<L>::THREADS) boot_kernel(const Bo
             } else {
                 for (uint32_t i = tid; i < GW; i += THREADS) diff[i] = g0[i];
             }
-            __syncthreads();
             s.diff = diff;
             s.add_acc = (a.mode == BOOT_CMUX) ? 1 : 0;
             s.gout = gout;
-            s.rot = 0;
-            s.ggsw = a.bsk;
+        }
+        __syncthreads();
+        // one call site for the step body: the unrolled passes are large, keep a single copy of them
+        for (uint32_t i = 0; i < nsteps; ++i) {
+            if (a.mode == BOOT_BLIND) {
+                const uint32_t rot = rots[i];
+                if (rot == 0) continue;  // :566 (block-uniform)
+                s.rot = rot;
+                s.ggsw = a.bsk + (size_t)i * ggsw_words;
+            }
             boot_run_step<L, LAZY, KP1>(tid, THREADS, s, a);
         }
+        if (a.mode == BOOT_BLIND) {
+            for (uint32_t i = tid; i < GW; i += THREADS) gout[i] = acc[i];
+        }
+        __syncthreads();  // the next ciphertext overwrites acc / rots / diff
     }
 }
 
@@ -126,6 +133,10 @@ int boot_launch_one(const BootLaunch& a, cudaStream_t stream) {
                          "bootstrap working set (%zu bytes) exceeds the shared memory of one SM; reduce N, k or the level count",
                          smem);
     if (smem > 48 * 1024) FHEB_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    {
+        const char* cv = getenv("FHEB_BOOT_CARVEOUT");  // tuning knob (percent of the unified L1/shared array)
+        if (cv) FHEB_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributePreferredSharedMemoryCarveout, atoi(cv)));
+    }
     int bps = 0;
     FHEB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, k, THREADS, smem));
     if (bps < 1) return set_error(FHEB_ERR_NATIVE, "bootstrap kernel does not fit on an SM");
