@@ -23,7 +23,7 @@ struct BootStep {          // block-uniform description of one step
     uint64_t* acc;         // smem [KP1][N], natural index: ct0 / running accumulator
     uint64_t* work;        // smem [max(rows, KP1)][N], swizzled index
     const uint64_t* diff;  // smem [KP1][N] natural index: precomputed ct1 - ct0 (or the GLWE itself); null = rotate acc
-    const Tw* ggsw;        // global [rows][KP1][N], position order, (value, Shoup companion)
+    const Tw* ggsw;        // global [rows][KP1][N], position order: (value, Shoup companion) pairs, or doubles in DP mode
     uint64_t* gout;        // when non-null the final pass stores here ([KP1][N], global) instead of acc
     uint32_t rot;          // normalised rotation in [0, 2N) (used when diff == null)
     uint32_t levels;
@@ -56,13 +56,12 @@ template <int L>
 constexpr int boot_phases() { return 2 * Plan<L>::P - 1; }
 
 // ---- phase 0: difference, decomposition and the first forward pass ------------------------
-template <int L, bool LAZY, int KP1>
+template <int L, bool DP, int KP1>
 FHEB_HD void boot_first_pass(uint32_t tid, uint32_t nthreads, const BootStep& s, const Tw* __restrict__ tw,
                              const ModQ& m) {
     constexpr int R = Plan<L>::R[0];
     constexpr int E = 1 << R;
     constexpr int EB = L - R;
-    constexpr int CAP = cap_of<LAZY>();
     constexpr uint32_t N = 1u << L;
     constexpr uint32_t ITEMS = N >> R;
     static_assert(Plan<L>::P >= 2, "bootstrap kernels need at least two passes (N >= 32)");
@@ -91,8 +90,11 @@ FHEB_HD void boot_first_pass(uint32_t tid, uint32_t nthreads, const BootStep& s,
             const uint32_t shift = (s.levels - 1 - l) * s.base_log;
             uint64_t x[E];
 #pragma unroll
-            for (int e = 0; e < E; ++e) x[e] = gadget_digit(d[e], shift, mask, base, m);
-            fwd_stages<R, 1, CAP, true>(x, tw, 1u, m);
+            for (int e = 0; e < E; ++e) {
+                const uint64_t g = gadget_digit(d[e], shift, mask, base, m);
+                x[e] = DP ? double_to_bits(dp_from_uint(g)) : g;
+            }
+            fwd_stages<R, 1, DP, true>(x, tw, 1u, m);
             uint64_t* dst = s.work + (size_t)(c * s.levels + l) * N;
 #pragma unroll
             for (int e = 0; e < E; ++e) dst[pb ^ swz((uint32_t)e << EB)] = x[e];
@@ -102,15 +104,14 @@ FHEB_HD void boot_first_pass(uint32_t tid, uint32_t nthreads, const BootStep& s,
 
 // ---- phase P-1: last forward pass of every digit row, multiply-accumulate with the GGSW, first
 //      inverse pass of every output component -------------------------------------------------
-template <int L, bool LAZY, int KP1>
+template <int L, bool DP, int KP1>
 FHEB_HD void boot_mid_pass(uint32_t tid, uint32_t nthreads, const BootStep& s, const Tw* __restrict__ twf,
                            const Tw* __restrict__ twi, const ModQ& m) {
     constexpr int PASS = Plan<L>::P - 1;
     constexpr int R = Plan<L>::R[PASS];
     constexpr int E = 1 << R;
     constexpr int S0 = plan_s0<L, PASS>();
-    constexpr int CAP = cap_of<LAZY>();
-    constexpr int KIN = plan_fwd_kin<L, LAZY, PASS>();
+    constexpr int KIN = plan_fwd_kin<L, DP, PASS>();
     constexpr uint32_t N = 1u << L;
     constexpr uint32_t ITEMS = N >> R;
     static_assert(L - S0 - R == 0, "the last forward pass covers the lowest position bits");
@@ -129,27 +130,29 @@ FHEB_HD void boot_mid_pass(uint32_t tid, uint32_t nthreads, const BootStep& s, c
             uint64_t x[E];
 #pragma unroll
             for (int e = 0; e < E; ++e) x[e] = src[pb ^ swz((uint32_t)e)];
-            fwd_stages<R, KIN, CAP, false>(x, twf, T0, m);
-            const Tw* g = s.ggsw + ((size_t)row * KP1) * N + base;
+            fwd_stages<R, KIN, DP, false>(x, twf, T0, m);
+            const uint32_t g0 = row * (uint32_t)KP1 * N + base;  // element index inside this GGSW
 #pragma unroll
             for (int j = 0; j < KP1; ++j) {
 #pragma unroll
                 for (int e = 0; e < E; ++e) {
-                    const Tw w = load_tw(g, (uint32_t)j * N + (uint32_t)e);
-                    const uint64_t t = shoup_lazy(x[e], w.w, w.wp, m.q);  // [0, 2q) for any x
-                    // lazy moduli (q < 2^46): plain sums, 2q * rows stays far below 2^64;
-                    // otherwise keep the running sum in [0, 2q)
-                    out[j][e] = LAZY ? out[j][e] + t : csub(out[j][e] + t, m.q2);
+                    const Tw w = load_tw<DP>(s.ggsw, g0 + (uint32_t)j * N + (uint32_t)e);
+                    if constexpr (DP) {  // |t| < q: plain sums (rows <= CAP_DP checked at key upload)
+                        const double t = dp_mulmod(bits_to_double(x[e]), bits_to_double(w.w), m);
+                        out[j][e] = double_to_bits(dp_add(bits_to_double(out[j][e]), t));
+                    } else {  // t in [0, 2q) for any x; keep the running sum in [0, 2q)
+                        out[j][e] = csub(out[j][e] + shoup_lazy(x[e], w.w, w.wp, m.q), m.q2);
+                    }
                 }
             }
         }
 #pragma unroll
         for (int j = 0; j < KP1; ++j) {
-            if (LAZY) {
+            if constexpr (DP) {  // back to |v| <= q/2 + 1 so that the inverse passes' static bounds hold
 #pragma unroll
-                for (int e = 0; e < E; ++e) out[j][e] = reduce64(out[j][e], m);
+                for (int e = 0; e < E; ++e) out[j][e] = double_to_bits(dp_reduce(bits_to_double(out[j][e]), m));
             }
-            inv_stages<R, LAZY ? 1 : 2, CAP, false>(out[j], twi, T0, m);
+            inv_stages<R, DP ? 1 : 2, DP, false>(out[j], twi, T0, m);
             uint64_t* dst = s.work + (size_t)j * N;
 #pragma unroll
             for (int e = 0; e < E; ++e) dst[pb ^ swz((uint32_t)e)] = out[j][e];
@@ -158,14 +161,13 @@ FHEB_HD void boot_mid_pass(uint32_t tid, uint32_t nthreads, const BootStep& s, c
 }
 
 // ---- last phase: final inverse pass, scaling by N^-1, `+ ct0` ------------------------------------
-template <int L, bool LAZY, int KP1>
+template <int L, bool DP, int KP1>
 FHEB_HD void boot_final_pass(uint32_t tid, uint32_t nthreads, const BootStep& s, const Tw* __restrict__ twi,
                              const Tw ninv, const ModQ& m) {
     constexpr int R = Plan<L>::R[0];
     constexpr int E = 1 << R;
     constexpr int EB = L - R;
-    constexpr int CAP = cap_of<LAZY>();
-    constexpr int KIN = plan_inv_kin<L, LAZY, 0>();
+    constexpr int KIN = plan_inv_kin<L, DP, 0>();
     constexpr uint32_t N = 1u << L;
     constexpr uint32_t ITEMS = N >> R;
     for (uint32_t U = tid; U < (uint32_t)KP1 * ITEMS; U += nthreads) {
@@ -176,13 +178,13 @@ FHEB_HD void boot_final_pass(uint32_t tid, uint32_t nthreads, const BootStep& s,
         uint64_t x[E];
 #pragma unroll
         for (int e = 0; e < E; ++e) x[e] = src[pb ^ swz((uint32_t)e << EB)];
-        inv_stages<R, KIN, CAP, true>(x, twi, 1u, m);
+        inv_stages<R, KIN, DP, true>(x, twi, 1u, m);
         const uint64_t* a = s.acc + (size_t)c * N;
         uint64_t* dst = (s.gout ? s.gout : s.acc) + (size_t)c * N;
 #pragma unroll
         for (int e = 0; e < E; ++e) {
             const uint32_t pos = u | ((uint32_t)e << EB);
-            uint64_t v = csub(shoup_lazy(x[e], ninv.w, ninv.wp, m.q), m.q);
+            uint64_t v = scale_word<DP>(x[e], ninv, m);
             if (s.add_acc) v = addmod_canon(v, canon_any(a[pos], m), m.q);  // PolynomialRing::add(result, ct0), :533-537
             dst[pos] = v;
         }
@@ -190,21 +192,21 @@ FHEB_HD void boot_final_pass(uint32_t tid, uint32_t nthreads, const BootStep& s,
 }
 
 // Phase PH of a step; the caller puts a block barrier after every phase.
-template <int L, bool LAZY, int KP1, int PH>
+template <int L, bool DP, int KP1, int PH>
 FHEB_HD void boot_phase(uint32_t tid, uint32_t nthreads, const BootStep& s, const Tw* __restrict__ twf,
                         const Tw* __restrict__ twi, const Tw ninv, const ModQ& m) {
     constexpr int P = Plan<L>::P;
     static_assert(PH >= 0 && PH < 2 * P - 1, "phase out of range");
     if constexpr (PH == 0) {
-        boot_first_pass<L, LAZY, KP1>(tid, nthreads, s, twf, m);
+        boot_first_pass<L, DP, KP1>(tid, nthreads, s, twf, m);
     } else if constexpr (PH < P - 1) {
-        fwd_pass<L, LAZY, PH, IO_SMEM, IO_SMEM>(tid, nthreads, (uint32_t)KP1 * s.levels, nullptr, nullptr, s.work, twf, m);
+        fwd_pass<L, DP, PH, IO_SMEM, IO_SMEM>(tid, nthreads, (uint32_t)KP1 * s.levels, nullptr, nullptr, s.work, twf, m);
     } else if constexpr (PH == P - 1) {
-        boot_mid_pass<L, LAZY, KP1>(tid, nthreads, s, twf, twi, m);
+        boot_mid_pass<L, DP, KP1>(tid, nthreads, s, twf, twi, m);
     } else if constexpr (PH < 2 * P - 2) {
-        inv_pass<L, LAZY, 2 * P - 2 - PH, IO_SMEM, IO_SMEM>(tid, nthreads, (uint32_t)KP1, nullptr, nullptr, s.work, twi, ninv, m);
+        inv_pass<L, DP, 2 * P - 2 - PH, IO_SMEM, IO_SMEM>(tid, nthreads, (uint32_t)KP1, nullptr, nullptr, s.work, twi, ninv, m);
     } else {
-        boot_final_pass<L, LAZY, KP1>(tid, nthreads, s, twi, ninv, m);
+        boot_final_pass<L, DP, KP1>(tid, nthreads, s, twi, ninv, m);
     }
 }
 

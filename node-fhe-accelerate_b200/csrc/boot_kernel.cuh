@@ -43,16 +43,16 @@ inline size_t boot_smem_bytes(int mode, uint32_t N, uint32_t kp1, uint32_t level
     return bytes;
 }
 
-template <int L, bool LAZY, int KP1, int PH = 0>
+template <int L, bool DP, int KP1, int PH = 0>
 __device__ __forceinline__ void boot_run_step(uint32_t tid, uint32_t nthreads, const BootStep& s, const BootLaunch& a) {
     if constexpr (PH < boot_phases<L>()) {
-        boot_phase<L, LAZY, KP1, PH>(tid, nthreads, s, a.twf, a.twi, a.ninv, a.m);
+        boot_phase<L, DP, KP1, PH>(tid, nthreads, s, a.twf, a.twi, a.ninv, a.m);
         __syncthreads();
-        boot_run_step<L, LAZY, KP1, PH + 1>(tid, nthreads, s, a);
+        boot_run_step<L, DP, KP1, PH + 1>(tid, nthreads, s, a);
     }
 }
 
-template <int L, bool LAZY, int KP1>
+template <int L, bool DP, int KP1>
 __global__ void __launch_bounds__(BootGeometry<L>::THREADS, BootGeometry<L>::MIN_BLOCKS) boot_kernel(const BootLaunch a) {
     extern __shared__ __align__(16) uint64_t smem[];
     constexpr uint32_t N = 1u << L;
@@ -112,9 +112,9 @@ __global__ void __launch_bounds__(BootGeometry<L>::THREADS, BootGeometry<L>::MIN
                 const uint32_t rot = rots[i];
                 if (rot == 0) continue;  // :566 (block-uniform)
                 s.rot = rot;
-                s.ggsw = a.bsk + (size_t)i * ggsw_words;
+                s.ggsw = reinterpret_cast<const Tw*>(reinterpret_cast<const char*>(a.bsk) + (size_t)i * ggsw_words * (DP ? 8 : 16));
             }
-            boot_run_step<L, LAZY, KP1>(tid, THREADS, s, a);
+            boot_run_step<L, DP, KP1>(tid, THREADS, s, a);
         }
         if (a.mode == BOOT_BLIND) {
             for (uint32_t i = tid; i < GW; i += THREADS) gout[i] = acc[i];
@@ -123,11 +123,11 @@ __global__ void __launch_bounds__(BootGeometry<L>::THREADS, BootGeometry<L>::MIN
     }
 }
 
-template <int L, bool LAZY, int KP1>
+template <int L, bool DP, int KP1>
 int boot_launch_one(const BootLaunch& a, cudaStream_t stream) {
     constexpr int THREADS = BootGeometry<L>::THREADS;
     const size_t smem = boot_smem_bytes(a.mode, 1u << L, KP1, a.levels, a.n);
-    auto k = boot_kernel<L, LAZY, KP1>;
+    auto k = boot_kernel<L, DP, KP1>;
     if (smem > (size_t)ctx().prop.sharedMemPerBlockOptin)
         return set_error(FHEB_ERR_INVALID_PARAMETERS,
                          "bootstrap working set (%zu bytes) exceeds the shared memory of one SM; reduce N, k or the level count",
@@ -149,10 +149,10 @@ int boot_launch_one(const BootLaunch& a, cudaStream_t stream) {
 }
 
 template <int KP1>
-int boot_launch_kp1(uint32_t logn, bool lazy, const BootLaunch& a, cudaStream_t stream) {
+int boot_launch_kp1(uint32_t logn, bool dp, const BootLaunch& a, cudaStream_t stream) {
 #define FHEB_BOOT_CASE(L_) \
     case L_:               \
-        return lazy ? boot_launch_one<L_, true, KP1>(a, stream) : boot_launch_one<L_, false, KP1>(a, stream);
+        return dp ? boot_launch_one<L_, true, KP1>(a, stream) : boot_launch_one<L_, false, KP1>(a, stream);
     switch (logn) {
         FHEB_BOOT_CASE(5)
         FHEB_BOOT_CASE(6)
@@ -168,8 +168,8 @@ int boot_launch_kp1(uint32_t logn, bool lazy, const BootLaunch& a, cudaStream_t 
 }
 
 // one translation unit per GLWE dimension (parallel compilation)
-int boot_launch_k1(uint32_t logn, bool lazy, const BootLaunch& a, cudaStream_t stream);
-int boot_launch_k2(uint32_t logn, bool lazy, const BootLaunch& a, cudaStream_t stream);
-int boot_launch_k3(uint32_t logn, bool lazy, const BootLaunch& a, cudaStream_t stream);
+int boot_launch_k1(uint32_t logn, bool dp, const BootLaunch& a, cudaStream_t stream);
+int boot_launch_k2(uint32_t logn, bool dp, const BootLaunch& a, cudaStream_t stream);
+int boot_launch_k3(uint32_t logn, bool dp, const BootLaunch& a, cudaStream_t stream);
 
 }  // namespace fheb

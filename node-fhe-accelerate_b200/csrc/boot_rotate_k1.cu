@@ -2,7 +2,7 @@
 #include "boot_kernel.cuh"
 
 namespace fheb {
-int boot_launch_k1(uint32_t logn, bool lazy, const BootLaunch& a, cudaStream_t stream) {
-    return boot_launch_kp1<2>(logn, lazy, a, stream);
+int boot_launch_k1(uint32_t logn, bool dp, const BootLaunch& a, cudaStream_t stream) {
+    return boot_launch_kp1<2>(logn, dp, a, stream);
 }
 }  // namespace fheb

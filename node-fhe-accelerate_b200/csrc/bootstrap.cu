@@ -13,7 +13,7 @@ namespace fheb {
 struct BootKey {
     const NttPlan* plan = nullptr;  // borrowed: the plan must outlive the key
     uint32_t n = 0, k = 0, base_log = 0, levels = 0;
-    Tw* d_bsk = nullptr;            // [n][rows][k+1][N], transformed, position order, Shoup pairs
+    Tw* d_bsk = nullptr;            // [n][rows][k+1][N], transformed, position order: Shoup pairs, or doubles (mod.dp)
     uint64_t* d_ksk = nullptr;      // [entries][n_out + 1] raw words
     size_t ksk_entries = 0;
     uint32_t ksk_n_out = 0, ksk_base_log = 0, ksk_levels = 0;
@@ -23,17 +23,21 @@ struct BootKey {
 // in: transforms in the reference's output order (index p of the permuted array); out: the same
 // values in position order (index bitrev(p)) with their Shoup companions floor(w * 2^64 / q).
 __global__ void __launch_bounds__(256) bsk_pack_kernel(const uint64_t* __restrict__ y, Tw* __restrict__ g, size_t words,
-                                                       uint32_t logn, uint64_t q) {
+                                                       uint32_t logn, uint64_t q, int dp) {
     const size_t stride = (size_t)gridDim.x * blockDim.x;
     const uint32_t nmask = (1u << logn) - 1u;
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < words; i += stride) {
         const uint32_t pos = (uint32_t)i & nmask;
         const size_t src = (i - pos) + bitrev_rt(pos, (int)logn);
         const uint64_t w = y[src];
-        Tw t;
-        t.w = w;
-        t.wp = (uint64_t)((((u128)w) << 64) / q);
-        g[i] = t;
+        if (dp) {  // FP64 mode: the value as a double, 8 bytes per entry
+            reinterpret_cast<uint64_t*>(g)[i] = double_to_bits((double)w);
+        } else {
+            Tw t;
+            t.w = w;
+            t.wp = (uint64_t)((((u128)w) << 64) / q);
+            g[i] = t;
+        }
     }
 }
 
@@ -111,11 +115,11 @@ __global__ void __launch_bounds__(KS_COLS) key_switch_kernel(const uint64_t* __r
 }
 
 static int boot_dispatch(const BootKey* key, const BootLaunch& a, cudaStream_t s) {
-    const bool lazy = key->plan->mod.lazy != 0;
+    const bool dp = key->plan->mod.dp != 0;
     switch (key->k) {
-        case 1: return boot_launch_k1(key->plan->logn, lazy, a, s);
-        case 2: return boot_launch_k2(key->plan->logn, lazy, a, s);
-        case 3: return boot_launch_k3(key->plan->logn, lazy, a, s);
+        case 1: return boot_launch_k1(key->plan->logn, dp, a, s);
+        case 2: return boot_launch_k2(key->plan->logn, dp, a, s);
+        case 3: return boot_launch_k3(key->plan->logn, dp, a, s);
     }
     return set_error(FHEB_ERR_INVALID_PARAMETERS, "glwe_dimension must be 1, 2 or 3 on this backend (got %u)", key->k);
 }
@@ -194,6 +198,7 @@ int fheb_boot_key_create(const fheb_ntt_plan* plan, const fheb_boot_params* para
                  "decomposition must satisfy 1 <= base_log <= 63 and level * base_log <= 64");
     FHEB_REQUIRE(params->lwe_dimension >= 1, "lwe_dimension must be positive");
     FHEB_REQUIRE(p->logn >= 5 && p->logn <= 12, "bootstrap kernels support polynomial degrees 32..4096");
+    FHEB_REQUIRE((params->glwe_dimension + 1) * params->decomp_level <= 64, "at most 64 gadget rows ((k+1) * level)");
     BootKey* key = new BootKey();
     key->plan = p;
     key->n = params->lwe_dimension;
@@ -209,11 +214,11 @@ int fheb_boot_key_create(const fheb_ntt_plan* plan, const fheb_boot_params* para
         Staged in;
         rc = in.bind(bsk, words * 8, true, false, s);
         if (rc == FHEB_OK && cudaMalloc(&tmp, words * 8) != cudaSuccess) rc = set_error(FHEB_ERR_OUT_OF_MEMORY, "cudaMalloc of the key staging buffer failed");
-        if (rc == FHEB_OK && cudaMalloc(&key->d_bsk, words * sizeof(Tw)) != cudaSuccess) rc = set_error(FHEB_ERR_OUT_OF_MEMORY, "cudaMalloc of the device bootstrapping key failed");
+        if (rc == FHEB_OK && cudaMalloc(&key->d_bsk, words * (p->mod.dp ? 8 : sizeof(Tw))) != cudaSuccess) rc = set_error(FHEB_ERR_OUT_OF_MEMORY, "cudaMalloc of the device bootstrapping key failed");
         // T(row polynomial) once, here, instead of on every external product (bootstrap_engine.cpp:478-487)
         if (rc == FHEB_OK) rc = ntt_forward_device(p, in.ptr<const uint64_t>(), tmp, polys, s);
         if (rc == FHEB_OK) {
-            bsk_pack_kernel<<<stream_grid(words, 256, 8), 256, 0, s>>>(tmp, key->d_bsk, words, p->logn, p->modulus);
+            bsk_pack_kernel<<<stream_grid(words, 256, 8), 256, 0, s>>>(tmp, key->d_bsk, words, p->logn, p->modulus, (int)p->mod.dp);
             if (cudaGetLastError() != cudaSuccess) rc = set_error(FHEB_ERR_NATIVE, "bsk_pack_kernel launch failed");
             count_launch();
         }
@@ -274,7 +279,8 @@ static int one_step_entry(const fheb_boot_key* key_, uint32_t index, int mode, c
     FHEB_TRY(so.bind(out, bytes, false, true, s));
     BootLaunch a = base_launch(key);
     a.mode = mode;
-    a.bsk = key->d_bsk + (size_t)index * ggsw_words(key);
+    a.bsk = reinterpret_cast<const Tw*>(reinterpret_cast<const char*>(key->d_bsk) +
+                                        (size_t)index * ggsw_words(key) * (key->plan->mod.dp ? 8 : sizeof(Tw)));
     a.in0 = s0.ptr<const uint64_t>();
     a.in1 = (mode == BOOT_CMUX) ? s1.ptr<const uint64_t>() : nullptr;
     a.out = so.ptr<uint64_t>();

@@ -11,7 +11,9 @@
 // The header compiles under nvcc (device code) and under g++ (host emulation used by
 // tests/test_host_emulation.py to validate index math and range tracking without a GPU).
 #pragma once
+#include <cmath>
 #include <cstdint>
+#include <cstring>
 
 #if defined(__CUDACC__)
 #define FHEB_HD __host__ __device__ __forceinline__
@@ -36,7 +38,9 @@ struct ModQ {
     uint64_t dn;     // q << sh, normalised divisor (top bit set)
     uint64_t v;      // Moeller-Granlund reciprocal of dn: floor((2^128 - 1) / dn) - 2^64
     uint32_t sh;     // clz(q)
-    uint32_t lazy;   // 1 when q < 2^46: butterflies skip intermediate reductions
+    uint32_t dp;     // 1 when q < 2^42: transforms run on the FP64 pipe (exact integer arithmetic in doubles)
+    double qd;       // (double)q
+    double qinv;     // 1.0 / q, rounded to nearest
 };
 
 FHEB_HD uint64_t mulhi64(uint64_t a, uint64_t b) {
@@ -118,6 +122,83 @@ FHEB_HD uint64_t canon_any(uint64_t x, const ModQ& m) {  // x % q for any x
     return x >= m.q ? reduce64(x, m) : x;
 }
 
+// ---- exact modular arithmetic on the FP64 pipe (moduli below 2^42) ------------------------
+// On B200 a DFMA issues at 64 lanes/clk/SM, the same rate as a 32-bit IMAD, while the 64-bit
+// Shoup product needs six IMAD.WIDE (half rate) plus four IMAD (tools/microbench/pipes.cu).  For
+// q < 2^42 a residue fits a double exactly, and a*b mod q is six FP64 operations:
+//     h = rn(a*b); l = fma(a, b, -h)   (h + l == a*b exactly)
+//     k = rint(h / q)                  (fma with the 1.5*2^52 rounding constant)
+//     r = fma(-k, q, h) + l            (exact: |h - k q| < q, l tiny)  =>  r == a*b (mod q), |r| < q
+// Values are integers held in doubles, |v| < CAP_DP * q <= 2^50, congruent to the true residue;
+// every word handed back to the caller is converted to the canonical residue, so results are
+// bit-identical to the integer path and to the reference.
+constexpr int DP_QBITS = 42;
+constexpr double DP_MAGIC = 6755399441055744.0;      // 1.5 * 2^52: x + MAGIC - MAGIC == rint(x) for |x| < 2^51
+constexpr double DP_TWO52 = 4503599627370496.0;      // 2^52
+
+FHEB_HD double bits_to_double(uint64_t b) {
+#if defined(__CUDA_ARCH__)
+    return __longlong_as_double((long long)b);
+#else
+    double d;
+    std::memcpy(&d, &b, 8);
+    return d;
+#endif
+}
+FHEB_HD uint64_t double_to_bits(double d) {
+#if defined(__CUDA_ARCH__)
+    return (uint64_t)__double_as_longlong(d);
+#else
+    uint64_t b;
+    std::memcpy(&b, &d, 8);
+    return b;
+#endif
+}
+FHEB_HD double dp_mul(double a, double b) {  // rounded product, never contracted into an fma
+#if defined(__CUDA_ARCH__)
+    return __dmul_rn(a, b);
+#else
+    volatile double p = a * b;
+    return p;
+#endif
+}
+FHEB_HD double dp_fma(double a, double b, double c) {
+#if defined(__CUDA_ARCH__)
+    return __fma_rn(a, b, c);
+#else
+    return std::fma(a, b, c);
+#endif
+}
+FHEB_HD double dp_add(double a, double b) {
+#if defined(__CUDA_ARCH__)
+    return __dadd_rn(a, b);
+#else
+    volatile double s = a + b;
+    return s;
+#endif
+}
+// integer v < 2^51 -> double, and back for 0 <= r < 2^51 (no I2F / F2I conversion instructions)
+FHEB_HD double dp_from_uint(uint64_t v) { return dp_add(bits_to_double(v | 0x4330000000000000ull), -DP_TWO52); }
+FHEB_HD double dp_from_sint(int64_t v) {  // |v| < 2^50
+    return dp_add(bits_to_double((uint64_t)(v + 0x4338000000000000ll)), -DP_MAGIC);
+}
+FHEB_HD uint64_t dp_to_uint(double r) { return double_to_bits(dp_add(r, DP_TWO52)) & 0x000FFFFFFFFFFFFFull; }
+
+// a*b mod q, |result| < q, for |a*b| < 2^51 * q
+FHEB_HD double dp_mulmod(double a, double b, const ModQ& m) {
+    const double h = dp_mul(a, b);
+    const double l = dp_fma(a, b, -h);
+    const double k = dp_add(dp_fma(h, m.qinv, DP_MAGIC), -DP_MAGIC);
+    return dp_add(dp_fma(-k, m.qd, h), l);
+}
+// |s| < 2^51 -> |result| <= q/2 + 1
+FHEB_HD double dp_reduce(double s, const ModQ& m) {
+    const double k = dp_add(dp_fma(s, m.qinv, DP_MAGIC), -DP_MAGIC);
+    return dp_fma(-k, m.qd, s);
+}
+// |r| < q -> canonical residue as an integer word
+FHEB_HD uint64_t dp_canon_word(double r, const ModQ& m) { return dp_to_uint(r < 0.0 ? dp_add(r, m.qd) : r); }
+
 // ---- host-side constant builders (plan creation) ----------------------------------------
 inline uint64_t shoup_companion(uint64_t w, uint64_t q) { return (uint64_t)((((u128)w) << 64) / q); }
 
@@ -129,7 +210,9 @@ inline ModQ make_modq(uint64_t q) {
     m.sh = (uint32_t)__builtin_clzll(q);
     m.dn = q << m.sh;
     m.v = (uint64_t)((~(u128)0) / m.dn - (((u128)1) << 64));
-    m.lazy = (q < (1ULL << 46)) ? 1u : 0u;
+    m.dp = (q < (1ULL << DP_QBITS)) ? 1u : 0u;
+    m.qd = (double)q;
+    m.qinv = 1.0 / (double)q;
     return m;
 }
 

@@ -71,9 +71,10 @@ static int validate_degree_modulus(uint32_t degree, uint64_t modulus) {
     return FHEB_OK;
 }
 
-static int upload_heap(const std::vector<Tw>& heap, Tw** out) {
-    FHEB_CUDA(cudaMalloc(out, heap.size() * sizeof(Tw)));
-    FHEB_CUDA(cudaMemcpy(*out, heap.data(), heap.size() * sizeof(Tw), cudaMemcpyHostToDevice));
+template <class T>
+static int upload_heap(const std::vector<T>& heap, Tw** out) {
+    FHEB_CUDA(cudaMalloc(out, heap.size() * sizeof(T)));
+    FHEB_CUDA(cudaMemcpy(*out, heap.data(), heap.size() * sizeof(T), cudaMemcpyHostToDevice));
     return FHEB_OK;
 }
 
@@ -81,11 +82,16 @@ static int plan_finish(NttPlan* p) {
     const uint64_t q = p->modulus;
     p->logn = log2_exact(p->degree);
     p->mod = make_modq(q);
-    p->ninv = Tw{p->inv_n % q, shoup_companion(p->inv_n % q, q)};
+    p->ninv = p->mod.dp ? Tw{double_to_bits((double)(p->inv_n % q)), 0} : Tw{p->inv_n % q, shoup_companion(p->inv_n % q, q)};
     p->unit_first = (p->fwd_table[0] % q == 1) && (p->inv_table[0] % q == 1);
     FHEB_REQUIRE(p->unit_first, "twiddle tables must start with 1 (root^0)");
-    FHEB_TRY(upload_heap(build_heap_table(p->fwd_table.data(), p->logn, q), &p->d_fwd));
-    FHEB_TRY(upload_heap(build_heap_table(p->inv_table.data(), p->logn, q), &p->d_inv));
+    if (p->mod.dp) {  // FP64 mode: one double per twiddle
+        FHEB_TRY(upload_heap(build_heap_table_dp(p->fwd_table.data(), p->logn, q), &p->d_fwd));
+        FHEB_TRY(upload_heap(build_heap_table_dp(p->inv_table.data(), p->logn, q), &p->d_inv));
+    } else {
+        FHEB_TRY(upload_heap(build_heap_table(p->fwd_table.data(), p->logn, q), &p->d_fwd));
+        FHEB_TRY(upload_heap(build_heap_table(p->inv_table.data(), p->logn, q), &p->d_inv));
+    }
     return FHEB_OK;
 }
 
@@ -114,21 +120,21 @@ static unsigned persistent_grid(size_t work_groups, int blocks_per_sm) {
 
 enum { DIR_FWD = 0, DIR_INV = 1, DIR_INV_FWDNET = 2 };
 
-template <int L, bool LAZY>
+template <int L, bool DP>
 static int launch_transform(const NttPlan* p, int dir, const uint64_t* in, uint64_t* out, size_t batch, cudaStream_t s) {
     using G = Geometry<L>;
     const size_t groups = (batch + G::PPC - 1) / G::PPC;
     int bps = 0;
     if (dir == DIR_INV) {
-        auto k = ntt_inverse_kernel<L, LAZY, G::THREADS, G::PPC>;
+        auto k = ntt_inverse_kernel<L, DP, G::THREADS, G::PPC>;
         FHEB_TRY(configure(k, G::SMEM, G::THREADS, &bps));
         k<<<persistent_grid(groups, bps), G::THREADS, G::SMEM, s>>>(in, out, batch, p->d_inv, p->ninv, p->mod);
     } else if (dir == DIR_FWD) {
-        auto k = ntt_forward_kernel<L, LAZY, G::THREADS, G::PPC, false>;
+        auto k = ntt_forward_kernel<L, DP, G::THREADS, G::PPC, false>;
         FHEB_TRY(configure(k, G::SMEM, G::THREADS, &bps));
         k<<<persistent_grid(groups, bps), G::THREADS, G::SMEM, s>>>(in, out, batch, p->d_fwd, p->ninv, p->mod);
     } else {
-        auto k = ntt_forward_kernel<L, LAZY, G::THREADS, G::PPC, true>;
+        auto k = ntt_forward_kernel<L, DP, G::THREADS, G::PPC, true>;
         FHEB_TRY(configure(k, G::SMEM, G::THREADS, &bps));
         k<<<persistent_grid(groups, bps), G::THREADS, G::SMEM, s>>>(in, out, batch, p->d_inv, p->ninv, p->mod);
     }
@@ -137,7 +143,7 @@ static int launch_transform(const NttPlan* p, int dir, const uint64_t* in, uint6
     return FHEB_OK;
 }
 
-template <int L, bool LAZY>
+template <int L, bool DP>
 static int launch_polymul(const NttPlan* p, const uint64_t* a, const uint64_t* b, uint64_t* c, size_t batch,
                           cudaStream_t s) {
     using G = Geometry<L>;
@@ -145,7 +151,7 @@ static int launch_polymul(const NttPlan* p, const uint64_t* a, const uint64_t* b
     constexpr size_t SMEM = STASH_GLOBAL ? G::SMEM : 2 * (size_t)G::PPC * (1u << L) * 8;
     const size_t groups = (batch + G::PPC - 1) / G::PPC;
     int bps = 0;
-    auto k = polymul_kernel<L, LAZY, G::THREADS, G::PPC, STASH_GLOBAL>;
+    auto k = polymul_kernel<L, DP, G::THREADS, G::PPC, STASH_GLOBAL>;
     FHEB_TRY(configure(k, SMEM, G::THREADS, &bps));
     const unsigned grid = persistent_grid(groups, bps);
     uint64_t* stash = nullptr;
@@ -162,10 +168,10 @@ static int launch_polymul(const NttPlan* p, const uint64_t* a, const uint64_t* b
 
 #define FHEB_DISPATCH_L(FN, L_, ...)                                         \
     case L_:                                                                 \
-        return lazy ? FN<L_, true>(__VA_ARGS__) : FN<L_, false>(__VA_ARGS__);
+        return dp ? FN<L_, true>(__VA_ARGS__) : FN<L_, false>(__VA_ARGS__);
 
 static int dispatch_transform(const NttPlan* p, int dir, const uint64_t* in, uint64_t* out, size_t batch, cudaStream_t s) {
-    const bool lazy = p->mod.lazy != 0;
+    const bool dp = p->mod.dp != 0;
     switch (p->logn) {
         FHEB_DISPATCH_L(launch_transform, 2, p, dir, in, out, batch, s)
         FHEB_DISPATCH_L(launch_transform, 3, p, dir, in, out, batch, s)
@@ -185,7 +191,7 @@ static int dispatch_transform(const NttPlan* p, int dir, const uint64_t* in, uin
 }
 
 static int dispatch_polymul(const NttPlan* p, const uint64_t* a, const uint64_t* b, uint64_t* c, size_t batch, cudaStream_t s) {
-    const bool lazy = p->mod.lazy != 0;
+    const bool dp = p->mod.dp != 0;
     switch (p->logn) {
         FHEB_DISPATCH_L(launch_polymul, 2, p, a, b, c, batch, s)
         FHEB_DISPATCH_L(launch_polymul, 3, p, a, b, c, batch, s)

@@ -15,9 +15,13 @@
 // (A,B) <- (A + B, (A - B)*w), then the bit-reversal (which brings entry p back to position
 // bitrev(bitrev(i)) = i, i.e. nothing to move) and the scaling by N^-1.
 //
-// Values are kept lazily in [0, K*q) with K tracked at compile time (Harvey butterflies);
-// every function states the bound it needs and the bound it leaves.  Outputs handed back
-// to the caller are always canonical, so results are bit-identical to the reference's.
+// Two arithmetic modes, chosen per modulus at plan creation (ModQ::dp):
+//   integer (q < 2^62): values kept lazily in [0, K*q), Shoup products on the integer pipe;
+//   DP      (q < 2^42): values are integers held in doubles, |v| < K*q, products on the FP64 pipe
+//                       (modarith.cuh); register arrays and shared memory carry the double's bits.
+// K is tracked at compile time (Harvey-style lazy butterflies); every function states the bound it
+// needs and the bound it leaves.  Outputs handed back to the caller are always canonical, so
+// results are bit-identical to the reference's in both modes.
 #pragma once
 #include "modarith.cuh"
 
@@ -43,25 +47,33 @@ FHEB_HD uint32_t bitrev_rt(uint32_t x, int bits) {
 #endif
 }
 
-constexpr int CAP_STRICT = 4;        // q < 2^62: 4q fits a word
-constexpr int CAP_LAZY = 1 << 18;    // q < 2^46: 2^18 q fits a word
+constexpr int CAP_STRICT = 4;   // q < 2^62: 4q fits a word
+constexpr int CAP_DP = 128;     // q < 2^42: |v| < 128 q <= 2^49 keeps every FP64 step exact with margin
 
-template <bool LAZY>
-constexpr int cap_of() { return LAZY ? CAP_LAZY : CAP_STRICT; }
+template <bool DP>
+constexpr int cap_of() { return DP ? CAP_DP : CAP_STRICT; }
 
 // ---- compile-time range tracking -----------------------------------------------------
-constexpr int fwd_next_k(int K, bool has_unit, bool has_nonunit, int cap) {
-    int kn = has_nonunit ? (((K + 2 > cap) ? 2 : K) + 2) : 0;
-    int ku = has_unit ? ((2 * K > cap) ? 4 : 2 * K) : 0;
+constexpr int fwd_next_k(int K, bool has_unit, bool has_nonunit, bool dp) {
+    if (dp) {  // |A +- t| <= K + 1 (|t| < q), |A +- B| <= 2K; never reduced (static_assert at the use)
+        int kn = has_nonunit ? K + 1 : 0;
+        int ku = has_unit ? 2 * K : 0;
+        return kn > ku ? kn : ku;
+    }
+    int kn = has_nonunit ? (((K + 2 > CAP_STRICT) ? 2 : K) + 2) : 0;
+    int ku = has_unit ? ((2 * K > CAP_STRICT) ? 4 : 2 * K) : 0;
     return kn > ku ? kn : ku;
 }
-constexpr int fwd_pass_k(int K, int R, bool unit_first, int cap) {
-    for (int a = 0; a < R; ++a) K = fwd_next_k(K, unit_first, !(unit_first && a == 0), cap);
+constexpr int fwd_pass_k(int K, int R, bool unit_first, bool dp) {
+    for (int a = 0; a < R; ++a) K = fwd_next_k(K, unit_first, !(unit_first && a == 0), dp);
     return K;
 }
-constexpr int inv_next_k(int K, int cap) { return (2 * K > cap / 2) ? 2 : 2 * K; }
-constexpr int inv_pass_k(int K, int R, int cap) {
-    for (int a = 0; a < R; ++a) K = inv_next_k(K, cap);
+constexpr int inv_next_k(int K, bool dp) {
+    if (dp) return (2 * K > CAP_DP) ? 1 : 2 * K;
+    return (2 * K > CAP_STRICT / 2) ? 2 : 2 * K;
+}
+constexpr int inv_pass_k(int K, int R, bool dp) {
+    for (int a = 0; a < R; ++a) K = inv_next_k(K, dp);
     return K;
 }
 
@@ -72,11 +84,17 @@ FHEB_HD uint64_t kq(const ModQ& m) {
     else return m.q * (uint64_t)K;
 }
 
-// Forward butterfly on values < K*q; leaves values < fwd_next_k(K)*q.
-template <int K, int CAP, bool UNIT>
+// Forward butterfly on values bounded by K*q; leaves values bounded by fwd_next_k(K)*q.
+template <int K, bool DP, bool UNIT>
 FHEB_HD void fwd_bfly(uint64_t& A, uint64_t& B, const Tw& w, const ModQ& m) {
-    if constexpr (UNIT) {  // twiddle == 1: no multiplication
-        constexpr bool red = (2 * K > CAP);
+    if constexpr (DP) {
+        static_assert(fwd_next_k(K, UNIT, !UNIT, true) <= CAP_DP, "FP64 range exceeded in a forward stage");
+        const double a = bits_to_double(A);
+        const double t = UNIT ? bits_to_double(B) : dp_mulmod(bits_to_double(B), bits_to_double(w.w), m);
+        A = double_to_bits(dp_add(a, t));
+        B = double_to_bits(dp_add(a, -t));
+    } else if constexpr (UNIT) {  // twiddle == 1: no multiplication
+        constexpr bool red = (2 * K > CAP_STRICT);
         static_assert(!red || K <= 4, "conditional subtraction only halves [0,4q)");
         uint64_t a = A, t = B;
         if constexpr (red) {
@@ -87,7 +105,7 @@ FHEB_HD void fwd_bfly(uint64_t& A, uint64_t& B, const Tw& w, const ModQ& m) {
         A = a + t;
         B = a - t + kq<KT>(m);
     } else {
-        constexpr bool red = (K + 2 > CAP);
+        constexpr bool red = (K + 2 > CAP_STRICT);
         static_assert(!red || K <= 4, "conditional subtraction only halves [0,4q)");
         uint64_t a = A;
         if constexpr (red) a = csub(a, m.q2);
@@ -97,39 +115,67 @@ FHEB_HD void fwd_bfly(uint64_t& A, uint64_t& B, const Tw& w, const ModQ& m) {
     }
 }
 
-// Inverse (Gentleman-Sande) butterfly on values < K*q; leaves values < inv_next_k(K)*q.
-template <int K, int CAP, bool UNIT>
+// Inverse (Gentleman-Sande) butterfly on values bounded by K*q; leaves values bounded by inv_next_k(K)*q.
+template <int K, bool DP, bool UNIT>
 FHEB_HD void inv_bfly(uint64_t& A, uint64_t& B, const Tw& w, const ModQ& m) {
-    static_assert(2 * K <= CAP, "sum would overflow the word");
-    constexpr bool red = (2 * K > CAP / 2);
-    static_assert(!red || 2 * K <= 4, "conditional subtraction only halves [0,4q)");
-    uint64_t s = A + B;
-    uint64_t d = A - B + kq<K>(m);
-    if constexpr (red) s = csub(s, m.q2);
-    A = s;
-    if constexpr (UNIT) {
-        if constexpr (red) d = csub(d, m.q2);
-        B = d;
+    if constexpr (DP) {
+        static_assert(2 * K <= 2 * CAP_DP, "FP64 range exceeded in an inverse stage");
+        constexpr bool red = (2 * K > CAP_DP);
+        const double a = bits_to_double(A), b = bits_to_double(B);
+        double s = dp_add(a, b);
+        double d = dp_add(a, -b);
+        if constexpr (red) s = dp_reduce(s, m);
+        if constexpr (UNIT) {
+            if constexpr (red) d = dp_reduce(d, m);
+        } else {
+            d = dp_mulmod(d, bits_to_double(w.w), m);
+        }
+        A = double_to_bits(s);
+        B = double_to_bits(d);
     } else {
-        B = shoup_lazy(d, w.w, w.wp, m.q);
+        static_assert(2 * K <= CAP_STRICT, "sum would overflow the word");
+        constexpr bool red = (2 * K > CAP_STRICT / 2);
+        static_assert(!red || 2 * K <= 4, "conditional subtraction only halves [0,4q)");
+        uint64_t s = A + B;
+        uint64_t d = A - B + kq<K>(m);
+        if constexpr (red) s = csub(s, m.q2);
+        A = s;
+        if constexpr (UNIT) {
+            if constexpr (red) d = csub(d, m.q2);
+            B = d;
+        } else {
+            B = shoup_lazy(d, w.w, w.wp, m.q);
+        }
     }
 }
 
+// Twiddle tables: integer mode = (value, Shoup companion) pairs, 16 bytes; DP mode = one double, 8 bytes.
+template <bool DP>
 FHEB_HD Tw load_tw(const Tw* __restrict__ tw, uint32_t idx) {
-#if defined(__CUDA_ARCH__)
-    const ulonglong2 v = __ldg(reinterpret_cast<const ulonglong2*>(tw) + idx);
     Tw t;
-    t.w = v.x;
-    t.wp = v.y;
-    return t;
+    if constexpr (DP) {
+        const uint64_t* p = reinterpret_cast<const uint64_t*>(tw);
+#if defined(__CUDA_ARCH__)
+        t.w = __ldg(p + idx);
 #else
-    return tw[idx];
+        t.w = p[idx];
 #endif
+        t.wp = 0;
+    } else {
+#if defined(__CUDA_ARCH__)
+        const ulonglong2 v = __ldg(reinterpret_cast<const ulonglong2*>(tw) + idx);
+        t.w = v.x;
+        t.wp = v.y;
+#else
+        t = tw[idx];
+#endif
+    }
+    return t;
 }
 
 // R forward stages on 2^R register-resident values; element bit (R-1) is the highest
 // position bit of the pass.  T0 = heap index of the first stage's twiddle for this block.
-template <int R, int K, int CAP, bool UNITFIRST, int A = 0>
+template <int R, int K, bool DP, bool UNITFIRST, int A = 0>
 FHEB_HD void fwd_stages(uint64_t (&x)[1 << R], const Tw* __restrict__ tw, uint32_t T0, const ModQ& m) {
     if constexpr (A < R) {
         constexpr int half = 1 << (R - 1 - A);
@@ -138,19 +184,19 @@ FHEB_HD void fwd_stages(uint64_t (&x)[1 << R], const Tw* __restrict__ tw, uint32
             if (UNITFIRST && g == 0) {
                 Tw dummy{0, 0};
 #pragma unroll
-                for (int j = 0; j < half; ++j) fwd_bfly<K, CAP, true>(x[g * 2 * half + j], x[g * 2 * half + j + half], dummy, m);
+                for (int j = 0; j < half; ++j) fwd_bfly<K, DP, true>(x[g * 2 * half + j], x[g * 2 * half + j + half], dummy, m);
             } else {
-                const Tw w = load_tw(tw, (T0 << A) + g);
+                const Tw w = load_tw<DP>(tw, (T0 << A) + g);
 #pragma unroll
-                for (int j = 0; j < half; ++j) fwd_bfly<K, CAP, false>(x[g * 2 * half + j], x[g * 2 * half + j + half], w, m);
+                for (int j = 0; j < half; ++j) fwd_bfly<K, DP, false>(x[g * 2 * half + j], x[g * 2 * half + j + half], w, m);
             }
         }
-        fwd_stages<R, fwd_next_k(K, UNITFIRST, !(UNITFIRST && A == 0), CAP), CAP, UNITFIRST, A + 1>(x, tw, T0, m);
+        fwd_stages<R, fwd_next_k(K, UNITFIRST, !(UNITFIRST && A == 0), DP), DP, UNITFIRST, A + 1>(x, tw, T0, m);
     }
 }
 
 // R inverse stages, highest stage of the pass first (element bit 0 first).
-template <int R, int K, int CAP, bool UNITFIRST, int A = R - 1>
+template <int R, int K, bool DP, bool UNITFIRST, int A = R - 1>
 FHEB_HD void inv_stages(uint64_t (&x)[1 << R], const Tw* __restrict__ tw, uint32_t T0, const ModQ& m) {
     if constexpr (A >= 0) {
         constexpr int half = 1 << (R - 1 - A);
@@ -159,24 +205,50 @@ FHEB_HD void inv_stages(uint64_t (&x)[1 << R], const Tw* __restrict__ tw, uint32
             if (UNITFIRST && g == 0) {
                 Tw dummy{0, 0};
 #pragma unroll
-                for (int j = 0; j < half; ++j) inv_bfly<K, CAP, true>(x[g * 2 * half + j], x[g * 2 * half + j + half], dummy, m);
+                for (int j = 0; j < half; ++j) inv_bfly<K, DP, true>(x[g * 2 * half + j], x[g * 2 * half + j + half], dummy, m);
             } else {
-                const Tw w = load_tw(tw, (T0 << A) + g);
+                const Tw w = load_tw<DP>(tw, (T0 << A) + g);
 #pragma unroll
-                for (int j = 0; j < half; ++j) inv_bfly<K, CAP, false>(x[g * 2 * half + j], x[g * 2 * half + j + half], w, m);
+                for (int j = 0; j < half; ++j) inv_bfly<K, DP, false>(x[g * 2 * half + j], x[g * 2 * half + j + half], w, m);
             }
         }
-        inv_stages<R, inv_next_k(K, CAP), CAP, UNITFIRST, A - 1>(x, tw, T0, m);
+        inv_stages<R, inv_next_k(K, DP), DP, UNITFIRST, A - 1>(x, tw, T0, m);
     }
 }
 
-// value < K*q  ->  canonical
-template <int K>
+// value bounded by K*q  ->  canonical word
+template <int K, bool DP = false>
 FHEB_HD uint64_t canon_k(uint64_t x, const ModQ& m) {
-    if constexpr (K <= 1) return x;
+    if constexpr (DP) {
+        double r = bits_to_double(x);
+        if constexpr (K > 1) r = dp_reduce(r, m);
+        return dp_canon_word(r, m);
+    } else if constexpr (K <= 1) return x;
     else if constexpr (K == 2) return csub(x, m.q);
     else if constexpr (K <= 4) return csub(csub(x, m.q2), m.q);
     else return reduce64(x, m);
+}
+
+// caller word (any 64-bit value) -> the mode's register representation of its residue
+template <bool DP>
+FHEB_HD uint64_t load_word(uint64_t v, const ModQ& m) {
+    const uint64_t c = canon_any(v, m);
+    if constexpr (DP) return double_to_bits(dp_from_uint(c));
+    else return c;
+}
+
+// finished transform parked for the fused product: canonical word (integer) / reduced double (DP)
+template <int K, bool DP>
+FHEB_HD uint64_t park_word(uint64_t x, const ModQ& m) {
+    if constexpr (DP) return (K > 1) ? double_to_bits(dp_reduce(bits_to_double(x), m)) : x;
+    else return canon_k<K>(x, m);
+}
+
+// x * N^-1 -> canonical word (x bounded by K*q, K within the mode's cap)
+template <bool DP>
+FHEB_HD uint64_t scale_word(uint64_t x, const Tw& ninv, const ModQ& m) {
+    if constexpr (DP) return dp_canon_word(dp_mulmod(bits_to_double(x), bits_to_double(ninv.w), m), m);
+    else return csub(shoup_lazy(x, ninv.w, ninv.wp, m.q), m.q);
 }
 
 // ---- pass plans: how the L stages are split into register passes ----------------------
@@ -208,16 +280,16 @@ constexpr int plan_s0() {  // first stage of pass PASS
     for (int p = 0; p < PASS; ++p) s += Plan<L>::R[p];
     return s;
 }
-template <int L, bool LAZY, int PASS>
+template <int L, bool DP, int PASS>
 constexpr int plan_fwd_kin() {  // bound on values entering forward pass PASS (inputs canonical)
     int K = 1;
-    for (int p = 0; p < PASS; ++p) K = fwd_pass_k(K, Plan<L>::R[p], p == 0, cap_of<LAZY>());
+    for (int p = 0; p < PASS; ++p) K = fwd_pass_k(K, Plan<L>::R[p], p == 0, DP);
     return K;
 }
-template <int L, bool LAZY, int PASS>
+template <int L, bool DP, int PASS>
 constexpr int plan_inv_kin() {  // bound entering inverse pass PASS (run order P-1 .. 0), inputs < kin0*q
     int K = 1;
-    for (int p = Plan<L>::P - 1; p > PASS; --p) K = inv_pass_k(K, Plan<L>::R[p], cap_of<LAZY>());
+    for (int p = Plan<L>::P - 1; p > PASS; --p) K = inv_pass_k(K, Plan<L>::R[p], DP);
     return K;
 }
 
@@ -239,17 +311,16 @@ enum {
 // polynomial.  The last pass stores in the reference's (bit-reversed) output order.
 //   SCALE      : multiply the outputs by `ninv` (fast_ntt_inverse semantics)
 // OUT == IO_STASH_*: the finished transform is parked (position order, no bit reversal) in
-// `gout` for the fused polynomial product; canonical unless LAZY (then < KOUT*q, small).
-template <int L, bool LAZY, int PASS, int IN, int OUT, bool BITREV_OUT = true, bool SCALE = false>
+// `gout` for the fused polynomial product; canonical words in integer mode, lazy doubles (|v| < KOUT*q) in DP mode.
+template <int L, bool DP, int PASS, int IN, int OUT, bool BITREV_OUT = true, bool SCALE = false>
 FHEB_HD void fwd_pass(uint32_t tid, uint32_t nthreads, uint32_t polys, const uint64_t* gin, uint64_t* gout,
                       uint64_t* smem, const Tw* __restrict__ tw, const ModQ& m, const Tw ninv = Tw{0, 0}) {
     constexpr int R = Plan<L>::R[PASS];
     constexpr int E = 1 << R;
     constexpr int S0 = plan_s0<L, PASS>();
     constexpr int EB = L - S0 - R;  // lowest position bit handled by this pass
-    constexpr int CAP = cap_of<LAZY>();
-    constexpr int KIN = plan_fwd_kin<L, LAZY, PASS>();
-    constexpr int KOUT = fwd_pass_k(KIN, R, PASS == 0, CAP);
+    constexpr int KIN = plan_fwd_kin<L, DP, PASS>();
+    constexpr int KOUT = fwd_pass_k(KIN, R, PASS == 0, DP);
     constexpr bool LAST = (PASS == Plan<L>::P - 1);
     constexpr uint32_t N = 1u << L;
     constexpr uint32_t ITEMS = N >> R;  // per polynomial
@@ -268,7 +339,7 @@ FHEB_HD void fwd_pass(uint32_t tid, uint32_t nthreads, uint32_t polys, const uin
         if (IN == IO_GLOBAL) {
             const uint64_t* src = gin + (size_t)poly * N;
 #pragma unroll
-            for (int c = 0; c < E; ++c) x[c] = canon_any(src[base | ((uint32_t)c << EB)], m);
+            for (int c = 0; c < E; ++c) x[c] = load_word<DP>(src[base | ((uint32_t)c << EB)], m);
         } else {
             const uint64_t* src = smem + (size_t)poly * N;
             const uint32_t pb = swz(base);
@@ -276,25 +347,25 @@ FHEB_HD void fwd_pass(uint32_t tid, uint32_t nthreads, uint32_t polys, const uin
             for (int c = 0; c < E; ++c) x[c] = src[pb ^ swz((uint32_t)c << EB)];
         }
         const uint32_t T0 = (1u << S0) + (base >> (L - S0));
-        fwd_stages<R, KIN, CAP, PASS == 0>(x, tw, T0, m);
+        fwd_stages<R, KIN, DP, PASS == 0>(x, tw, T0, m);
         if (OUT == IO_GLOBAL) {
             uint64_t* dst = gout + (size_t)poly * N;
 #pragma unroll
             for (int c = 0; c < E; ++c) {
-                const uint64_t v = SCALE ? csub(shoup_lazy(x[c], ninv.w, ninv.wp, m.q), m.q) : canon_k<KOUT>(x[c], m);
+                const uint64_t v = SCALE ? scale_word<DP>(x[c], ninv, m) : canon_k<KOUT, DP>(x[c], m);
                 if (BITREV_OUT) dst[(bitrev_c((uint32_t)c, R) << (L - R)) | t] = v;
                 else dst[base | ((uint32_t)c << EB)] = v;
             }
         } else if (OUT == IO_STASH_GLOBAL) {
             uint64_t* dst = gout + (size_t)poly * N;
 #pragma unroll
-            for (int c = 0; c < E; ++c) dst[base | ((uint32_t)c << EB)] = LAZY ? x[c] : canon_k<KOUT>(x[c], m);
+            for (int c = 0; c < E; ++c) dst[base | ((uint32_t)c << EB)] = park_word<KOUT, DP>(x[c], m);
         } else {
             uint64_t* dst = (OUT == IO_STASH_SMEM ? gout : smem) + (size_t)poly * N;
             const uint32_t pb = swz(base);
 #pragma unroll
             for (int c = 0; c < E; ++c)
-                dst[pb ^ swz((uint32_t)c << EB)] = (OUT == IO_STASH_SMEM && !LAZY) ? canon_k<KOUT>(x[c], m) : x[c];
+                dst[pb ^ swz((uint32_t)c << EB)] = (OUT == IO_STASH_SMEM) ? park_word<KOUT, DP>(x[c], m) : x[c];
         }
     }
 }
@@ -306,7 +377,7 @@ FHEB_HD void fwd_pass(uint32_t tid, uint32_t nthreads, uint32_t polys, const uin
 //   IN    : IO_GLOBAL when the plan has a single pass (b read from caller memory), else IO_SMEM
 //   OUT   : IO_GLOBAL when the plan has a single pass (scaled, canonical), else IO_SMEM
 //   STASH : IO_STASH_SMEM or IO_STASH_GLOBAL (where fwd_pass parked T(a))
-template <int L, bool LAZY, int IN, int OUT, int STASH>
+template <int L, bool DP, int IN, int OUT, int STASH>
 FHEB_HD void polymul_mid_pass(uint32_t tid, uint32_t nthreads, uint32_t polys, const uint64_t* gin, uint64_t* gout,
                               uint64_t* smem, const uint64_t* stash, const Tw* __restrict__ twf,
                               const Tw* __restrict__ twi, const Tw ninv, const ModQ& m) {
@@ -315,14 +386,13 @@ FHEB_HD void polymul_mid_pass(uint32_t tid, uint32_t nthreads, uint32_t polys, c
     constexpr int E = 1 << R;
     constexpr int S0 = plan_s0<L, PASS>();
     constexpr int EB = L - S0 - R;  // == 0
-    constexpr int CAP = cap_of<LAZY>();
-    constexpr int KIN = plan_fwd_kin<L, LAZY, PASS>();
-    constexpr int KOUT = fwd_pass_k(KIN, R, PASS == 0, CAP);
+    constexpr int KIN = plan_fwd_kin<L, DP, PASS>();
+    constexpr int KOUT = fwd_pass_k(KIN, R, PASS == 0, DP);
     constexpr uint32_t N = 1u << L;
     constexpr uint32_t ITEMS = N >> R;
     static_assert(EB == 0, "the last forward pass covers the lowest position bits");
-    // lazy operands: (KOUT*q)^2 must stay below q*2^64 for reduce128
-    static_assert(!LAZY || (uint64_t)KOUT * KOUT < (1ull << 18), "lazy product bound");
+    // DP: the parked operand is reduced (|a| <= q/2 + 1), this one stays lazy: |a*b| <= KOUT q^2 / 2
+    static_assert(!DP || KOUT <= 2 * CAP_DP, "FP64 product bound");
 
     for (uint32_t U = tid; U < polys * ITEMS; U += nthreads) {
         const uint32_t poly = U >> (L - R);
@@ -333,26 +403,26 @@ FHEB_HD void polymul_mid_pass(uint32_t tid, uint32_t nthreads, uint32_t polys, c
         if (IN == IO_GLOBAL) {
             const uint64_t* src = gin + (size_t)poly * N;
 #pragma unroll
-            for (int c = 0; c < E; ++c) x[c] = canon_any(src[base | (uint32_t)c], m);
+            for (int c = 0; c < E; ++c) x[c] = load_word<DP>(src[base | (uint32_t)c], m);
         } else {
             const uint64_t* src = smem + (size_t)poly * N;
 #pragma unroll
             for (int c = 0; c < E; ++c) x[c] = src[pb ^ swz((uint32_t)c)];
         }
         const uint32_t T0 = (1u << S0) + (base >> (L - S0));
-        fwd_stages<R, KIN, CAP, PASS == 0>(x, twf, T0, m);
+        fwd_stages<R, KIN, DP, PASS == 0>(x, twf, T0, m);
         const uint64_t* sa = stash + (size_t)poly * N;
 #pragma unroll
         for (int c = 0; c < E; ++c) {
             const uint64_t av = (STASH == IO_STASH_GLOBAL) ? sa[base | (uint32_t)c] : sa[pb ^ swz((uint32_t)c)];
-            const uint64_t bv = LAZY ? x[c] : canon_k<KOUT>(x[c], m);
-            x[c] = mulmod(av, bv, m);
+            if constexpr (DP) x[c] = double_to_bits(dp_mulmod(bits_to_double(av), bits_to_double(x[c]), m));
+            else x[c] = mulmod(av, canon_k<KOUT>(x[c], m), m);
         }
-        inv_stages<R, 1, CAP, PASS == 0>(x, twi, T0, m);
+        inv_stages<R, 1, DP, PASS == 0>(x, twi, T0, m);
         if (OUT == IO_GLOBAL) {
             uint64_t* dst = gout + (size_t)poly * N;
 #pragma unroll
-            for (int c = 0; c < E; ++c) dst[base | (uint32_t)c] = csub(shoup_lazy(x[c], ninv.w, ninv.wp, m.q), m.q);
+            for (int c = 0; c < E; ++c) dst[base | (uint32_t)c] = scale_word<DP>(x[c], ninv, m);
         } else {
             uint64_t* dst = smem + (size_t)poly * N;
 #pragma unroll
@@ -365,15 +435,14 @@ FHEB_HD void polymul_mid_pass(uint32_t tid, uint32_t nthreads, uint32_t polys, c
 // may read the reference's input order (bit-reversed positions) from global memory; the
 // last one executed (PASS == 0) multiplies by N^-1 (`ninv`, Shoup pair) and stores canonical
 // values in natural order.
-template <int L, bool LAZY, int PASS, int IN, int OUT, bool BITREV_IN = true>
+template <int L, bool DP, int PASS, int IN, int OUT, bool BITREV_IN = true>
 FHEB_HD void inv_pass(uint32_t tid, uint32_t nthreads, uint32_t polys, const uint64_t* gin, uint64_t* gout,
                       uint64_t* smem, const Tw* __restrict__ tw, const Tw ninv, const ModQ& m) {
     constexpr int R = Plan<L>::R[PASS];
     constexpr int E = 1 << R;
     constexpr int S0 = plan_s0<L, PASS>();
     constexpr int EB = L - S0 - R;
-    constexpr int CAP = cap_of<LAZY>();
-    constexpr int KIN = plan_inv_kin<L, LAZY, PASS>();
+    constexpr int KIN = plan_inv_kin<L, DP, PASS>();
     constexpr bool FIRST = (PASS == Plan<L>::P - 1);
     constexpr uint32_t N = 1u << L;
     constexpr uint32_t ITEMS = N >> R;
@@ -391,10 +460,10 @@ FHEB_HD void inv_pass(uint32_t tid, uint32_t nthreads, uint32_t polys, const uin
             const uint64_t* src = gin + (size_t)poly * N;
             if (BITREV_IN) {
 #pragma unroll
-                for (int c = 0; c < E; ++c) x[c] = canon_any(src[(bitrev_c((uint32_t)c, R) << (L - R)) | t], m);
+                for (int c = 0; c < E; ++c) x[c] = load_word<DP>(src[(bitrev_c((uint32_t)c, R) << (L - R)) | t], m);
             } else {
 #pragma unroll
-                for (int c = 0; c < E; ++c) x[c] = canon_any(src[base | ((uint32_t)c << EB)], m);
+                for (int c = 0; c < E; ++c) x[c] = load_word<DP>(src[base | ((uint32_t)c << EB)], m);
             }
         } else {
             const uint64_t* src = smem + (size_t)poly * N;
@@ -403,12 +472,12 @@ FHEB_HD void inv_pass(uint32_t tid, uint32_t nthreads, uint32_t polys, const uin
             for (int c = 0; c < E; ++c) x[c] = src[pb ^ swz((uint32_t)c << EB)];
         }
         const uint32_t T0 = (1u << S0) + (base >> (L - S0));
-        inv_stages<R, KIN, CAP, PASS == 0>(x, tw, T0, m);
+        inv_stages<R, KIN, DP, PASS == 0>(x, tw, T0, m);
         if (OUT == IO_GLOBAL) {
             uint64_t* dst = gout + (size_t)poly * N;
 #pragma unroll
             for (int c = 0; c < E; ++c)
-                dst[base | ((uint32_t)c << EB)] = csub(shoup_lazy(x[c], ninv.w, ninv.wp, m.q), m.q);
+                dst[base | ((uint32_t)c << EB)] = scale_word<DP>(x[c], ninv, m);
         } else {
             uint64_t* dst = smem + (size_t)poly * N;
             const uint32_t pb = swz(base);

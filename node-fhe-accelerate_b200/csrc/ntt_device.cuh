@@ -14,29 +14,29 @@ __device__ __forceinline__ void prefetch_l2_bulk(const void* p, uint32_t bytes) 
         asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
 }
 
-template <int L, bool LAZY, int PASS>
+template <int L, bool DP, int PASS>
 __device__ __forceinline__ void fwd_middle(uint32_t tid, uint32_t nthreads, uint32_t polys, uint64_t* smem,
                                            const Tw* __restrict__ tw, const ModQ& m) {
     if constexpr (PASS < Plan<L>::P - 1) {
-        fwd_pass<L, LAZY, PASS, IO_SMEM, IO_SMEM>(tid, nthreads, polys, nullptr, nullptr, smem, tw, m);
+        fwd_pass<L, DP, PASS, IO_SMEM, IO_SMEM>(tid, nthreads, polys, nullptr, nullptr, smem, tw, m);
         __syncthreads();
-        fwd_middle<L, LAZY, PASS + 1>(tid, nthreads, polys, smem, tw, m);
+        fwd_middle<L, DP, PASS + 1>(tid, nthreads, polys, smem, tw, m);
     }
 }
 
-template <int L, bool LAZY, int PASS>
+template <int L, bool DP, int PASS>
 __device__ __forceinline__ void inv_middle(uint32_t tid, uint32_t nthreads, uint32_t polys, uint64_t* smem,
                                            const Tw* __restrict__ tw, const Tw ninv, const ModQ& m) {
     if constexpr (PASS > 0) {
-        inv_pass<L, LAZY, PASS, IO_SMEM, IO_SMEM>(tid, nthreads, polys, nullptr, nullptr, smem, tw, ninv, m);
+        inv_pass<L, DP, PASS, IO_SMEM, IO_SMEM>(tid, nthreads, polys, nullptr, nullptr, smem, tw, ninv, m);
         __syncthreads();
-        inv_middle<L, LAZY, PASS - 1>(tid, nthreads, polys, smem, tw, ninv, m);
+        inv_middle<L, DP, PASS - 1>(tid, nthreads, polys, smem, tw, ninv, m);
     }
 }
 
 // Forward transform of `batch` polynomials, [batch][N] -> [batch][N] (in may equal out).
 // SCALE = true gives fast_ntt_inverse semantics when `tw` is the inverse table.
-template <int L, bool LAZY, int THREADS, int PPC, bool SCALE>
+template <int L, bool DP, int THREADS, int PPC, bool SCALE>
 __global__ void __launch_bounds__(THREADS) ntt_forward_kernel(const uint64_t* in, uint64_t* out, size_t batch,
                                                               const Tw* __restrict__ tw, const Tw ninv, const ModQ m) {
     extern __shared__ __align__(16) uint64_t smem[];
@@ -55,12 +55,12 @@ __global__ void __launch_bounds__(THREADS) ntt_forward_kernel(const uint64_t* in
             prefetch_l2_bulk(in + q0 * N, (uint32_t)(np * N * 8));
         }
         if constexpr (P == 1) {
-            fwd_pass<L, LAZY, 0, IO_GLOBAL, IO_GLOBAL, true, SCALE>(tid, THREADS, polys, gin, gout, smem, tw, m, ninv);
+            fwd_pass<L, DP, 0, IO_GLOBAL, IO_GLOBAL, true, SCALE>(tid, THREADS, polys, gin, gout, smem, tw, m, ninv);
         } else {
-            fwd_pass<L, LAZY, 0, IO_GLOBAL, IO_SMEM>(tid, THREADS, polys, gin, gout, smem, tw, m);
+            fwd_pass<L, DP, 0, IO_GLOBAL, IO_SMEM>(tid, THREADS, polys, gin, gout, smem, tw, m);
             __syncthreads();
-            fwd_middle<L, LAZY, 1>(tid, THREADS, polys, smem, tw, m);
-            fwd_pass<L, LAZY, P - 1, IO_SMEM, IO_GLOBAL, true, SCALE>(tid, THREADS, polys, gin, gout, smem, tw, m, ninv);
+            fwd_middle<L, DP, 1>(tid, THREADS, polys, smem, tw, m);
+            fwd_pass<L, DP, P - 1, IO_SMEM, IO_GLOBAL, true, SCALE>(tid, THREADS, polys, gin, gout, smem, tw, m, ninv);
             __syncthreads();  // the next group's first pass overwrites the work buffer
         }
     }
@@ -68,7 +68,7 @@ __global__ void __launch_bounds__(THREADS) ntt_forward_kernel(const uint64_t* in
 
 // Inverse transform (Gentleman-Sande network, bit-reversal folded into the loads, N^-1 folded
 // into the last pass).
-template <int L, bool LAZY, int THREADS, int PPC>
+template <int L, bool DP, int THREADS, int PPC>
 __global__ void __launch_bounds__(THREADS) ntt_inverse_kernel(const uint64_t* in, uint64_t* out, size_t batch,
                                                               const Tw* __restrict__ tw, const Tw ninv, const ModQ m) {
     extern __shared__ __align__(16) uint64_t smem[];
@@ -87,12 +87,12 @@ __global__ void __launch_bounds__(THREADS) ntt_inverse_kernel(const uint64_t* in
             prefetch_l2_bulk(in + q0 * N, (uint32_t)(np * N * 8));
         }
         if constexpr (P == 1) {
-            inv_pass<L, LAZY, 0, IO_GLOBAL, IO_GLOBAL>(tid, THREADS, polys, gin, gout, smem, tw, ninv, m);
+            inv_pass<L, DP, 0, IO_GLOBAL, IO_GLOBAL>(tid, THREADS, polys, gin, gout, smem, tw, ninv, m);
         } else {
-            inv_pass<L, LAZY, P - 1, IO_GLOBAL, IO_SMEM>(tid, THREADS, polys, gin, gout, smem, tw, ninv, m);
+            inv_pass<L, DP, P - 1, IO_GLOBAL, IO_SMEM>(tid, THREADS, polys, gin, gout, smem, tw, ninv, m);
             __syncthreads();
-            inv_middle<L, LAZY, P - 2>(tid, THREADS, polys, smem, tw, ninv, m);
-            inv_pass<L, LAZY, 0, IO_SMEM, IO_GLOBAL>(tid, THREADS, polys, gin, gout, smem, tw, ninv, m);
+            inv_middle<L, DP, P - 2>(tid, THREADS, polys, smem, tw, ninv, m);
+            inv_pass<L, DP, 0, IO_SMEM, IO_GLOBAL>(tid, THREADS, polys, gin, gout, smem, tw, ninv, m);
             __syncthreads();
         }
     }
@@ -101,7 +101,7 @@ __global__ void __launch_bounds__(THREADS) ntt_inverse_kernel(const uint64_t* in
 // c = T^-1(T(a) . T(b)) in one launch (PolynomialRing::multiply, polynomial_ring.cpp:421-447).
 // T(a) is parked either in a second shared-memory buffer or, when two operands do not fit
 // (N = 16384), in a per-block global scratch that stays L2 resident.
-template <int L, bool LAZY, int THREADS, int PPC, bool STASH_GLOBAL>
+template <int L, bool DP, int THREADS, int PPC, bool STASH_GLOBAL>
 __global__ void __launch_bounds__(THREADS) polymul_kernel(const uint64_t* a, const uint64_t* b, uint64_t* c, size_t batch,
                                                           const Tw* __restrict__ twf, const Tw* __restrict__ twi,
                                                           const Tw ninv, const ModQ m, uint64_t* scratch) {
@@ -120,25 +120,25 @@ __global__ void __launch_bounds__(THREADS) polymul_kernel(const uint64_t* a, con
         uint64_t* gc = c + p0 * N;
         if (tid == 0) prefetch_l2_bulk(gb, (uint32_t)(polys * N * 8));
         if constexpr (P == 1) {
-            fwd_pass<L, LAZY, 0, IO_GLOBAL, STASH, false>(tid, THREADS, polys, ga, stash, smem, twf, m);
+            fwd_pass<L, DP, 0, IO_GLOBAL, STASH, false>(tid, THREADS, polys, ga, stash, smem, twf, m);
             if (!STASH_GLOBAL) __syncthreads();
-            polymul_mid_pass<L, LAZY, IO_GLOBAL, IO_GLOBAL, STASH>(tid, THREADS, polys, gb, gc, smem, stash, twf, twi, ninv, m);
+            polymul_mid_pass<L, DP, IO_GLOBAL, IO_GLOBAL, STASH>(tid, THREADS, polys, gb, gc, smem, stash, twf, twi, ninv, m);
             __syncthreads();
         } else {
             // operand a: all passes, result parked in the stash
-            fwd_pass<L, LAZY, 0, IO_GLOBAL, IO_SMEM>(tid, THREADS, polys, ga, nullptr, smem, twf, m);
+            fwd_pass<L, DP, 0, IO_GLOBAL, IO_SMEM>(tid, THREADS, polys, ga, nullptr, smem, twf, m);
             __syncthreads();
-            fwd_middle<L, LAZY, 1>(tid, THREADS, polys, smem, twf, m);
-            fwd_pass<L, LAZY, P - 1, IO_SMEM, STASH, false>(tid, THREADS, polys, nullptr, stash, smem, twf, m);
+            fwd_middle<L, DP, 1>(tid, THREADS, polys, smem, twf, m);
+            fwd_pass<L, DP, P - 1, IO_SMEM, STASH, false>(tid, THREADS, polys, nullptr, stash, smem, twf, m);
             __syncthreads();
             // operand b: all but the last pass, then the fused product + first inverse pass
-            fwd_pass<L, LAZY, 0, IO_GLOBAL, IO_SMEM>(tid, THREADS, polys, gb, nullptr, smem, twf, m);
+            fwd_pass<L, DP, 0, IO_GLOBAL, IO_SMEM>(tid, THREADS, polys, gb, nullptr, smem, twf, m);
             __syncthreads();
-            fwd_middle<L, LAZY, 1>(tid, THREADS, polys, smem, twf, m);
-            polymul_mid_pass<L, LAZY, IO_SMEM, IO_SMEM, STASH>(tid, THREADS, polys, nullptr, nullptr, smem, stash, twf, twi, ninv, m);
+            fwd_middle<L, DP, 1>(tid, THREADS, polys, smem, twf, m);
+            polymul_mid_pass<L, DP, IO_SMEM, IO_SMEM, STASH>(tid, THREADS, polys, nullptr, nullptr, smem, stash, twf, twi, ninv, m);
             __syncthreads();
-            inv_middle<L, LAZY, P - 2>(tid, THREADS, polys, smem, twi, ninv, m);
-            inv_pass<L, LAZY, 0, IO_SMEM, IO_GLOBAL>(tid, THREADS, polys, nullptr, gc, smem, twi, ninv, m);
+            inv_middle<L, DP, P - 2>(tid, THREADS, polys, smem, twi, ninv, m);
+            inv_pass<L, DP, 0, IO_SMEM, IO_GLOBAL>(tid, THREADS, polys, nullptr, gc, smem, twi, ninv, m);
             __syncthreads();
         }
     }

@@ -36,4 +36,18 @@ inline std::vector<Tw> build_heap_table(const uint64_t* table, uint32_t L, uint6
     return heap;
 }
 
+// DP mode (q < 2^42): the same heap holding each twiddle as a double, 8 bytes per entry
+inline std::vector<uint64_t> build_heap_table_dp(const uint64_t* table, uint32_t L, uint64_t q) {
+    const uint32_t N = 1u << L;
+    std::vector<uint64_t> heap(N);
+    heap[0] = 0;
+    for (uint32_t s = 0; s < L; ++s) {
+        for (uint32_t b = 0; b < (1u << s); ++b) {
+            const uint32_t e = bitrev_c(b, (int)s) << (L - 1 - s);
+            heap[(1u << s) + b] = double_to_bits((double)(table[e] % q));
+        }
+    }
+    return heap;
+}
+
 }  // namespace fheb

@@ -19,7 +19,7 @@ struct NttPlan {
     bool unit_first = false;
     ModQ mod{};
     Tw ninv{};
-    Tw* d_fwd = nullptr;  // heap-ordered (w, w') pairs, N entries
+    Tw* d_fwd = nullptr;  // heap-ordered twiddles, N entries: (w, w') pairs, or doubles when mod.dp
     Tw* d_inv = nullptr;
 };
 

@@ -5,8 +5,8 @@
 // barriers.  Running the threads of one phase sequentially on the host is therefore
 // equivalent.  This program drives them the way boot_kernel.cuh does (rotation table, initial
 // monomial rotation, n steps) and checks the results word-for-word against the C oracle
-// (oracle/fhe_oracle.c, pinned to the reference) for several shapes and both range-tracking
-// modes.  It validates the algebra (pre-transformed key, transform-domain accumulation, fused
+// (oracle/fhe_oracle.c, pinned to the reference) for several shapes and both arithmetic modes
+// (integer pipe for q < 2^62, FP64 pipe for q < 2^42).  It validates the algebra (pre-transformed key, transform-domain accumulation, fused
 // passes, digit extraction, rotations); it says nothing about launch geometry or memory spaces.
 #include <cstdio>
 #include <cstdlib>
@@ -20,15 +20,23 @@
 
 using namespace fheb;
 
-template <int L, bool LAZY, int KP1, int PH = 0>
+static std::vector<uint64_t> heap_words(const uint64_t* table, uint32_t L, uint64_t q, bool dp) {
+    if (dp) return build_heap_table_dp(table, L, q);
+    const std::vector<Tw> h = build_heap_table(table, L, q);
+    std::vector<uint64_t> w(h.size() * 2);
+    std::memcpy(w.data(), h.data(), w.size() * 8);
+    return w;
+}
+
+template <int L, bool DP, int KP1, int PH = 0>
 static void run_step(uint32_t threads, const BootStep& s, const Tw* twf, const Tw* twi, const Tw& ninv, const ModQ& m) {
     if constexpr (PH < boot_phases<L>()) {
-        for (uint32_t tid = 0; tid < threads; ++tid) boot_phase<L, LAZY, KP1, PH>(tid, threads, s, twf, twi, ninv, m);
-        run_step<L, LAZY, KP1, PH + 1>(threads, s, twf, twi, ninv, m);
+        for (uint32_t tid = 0; tid < threads; ++tid) boot_phase<L, DP, KP1, PH>(tid, threads, s, twf, twi, ninv, m);
+        run_step<L, DP, KP1, PH + 1>(threads, s, twf, twi, ninv, m);
     }
 }
 
-template <int L, bool LAZY, int KP1>
+template <int L, bool DP, int KP1>
 static int check(uint32_t threads, uint32_t levels, uint32_t base_log, uint32_t n, uint64_t q, bool raw_inputs) {
     const uint32_t N = 1u << L, k = KP1 - 1, rows = KP1 * levels;
     std::vector<uint64_t> fwd(N), inv(N);
@@ -38,20 +46,23 @@ static int check(uint32_t threads, uint32_t levels, uint32_t base_log, uint32_t 
         return 1;
     }
     const ModQ m = make_modq(q);
-    if ((m.lazy != 0) != LAZY) {
+    if ((m.dp != 0) != DP) {
         std::printf("mode mismatch for q=%llu\n", (unsigned long long)q);
         return 1;
     }
-    const std::vector<Tw> hf = build_heap_table(fwd.data(), L, q), hi = build_heap_table(inv.data(), L, q);
-    const Tw ninv{sc[2], shoup_companion(sc[2], q)};
+    const std::vector<uint64_t> hfw = heap_words(fwd.data(), L, q, DP), hiw = heap_words(inv.data(), L, q, DP);
+    const Tw* hf = reinterpret_cast<const Tw*>(hfw.data());
+    const Tw* hi = reinterpret_cast<const Tw*>(hiw.data());
+    const Tw ninv = DP ? Tw{double_to_bits((double)sc[2]), 0} : Tw{sc[2], shoup_companion(sc[2], q)};
     orc_boot_params p{N, k, n, base_log, levels, q, 4, fwd.data(), inv.data(), sc[2]};
 
     std::mt19937_64 rng(77 * L + KP1 + levels);
     const size_t gw = (size_t)KP1 * N, ggsw_w = (size_t)rows * KP1 * N;
     std::vector<uint64_t> bsk((size_t)n * ggsw_w);
     for (auto& v : bsk) v = rng() % q;
-    // key upload: T(poly) in position order + Shoup companions (what bsk_pack_kernel does)
-    std::vector<Tw> g(bsk.size());
+    // key upload: T(poly) in position order + Shoup companions, or doubles in DP mode (what bsk_pack_kernel does)
+    constexpr size_t GE = DP ? 1 : 2;  // words per key element
+    std::vector<uint64_t> g(bsk.size() * GE);
     {
         std::vector<uint64_t> t(N);
         for (size_t poly = 0; poly < bsk.size() / N; ++poly) {
@@ -59,7 +70,8 @@ static int check(uint32_t threads, uint32_t levels, uint32_t base_log, uint32_t 
             orc_forward_ntt(t.data(), N, q, fwd.data());
             for (uint32_t pos = 0; pos < N; ++pos) {
                 const uint64_t w = t[bitrev_c(pos, L)];
-                g[poly * N + pos] = Tw{w, shoup_companion(w, q)};
+                if (DP) g[poly * N + pos] = double_to_bits((double)w);
+                else { g[2 * (poly * N + pos)] = w; g[2 * (poly * N + pos) + 1] = shoup_companion(w, q); }
             }
         }
     }
@@ -76,21 +88,21 @@ static int check(uint32_t threads, uint32_t levels, uint32_t base_log, uint32_t 
     for (auto& v : ct0) v = raw_inputs ? rng() : rng() % q;
     for (auto& v : ct1) v = raw_inputs ? rng() : rng() % q;
     const size_t gi = 1 % n;
-    s.ggsw = g.data() + gi * ggsw_w;
+    s.ggsw = reinterpret_cast<const Tw*>(g.data() + gi * ggsw_w * GE);
     s.gout = out.data();
     s.rot = 0;
     diff = ct0;
     s.diff = diff.data();
     s.add_acc = 0;
-    run_step<L, LAZY, KP1>(threads, s, hf.data(), hi.data(), ninv, m);
+    run_step<L, DP, KP1>(threads, s, hf, hi, ninv, m);
     orc_external_product(&p, ct0.data(), bsk.data() + gi * ggsw_w, ref.data());
-    if (out != ref) { std::printf("L=%d lazy=%d kp1=%d levels=%u: EXTERNAL PRODUCT mismatch\n", L, LAZY, KP1, levels); ++bad; }
+    if (out != ref) { std::printf("L=%d dp=%d kp1=%d levels=%u: EXTERNAL PRODUCT mismatch\n", L, DP, KP1, levels); ++bad; }
     acc = ct0;
     for (size_t i = 0; i < gw; ++i) diff[i] = submod_canon(canon_any(ct1[i], m), canon_any(ct0[i], m), q);
     s.add_acc = 1;
-    run_step<L, LAZY, KP1>(threads, s, hf.data(), hi.data(), ninv, m);
+    run_step<L, DP, KP1>(threads, s, hf, hi, ninv, m);
     orc_cmux(&p, bsk.data() + gi * ggsw_w, ct0.data(), ct1.data(), ref.data());
-    if (out != ref) { std::printf("L=%d lazy=%d kp1=%d levels=%u: CMUX mismatch\n", L, LAZY, KP1, levels); ++bad; }
+    if (out != ref) { std::printf("L=%d dp=%d kp1=%d levels=%u: CMUX mismatch\n", L, DP, KP1, levels); ++bad; }
 
     // --- blind rotation
     for (int trial = 0; trial < 2; ++trial) {
@@ -110,10 +122,10 @@ static int check(uint32_t threads, uint32_t levels, uint32_t base_log, uint32_t 
             const uint32_t rot = lwe_rotation(lwe[i], false, N, q);
             if (rot == 0) continue;
             s.rot = rot;
-            s.ggsw = g.data() + (size_t)i * ggsw_w;
-            run_step<L, LAZY, KP1>(threads, s, hf.data(), hi.data(), ninv, m);
+            s.ggsw = reinterpret_cast<const Tw*>(g.data() + (size_t)i * ggsw_w * GE);
+            run_step<L, DP, KP1>(threads, s, hf, hi, ninv, m);
         }
-        if (acc != ref) { std::printf("L=%d lazy=%d kp1=%d levels=%u trial=%d: BLIND ROTATE mismatch\n", L, LAZY, KP1, levels, trial); ++bad; }
+        if (acc != ref) { std::printf("L=%d dp=%d kp1=%d levels=%u trial=%d: BLIND ROTATE mismatch\n", L, DP, KP1, levels, trial); ++bad; }
         // sample extraction
         std::vector<uint64_t> ext((size_t)k * N + 1), ext_ref((size_t)k * N + 1);
         orc_sample_extract(ref.data(), k, N, q, ext_ref.data());

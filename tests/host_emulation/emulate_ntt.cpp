@@ -7,7 +7,7 @@
 // device execution.  This program runs them that way for every supported degree and both
 // range-tracking modes and checks the results word-for-word against the C oracle
 // (oracle/fhe_oracle.c, which is pinned to the reference).  It validates index math,
-// twiddle ordering, swizzling, bit-reversed I/O and the lazy-range bookkeeping; it says
+// twiddle ordering, swizzling, bit-reversed I/O and the range bookkeeping of both arithmetic modes (integer / FP64); it says
 // nothing about device-only code (launch geometry, PTX, memory spaces).
 //
 // Build + run: see tests/test_host_emulation.py.
@@ -22,34 +22,43 @@
 
 using namespace fheb;
 
-template <int L, bool LAZY, int PASS>
+template <int L, bool DP, int PASS>
 static void run_fwd(uint32_t threads, uint32_t polys, const uint64_t* gin, uint64_t* gout, uint64_t* smem,
                     const Tw* tw, const ModQ& m) {
     constexpr int P = Plan<L>::P;
     if constexpr (PASS < P) {
         for (uint32_t tid = 0; tid < threads; ++tid) {
-            if constexpr (P == 1) fwd_pass<L, LAZY, PASS, IO_GLOBAL, IO_GLOBAL>(tid, threads, polys, gin, gout, smem, tw, m);
-            else if constexpr (PASS == 0) fwd_pass<L, LAZY, PASS, IO_GLOBAL, IO_SMEM>(tid, threads, polys, gin, gout, smem, tw, m);
-            else if constexpr (PASS == P - 1) fwd_pass<L, LAZY, PASS, IO_SMEM, IO_GLOBAL>(tid, threads, polys, gin, gout, smem, tw, m);
-            else fwd_pass<L, LAZY, PASS, IO_SMEM, IO_SMEM>(tid, threads, polys, gin, gout, smem, tw, m);
+            if constexpr (P == 1) fwd_pass<L, DP, PASS, IO_GLOBAL, IO_GLOBAL>(tid, threads, polys, gin, gout, smem, tw, m);
+            else if constexpr (PASS == 0) fwd_pass<L, DP, PASS, IO_GLOBAL, IO_SMEM>(tid, threads, polys, gin, gout, smem, tw, m);
+            else if constexpr (PASS == P - 1) fwd_pass<L, DP, PASS, IO_SMEM, IO_GLOBAL>(tid, threads, polys, gin, gout, smem, tw, m);
+            else fwd_pass<L, DP, PASS, IO_SMEM, IO_SMEM>(tid, threads, polys, gin, gout, smem, tw, m);
         }
-        run_fwd<L, LAZY, PASS + 1>(threads, polys, gin, gout, smem, tw, m);
+        run_fwd<L, DP, PASS + 1>(threads, polys, gin, gout, smem, tw, m);
     }
 }
 
-template <int L, bool LAZY, int PASS>
+template <int L, bool DP, int PASS>
 static void run_inv(uint32_t threads, uint32_t polys, const uint64_t* gin, uint64_t* gout, uint64_t* smem,
                     const Tw* tw, const Tw& ninv, const ModQ& m) {
     constexpr int P = Plan<L>::P;
     if constexpr (PASS >= 0) {
         for (uint32_t tid = 0; tid < threads; ++tid) {
-            if constexpr (P == 1) inv_pass<L, LAZY, PASS, IO_GLOBAL, IO_GLOBAL>(tid, threads, polys, gin, gout, smem, tw, ninv, m);
-            else if constexpr (PASS == P - 1) inv_pass<L, LAZY, PASS, IO_GLOBAL, IO_SMEM>(tid, threads, polys, gin, gout, smem, tw, ninv, m);
-            else if constexpr (PASS == 0) inv_pass<L, LAZY, PASS, IO_SMEM, IO_GLOBAL>(tid, threads, polys, gin, gout, smem, tw, ninv, m);
-            else inv_pass<L, LAZY, PASS, IO_SMEM, IO_SMEM>(tid, threads, polys, gin, gout, smem, tw, ninv, m);
+            if constexpr (P == 1) inv_pass<L, DP, PASS, IO_GLOBAL, IO_GLOBAL>(tid, threads, polys, gin, gout, smem, tw, ninv, m);
+            else if constexpr (PASS == P - 1) inv_pass<L, DP, PASS, IO_GLOBAL, IO_SMEM>(tid, threads, polys, gin, gout, smem, tw, ninv, m);
+            else if constexpr (PASS == 0) inv_pass<L, DP, PASS, IO_SMEM, IO_GLOBAL>(tid, threads, polys, gin, gout, smem, tw, ninv, m);
+            else inv_pass<L, DP, PASS, IO_SMEM, IO_SMEM>(tid, threads, polys, gin, gout, smem, tw, ninv, m);
         }
-        run_inv<L, LAZY, PASS - 1>(threads, polys, gin, gout, smem, tw, ninv, m);
+        run_inv<L, DP, PASS - 1>(threads, polys, gin, gout, smem, tw, ninv, m);
     }
+}
+
+// the device twiddle heap as raw words: (w, w') pairs, or one double per entry in DP mode
+static std::vector<uint64_t> heap_words(const uint64_t* table, uint32_t L, uint64_t q, bool dp) {
+    if (dp) return build_heap_table_dp(table, L, q);
+    const std::vector<Tw> h = build_heap_table(table, L, q);
+    std::vector<uint64_t> w(h.size() * 2);
+    std::memcpy(w.data(), h.data(), w.size() * 8);
+    return w;
 }
 
 static uint64_t pick_prime(int L, bool lazy) {
@@ -58,11 +67,11 @@ static uint64_t pick_prime(int L, bool lazy) {
     return 4611686018326724609ULL;  // 62 bit
 }
 
-template <int L, bool LAZY>
+template <int L, bool DP>
 static int check(uint32_t threads, uint32_t polys) {
     const uint32_t N = 1u << L;
-    uint64_t q = pick_prime(L, LAZY);
-    if (L <= 3 && !LAZY) q = 4611686018326724609ULL;
+    uint64_t q = pick_prime(L, DP);
+    if (L <= 3 && !DP) q = 4611686018326724609ULL;
     std::vector<uint64_t> fwd(N), inv(N);
     uint64_t sc[3];
     if (orc_precompute_twiddles(N, q, fwd.data(), inv.data(), sc) != 0) {
@@ -70,12 +79,14 @@ static int check(uint32_t threads, uint32_t polys) {
         return 1;
     }
     ModQ m = make_modq(q);
-    if ((m.lazy != 0) != LAZY) {
+    if ((m.dp != 0) != DP) {
         std::printf("L=%d: mode mismatch\n", L);
         return 1;
     }
-    std::vector<Tw> hf = build_heap_table(fwd.data(), L, q), hi = build_heap_table(inv.data(), L, q);
-    Tw ninv{sc[2], shoup_companion(sc[2], q)};
+    const std::vector<uint64_t> hfw = heap_words(fwd.data(), L, q, DP), hiw = heap_words(inv.data(), L, q, DP);
+    const Tw* hf = reinterpret_cast<const Tw*>(hfw.data());
+    const Tw* hi = reinterpret_cast<const Tw*>(hiw.data());
+    const Tw ninv = DP ? Tw{double_to_bits((double)sc[2]), 0} : Tw{sc[2], shoup_companion(sc[2], q)};
     std::mt19937_64 rng(1234 + L);
     std::vector<uint64_t> x((size_t)polys * N), ref, got((size_t)polys * N), smem((size_t)polys * N);
     int bad = 0;
@@ -84,16 +95,16 @@ static int check(uint32_t threads, uint32_t polys) {
         ref = x;
         orc_forward_ntt_batch(ref.data(), polys, N, q, fwd.data());
         std::fill(smem.begin(), smem.end(), 0xDEADBEEFDEADBEEFULL);
-        run_fwd<L, LAZY, 0>(threads, polys, x.data(), got.data(), smem.data(), hf.data(), m);
+        run_fwd<L, DP, 0>(threads, polys, x.data(), got.data(), smem.data(), hf, m);
         if (std::memcmp(ref.data(), got.data(), got.size() * 8) != 0) {
-            std::printf("L=%d lazy=%d variant=%d threads=%u polys=%u: FORWARD mismatch\n", L, LAZY, variant, threads, polys);
+            std::printf("L=%d dp=%d variant=%d threads=%u polys=%u: FORWARD mismatch\n", L, DP, variant, threads, polys);
             ++bad;
         }
         ref = x;
         orc_inverse_ntt_batch(ref.data(), polys, N, q, inv.data(), sc[2]);
-        run_inv<L, LAZY, Plan<L>::P - 1>(threads, polys, x.data(), got.data(), smem.data(), hi.data(), ninv, m);
+        run_inv<L, DP, Plan<L>::P - 1>(threads, polys, x.data(), got.data(), smem.data(), hi, ninv, m);
         if (std::memcmp(ref.data(), got.data(), got.size() * 8) != 0) {
-            std::printf("L=%d lazy=%d variant=%d threads=%u polys=%u: INVERSE mismatch\n", L, LAZY, variant, threads, polys);
+            std::printf("L=%d dp=%d variant=%d threads=%u polys=%u: INVERSE mismatch\n", L, DP, variant, threads, polys);
             ++bad;
         }
     }
