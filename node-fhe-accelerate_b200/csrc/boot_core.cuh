@@ -23,7 +23,7 @@ struct BootStep {          // block-uniform description of one step
     uint64_t* acc;         // smem [KP1][N], natural index: ct0 / running accumulator
     uint64_t* work;        // smem [max(rows, KP1)][N], swizzled index
     const uint64_t* diff;  // smem [KP1][N] natural index: precomputed ct1 - ct0 (or the GLWE itself); null = rotate acc
-    const Tw* ggsw;        // global [rows][KP1][N], position order: (value, Shoup companion) pairs, or doubles in DP mode
+    const Tw* ggsw;        // global [rows][KP1][E][N/E] (position u*E + e at [e][u], E = width of the last pass): (value, Shoup companion) pairs, or doubles in DP mode
     uint64_t* gout;        // when non-null the final pass stores here ([KP1][N], global) instead of acc
     uint32_t rot;          // normalised rotation in [0, 2N) (used when diff == null)
     uint32_t levels;
@@ -94,7 +94,7 @@ FHEB_HD void boot_first_pass(uint32_t tid, uint32_t nthreads, const BootStep& s,
                 const uint64_t g = gadget_digit(d[e], shift, mask, base, m);
                 x[e] = DP ? double_to_bits(dp_from_uint(g)) : g;
             }
-            fwd_stages<R, 1, DP, true>(x, tw, 1u, m);
+            fwd_stages<R, 0, 1, DP, true>(x, tw, 0u, m);
             uint64_t* dst = s.work + (size_t)(c * s.levels + l) * N;
 #pragma unroll
             for (int e = 0; e < E; ++e) dst[pb ^ swz((uint32_t)e << EB)] = x[e];
@@ -119,7 +119,7 @@ FHEB_HD void boot_mid_pass(uint32_t tid, uint32_t nthreads, const BootStep& s, c
     for (uint32_t u = tid; u < ITEMS; u += nthreads) {
         const uint32_t base = u << R;
         const uint32_t pb = swz(base);
-        const uint32_t T0 = (1u << S0) + (base >> (L - S0));
+        const uint32_t TB = plan_tw_offset<L, PASS>() + (base >> (L - S0));
         uint64_t out[KP1][E];
 #pragma unroll
         for (int j = 0; j < KP1; ++j)
@@ -130,13 +130,14 @@ FHEB_HD void boot_mid_pass(uint32_t tid, uint32_t nthreads, const BootStep& s, c
             uint64_t x[E];
 #pragma unroll
             for (int e = 0; e < E; ++e) x[e] = src[pb ^ swz((uint32_t)e)];
-            fwd_stages<R, KIN, DP, false>(x, twf, T0, m);
-            const uint32_t g0 = row * (uint32_t)KP1 * N + base;  // element index inside this GGSW
+            fwd_stages<R, S0, KIN, DP, false>(x, twf, TB, m);
+            // key element (row, j, position u*E + e) lives at ((row*KP1 + j)*E + e)*ITEMS + u: lanes
+            // (consecutive u) read consecutive entries with every load
 #pragma unroll
             for (int j = 0; j < KP1; ++j) {
 #pragma unroll
                 for (int e = 0; e < E; ++e) {
-                    const Tw w = load_tw<DP>(s.ggsw, g0 + (uint32_t)j * N + (uint32_t)e);
+                    const Tw w = load_tw<DP>(s.ggsw, ((row * (uint32_t)KP1 + (uint32_t)j) * E + (uint32_t)e) * ITEMS + u);
                     if constexpr (DP) {  // |t| < q: plain sums (rows <= CAP_DP checked at key upload)
                         const double t = dp_mulmod(bits_to_double(x[e]), bits_to_double(w.w), m);
                         out[j][e] = double_to_bits(dp_add(bits_to_double(out[j][e]), t));
@@ -152,7 +153,7 @@ FHEB_HD void boot_mid_pass(uint32_t tid, uint32_t nthreads, const BootStep& s, c
 #pragma unroll
                 for (int e = 0; e < E; ++e) out[j][e] = double_to_bits(dp_reduce(bits_to_double(out[j][e]), m));
             }
-            inv_stages<R, DP ? 1 : 2, DP, false>(out[j], twi, T0, m);
+            inv_stages<R, S0, DP ? 1 : 2, DP, false>(out[j], twi, TB, m);
             uint64_t* dst = s.work + (size_t)j * N;
 #pragma unroll
             for (int e = 0; e < E; ++e) dst[pb ^ swz((uint32_t)e)] = out[j][e];
@@ -178,7 +179,7 @@ FHEB_HD void boot_final_pass(uint32_t tid, uint32_t nthreads, const BootStep& s,
         uint64_t x[E];
 #pragma unroll
         for (int e = 0; e < E; ++e) x[e] = src[pb ^ swz((uint32_t)e << EB)];
-        inv_stages<R, KIN, DP, true>(x, twi, 1u, m);
+        inv_stages<R, 0, KIN, DP, true>(x, twi, 0u, m);
         const uint64_t* a = s.acc + (size_t)c * N;
         uint64_t* dst = (s.gout ? s.gout : s.acc) + (size_t)c * N;
 #pragma unroll

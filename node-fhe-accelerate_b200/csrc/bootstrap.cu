@@ -6,6 +6,7 @@
 // fheb_sample_extract_batch, fheb_key_switch_batch, fheb_bootstrap_batch, fheb_make_test_poly.
 #include "boot_kernel.cuh"
 #include "elementwise.hpp"
+#include "ntt_plan.hpp"
 #include "plan.hpp"
 
 namespace fheb {
@@ -20,15 +21,19 @@ struct BootKey {
 };
 
 // ---- key preparation --------------------------------------------------------------------
-// in: transforms in the reference's output order (index p of the permuted array); out: the same
-// values in position order (index bitrev(p)) with their Shoup companions floor(w * 2^64 / q).
+// in: transforms in the reference's output order (index p of the permuted array); out: the value of
+// position u * 2^rlast + e (i.e. index bitrev(position)) at [e][u] of its polynomial, with its Shoup
+// companion floor(w * 2^64 / q), or as a double in DP mode.
 __global__ void __launch_bounds__(256) bsk_pack_kernel(const uint64_t* __restrict__ y, Tw* __restrict__ g, size_t words,
-                                                       uint32_t logn, uint64_t q, int dp) {
+                                                       uint32_t logn, uint32_t rlast, uint64_t q, int dp) {
     const size_t stride = (size_t)gridDim.x * blockDim.x;
     const uint32_t nmask = (1u << logn) - 1u;
+    const uint32_t items_log = logn - rlast;  // out index within a polynomial = e * (N >> rlast) + u  <->  position u * 2^rlast + e
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < words; i += stride) {
-        const uint32_t pos = (uint32_t)i & nmask;
-        const size_t src = (i - pos) + bitrev_rt(pos, (int)logn);
+        const uint32_t rem = (uint32_t)i & nmask;
+        const uint32_t e = rem >> items_log, u = rem & ((1u << items_log) - 1u);
+        const uint32_t pos = (u << rlast) | e;
+        const size_t src = (i - rem) + bitrev_rt(pos, (int)logn);
         const uint64_t w = y[src];
         if (dp) {  // FP64 mode: the value as a double, 8 bytes per entry
             reinterpret_cast<uint64_t*>(g)[i] = double_to_bits((double)w);
@@ -218,7 +223,7 @@ int fheb_boot_key_create(const fheb_ntt_plan* plan, const fheb_boot_params* para
         // T(row polynomial) once, here, instead of on every external product (bootstrap_engine.cpp:478-487)
         if (rc == FHEB_OK) rc = ntt_forward_device(p, in.ptr<const uint64_t>(), tmp, polys, s);
         if (rc == FHEB_OK) {
-            bsk_pack_kernel<<<stream_grid(words, 256, 8), 256, 0, s>>>(tmp, key->d_bsk, words, p->logn, p->modulus, (int)p->mod.dp);
+            bsk_pack_kernel<<<stream_grid(words, 256, 8), 256, 0, s>>>(tmp, key->d_bsk, words, p->logn, last_pass_width(p->logn), p->modulus, (int)p->mod.dp);
             if (cudaGetLastError() != cudaSuccess) rc = set_error(FHEB_ERR_NATIVE, "bsk_pack_kernel launch failed");
             count_launch();
         }

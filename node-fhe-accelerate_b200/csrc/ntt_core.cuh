@@ -149,6 +149,14 @@ FHEB_HD void inv_bfly(uint64_t& A, uint64_t& B, const Tw& w, const ModQ& m) {
     }
 }
 
+// Device twiddle table order.  Stage s = S0 + a of a pass uses one twiddle per block of N/2^s
+// positions; block (blk << a) + g belongs to the item whose stage-S0 block is blk (g < 2^a).  The
+// table is stored pass by pass as [a][g][blk], so that the lanes of a warp - consecutive items,
+// i.e. consecutive blk in the late passes - read consecutive entries with every load
+// instruction (a plain heap order makes each load stride 2^a entries).
+template <int S0>
+FHEB_HD constexpr uint32_t tw_index(int a, int g) { return (uint32_t)(((1 << a) - 1) + g) << S0; }
+
 // Twiddle tables: integer mode = (value, Shoup companion) pairs, 16 bytes; DP mode = one double, 8 bytes.
 template <bool DP>
 FHEB_HD Tw load_tw(const Tw* __restrict__ tw, uint32_t idx) {
@@ -174,9 +182,10 @@ FHEB_HD Tw load_tw(const Tw* __restrict__ tw, uint32_t idx) {
 }
 
 // R forward stages on 2^R register-resident values; element bit (R-1) is the highest
-// position bit of the pass.  T0 = heap index of the first stage's twiddle for this block.
-template <int R, int K, bool DP, bool UNITFIRST, int A = 0>
-FHEB_HD void fwd_stages(uint64_t (&x)[1 << R], const Tw* __restrict__ tw, uint32_t T0, const ModQ& m) {
+// position bit of the pass.  The pass starts at stage S0; TB = table offset of the pass + the index
+// of this item's block among the 2^S0 blocks of stage S0 (see tw_index below).
+template <int R, int S0, int K, bool DP, bool UNITFIRST, int A = 0>
+FHEB_HD void fwd_stages(uint64_t (&x)[1 << R], const Tw* __restrict__ tw, uint32_t TB, const ModQ& m) {
     if constexpr (A < R) {
         constexpr int half = 1 << (R - 1 - A);
 #pragma unroll
@@ -186,18 +195,18 @@ FHEB_HD void fwd_stages(uint64_t (&x)[1 << R], const Tw* __restrict__ tw, uint32
 #pragma unroll
                 for (int j = 0; j < half; ++j) fwd_bfly<K, DP, true>(x[g * 2 * half + j], x[g * 2 * half + j + half], dummy, m);
             } else {
-                const Tw w = load_tw<DP>(tw, (T0 << A) + g);
+                const Tw w = load_tw<DP>(tw, TB + tw_index<S0>(A, g));
 #pragma unroll
                 for (int j = 0; j < half; ++j) fwd_bfly<K, DP, false>(x[g * 2 * half + j], x[g * 2 * half + j + half], w, m);
             }
         }
-        fwd_stages<R, fwd_next_k(K, UNITFIRST, !(UNITFIRST && A == 0), DP), DP, UNITFIRST, A + 1>(x, tw, T0, m);
+        fwd_stages<R, S0, fwd_next_k(K, UNITFIRST, !(UNITFIRST && A == 0), DP), DP, UNITFIRST, A + 1>(x, tw, TB, m);
     }
 }
 
 // R inverse stages, highest stage of the pass first (element bit 0 first).
-template <int R, int K, bool DP, bool UNITFIRST, int A = R - 1>
-FHEB_HD void inv_stages(uint64_t (&x)[1 << R], const Tw* __restrict__ tw, uint32_t T0, const ModQ& m) {
+template <int R, int S0, int K, bool DP, bool UNITFIRST, int A = R - 1>
+FHEB_HD void inv_stages(uint64_t (&x)[1 << R], const Tw* __restrict__ tw, uint32_t TB, const ModQ& m) {
     if constexpr (A >= 0) {
         constexpr int half = 1 << (R - 1 - A);
 #pragma unroll
@@ -207,12 +216,12 @@ FHEB_HD void inv_stages(uint64_t (&x)[1 << R], const Tw* __restrict__ tw, uint32
 #pragma unroll
                 for (int j = 0; j < half; ++j) inv_bfly<K, DP, true>(x[g * 2 * half + j], x[g * 2 * half + j + half], dummy, m);
             } else {
-                const Tw w = load_tw<DP>(tw, (T0 << A) + g);
+                const Tw w = load_tw<DP>(tw, TB + tw_index<S0>(A, g));
 #pragma unroll
                 for (int j = 0; j < half; ++j) inv_bfly<K, DP, false>(x[g * 2 * half + j], x[g * 2 * half + j + half], w, m);
             }
         }
-        inv_stages<R, inv_next_k(K, DP), DP, UNITFIRST, A - 1>(x, tw, T0, m);
+        inv_stages<R, S0, inv_next_k(K, DP), DP, UNITFIRST, A - 1>(x, tw, TB, m);
     }
 }
 
@@ -280,6 +289,32 @@ constexpr int plan_s0() {  // first stage of pass PASS
     for (int p = 0; p < PASS; ++p) s += Plan<L>::R[p];
     return s;
 }
+template <int L, int PASS>
+constexpr uint32_t plan_tw_offset() {  // first table entry of pass PASS: sum over earlier passes of (2^R - 1) * 2^S0
+    uint32_t off = 0;
+    int s = 0;
+    for (int p = 0; p < PASS; ++p) {
+        off += (uint32_t)((1 << Plan<L>::R[p]) - 1) << s;
+        s += Plan<L>::R[p];
+    }
+    return off;
+}
+// runtime view of the plan for the host-side table builders
+inline void plan_runtime(int L, int& P, int (&R)[4]) {
+    P = 0;
+    R[0] = R[1] = R[2] = R[3] = 0;
+    switch (L) {
+#define FHEB_PLAN_RT(L_)                                          \
+    case L_:                                                      \
+        P = Plan<L_>::P;                                          \
+        for (int i = 0; i < 4; ++i) R[i] = Plan<L_>::R[i];        \
+        break;
+        FHEB_PLAN_RT(2) FHEB_PLAN_RT(3) FHEB_PLAN_RT(4) FHEB_PLAN_RT(5) FHEB_PLAN_RT(6) FHEB_PLAN_RT(7) FHEB_PLAN_RT(8)
+        FHEB_PLAN_RT(9) FHEB_PLAN_RT(10) FHEB_PLAN_RT(11) FHEB_PLAN_RT(12) FHEB_PLAN_RT(13) FHEB_PLAN_RT(14)
+#undef FHEB_PLAN_RT
+    }
+}
+
 template <int L, bool DP, int PASS>
 constexpr int plan_fwd_kin() {  // bound on values entering forward pass PASS (inputs canonical)
     int K = 1;
@@ -346,8 +381,8 @@ FHEB_HD void fwd_pass(uint32_t tid, uint32_t nthreads, uint32_t polys, const uin
 #pragma unroll
             for (int c = 0; c < E; ++c) x[c] = src[pb ^ swz((uint32_t)c << EB)];
         }
-        const uint32_t T0 = (1u << S0) + (base >> (L - S0));
-        fwd_stages<R, KIN, DP, PASS == 0>(x, tw, T0, m);
+        const uint32_t TB = plan_tw_offset<L, PASS>() + (S0 ? (base >> (L - S0)) : 0u);
+        fwd_stages<R, S0, KIN, DP, PASS == 0>(x, tw, TB, m);
         if (OUT == IO_GLOBAL) {
             uint64_t* dst = gout + (size_t)poly * N;
 #pragma unroll
@@ -409,8 +444,8 @@ FHEB_HD void polymul_mid_pass(uint32_t tid, uint32_t nthreads, uint32_t polys, c
 #pragma unroll
             for (int c = 0; c < E; ++c) x[c] = src[pb ^ swz((uint32_t)c)];
         }
-        const uint32_t T0 = (1u << S0) + (base >> (L - S0));
-        fwd_stages<R, KIN, DP, PASS == 0>(x, twf, T0, m);
+        const uint32_t TB = plan_tw_offset<L, PASS>() + (S0 ? (base >> (L - S0)) : 0u);
+        fwd_stages<R, S0, KIN, DP, PASS == 0>(x, twf, TB, m);
         const uint64_t* sa = stash + (size_t)poly * N;
 #pragma unroll
         for (int c = 0; c < E; ++c) {
@@ -418,7 +453,7 @@ FHEB_HD void polymul_mid_pass(uint32_t tid, uint32_t nthreads, uint32_t polys, c
             if constexpr (DP) x[c] = double_to_bits(dp_mulmod(bits_to_double(av), bits_to_double(x[c]), m));
             else x[c] = mulmod(av, canon_k<KOUT>(x[c], m), m);
         }
-        inv_stages<R, 1, DP, PASS == 0>(x, twi, T0, m);
+        inv_stages<R, S0, 1, DP, PASS == 0>(x, twi, TB, m);
         if (OUT == IO_GLOBAL) {
             uint64_t* dst = gout + (size_t)poly * N;
 #pragma unroll
@@ -471,8 +506,8 @@ FHEB_HD void inv_pass(uint32_t tid, uint32_t nthreads, uint32_t polys, const uin
 #pragma unroll
             for (int c = 0; c < E; ++c) x[c] = src[pb ^ swz((uint32_t)c << EB)];
         }
-        const uint32_t T0 = (1u << S0) + (base >> (L - S0));
-        inv_stages<R, KIN, DP, PASS == 0>(x, tw, T0, m);
+        const uint32_t TB = plan_tw_offset<L, PASS>() + (S0 ? (base >> (L - S0)) : 0u);
+        inv_stages<R, S0, KIN, DP, PASS == 0>(x, tw, TB, m);
         if (OUT == IO_GLOBAL) {
             uint64_t* dst = gout + (size_t)poly * N;
 #pragma unroll

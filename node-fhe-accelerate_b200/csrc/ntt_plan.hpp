@@ -4,8 +4,8 @@
 // (reference cpp/src/ntt_processor.cpp:168-208): table[i] = root^i mod q, i < N, natural
 // exponent order, plus inv_n.  The kernels never index them as the reference does
 // (`table[j * (n / group_size)]`, ntt_processor.cpp:286); instead the entries the network
-// actually touches (only exponents below N/2) are re-ordered into the block-ordered heap
-// described in ntt_core.cuh and paired with their Shoup companions.
+// actually touches (only exponents below N/2) are re-ordered pass by pass as described in
+// ntt_core.cuh (tw_index) and paired with their Shoup companions.
 #pragma once
 #include <cstdint>
 #include <vector>
@@ -21,33 +21,49 @@ inline uint32_t log2_exact(uint32_t n) {
     return l;
 }
 
-// heap[2^s + b] = table[bitrev_s(b) << (L-1-s)]  (entry 0 unused)
-inline std::vector<Tw> build_heap_table(const uint64_t* table, uint32_t L, uint64_t q) {
-    const uint32_t N = 1u << L;
-    std::vector<Tw> heap(N);
-    heap[0] = Tw{0, 0};
-    for (uint32_t s = 0; s < L; ++s) {
-        for (uint32_t b = 0; b < (1u << s); ++b) {
-            const uint32_t e = bitrev_c(b, (int)s) << (L - 1 - s);
-            const uint64_t w = table[e] % q;
-            heap[(1u << s) + b] = Tw{w, shoup_companion(w, q)};
+// Entry order (see tw_index in ntt_core.cuh): pass by pass, [a][g][blk]; the twiddle of block
+// b = (blk << a) + g at stage s = S0 + a is table[bitrev_s(b) << (L-1-s)].  N - 1 entries, padded to N.
+template <class Put>
+inline void for_each_twiddle(uint32_t L, Put put) {
+    int P, R[4];
+    plan_runtime((int)L, P, R);
+    uint32_t idx = 0;
+    int s0 = 0;
+    for (int p = 0; p < P; ++p) {
+        for (int a = 0; a < R[p]; ++a) {
+            const int s = s0 + a;
+            for (uint32_t g = 0; g < (1u << a); ++g)
+                for (uint32_t blk = 0; blk < (1u << s0); ++blk) {
+                    const uint32_t b = (blk << a) + g;
+                    put(idx + ((((1u << a) - 1u) + g) << s0) + blk, bitrev_c(b, s) << (L - 1 - s));
+                }
         }
+        idx += ((1u << R[p]) - 1u) << s0;
+        s0 += R[p];
     }
-    return heap;
 }
 
-// DP mode (q < 2^42): the same heap holding each twiddle as a double, 8 bytes per entry
+inline std::vector<Tw> build_heap_table(const uint64_t* table, uint32_t L, uint64_t q) {
+    std::vector<Tw> out((size_t)1 << L, Tw{0, 0});
+    for_each_twiddle(L, [&](uint32_t at, uint32_t e) {
+        const uint64_t w = table[e] % q;
+        out[at] = Tw{w, shoup_companion(w, q)};
+    });
+    return out;
+}
+
+// DP mode (q < 2^42): each twiddle as a double, 8 bytes per entry
 inline std::vector<uint64_t> build_heap_table_dp(const uint64_t* table, uint32_t L, uint64_t q) {
-    const uint32_t N = 1u << L;
-    std::vector<uint64_t> heap(N);
-    heap[0] = 0;
-    for (uint32_t s = 0; s < L; ++s) {
-        for (uint32_t b = 0; b < (1u << s); ++b) {
-            const uint32_t e = bitrev_c(b, (int)s) << (L - 1 - s);
-            heap[(1u << s) + b] = double_to_bits((double)(table[e] % q));
-        }
-    }
-    return heap;
+    std::vector<uint64_t> out((size_t)1 << L, 0);
+    for_each_twiddle(L, [&](uint32_t at, uint32_t e) { out[at] = double_to_bits((double)(table[e] % q)); });
+    return out;
+}
+
+// width (log2) of the last register pass: the bootstrapping key is stored [..][e][u] for position u*2^R + e
+inline uint32_t last_pass_width(uint32_t L) {
+    int P, R[4];
+    plan_runtime((int)L, P, R);
+    return (uint32_t)R[P - 1];
 }
 
 }  // namespace fheb

@@ -68,10 +68,12 @@ static int check(uint32_t threads, uint32_t levels, uint32_t base_log, uint32_t 
         for (size_t poly = 0; poly < bsk.size() / N; ++poly) {
             std::memcpy(t.data(), bsk.data() + poly * N, N * 8);
             orc_forward_ntt(t.data(), N, q, fwd.data());
+            const uint32_t rl = last_pass_width(L), items = N >> rl;
             for (uint32_t pos = 0; pos < N; ++pos) {
                 const uint64_t w = t[bitrev_c(pos, L)];
-                if (DP) g[poly * N + pos] = double_to_bits((double)w);
-                else { g[2 * (poly * N + pos)] = w; g[2 * (poly * N + pos) + 1] = shoup_companion(w, q); }
+                const size_t at = poly * N + (size_t)(pos & ((1u << rl) - 1u)) * items + (pos >> rl);  // [e][u]
+                if (DP) g[at] = double_to_bits((double)w);
+                else { g[2 * at] = w; g[2 * at + 1] = shoup_companion(w, q); }
             }
         }
     }
