@@ -10,7 +10,7 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libfheb200.so")
+LIB_PATH = os.path.join(HERE, os.environ.get("FHEB_LIB", "libfheb200.so"))  # FHEB_LIB: kernel experiments only
 
 OK, INVALID_PARAMETERS, KEY_MISMATCH, HARDWARE_UNAVAILABLE, NATIVE_ERROR, OUT_OF_MEMORY = range(6)
 _CODE_NAMES = {

@@ -19,12 +19,17 @@ ROOT = os.path.dirname(HERE)
 CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(ROOT, "build", "obj")
 LIB = os.path.join(HERE, "libfheb200.so")
+# experiments: FHEB_BUILD_TAG=<tag> FHEB_BUILD_DEFINES="-DX=1 ..." builds libfheb200_<tag>.so from separate objects
+_TAG = os.environ.get("FHEB_BUILD_TAG", "")
+if _TAG:
+    OBJ = os.path.join(ROOT, "build", "obj_" + _TAG)
+    LIB = os.path.join(HERE, f"libfheb200_{_TAG}.so")
 
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 NVCC_FLAGS = [
     "-std=c++17", "-O3", "--expt-relaxed-constexpr", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
     "-Xcompiler", "-fPIC,-fvisibility=hidden", "-I", os.path.join(ROOT, "include"),
-]
+] + os.environ.get("FHEB_BUILD_DEFINES", "").split()
 
 
 def _newest_header() -> float:

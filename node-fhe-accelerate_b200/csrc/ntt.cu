@@ -96,10 +96,12 @@ static int plan_finish(NttPlan* p) {
 }
 
 // ---- kernel dispatch --------------------------------------------------------------------
-template <int L>
+template <int L, bool DP>
 struct Geometry {  // threads per block, polynomials per block
     static constexpr int PPC = (L <= 9) ? (1024 >> L) : (L == 10 ? 2 : 1);
-    static constexpr int THREADS = (L <= 11) ? 128 : (L == 12 ? 256 : 512);
+    // one block per SM holds a 64/128 KB polynomial: the FP64 kernels fit 64 registers, so they run
+    // twice the warps to cover latencies; the integer kernels need ~100-128 registers
+    static constexpr int THREADS = (L <= 11) ? 128 : (L == 12 ? 256 : (DP ? 1024 : 512));
     static constexpr size_t SMEM = (Plan<L>::P > 1) ? (size_t)PPC * (1u << L) * 8 : 0;
 };
 
@@ -122,7 +124,7 @@ enum { DIR_FWD = 0, DIR_INV = 1, DIR_INV_FWDNET = 2 };
 
 template <int L, bool DP>
 static int launch_transform(const NttPlan* p, int dir, const uint64_t* in, uint64_t* out, size_t batch, cudaStream_t s) {
-    using G = Geometry<L>;
+    using G = Geometry<L, DP>;
     const size_t groups = (batch + G::PPC - 1) / G::PPC;
     int bps = 0;
     if (dir == DIR_INV) {
@@ -146,7 +148,7 @@ static int launch_transform(const NttPlan* p, int dir, const uint64_t* in, uint6
 template <int L, bool DP>
 static int launch_polymul(const NttPlan* p, const uint64_t* a, const uint64_t* b, uint64_t* c, size_t batch,
                           cudaStream_t s) {
-    using G = Geometry<L>;
+    using G = Geometry<L, DP>;
     constexpr bool STASH_GLOBAL = (L >= 14);  // two 128 KB operands do not fit in shared memory
     constexpr size_t SMEM = STASH_GLOBAL ? G::SMEM : 2 * (size_t)G::PPC * (1u << L) * 8;
     const size_t groups = (batch + G::PPC - 1) / G::PPC;

@@ -27,11 +27,27 @@
 
 namespace fheb {
 
-// Bank swizzle for 8-byte words in shared memory: XOR-fold the higher index nibbles into
-// the low nibble (16 word-banks).  Any 5 index bits that cover all residues mod 4 - which
-// holds for every access pattern of the passes below, including the bit-reversed one - hit
-// 16 distinct word-banks twice, i.e. the 2-wavefront minimum for a 256-byte warp access.
-FHEB_HD constexpr uint32_t swz(uint32_t i) { return i ^ ((i >> 4) & 15u) ^ ((i >> 8) & 15u) ^ ((i >> 12) & 15u); }
+// Bank swizzle for 8-byte words in shared memory.  A warp-wide 8-byte access is served in two
+// wavefronts of 16 lanes, and 16 lanes hit 16 distinct word-banks iff the four index bits that vary
+// across them map to independent vectors of GF(2)^4.  The passes vary, depending on their geometry,
+// index bits {0,1,2,3}, {0,1,2,6}, {0,1,2,7}, {0,1,5,6}, any four consecutive bits (last pass,
+// natural item order) or the four top bits (last pass, bit-reversed item order).  Mapping index
+// bit j to alpha^j, alpha a primitive element of GF(16) (x^4 + x + 1), makes every one of those
+// sets independent (any 4 consecutive powers of alpha are a basis; the mixed sets were checked
+// exhaustively, tools/check_swizzle.py).  alpha^0..alpha^3 are the unit vectors, so the map only
+// XORs a function of the high index bits into the low nibble: a bijection on every aligned 16-word
+// group, linear over GF(2) (swz(a | b) == swz(a) ^ swz(b) for disjoint a, b).
+FHEB_HD uint32_t parity32(uint32_t v) {
+#if defined(__CUDA_ARCH__)
+    return (uint32_t)__popc(v) & 1u;
+#else
+    return (uint32_t)__builtin_popcount(v) & 1u;
+#endif
+}
+FHEB_HD uint32_t swz(uint32_t i) {
+    const uint32_t h = i >> 4;  // bank bit k = parity of the index bits j >= 4 whose alpha^j has bit k set
+    return i ^ (parity32(h & 0xF59u) | (parity32(h & 0x1EBu) << 1) | (parity32(h & 0x3D6u) << 2) | (parity32(h & 0x7ACu) << 3));
+}
 
 FHEB_HD constexpr uint32_t bitrev_c(uint32_t x, int bits) {
     uint32_t r = 0;
