@@ -178,6 +178,30 @@ static int key_switch_device(const BootKey* key, const uint64_t* lwe, uint64_t* 
     return FHEB_OK;
 }
 
+// blind rotation -> sample extraction (-> key switching when a KSK is set), device pointers
+static int bootstrap_chain_device(const BootKey* key, const uint64_t* lwe, const uint64_t* test_poly, uint64_t* out, size_t batch,
+                                  cudaStream_t s) {
+    const size_t ext_w = (size_t)key->k * key->plan->degree + 1;
+    uint64_t* acc = nullptr;
+    uint64_t* ext = nullptr;
+    FHEB_CUDA(cudaMallocAsync(&acc, batch * glwe_words(key) * 8, s));
+    int rc = blind_rotate_device(key, lwe, test_poly, acc, batch, s);
+    if (rc == FHEB_OK && key->d_ksk) {
+        if (cudaMallocAsync(&ext, batch * ext_w * 8, s) != cudaSuccess) rc = set_error(FHEB_ERR_OUT_OF_MEMORY, "cudaMallocAsync failed");
+        if (rc == FHEB_OK) rc = sample_extract_device(key, acc, ext, batch, s);
+        if (rc == FHEB_OK) rc = key_switch_device(key, ext, out, batch, s);
+    } else if (rc == FHEB_OK) {
+        rc = sample_extract_device(key, acc, out, batch, s);
+    }
+    cudaFreeAsync(acc, s);
+    if (ext) cudaFreeAsync(ext, s);
+    return rc;
+}
+
+// The chain is compute bound (tens of microseconds per ciphertext, a few KB each way): host batches are
+// cut only into very large chunks so that every launch still fills the GPU for many waves.
+constexpr size_t BOOT_HOST_CHUNK = 16384;
+
 static int check_key(const fheb_boot_key* key) {
     FHEB_TRY(ensure_ready());
     FHEB_REQUIRE(key != nullptr, "bootstrap key must not be null");
@@ -313,6 +337,15 @@ int fheb_blind_rotate_batch(const fheb_boot_key* key_, const uint64_t* lwe, cons
     if (batch == 0) return FHEB_OK;
     FHEB_REQUIRE(lwe != nullptr && test_poly != nullptr && out != nullptr, "ciphertext pointers must not be null");
     cudaStream_t s = (cudaStream_t)stream;
+    if (all_host({lwe, test_poly, out})) {
+        return run_host_pipeline(batch, {{lwe, ((size_t)key->n + 1) * 8, 0, true, false}, {test_poly, 0, (size_t)key->plan->degree * 8, true, false},
+                                         {out, glwe_words(key) * 8, 0, false, true}},
+                                 [&](void* const* d, size_t, size_t n, cudaStream_t ps) {
+                                     return blind_rotate_device(key, static_cast<const uint64_t*>(d[0]), static_cast<const uint64_t*>(d[1]),
+                                                                static_cast<uint64_t*>(d[2]), n, ps);
+                                 },
+                                 BOOT_HOST_CHUNK);
+    }
     Staged sl, st, so;
     FHEB_TRY(sl.bind(lwe, batch * ((size_t)key->n + 1) * 8, true, false, s));
     FHEB_TRY(st.bind(test_poly, (size_t)key->plan->degree * 8, true, false, s));
@@ -360,24 +393,20 @@ int fheb_bootstrap_batch(const fheb_boot_key* key_, const uint64_t* lwe, const u
     cudaStream_t s = (cudaStream_t)stream;
     const size_t ext_w = (size_t)key->k * key->plan->degree + 1;
     const size_t out_w = key->d_ksk ? (size_t)key->ksk_n_out + 1 : ext_w;
+    if (all_host({lwe, test_poly, out})) {
+        return run_host_pipeline(batch, {{lwe, ((size_t)key->n + 1) * 8, 0, true, false}, {test_poly, 0, (size_t)key->plan->degree * 8, true, false},
+                                         {out, out_w * 8, 0, false, true}},
+                                 [&](void* const* d, size_t, size_t n, cudaStream_t ps) {
+                                     return bootstrap_chain_device(key, static_cast<const uint64_t*>(d[0]), static_cast<const uint64_t*>(d[1]),
+                                                                   static_cast<uint64_t*>(d[2]), n, ps);
+                                 },
+                                 BOOT_HOST_CHUNK);
+    }
     Staged sl, st, so;
     FHEB_TRY(sl.bind(lwe, batch * ((size_t)key->n + 1) * 8, true, false, s));
     FHEB_TRY(st.bind(test_poly, (size_t)key->plan->degree * 8, true, false, s));
     FHEB_TRY(so.bind(out, batch * out_w * 8, false, true, s));
-    uint64_t* acc = nullptr;
-    uint64_t* ext = nullptr;
-    FHEB_CUDA(cudaMallocAsync(&acc, batch * glwe_words(key) * 8, s));
-    int rc = blind_rotate_device(key, sl.ptr<const uint64_t>(), st.ptr<const uint64_t>(), acc, batch, s);
-    if (rc == FHEB_OK && key->d_ksk) {
-        if (cudaMallocAsync(&ext, batch * ext_w * 8, s) != cudaSuccess) rc = set_error(FHEB_ERR_OUT_OF_MEMORY, "cudaMallocAsync failed");
-        if (rc == FHEB_OK) rc = sample_extract_device(key, acc, ext, batch, s);
-        if (rc == FHEB_OK) rc = key_switch_device(key, ext, so.ptr<uint64_t>(), batch, s);
-    } else if (rc == FHEB_OK) {
-        rc = sample_extract_device(key, acc, so.ptr<uint64_t>(), batch, s);
-    }
-    cudaFreeAsync(acc, s);
-    if (ext) cudaFreeAsync(ext, s);
-    FHEB_TRY(rc);
+    FHEB_TRY(bootstrap_chain_device(key, sl.ptr<const uint64_t>(), st.ptr<const uint64_t>(), so.ptr<uint64_t>(), batch, s));
     FHEB_TRY(so.finish());
     return sync_if_staged(s, {&sl, &st, &so});
 }

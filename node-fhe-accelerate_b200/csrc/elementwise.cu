@@ -92,6 +92,16 @@ static int elementwise_entry(int op, const uint64_t* a, const uint64_t* b, uint6
     FHEB_REQUIRE(a != nullptr && r != nullptr && (!binary || b != nullptr), "operand pointers must not be null");
     cudaStream_t s = (cudaStream_t)stream;
     const size_t bytes = count * 8;
+    if (count >= (1u << 21) && all_host({a, b, r})) {  // large host vectors: pipelined in 4096-word items
+        const size_t item = 4096, items = count / item, tail = count - items * item;
+        FHEB_TRY(run_host_pipeline(items, {{a, item * 8, 0, true, false}, {binary ? b : nullptr, item * 8, 0, true, false}, {r, item * 8, 0, false, true}},
+                                   [&](void* const* d, size_t, size_t n, cudaStream_t ps) {
+                                       return elementwise_device(op, static_cast<const uint64_t*>(d[0]), static_cast<const uint64_t*>(d[1]), scalar,
+                                                                 static_cast<uint64_t*>(d[2]), n * item, q, ps);
+                                   }));
+        if (tail == 0) return FHEB_OK;
+        return elementwise_entry(op, a + items * item, binary ? b + items * item : nullptr, scalar, r + items * item, tail, q, stream);
+    }
     Staged sa, sb, sr;
     FHEB_TRY(sa.bind(a, bytes, true, false, s));
     if (binary) {
@@ -278,6 +288,25 @@ static int mlimb_entry(int op, const uint64_t* a, const uint64_t* b, uint64_t* r
     mq.q_inv = q_inv;
     cudaStream_t s = (cudaStream_t)stream;
     const size_t bytes = count * limbs * 8;
+    auto launch = [&](const uint64_t* da, const uint64_t* db, uint64_t* dr, size_t n, cudaStream_t ps) {
+        switch (limbs) {
+            case 1: return launch_mlimb<1>(op, da, db, dr, n, mq, ps);
+            case 2: return launch_mlimb<2>(op, da, db, dr, n, mq, ps);
+            case 3: return launch_mlimb<3>(op, da, db, dr, n, mq, ps);
+            case 4: return launch_mlimb<4>(op, da, db, dr, n, mq, ps);
+            case 5: return launch_mlimb<5>(op, da, db, dr, n, mq, ps);
+            case 6: return launch_mlimb<6>(op, da, db, dr, n, mq, ps);
+            case 7: return launch_mlimb<7>(op, da, db, dr, n, mq, ps);
+            default: return launch_mlimb<8>(op, da, db, dr, n, mq, ps);
+        }
+    };
+    if (bytes >= (16u << 20) && all_host({a, b, r})) {
+        const size_t row = (size_t)limbs * 8;
+        return run_host_pipeline(count, {{a, row, 0, true, false}, {b, row, 0, true, false}, {r, row, 0, false, true}},
+                                 [&](void* const* d, size_t, size_t n, cudaStream_t ps) {
+                                     return launch(static_cast<const uint64_t*>(d[0]), static_cast<const uint64_t*>(d[1]), static_cast<uint64_t*>(d[2]), n, ps);
+                                 });
+    }
     Staged sa, sb, sr;
     FHEB_TRY(sa.bind(a, bytes, true, false, s));
     if (b == a) FHEB_TRY(sb.bind_alias(sa, false));
@@ -287,17 +316,7 @@ static int mlimb_entry(int op, const uint64_t* a, const uint64_t* b, uint64_t* r
     else FHEB_TRY(sr.bind(r, bytes, false, true, s));
     const uint64_t *da = sa.ptr<const uint64_t>(), *db = sb.ptr<const uint64_t>();
     uint64_t* dr = sr.ptr<uint64_t>();
-    int rc = FHEB_OK;
-    switch (limbs) {
-        case 1: rc = launch_mlimb<1>(op, da, db, dr, count, mq, s); break;
-        case 2: rc = launch_mlimb<2>(op, da, db, dr, count, mq, s); break;
-        case 3: rc = launch_mlimb<3>(op, da, db, dr, count, mq, s); break;
-        case 4: rc = launch_mlimb<4>(op, da, db, dr, count, mq, s); break;
-        case 5: rc = launch_mlimb<5>(op, da, db, dr, count, mq, s); break;
-        case 6: rc = launch_mlimb<6>(op, da, db, dr, count, mq, s); break;
-        case 7: rc = launch_mlimb<7>(op, da, db, dr, count, mq, s); break;
-        default: rc = launch_mlimb<8>(op, da, db, dr, count, mq, s); break;
-    }
+    int rc = launch(da, db, dr, count, s);
     FHEB_TRY(rc);
     FHEB_TRY(sa.finish());
     FHEB_TRY(sb.finish());

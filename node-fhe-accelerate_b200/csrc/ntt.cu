@@ -228,6 +228,13 @@ static int transform_entry(const fheb_ntt_plan* plan, int dir, const uint64_t* i
     const NttPlan* p = reinterpret_cast<const NttPlan*>(plan);
     cudaStream_t s = (cudaStream_t)stream;
     const size_t bytes = batch * (size_t)p->degree * 8;
+    if (all_host({in, out})) {  // host buffers: chunked copy-in / transform / copy-out pipeline
+        const size_t row = (size_t)p->degree * 8;
+        return run_host_pipeline(batch, {{in, row, 0, true, false}, {out, row, 0, false, true}},
+                                 [&](void* const* d, size_t, size_t n, cudaStream_t ps) {
+                                     return dispatch_transform(p, dir, static_cast<const uint64_t*>(d[0]), static_cast<uint64_t*>(d[1]), n, ps);
+                                 });
+    }
     Staged sin, sout;
     FHEB_TRY(sin.bind(in, bytes, true, false, s));
     if (out == in) FHEB_TRY(sout.bind_alias(sin, true));
@@ -341,6 +348,14 @@ int fheb_polymul_batch(const fheb_ntt_plan* plan, const uint64_t* a, const uint6
     const NttPlan* p = reinterpret_cast<const NttPlan*>(plan);
     cudaStream_t s = (cudaStream_t)stream;
     const size_t bytes = batch * (size_t)p->degree * 8;
+    if (all_host({a, b, c})) {
+        const size_t row = (size_t)p->degree * 8;
+        return run_host_pipeline(batch, {{a, row, 0, true, false}, {b, row, 0, true, false}, {c, row, 0, false, true}},
+                                 [&](void* const* d, size_t, size_t n, cudaStream_t ps) {
+                                     return dispatch_polymul(p, static_cast<const uint64_t*>(d[0]), static_cast<const uint64_t*>(d[1]),
+                                                             static_cast<uint64_t*>(d[2]), n, ps);
+                                 });
+    }
     Staged sa, sb, sc;
     FHEB_TRY(sa.bind(a, bytes, true, false, s));
     if (b == a) FHEB_TRY(sb.bind_alias(sa, false));

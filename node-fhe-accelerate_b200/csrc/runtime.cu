@@ -49,6 +49,7 @@ static int init_locked(int device) {
         cudaStreamDestroy(g_ctx.copy_in);
         cudaStreamDestroy(g_ctx.copy_out);
         cudaStreamDestroy(g_ctx.work);
+        for (auto& ps : g_ctx.pipe) cudaStreamDestroy(ps);
         g_ctx.ready = false;
     }
     if (!g_ctx.ready) {
@@ -58,6 +59,15 @@ static int init_locked(int device) {
         FHEB_CUDA(cudaStreamCreateWithFlags(&g_ctx.copy_in, cudaStreamNonBlocking));
         FHEB_CUDA(cudaStreamCreateWithFlags(&g_ctx.copy_out, cudaStreamNonBlocking));
         FHEB_CUDA(cudaStreamCreateWithFlags(&g_ctx.work, cudaStreamNonBlocking));
+        for (auto& ps : g_ctx.pipe) FHEB_CUDA(cudaStreamCreateWithFlags(&ps, cudaStreamNonBlocking));
+        {   // staging buffers come from the stream-ordered allocator on every call: keep its memory cached
+            // across synchronisations instead of returning it to the driver each time
+            cudaMemPool_t pool = nullptr;
+            if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+                unsigned long long keep = ~0ull;
+                cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+            }
+        }
         g_ctx.ready = true;
     }
     return FHEB_OK;
@@ -132,6 +142,102 @@ int sync_if_staged(cudaStream_t stream, std::initializer_list<const Staged*> buf
     return FHEB_OK;
 }
 
+bool all_host(std::initializer_list<const void*> ptrs) {
+    for (const void* p : ptrs)
+        if (p != nullptr && is_device_pointer(p)) return false;
+    return true;
+}
+
+int run_host_pipeline(size_t items, std::vector<PipeArg> args, const PipeFn& fn, size_t chunk_items) {
+    constexpr int SLOTS = Context::PIPE_SLOTS;
+    Context& c = ctx();
+    const size_t na = args.size();
+    std::vector<size_t> rep(na);  // first argument with the same host pointer owns the device buffer
+    size_t max_stride = 1;
+    for (size_t i = 0; i < na; ++i) {
+        rep[i] = i;
+        for (size_t j = 0; j < i; ++j)
+            if (args[j].host == args[i].host && args[j].stride == args[i].stride) {
+                rep[i] = j;
+                args[j].in = args[j].in || args[i].in;
+                args[j].out = args[j].out || args[i].out;
+                break;
+            }
+        if (args[i].stride > max_stride) max_stride = args[i].stride;
+    }
+    // ~8 MB per buffer per chunk: long enough for PCIe efficiency, short enough to pipeline
+    size_t chunk = chunk_items ? chunk_items : (8u << 20) / max_stride;
+    if (chunk < 1) chunk = 1;
+    if (chunk > items) chunk = items;
+    const size_t nchunks = (items + chunk - 1) / chunk;
+    const int slots = (int)(nchunks < (size_t)SLOTS ? nchunks : (size_t)SLOTS);
+
+    std::vector<void*> shared(na, nullptr);
+    std::vector<std::vector<void*>> dev(slots, std::vector<void*>(na, nullptr));
+    cudaEvent_t shared_ready = nullptr;
+    int rc = FHEB_OK;
+    auto fail = [&](cudaError_t e, const char* what) {
+        if (rc == FHEB_OK) rc = set_error(e == cudaErrorMemoryAllocation ? FHEB_ERR_OUT_OF_MEMORY : FHEB_ERR_NATIVE, "%s failed: %s", what, cudaGetErrorString(e));
+    };
+    bool any_shared = false;
+    for (size_t i = 0; i < na && rc == FHEB_OK; ++i) {
+        if (args[i].stride != 0 || rep[i] != i || args[i].host == nullptr) continue;
+        cudaError_t e = cudaMallocAsync(&shared[i], args[i].total ? args[i].total : 1, c.pipe[0]);
+        if (e != cudaSuccess) { fail(e, "cudaMallocAsync"); break; }
+        if (args[i].in) {
+            e = cudaMemcpyAsync(shared[i], args[i].host, args[i].total, cudaMemcpyHostToDevice, c.pipe[0]);
+            if (e != cudaSuccess) fail(e, "cudaMemcpyAsync");
+        }
+        any_shared = true;
+    }
+    if (rc == FHEB_OK && any_shared) {
+        cudaError_t e = cudaEventCreateWithFlags(&shared_ready, cudaEventDisableTiming);
+        if (e == cudaSuccess) e = cudaEventRecord(shared_ready, c.pipe[0]);
+        for (int sl = 1; sl < slots && e == cudaSuccess; ++sl) e = cudaStreamWaitEvent(c.pipe[sl], shared_ready, 0);
+        if (e != cudaSuccess) fail(e, "cudaEventRecord");
+    }
+    for (int sl = 0; sl < slots && rc == FHEB_OK; ++sl)
+        for (size_t i = 0; i < na && rc == FHEB_OK; ++i) {
+            if (args[i].stride == 0 || rep[i] != i || args[i].host == nullptr) continue;
+            cudaError_t e = cudaMallocAsync(&dev[sl][i], chunk * args[i].stride, c.pipe[sl]);
+            if (e != cudaSuccess) fail(e, "cudaMallocAsync");
+        }
+    std::vector<void*> ptrs(na);
+    for (size_t k = 0; k < nchunks && rc == FHEB_OK; ++k) {
+        const int sl = (int)(k % slots);
+        cudaStream_t s = c.pipe[sl];
+        const size_t first = k * chunk;
+        const size_t n = (items - first) < chunk ? (items - first) : chunk;
+        for (size_t i = 0; i < na; ++i) ptrs[i] = args[i].host == nullptr ? nullptr : (args[i].stride ? dev[sl][rep[i]] : shared[rep[i]]);
+        for (size_t i = 0; i < na && rc == FHEB_OK; ++i) {
+            if (args[i].stride == 0 || rep[i] != i || !args[i].in || args[i].host == nullptr) continue;
+            cudaError_t e = cudaMemcpyAsync(dev[sl][i], static_cast<const char*>(args[i].host) + first * args[i].stride,
+                                            n * args[i].stride, cudaMemcpyHostToDevice, s);
+            if (e != cudaSuccess) fail(e, "cudaMemcpyAsync");
+        }
+        if (rc == FHEB_OK) rc = fn(ptrs.data(), first, n, s);
+        for (size_t i = 0; i < na && rc == FHEB_OK; ++i) {
+            if (args[i].stride == 0 || rep[i] != i || !args[i].out || args[i].host == nullptr) continue;
+            cudaError_t e = cudaMemcpyAsync(const_cast<char*>(static_cast<const char*>(args[i].host)) + first * args[i].stride,
+                                            dev[sl][i], n * args[i].stride, cudaMemcpyDeviceToHost, s);
+            if (e != cudaSuccess) fail(e, "cudaMemcpyAsync");
+        }
+    }
+    // shared outputs (none today) would be copied here; release and drain
+    for (int sl = 0; sl < slots; ++sl) {
+        for (size_t i = 0; i < na; ++i)
+            if (dev[sl][i]) cudaFreeAsync(dev[sl][i], c.pipe[sl]);
+    }
+    for (int sl = 0; sl < slots; ++sl) {
+        cudaError_t e = cudaStreamSynchronize(c.pipe[sl]);
+        if (e != cudaSuccess) fail(e, "cudaStreamSynchronize");
+    }
+    for (size_t i = 0; i < na; ++i)
+        if (shared[i]) cudaFree(shared[i]);
+    if (shared_ready) cudaEventDestroy(shared_ready);
+    return rc;
+}
+
 }  // namespace fheb
 
 using namespace fheb;
@@ -149,6 +255,7 @@ int fheb_shutdown(void) {
         cudaStreamDestroy(g_ctx.copy_in);
         cudaStreamDestroy(g_ctx.copy_out);
         cudaStreamDestroy(g_ctx.work);
+        for (auto& ps : g_ctx.pipe) cudaStreamDestroy(ps);
         g_ctx = Context{};
     }
     return FHEB_OK;

@@ -5,6 +5,7 @@
 #include <cuda_runtime.h>
 
 #include <atomic>
+#include <functional>
 #include <cstdarg>
 #include <cstdint>
 #include <cstdio>
@@ -25,6 +26,8 @@ struct Context {
     cudaStream_t copy_in = nullptr;   // staging streams for host buffers
     cudaStream_t copy_out = nullptr;
     cudaStream_t work = nullptr;
+    static constexpr int PIPE_SLOTS = 3;
+    cudaStream_t pipe[PIPE_SLOTS] = {nullptr, nullptr, nullptr};  // host-buffer pipeline: copy-in / kernels / copy-out per chunk
 };
 
 Context& ctx();
@@ -88,5 +91,19 @@ class Staged {
 };
 
 int sync_if_staged(cudaStream_t stream, std::initializer_list<const Staged*> bufs);
+
+// ---- host-buffer pipeline -------------------------------------------------------------------
+// When every buffer of a call lives in host memory the batch is cut into chunks and each chunk's
+// host->device copy, kernels and device->host copy run on one of PIPE_SLOTS streams, so the two
+// PCIe directions and the SMs work concurrently (instead of copy-all, compute, copy-all).
+struct PipeArg {
+    const void* host;   // caller pointer; arguments with the same pointer share one device buffer
+    size_t stride;      // bytes per item; 0 = one block of `total` bytes shared by all items (staged once)
+    size_t total;       // bytes when stride == 0
+    bool in, out;       // copied to the device before / back to the host after the chunk's kernels
+};
+using PipeFn = std::function<int(void* const* dev, size_t first_item, size_t n_items, cudaStream_t s)>;
+bool all_host(std::initializer_list<const void*> ptrs);  // true when no non-null pointer is device memory
+int run_host_pipeline(size_t items, std::vector<PipeArg> args, const PipeFn& fn, size_t chunk_items = 0 /* 0: ~8 MB per buffer */);
 
 }  // namespace fheb

@@ -131,6 +131,28 @@ static int tally_entry(const uint64_t* cts, size_t count, uint32_t degree, uint6
     FHEB_REQUIRE(cts != nullptr && out != nullptr, "ciphertext pointers must not be null");
     cudaStream_t s = (cudaStream_t)stream;
     const uint32_t width = 2 * degree;
+    if (count > 1 && all_host({cts, out}) && count * (size_t)width * 8 >= (16u << 20)) {
+        // host ballots: each chunk is copied in and folded to one partial tally while the next chunk is in
+        // flight; the partials are folded at the end (any grouping gives the same words)
+        const size_t row = (size_t)width * 8;
+        size_t chunk = (8u << 20) / row;
+        if (chunk < 1) chunk = 1;
+        const size_t nchunks = (count + chunk - 1) / chunk;
+        uint64_t* partial = nullptr;
+        FHEB_CUDA(cudaMalloc(&partial, nchunks * row));
+        int rc = run_host_pipeline(count, {{cts, row, 0, true, false}},
+                                   [&](void* const* d, size_t first, size_t n, cudaStream_t ps) {
+                                       return tally_device(static_cast<const uint64_t*>(d[0]), n, width, q, partial + (first / chunk) * width, false, ps);
+                                   });
+        uint64_t* dout = nullptr;
+        if (rc == FHEB_OK && cudaMalloc(&dout, row) != cudaSuccess) rc = set_error(FHEB_ERR_OUT_OF_MEMORY, "cudaMalloc failed");
+        if (rc == FHEB_OK) rc = tally_device(partial, nchunks, width, q, dout, false, s);
+        if (rc == FHEB_OK && cudaMemcpyAsync(out, dout, row, cudaMemcpyDeviceToHost, s) != cudaSuccess) rc = set_error(FHEB_ERR_NATIVE, "copy of the tally failed");
+        if (rc == FHEB_OK && cudaStreamSynchronize(s) != cudaSuccess) rc = set_error(FHEB_ERR_NATIVE, "tally failed");
+        cudaFree(partial);
+        if (dout) cudaFree(dout);
+        return rc;
+    }
     Staged sin, sout;
     FHEB_TRY(sin.bind(cts, count * (size_t)width * 8, true, false, s));
     FHEB_TRY(sout.bind(out, (size_t)width * 8, false, true, s));

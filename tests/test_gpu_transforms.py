@@ -314,3 +314,38 @@ def test_synthetic_ballots_reproducible_and_tally_checksum(fhe, torch, oracle):
     total = host(fhe.tally_votes(cts, n, q))
     chunks = np.stack([oracle.tally(host(cts[i:i + 8192]), q) for i in range(0, count, 8192)])
     eq(total, oracle.tally(chunks, q))
+
+
+# ------------------------------------------------------------------- host-buffer pipeline --
+def test_host_buffers_are_pipelined_in_chunks_and_match_device_path(fhe, torch, oracle):
+    """Host buffers larger than one staging chunk (8 MB) go through the chunked copy/compute/copy
+    pipeline; results must be identical to the device-buffer path (and to the oracle on a sample)."""
+    n, q = 16384, Q62
+    ring = fhe.PolynomialRing(n, q)
+    rng = np.random.default_rng(77)
+    a = rng.integers(0, q, size=(203, n), dtype=np.uint64)  # 26.6 MB: 4 chunks, the last one ragged
+    b = rng.integers(0, q, size=(203, n), dtype=np.uint64)
+    ad, bd = dev(torch, a), dev(torch, b)
+    fa = ring.to_ntt(a)
+    eq(fa, host(ring.to_ntt(ad)))
+    eq(ring.from_ntt(fa), a)
+    inplace = a.copy()
+    ring.to_ntt(inplace, out=inplace)  # in == out on the host
+    eq(inplace, fa)
+    prod = ring.multiply(a, b)
+    eq(prod, host(ring.multiply(ad, bd)))
+    fwd, inv, _, _, inv_n = oracle.twiddles(n, q)
+    eq(prod[[0, 64, 202]], oracle.multiply(a[[0, 64, 202]], b[[0, 64, 202]], q, fwd, inv, inv_n))
+    # element-wise and multi-limb vectors above the pipelining threshold, ragged tail
+    x = rng.integers(0, 2**64, size=(1 << 21) + 4099, dtype=np.uint64)
+    y = rng.integers(0, 2**64, size=(1 << 21) + 4099, dtype=np.uint64)
+    eq(fhe.modmul_batch(x, y, q), host(fhe.modmul_batch(dev(torch, x), dev(torch, y), q)))
+    eq(fhe.modneg_batch(x % np.uint64(q), q), oracle.negate(x % np.uint64(q), q))
+    ml = fhe.MultiLimbModularArithmetic([0xFFFFFFFFFFFFFF43, 1])
+    u = rng.integers(0, 2**64, size=(1 << 20, 2), dtype=np.uint64)
+    u[:, 1] &= np.uint64(1)
+    v = u[::-1].copy()
+    eq(ml.montgomery_mul(u, v), host(ml.montgomery_mul(dev(torch, u), dev(torch, v))))
+    # tally of host ballots: chunk partials folded at the end
+    cts = rng.integers(0, QT, size=(3001, 2, 1024), dtype=np.uint64)
+    eq(fhe.tally_votes(cts, 1024, QT), oracle.tally(cts, QT))
