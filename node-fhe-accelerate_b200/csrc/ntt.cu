@@ -99,9 +99,7 @@ static int plan_finish(NttPlan* p) {
 template <int L, bool DP>
 struct Geometry {  // threads per block, polynomials per block
     static constexpr int PPC = (L <= 9) ? (1024 >> L) : (L == 10 ? 2 : 1);
-    // one block per SM holds a 64/128 KB polynomial: the FP64 kernels fit 64 registers, so they run
-    // twice the warps to cover latencies; the integer kernels need ~100-128 registers
-    static constexpr int THREADS = (L <= 11) ? 128 : (L == 12 ? 256 : (DP ? 1024 : 512));
+    static constexpr int THREADS = (L <= 11) ? 128 : (L == 12 ? 256 : 512);
     static constexpr size_t SMEM = (Plan<L>::P > 1) ? (size_t)PPC * (1u << L) * 8 : 0;
 };
 

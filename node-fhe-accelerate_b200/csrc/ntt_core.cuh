@@ -173,6 +173,23 @@ FHEB_HD void inv_bfly(uint64_t& A, uint64_t& B, const Tw& w, const ModQ& m) {
 template <int S0>
 FHEB_HD constexpr uint32_t tw_index(int a, int g) { return (uint32_t)(((1 << a) - 1) + g) << S0; }
 
+// Caller data streams through once per launch: mark it evict-first so that it does not push the
+// twiddle tables (re-read for every polynomial) out of L1/L2.
+FHEB_HD uint64_t stream_load(const uint64_t* p) {
+#if defined(__CUDA_ARCH__)
+    return (uint64_t)__ldcs(reinterpret_cast<const unsigned long long*>(p));
+#else
+    return *p;
+#endif
+}
+FHEB_HD void stream_store(uint64_t* p, uint64_t v) {
+#if defined(__CUDA_ARCH__)
+    __stcs(reinterpret_cast<unsigned long long*>(p), (unsigned long long)v);
+#else
+    *p = v;
+#endif
+}
+
 // Twiddle tables: integer mode = (value, Shoup companion) pairs, 16 bytes; DP mode = one double, 8 bytes.
 template <bool DP>
 FHEB_HD Tw load_tw(const Tw* __restrict__ tw, uint32_t idx) {
@@ -200,7 +217,8 @@ FHEB_HD Tw load_tw(const Tw* __restrict__ tw, uint32_t idx) {
 // R forward stages on 2^R register-resident values; element bit (R-1) is the highest
 // position bit of the pass.  The pass starts at stage S0; TB = table offset of the pass + the index
 // of this item's block among the 2^S0 blocks of stage S0 (see tw_index below).
-template <int R, int S0, int K, bool DP, bool UNITFIRST, int A = 0>
+// REGTW: `tw` points at this item's twiddles already held in registers, entry ((1 << a) - 1) + g.
+template <int R, int S0, int K, bool DP, bool UNITFIRST, int A = 0, bool REGTW = false>
 FHEB_HD void fwd_stages(uint64_t (&x)[1 << R], const Tw* __restrict__ tw, uint32_t TB, const ModQ& m) {
     if constexpr (A < R) {
         constexpr int half = 1 << (R - 1 - A);
@@ -211,17 +229,17 @@ FHEB_HD void fwd_stages(uint64_t (&x)[1 << R], const Tw* __restrict__ tw, uint32
 #pragma unroll
                 for (int j = 0; j < half; ++j) fwd_bfly<K, DP, true>(x[g * 2 * half + j], x[g * 2 * half + j + half], dummy, m);
             } else {
-                const Tw w = load_tw<DP>(tw, TB + tw_index<S0>(A, g));
+                const Tw w = REGTW ? tw[((1 << A) - 1) + g] : load_tw<DP>(tw, TB + tw_index<S0>(A, g));
 #pragma unroll
                 for (int j = 0; j < half; ++j) fwd_bfly<K, DP, false>(x[g * 2 * half + j], x[g * 2 * half + j + half], w, m);
             }
         }
-        fwd_stages<R, S0, fwd_next_k(K, UNITFIRST, !(UNITFIRST && A == 0), DP), DP, UNITFIRST, A + 1>(x, tw, TB, m);
+        fwd_stages<R, S0, fwd_next_k(K, UNITFIRST, !(UNITFIRST && A == 0), DP), DP, UNITFIRST, A + 1, REGTW>(x, tw, TB, m);
     }
 }
 
 // R inverse stages, highest stage of the pass first (element bit 0 first).
-template <int R, int S0, int K, bool DP, bool UNITFIRST, int A = R - 1>
+template <int R, int S0, int K, bool DP, bool UNITFIRST, int A = R - 1, bool REGTW = false>
 FHEB_HD void inv_stages(uint64_t (&x)[1 << R], const Tw* __restrict__ tw, uint32_t TB, const ModQ& m) {
     if constexpr (A >= 0) {
         constexpr int half = 1 << (R - 1 - A);
@@ -232,13 +250,22 @@ FHEB_HD void inv_stages(uint64_t (&x)[1 << R], const Tw* __restrict__ tw, uint32
 #pragma unroll
                 for (int j = 0; j < half; ++j) inv_bfly<K, DP, true>(x[g * 2 * half + j], x[g * 2 * half + j + half], dummy, m);
             } else {
-                const Tw w = load_tw<DP>(tw, TB + tw_index<S0>(A, g));
+                const Tw w = REGTW ? tw[((1 << A) - 1) + g] : load_tw<DP>(tw, TB + tw_index<S0>(A, g));
 #pragma unroll
                 for (int j = 0; j < half; ++j) inv_bfly<K, DP, false>(x[g * 2 * half + j], x[g * 2 * half + j + half], w, m);
             }
         }
-        inv_stages<R, S0, inv_next_k(K, DP), DP, UNITFIRST, A - 1>(x, tw, TB, m);
+        inv_stages<R, S0, inv_next_k(K, DP), DP, UNITFIRST, A - 1, REGTW>(x, tw, TB, m);
     }
+}
+
+// all (2^R - 1) twiddles of one item into registers, entry ((1 << a) - 1) + g
+template <int R, int S0, bool DP>
+FHEB_HD void load_item_tw(const Tw* __restrict__ tw, uint32_t TB, Tw (&w)[(1 << R) - 1]) {
+#pragma unroll
+    for (int a = 0; a < R; ++a)
+#pragma unroll
+        for (int g = 0; g < (1 << a); ++g) w[((1 << a) - 1) + g] = load_tw<DP>(tw, TB + tw_index<S0>(a, g));
 }
 
 // value bounded by K*q  ->  canonical word
@@ -363,7 +390,7 @@ enum {
 //   SCALE      : multiply the outputs by `ninv` (fast_ntt_inverse semantics)
 // OUT == IO_STASH_*: the finished transform is parked (position order, no bit reversal) in
 // `gout` for the fused polynomial product; canonical words in integer mode, lazy doubles (|v| < KOUT*q) in DP mode.
-template <int L, bool DP, int PASS, int IN, int OUT, bool BITREV_OUT = true, bool SCALE = false>
+template <int L, bool DP, int PASS, int IN, int OUT, bool BITREV_OUT = true, bool SCALE = false, int IPT = 0>
 FHEB_HD void fwd_pass(uint32_t tid, uint32_t nthreads, uint32_t polys, const uint64_t* gin, uint64_t* gout,
                       uint64_t* smem, const Tw* __restrict__ tw, const ModQ& m, const Tw ninv = Tw{0, 0}) {
     constexpr int R = Plan<L>::R[PASS];
@@ -378,7 +405,29 @@ FHEB_HD void fwd_pass(uint32_t tid, uint32_t nthreads, uint32_t polys, const uin
     static_assert(IN == IO_SMEM || PASS == 0, "only the first pass reads global memory");
     static_assert(OUT == IO_SMEM || LAST, "only the last pass writes outside the work buffer");
 
-    for (uint32_t U = tid; U < polys * ITEMS; U += nthreads) {
+    // IPT > 0: the thread's item count is known (IPT items, stride nthreads) and all their twiddles are
+    // requested before the first item is computed - in the late passes every item has its own
+    // twiddles, they stream from L2, and nothing else in a barrier-synchronised block hides that latency.
+    constexpr int NW = E - 1;
+    constexpr int TRIPS = IPT > 0 ? IPT : 1;
+    Tw wall[TRIPS][NW];
+    if constexpr (IPT > 0) {
+#pragma unroll
+        for (int k = 0; k < IPT; ++k) {
+            const uint32_t U = tid + (uint32_t)k * nthreads;
+            if (U < polys * ITEMS) {
+                uint32_t u = U & (ITEMS - 1);
+                if (OUT == IO_GLOBAL && BITREV_OUT) u = bitrev_rt(u, L - R);
+                const uint32_t base = ((u >> EB) << (EB + R)) | (u & ((1u << EB) - 1u));
+                load_item_tw<R, S0, DP>(tw, plan_tw_offset<L, PASS>() + (S0 ? (base >> (L - S0)) : 0u), wall[k]);
+            }
+        }
+    }
+    for (uint32_t U0 = tid; U0 < (IPT > 0 ? tid + 1 : polys * ITEMS); U0 += nthreads) {
+#pragma unroll
+      for (int k = 0; k < TRIPS; ++k) {
+        const uint32_t U = U0 + (uint32_t)k * nthreads;
+        if (IPT > 0 && U >= polys * ITEMS) break;
         const uint32_t poly = U >> (L - R);
         uint32_t u = U & (ITEMS - 1);
         // In the last pass consecutive threads take bit-reversed item indices so that the
@@ -390,7 +439,7 @@ FHEB_HD void fwd_pass(uint32_t tid, uint32_t nthreads, uint32_t polys, const uin
         if (IN == IO_GLOBAL) {
             const uint64_t* src = gin + (size_t)poly * N;
 #pragma unroll
-            for (int c = 0; c < E; ++c) x[c] = load_word<DP>(src[base | ((uint32_t)c << EB)], m);
+            for (int c = 0; c < E; ++c) x[c] = load_word<DP>(stream_load(src + (base | ((uint32_t)c << EB))), m);
         } else {
             const uint64_t* src = smem + (size_t)poly * N;
             const uint32_t pb = swz(base);
@@ -398,14 +447,15 @@ FHEB_HD void fwd_pass(uint32_t tid, uint32_t nthreads, uint32_t polys, const uin
             for (int c = 0; c < E; ++c) x[c] = src[pb ^ swz((uint32_t)c << EB)];
         }
         const uint32_t TB = plan_tw_offset<L, PASS>() + (S0 ? (base >> (L - S0)) : 0u);
-        fwd_stages<R, S0, KIN, DP, PASS == 0>(x, tw, TB, m);
+        if constexpr (IPT > 0) fwd_stages<R, S0, KIN, DP, PASS == 0, 0, true>(x, wall[k], 0u, m);
+        else fwd_stages<R, S0, KIN, DP, PASS == 0>(x, tw, TB, m);
         if (OUT == IO_GLOBAL) {
             uint64_t* dst = gout + (size_t)poly * N;
 #pragma unroll
             for (int c = 0; c < E; ++c) {
                 const uint64_t v = SCALE ? scale_word<DP>(x[c], ninv, m) : canon_k<KOUT, DP>(x[c], m);
-                if (BITREV_OUT) dst[(bitrev_c((uint32_t)c, R) << (L - R)) | t] = v;
-                else dst[base | ((uint32_t)c << EB)] = v;
+                if (BITREV_OUT) stream_store(dst + ((bitrev_c((uint32_t)c, R) << (L - R)) | t), v);
+                else stream_store(dst + (base | ((uint32_t)c << EB)), v);
             }
         } else if (OUT == IO_STASH_GLOBAL) {
             uint64_t* dst = gout + (size_t)poly * N;
@@ -418,6 +468,7 @@ FHEB_HD void fwd_pass(uint32_t tid, uint32_t nthreads, uint32_t polys, const uin
             for (int c = 0; c < E; ++c)
                 dst[pb ^ swz((uint32_t)c << EB)] = (OUT == IO_STASH_SMEM) ? park_word<KOUT, DP>(x[c], m) : x[c];
         }
+      }
     }
 }
 
@@ -454,7 +505,7 @@ FHEB_HD void polymul_mid_pass(uint32_t tid, uint32_t nthreads, uint32_t polys, c
         if (IN == IO_GLOBAL) {
             const uint64_t* src = gin + (size_t)poly * N;
 #pragma unroll
-            for (int c = 0; c < E; ++c) x[c] = load_word<DP>(src[base | (uint32_t)c], m);
+            for (int c = 0; c < E; ++c) x[c] = load_word<DP>(stream_load(src + (base | (uint32_t)c)), m);
         } else {
             const uint64_t* src = smem + (size_t)poly * N;
 #pragma unroll
@@ -473,7 +524,7 @@ FHEB_HD void polymul_mid_pass(uint32_t tid, uint32_t nthreads, uint32_t polys, c
         if (OUT == IO_GLOBAL) {
             uint64_t* dst = gout + (size_t)poly * N;
 #pragma unroll
-            for (int c = 0; c < E; ++c) dst[base | (uint32_t)c] = scale_word<DP>(x[c], ninv, m);
+            for (int c = 0; c < E; ++c) stream_store(dst + (base | (uint32_t)c), scale_word<DP>(x[c], ninv, m));
         } else {
             uint64_t* dst = smem + (size_t)poly * N;
 #pragma unroll
@@ -486,7 +537,7 @@ FHEB_HD void polymul_mid_pass(uint32_t tid, uint32_t nthreads, uint32_t polys, c
 // may read the reference's input order (bit-reversed positions) from global memory; the
 // last one executed (PASS == 0) multiplies by N^-1 (`ninv`, Shoup pair) and stores canonical
 // values in natural order.
-template <int L, bool DP, int PASS, int IN, int OUT, bool BITREV_IN = true>
+template <int L, bool DP, int PASS, int IN, int OUT, bool BITREV_IN = true, int IPT = 0>
 FHEB_HD void inv_pass(uint32_t tid, uint32_t nthreads, uint32_t polys, const uint64_t* gin, uint64_t* gout,
                       uint64_t* smem, const Tw* __restrict__ tw, const Tw ninv, const ModQ& m) {
     constexpr int R = Plan<L>::R[PASS];
@@ -500,7 +551,26 @@ FHEB_HD void inv_pass(uint32_t tid, uint32_t nthreads, uint32_t polys, const uin
     static_assert(IN == IO_SMEM || FIRST, "only the first executed pass reads global memory");
     static_assert(OUT == IO_SMEM || PASS == 0, "only the last executed pass writes global memory");
 
-    for (uint32_t U = tid; U < polys * ITEMS; U += nthreads) {
+    constexpr int NW = E - 1;  // IPT > 0: all twiddles of the thread's IPT items requested up front (see fwd_pass)
+    constexpr int TRIPS = IPT > 0 ? IPT : 1;
+    Tw wall[TRIPS][NW];
+    if constexpr (IPT > 0) {
+#pragma unroll
+        for (int k = 0; k < IPT; ++k) {
+            const uint32_t U = tid + (uint32_t)k * nthreads;
+            if (U < polys * ITEMS) {
+                uint32_t u = U & (ITEMS - 1);
+                if (FIRST && IN == IO_GLOBAL && BITREV_IN) u = bitrev_rt(u, L - R);
+                const uint32_t base = ((u >> EB) << (EB + R)) | (u & ((1u << EB) - 1u));
+                load_item_tw<R, S0, DP>(tw, plan_tw_offset<L, PASS>() + (S0 ? (base >> (L - S0)) : 0u), wall[k]);
+            }
+        }
+    }
+    for (uint32_t U0 = tid; U0 < (IPT > 0 ? tid + 1 : polys * ITEMS); U0 += nthreads) {
+#pragma unroll
+      for (int k = 0; k < TRIPS; ++k) {
+        const uint32_t U = U0 + (uint32_t)k * nthreads;
+        if (IPT > 0 && U >= polys * ITEMS) break;
         const uint32_t poly = U >> (L - R);
         uint32_t u = U & (ITEMS - 1);
         const uint32_t t = u;
@@ -511,10 +581,10 @@ FHEB_HD void inv_pass(uint32_t tid, uint32_t nthreads, uint32_t polys, const uin
             const uint64_t* src = gin + (size_t)poly * N;
             if (BITREV_IN) {
 #pragma unroll
-                for (int c = 0; c < E; ++c) x[c] = load_word<DP>(src[(bitrev_c((uint32_t)c, R) << (L - R)) | t], m);
+                for (int c = 0; c < E; ++c) x[c] = load_word<DP>(stream_load(src + ((bitrev_c((uint32_t)c, R) << (L - R)) | t)), m);
             } else {
 #pragma unroll
-                for (int c = 0; c < E; ++c) x[c] = load_word<DP>(src[base | ((uint32_t)c << EB)], m);
+                for (int c = 0; c < E; ++c) x[c] = load_word<DP>(stream_load(src + (base | ((uint32_t)c << EB))), m);
             }
         } else {
             const uint64_t* src = smem + (size_t)poly * N;
@@ -523,18 +593,20 @@ FHEB_HD void inv_pass(uint32_t tid, uint32_t nthreads, uint32_t polys, const uin
             for (int c = 0; c < E; ++c) x[c] = src[pb ^ swz((uint32_t)c << EB)];
         }
         const uint32_t TB = plan_tw_offset<L, PASS>() + (S0 ? (base >> (L - S0)) : 0u);
-        inv_stages<R, S0, KIN, DP, PASS == 0>(x, tw, TB, m);
+        if constexpr (IPT > 0) inv_stages<R, S0, KIN, DP, PASS == 0, R - 1, true>(x, wall[k], 0u, m);
+        else inv_stages<R, S0, KIN, DP, PASS == 0>(x, tw, TB, m);
         if (OUT == IO_GLOBAL) {
             uint64_t* dst = gout + (size_t)poly * N;
 #pragma unroll
             for (int c = 0; c < E; ++c)
-                dst[base | ((uint32_t)c << EB)] = scale_word<DP>(x[c], ninv, m);
+                stream_store(dst + (base | ((uint32_t)c << EB)), scale_word<DP>(x[c], ninv, m));
         } else {
             uint64_t* dst = smem + (size_t)poly * N;
             const uint32_t pb = swz(base);
 #pragma unroll
             for (int c = 0; c < E; ++c) dst[pb ^ swz((uint32_t)c << EB)] = x[c];
         }
+      }
     }
 }
 
