@@ -46,10 +46,11 @@ FHEB_HD uint64_t rotated_at(const uint64_t* p, uint32_t j, uint32_t rot, uint32_
 }
 
 // gadget digit l of coefficient c (decompose_polynomial, :165-178), as a canonical residue
-FHEB_HD uint64_t gadget_digit(uint64_t c, uint32_t shift, uint64_t mask, uint64_t base, const ModQ& m) {
+// `small_base` (base <= q, block-uniform): both branches are already below q
+FHEB_HD uint64_t gadget_digit(uint64_t c, uint32_t shift, uint64_t mask, uint64_t base, bool small_base, const ModQ& m) {
     const uint64_t d = (c >> shift) & mask;
     const uint64_t v = (d > (base >> 1)) ? (m.q - (base - d)) : d;
-    return canon_any(v, m);
+    return small_base ? v : canon_any(v, m);
 }
 
 template <int L>
@@ -67,6 +68,7 @@ FHEB_HD void boot_first_pass(uint32_t tid, uint32_t nthreads, const BootStep& s,
     static_assert(Plan<L>::P >= 2, "bootstrap kernels need at least two passes (N >= 32)");
     const uint64_t base = 1ull << s.base_log;
     const uint64_t mask = base - 1;
+    const bool small_base = base <= m.q;
     for (uint32_t U = tid; U < (uint32_t)KP1 * ITEMS; U += nthreads) {
         const uint32_t c = U >> (L - R);
         const uint32_t u = U & (ITEMS - 1);
@@ -76,13 +78,35 @@ FHEB_HD void boot_first_pass(uint32_t tid, uint32_t nthreads, const BootStep& s,
 #pragma unroll
             for (int e = 0; e < E; ++e) d[e] = src[u | ((uint32_t)e << EB)];
         } else {
+            // X^rot * acc - acc.  After the first executed step every accumulator word is canonical; only
+            // the words of a caller's test polynomial can be unreduced.  One test per item (not per word)
+            // picks between the plain formulas and the reference's exact unsigned wrap-around ones.
             const uint64_t* a = s.acc + (size_t)c * N;
+            uint64_t ct0[E], src[E];
+            bool raw = false;
 #pragma unroll
             for (int e = 0; e < E; ++e) {
                 const uint32_t pos = u | ((uint32_t)e << EB);
-                const uint64_t ct0 = canon_any(a[pos], m);
-                const uint64_t ct1 = canon_any(rotated_at(a, pos, s.rot, N, m), m);
-                d[e] = submod_canon(ct1, ct0, m.q);  // PolynomialRing::subtract(ct1, ct0), :527-530
+                const uint32_t sidx = (pos + 2u * N - s.rot) & (2u * N - 1u);
+                ct0[e] = a[pos];
+                src[e] = a[sidx & (N - 1u)];
+                raw = raw || ct0[e] >= m.q || src[e] >= m.q;
+            }
+            if (!raw) {
+#pragma unroll
+                for (int e = 0; e < E; ++e) {
+                    const uint32_t pos = u | ((uint32_t)e << EB);
+                    const uint32_t sidx = (pos + 2u * N - s.rot) & (2u * N - 1u);
+                    const uint64_t ct1 = (sidx < N) ? src[e] : (src[e] ? m.q - src[e] : 0);  // (q - v) % q for canonical v
+                    d[e] = submod_canon(ct1, ct0[e], m.q);  // PolynomialRing::subtract(ct1, ct0), :527-530
+                }
+            } else {
+#pragma unroll
+                for (int e = 0; e < E; ++e) {
+                    const uint32_t pos = u | ((uint32_t)e << EB);
+                    const uint64_t ct1 = canon_any(rotated_at(a, pos, s.rot, N, m), m);
+                    d[e] = submod_canon(ct1, canon_any(ct0[e], m), m.q);
+                }
             }
         }
         const uint32_t pb = swz(u);
@@ -91,7 +115,7 @@ FHEB_HD void boot_first_pass(uint32_t tid, uint32_t nthreads, const BootStep& s,
             uint64_t x[E];
 #pragma unroll
             for (int e = 0; e < E; ++e) {
-                const uint64_t g = gadget_digit(d[e], shift, mask, base, m);
+                const uint64_t g = gadget_digit(d[e], shift, mask, base, small_base, m);
                 x[e] = DP ? double_to_bits(dp_from_uint(g)) : g;
             }
             fwd_stages<R, 0, 1, DP, true>(x, tw, 0u, m);
@@ -182,13 +206,21 @@ FHEB_HD void boot_final_pass(uint32_t tid, uint32_t nthreads, const BootStep& s,
         inv_stages<R, 0, KIN, DP, true>(x, twi, 0u, m);
         const uint64_t* a = s.acc + (size_t)c * N;
         uint64_t* dst = (s.gout ? s.gout : s.acc) + (size_t)c * N;
+        uint64_t v[E], a0[E];
+        bool raw = false;
 #pragma unroll
         for (int e = 0; e < E; ++e) {
-            const uint32_t pos = u | ((uint32_t)e << EB);
-            uint64_t v = scale_word<DP>(x[e], ninv, m);
-            if (s.add_acc) v = addmod_canon(v, canon_any(a[pos], m), m.q);  // PolynomialRing::add(result, ct0), :533-537
-            dst[pos] = v;
+            v[e] = scale_word<DP>(x[e], ninv, m);
+            a0[e] = s.add_acc ? a[u | ((uint32_t)e << EB)] : 0;
+            raw = raw || a0[e] >= m.q;
         }
+        if (raw) {  // unreduced ct0 words (caller data): PolynomialRing::add reduces them first
+#pragma unroll
+            for (int e = 0; e < E; ++e) a0[e] = canon_any(a0[e], m);
+        }
+#pragma unroll
+        for (int e = 0; e < E; ++e)
+            dst[u | ((uint32_t)e << EB)] = s.add_acc ? addmod_canon(v[e], a0[e], m.q) : v[e];  // PolynomialRing::add(result, ct0), :533-537
     }
 }
 

@@ -29,12 +29,15 @@ struct BootLaunch {
 
 template <int L>
 struct BootGeometry {
-    static constexpr int THREADS = (L <= 6) ? 32 : (L <= 8) ? 64 : (L <= 10) ? 128 : (L == 11) ? 256 : 512;
-    // resident blocks per SM the register allocation must allow: 512 threads per SM, i.e. <= 128 registers
-    static constexpr int MIN_BLOCKS = 512 / THREADS;
+    // threads that work on ONE ciphertext; a block runs several ciphertexts in lockstep (groups of
+    // TPC threads) so that its 16 warps share one instruction stream - the unrolled passes of a step
+    // are ~80 KB of code, far beyond the instruction caches when four blocks run out of phase
+    static constexpr int TPC = (L <= 6) ? 32 : (L <= 8) ? 64 : (L <= 10) ? 128 : (L == 11) ? 256 : 512;
+    static constexpr int MAX_THREADS = 512;
+    static constexpr int MAX_GROUPS = MAX_THREADS / TPC;
 };
 
-// shared-memory words: acc [KP1][N] | work [rows][N] | (CMUX/EXT) diff [KP1][N] | (BLIND) rotations [n] (u32)
+// shared-memory bytes per ciphertext: acc [KP1][N] | work [rows][N] | (CMUX/EXT) diff [KP1][N] | (BLIND) rotations [n] (u32)
 inline size_t boot_smem_bytes(int mode, uint32_t N, uint32_t kp1, uint32_t levels, uint32_t n) {
     size_t words = (size_t)kp1 * N + (size_t)kp1 * levels * N;
     if (mode != BOOT_BLIND) words += (size_t)kp1 * N;
@@ -43,30 +46,35 @@ inline size_t boot_smem_bytes(int mode, uint32_t N, uint32_t kp1, uint32_t level
     return bytes;
 }
 
+// `active` is uniform per ciphertext group; idle groups still take part in the block barriers
 template <int L, bool DP, int KP1, int PH = 0>
-__device__ __forceinline__ void boot_run_step(uint32_t tid, uint32_t nthreads, const BootStep& s, const BootLaunch& a) {
+__device__ __forceinline__ void boot_run_step(bool active, uint32_t tid, uint32_t nthreads, const BootStep& s, const BootLaunch& a) {
     if constexpr (PH < boot_phases<L>()) {
-        boot_phase<L, DP, KP1, PH>(tid, nthreads, s, a.twf, a.twi, a.ninv, a.m);
+        if (active) boot_phase<L, DP, KP1, PH>(tid, nthreads, s, a.twf, a.twi, a.ninv, a.m);
         __syncthreads();
-        boot_run_step<L, DP, KP1, PH + 1>(tid, nthreads, s, a);
+        boot_run_step<L, DP, KP1, PH + 1>(active, tid, nthreads, s, a);
     }
 }
 
 template <int L, bool DP, int KP1>
-__global__ void __launch_bounds__(BootGeometry<L>::THREADS, BootGeometry<L>::MIN_BLOCKS) boot_kernel(const BootLaunch a) {
+__global__ void __launch_bounds__(BootGeometry<L>::MAX_THREADS, 1) boot_kernel(const BootLaunch a, const uint32_t ct_bytes) {
     extern __shared__ __align__(16) uint64_t smem[];
     constexpr uint32_t N = 1u << L;
-    constexpr uint32_t THREADS = BootGeometry<L>::THREADS;
+    constexpr uint32_t TPC = BootGeometry<L>::TPC;
     constexpr uint32_t GW = (uint32_t)KP1 * N;  // words per GLWE
-    const uint32_t tid = threadIdx.x;
+    const uint32_t group = threadIdx.x / TPC;    // which of the block's ciphertexts this thread works on
+    const uint32_t groups = blockDim.x / TPC;
+    const uint32_t tid = threadIdx.x % TPC;
     const uint32_t rows = (uint32_t)KP1 * a.levels;
-    uint64_t* acc = smem;
+    uint64_t* acc = smem + (size_t)group * (ct_bytes / 8);
     uint64_t* work = acc + GW;
     uint64_t* diff = work + (size_t)rows * N;                   // CMUX / EXT only
     uint32_t* rots = reinterpret_cast<uint32_t*>(work + (size_t)rows * N);  // BLIND only
     const size_t ggsw_words = (size_t)rows * KP1 * N;
 
-    for (size_t ct = blockIdx.x; ct < a.batch; ct += gridDim.x) {
+    for (size_t ct0 = (size_t)blockIdx.x * groups; ct0 < a.batch; ct0 += (size_t)gridDim.x * groups) {
+        const size_t ct = ct0 + group;
+        const bool valid = ct < a.batch;
         BootStep s;
         s.acc = acc;
         s.work = work;
@@ -74,32 +82,34 @@ __global__ void __launch_bounds__(BootGeometry<L>::THREADS, BootGeometry<L>::MIN
         s.base_log = a.base_log;
         s.rot = 0;
         s.ggsw = a.bsk;
+        s.diff = nullptr;
+        s.add_acc = 1;
+        s.gout = nullptr;
         uint64_t* gout = a.out + ct * GW;
         uint32_t nsteps = 1;
         if (a.mode == BOOT_BLIND) {
-            const uint64_t* lwe = a.in0 + ct * ((size_t)a.n + 1);
-            for (uint32_t i = tid; i < a.n; i += THREADS) rots[i] = lwe_rotation(lwe[i], false, N, a.m.q);
-            // acc = X^(-round(b * 2N / q)) * (0, .., 0, test_poly): multiply_glwe_by_monomial, :558-559
-            const uint32_t rb = lwe_rotation(lwe[a.n], true, N, a.m.q);
-            for (uint32_t i = tid; i < GW; i += THREADS) {
-                const uint32_t c = i >> L, j = i & (N - 1);
-                acc[i] = (c == (uint32_t)KP1 - 1) ? rotated_at(a.in1, j, rb, N, a.m) : 0;
+            if (valid) {
+                const uint64_t* lwe = a.in0 + ct * ((size_t)a.n + 1);
+                for (uint32_t i = tid; i < a.n; i += TPC) rots[i] = lwe_rotation(lwe[i], false, N, a.m.q);
+                // acc = X^(-round(b * 2N / q)) * (0, .., 0, test_poly): multiply_glwe_by_monomial, :558-559
+                const uint32_t rb = lwe_rotation(lwe[a.n], true, N, a.m.q);
+                for (uint32_t i = tid; i < GW; i += TPC) {
+                    const uint32_t c = i >> L, j = i & (N - 1);
+                    acc[i] = (c == (uint32_t)KP1 - 1) ? rotated_at(a.in1, j, rb, N, a.m) : 0;
+                }
             }
-            s.diff = nullptr;
-            s.add_acc = 1;
-            s.gout = nullptr;
             nsteps = a.n;
-        } else {
+        } else if (valid) {
             const uint64_t* g0 = a.in0 + ct * GW;
             if (a.mode == BOOT_CMUX) {
                 const uint64_t* g1 = a.in1 + ct * GW;
-                for (uint32_t i = tid; i < GW; i += THREADS) {
+                for (uint32_t i = tid; i < GW; i += TPC) {
                     const uint64_t c0 = g0[i];
                     acc[i] = c0;
                     diff[i] = submod_canon(canon_any(g1[i], a.m), canon_any(c0, a.m), a.m.q);
                 }
             } else {
-                for (uint32_t i = tid; i < GW; i += THREADS) diff[i] = g0[i];
+                for (uint32_t i = tid; i < GW; i += TPC) diff[i] = g0[i];
             }
             s.diff = diff;
             s.add_acc = (a.mode == BOOT_CMUX) ? 1 : 0;
@@ -108,41 +118,45 @@ __global__ void __launch_bounds__(BootGeometry<L>::THREADS, BootGeometry<L>::MIN
         __syncthreads();
         // one call site for the step body: the unrolled passes are large, keep a single copy of them
         for (uint32_t i = 0; i < nsteps; ++i) {
+            bool active = valid;
             if (a.mode == BOOT_BLIND) {
-                const uint32_t rot = rots[i];
-                if (rot == 0) continue;  // :566 (block-uniform)
+                const uint32_t rot = valid ? rots[i] : 0u;
+                active = rot != 0;  // :566 - a zero rotation skips the CMux (uniform per ciphertext)
                 s.rot = rot;
                 s.ggsw = reinterpret_cast<const Tw*>(reinterpret_cast<const char*>(a.bsk) + (size_t)i * ggsw_words * (DP ? 8 : 16));
             }
-            boot_run_step<L, DP, KP1>(tid, THREADS, s, a);
+            boot_run_step<L, DP, KP1>(active, tid, TPC, s, a);
         }
-        if (a.mode == BOOT_BLIND) {
-            for (uint32_t i = tid; i < GW; i += THREADS) gout[i] = acc[i];
+        if (a.mode == BOOT_BLIND && valid) {
+            for (uint32_t i = tid; i < GW; i += TPC) gout[i] = acc[i];
         }
-        __syncthreads();  // the next ciphertext overwrites acc / rots / diff
+        __syncthreads();  // the next ciphertexts overwrite acc / rots / diff
     }
 }
 
 template <int L, bool DP, int KP1>
 int boot_launch_one(const BootLaunch& a, cudaStream_t stream) {
-    constexpr int THREADS = BootGeometry<L>::THREADS;
-    const size_t smem = boot_smem_bytes(a.mode, 1u << L, KP1, a.levels, a.n);
+    using G = BootGeometry<L>;
+    const size_t ct_bytes = boot_smem_bytes(a.mode, 1u << L, KP1, a.levels, a.n);
+    const size_t cap = (size_t)ctx().prop.sharedMemPerBlockOptin;
     auto k = boot_kernel<L, DP, KP1>;
-    if (smem > (size_t)ctx().prop.sharedMemPerBlockOptin)
+    if (ct_bytes > cap)
         return set_error(FHEB_ERR_INVALID_PARAMETERS,
                          "bootstrap working set (%zu bytes) exceeds the shared memory of one SM; reduce N, k or the level count",
-                         smem);
+                         ct_bytes);
+    size_t groups = cap / ct_bytes;  // ciphertexts per block: as many as fit, at most 512 threads' worth
+    if (groups > (size_t)G::MAX_GROUPS) groups = G::MAX_GROUPS;
+    if (groups > a.batch) groups = a.batch;
+    const size_t smem = groups * ct_bytes;
+    const int threads = (int)groups * G::TPC;
     if (smem > 48 * 1024) FHEB_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    {
-        const char* cv = getenv("FHEB_BOOT_CARVEOUT");  // tuning knob (percent of the unified L1/shared array)
-        if (cv) FHEB_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributePreferredSharedMemoryCarveout, atoi(cv)));
-    }
     int bps = 0;
-    FHEB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, k, THREADS, smem));
+    FHEB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, k, threads, smem));
     if (bps < 1) return set_error(FHEB_ERR_NATIVE, "bootstrap kernel does not fit on an SM");
     const size_t resident = (size_t)ctx().sm_count * (size_t)bps;
-    const unsigned grid = (unsigned)(a.batch < resident ? a.batch : resident);
-    k<<<grid, THREADS, smem, stream>>>(a);
+    const size_t blocks = (a.batch + groups - 1) / groups;
+    const unsigned grid = (unsigned)(blocks < resident ? blocks : resident);
+    k<<<grid, threads, smem, stream>>>(a, (uint32_t)ct_bytes);
     FHEB_CHECK_LAUNCH();
     count_launch();
     return FHEB_OK;
