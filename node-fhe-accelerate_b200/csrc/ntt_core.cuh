@@ -288,6 +288,21 @@ FHEB_HD uint64_t load_word(uint64_t v, const ModQ& m) {
     if constexpr (DP) return double_to_bits(dp_from_uint(c));
     else return c;
 }
+// the same for a whole item: unreduced words are rare, so one test covers the item's 2^R words
+template <bool DP, int E>
+FHEB_HD void load_words(uint64_t (&x)[E], const ModQ& m) {
+    bool raw = false;
+#pragma unroll
+    for (int c = 0; c < E; ++c) raw = raw || x[c] >= m.q;
+    if (raw) {
+#pragma unroll
+        for (int c = 0; c < E; ++c) x[c] = canon_any(x[c], m);
+    }
+    if constexpr (DP) {
+#pragma unroll
+        for (int c = 0; c < E; ++c) x[c] = double_to_bits(dp_from_uint(x[c]));
+    }
+}
 
 // finished transform parked for the fused product: canonical word (integer) / reduced double (DP)
 template <int K, bool DP>
@@ -439,7 +454,8 @@ FHEB_HD void fwd_pass(uint32_t tid, uint32_t nthreads, uint32_t polys, const uin
         if (IN == IO_GLOBAL) {
             const uint64_t* src = gin + (size_t)poly * N;
 #pragma unroll
-            for (int c = 0; c < E; ++c) x[c] = load_word<DP>(stream_load(src + (base | ((uint32_t)c << EB))), m);
+            for (int c = 0; c < E; ++c) x[c] = stream_load(src + (base | ((uint32_t)c << EB)));
+            load_words<DP, E>(x, m);
         } else {
             const uint64_t* src = smem + (size_t)poly * N;
             const uint32_t pb = swz(base);
@@ -505,7 +521,8 @@ FHEB_HD void polymul_mid_pass(uint32_t tid, uint32_t nthreads, uint32_t polys, c
         if (IN == IO_GLOBAL) {
             const uint64_t* src = gin + (size_t)poly * N;
 #pragma unroll
-            for (int c = 0; c < E; ++c) x[c] = load_word<DP>(stream_load(src + (base | (uint32_t)c)), m);
+            for (int c = 0; c < E; ++c) x[c] = stream_load(src + (base | (uint32_t)c));
+            load_words<DP, E>(x, m);
         } else {
             const uint64_t* src = smem + (size_t)poly * N;
 #pragma unroll
@@ -581,11 +598,12 @@ FHEB_HD void inv_pass(uint32_t tid, uint32_t nthreads, uint32_t polys, const uin
             const uint64_t* src = gin + (size_t)poly * N;
             if (BITREV_IN) {
 #pragma unroll
-                for (int c = 0; c < E; ++c) x[c] = load_word<DP>(stream_load(src + ((bitrev_c((uint32_t)c, R) << (L - R)) | t)), m);
+                for (int c = 0; c < E; ++c) x[c] = stream_load(src + ((bitrev_c((uint32_t)c, R) << (L - R)) | t));
             } else {
 #pragma unroll
-                for (int c = 0; c < E; ++c) x[c] = load_word<DP>(stream_load(src + (base | ((uint32_t)c << EB))), m);
+                for (int c = 0; c < E; ++c) x[c] = stream_load(src + (base | ((uint32_t)c << EB)));
             }
+            load_words<DP, E>(x, m);
         } else {
             const uint64_t* src = smem + (size_t)poly * N;
             const uint32_t pb = swz(base);
