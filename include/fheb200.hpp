@@ -1,0 +1,222 @@
+// fheb200.hpp - header-only C++ mirror of the reference's classes for the hot path, over the C ABI
+// of fheb200.h.  Same class and method names as the reference (namespace fhe_accelerate there,
+// fheb200 here) so that its call sites and tests port by switching the include:
+//
+//   NTTProcessor                cpp/include/ntt_processor.h:49-303
+//   PolynomialRing              cpp/include/polynomial_ring.h:312-513   (flat word buffers instead of Polynomial)
+//   MultiLimbModularArithmetic  cpp/include/modular_arithmetic.h:124-194
+//   BootstrapEngine             cpp/include/bootstrap_engine.h:176-508  (deterministic part; keys are uploaded)
+//   tally_votes / batch_add     cpp/include/encryption.h tally slice
+//
+// Errors follow the reference: std::invalid_argument for bad parameters (with the reference's
+// message text), std::runtime_error for everything else.  Buffers may be host or device memory.
+#pragma once
+#include <cstddef>
+#include <cstdint>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "fheb200.h"
+
+namespace fheb200 {
+
+inline void check(int rc) {
+    if (rc == FHEB_OK) return;
+    const std::string msg = fheb_last_error();
+    if (rc == FHEB_ERR_INVALID_PARAMETERS) throw std::invalid_argument(msg);
+    throw std::runtime_error(msg);
+}
+
+inline void initialize(int device = -1) { check(fheb_init(device)); }
+
+struct TwiddleFactors {  // cpp/include/ntt_processor.h:29-41
+    std::vector<uint64_t> forward, inverse;
+    uint64_t primitive_root = 0, inv_primitive_root = 0, inv_n = 0;
+};
+
+class NTTProcessor {
+   public:
+    NTTProcessor(uint32_t degree, uint64_t modulus) : degree_(degree), modulus_(modulus) {
+        check(fheb_ntt_plan_create(degree, modulus, &plan_));
+    }
+    // caller-supplied tables (fast_ntt_forward / MetalComputeContext::batch_ntt_forward shape)
+    NTTProcessor(uint32_t degree, uint64_t modulus, const uint64_t* fwd, const uint64_t* inv, uint64_t inv_n)
+        : degree_(degree), modulus_(modulus) {
+        check(fheb_ntt_plan_create_with_tables(degree, modulus, fwd, inv, inv_n, &plan_));
+    }
+    ~NTTProcessor() { fheb_ntt_plan_destroy(plan_); }
+    NTTProcessor(const NTTProcessor&) = delete;
+    NTTProcessor& operator=(const NTTProcessor&) = delete;
+
+    uint32_t get_degree() const { return degree_; }
+    uint64_t get_modulus() const { return modulus_; }
+    TwiddleFactors get_twiddles() const {
+        TwiddleFactors t;
+        t.forward.resize(degree_);
+        t.inverse.resize(degree_);
+        uint64_t s[3];
+        check(fheb_ntt_plan_get_tables(plan_, t.forward.data(), t.inverse.data(), s));
+        t.primitive_root = s[0];
+        t.inv_primitive_root = s[1];
+        t.inv_n = s[2];
+        return t;
+    }
+    // in place, like NTTProcessor::forward_ntt(uint64_t*, size_t) - throws "Size must match polynomial degree"
+    void forward_ntt(uint64_t* coeffs, size_t n, void* stream = nullptr) const {
+        require_size(n);
+        check(fheb_ntt_forward_batch(plan_, coeffs, coeffs, 1, stream));
+    }
+    void inverse_ntt(uint64_t* coeffs, size_t n, void* stream = nullptr) const {
+        require_size(n);
+        check(fheb_ntt_inverse_batch(plan_, coeffs, coeffs, 1, stream));
+    }
+    void forward_ntt(const uint64_t* in, uint64_t* out, size_t n, void* stream = nullptr) const {
+        require_size(n);
+        check(fheb_ntt_forward_batch(plan_, in, out, 1, stream));
+    }
+    void inverse_ntt(const uint64_t* in, uint64_t* out, size_t n, void* stream = nullptr) const {
+        require_size(n);
+        check(fheb_ntt_inverse_batch(plan_, in, out, 1, stream));
+    }
+    // contiguous batches [batch][N] (the reference's pointer-array overload is a serial loop over these)
+    void forward_ntt_batch(const uint64_t* in, uint64_t* out, size_t batch, void* stream = nullptr) const {
+        check(fheb_ntt_forward_batch(plan_, in, out, batch, stream));
+    }
+    void inverse_ntt_batch(const uint64_t* in, uint64_t* out, size_t batch, void* stream = nullptr) const {
+        check(fheb_ntt_inverse_batch(plan_, in, out, batch, stream));
+    }
+    void forward_ntt_batch(uint64_t** coeffs_batch, size_t batch_size, size_t n) const {  // ntt_processor.h:143
+        for (size_t i = 0; i < batch_size; ++i) forward_ntt(coeffs_batch[i], n);
+    }
+    void inverse_ntt_batch(uint64_t** coeffs_batch, size_t batch_size, size_t n) const {
+        for (size_t i = 0; i < batch_size; ++i) inverse_ntt(coeffs_batch[i], n);
+    }
+    const fheb_ntt_plan* handle() const { return plan_; }
+
+   private:
+    void require_size(size_t n) const {
+        if (n != degree_) throw std::invalid_argument("Size must match polynomial degree");  // ntt_processor.cpp:263-265
+    }
+    fheb_ntt_plan* plan_ = nullptr;
+    uint32_t degree_;
+    uint64_t modulus_;
+};
+
+class PolynomialRing {
+   public:
+    PolynomialRing(uint32_t degree, uint64_t modulus) : ntt_(degree, modulus) {}
+    uint32_t degree() const { return ntt_.get_degree(); }
+    uint64_t modulus() const { return ntt_.get_modulus(); }
+    const NTTProcessor& ntt() const { return ntt_; }
+    // element-wise over `batch` polynomials (words = batch * degree); r may alias a or b
+    void add(const uint64_t* a, const uint64_t* b, uint64_t* r, size_t batch = 1, void* s = nullptr) const {
+        check(fheb_modadd_batch(a, b, r, batch * degree(), modulus(), s));
+    }
+    void subtract(const uint64_t* a, const uint64_t* b, uint64_t* r, size_t batch = 1, void* s = nullptr) const {
+        check(fheb_modsub_batch(a, b, r, batch * degree(), modulus(), s));
+    }
+    void negate(const uint64_t* a, uint64_t* r, size_t batch = 1, void* s = nullptr) const {
+        check(fheb_modneg_batch(a, r, batch * degree(), modulus(), s));
+    }
+    void multiply_scalar(const uint64_t* a, uint64_t scalar, uint64_t* r, size_t batch = 1, void* s = nullptr) const {
+        check(fheb_modmul_scalar_batch(a, scalar, r, batch * degree(), modulus(), s));
+    }
+    void pointwise_multiply(const uint64_t* a, const uint64_t* b, uint64_t* r, size_t batch = 1, void* s = nullptr) const {
+        check(fheb_modmul_batch(a, b, r, batch * degree(), modulus(), s));
+    }
+    void to_ntt(const uint64_t* a, uint64_t* r, size_t batch = 1, void* s = nullptr) const { ntt_.forward_ntt_batch(a, r, batch, s); }
+    void from_ntt(const uint64_t* a, uint64_t* r, size_t batch = 1, void* s = nullptr) const { ntt_.inverse_ntt_batch(a, r, batch, s); }
+    // coefficient-form product, PolynomialRing::multiply (polynomial_ring.cpp:421-447)
+    void multiply(const uint64_t* a, const uint64_t* b, uint64_t* c, size_t batch = 1, void* s = nullptr) const {
+        check(fheb_polymul_batch(ntt_.handle(), a, b, c, batch, s));
+    }
+    // EncryptionEngine::multiply tensor product: [batch][2][N] x [batch][2][N] -> [batch][3][N]
+    void tensor_multiply(const uint64_t* ct1, const uint64_t* ct2, uint64_t* out, size_t batch = 1, void* s = nullptr) const {
+        check(fheb_tensor_multiply_batch(ntt_.handle(), ct1, ct2, out, batch, s));
+    }
+
+   private:
+    NTTProcessor ntt_;
+};
+
+class MultiLimbModularArithmetic {
+   public:
+    explicit MultiLimbModularArithmetic(const std::vector<uint64_t>& q) : q_(q), consts_(1 + 2 * q.size()) {
+        check(fheb_mlimb_constants(q_.data(), (uint32_t)q_.size(), consts_.data()));
+    }
+    size_t limbs() const { return q_.size(); }
+    uint64_t q_inv() const { return consts_[0]; }
+    const uint64_t* r_mod_q() const { return consts_.data() + 1; }
+    const uint64_t* r2_mod_q() const { return consts_.data() + 1 + q_.size(); }
+    // [count][limbs] little-endian words
+    void montgomery_mul_neon(const uint64_t* a, const uint64_t* b, uint64_t* r, size_t count, void* s = nullptr) const {
+        check(fheb_mlimb_montmul_batch(a, b, r, count, (uint32_t)q_.size(), q_.data(), consts_[0], s));
+    }
+    void mod_add_neon(const uint64_t* a, const uint64_t* b, uint64_t* r, size_t count, void* s = nullptr) const {
+        check(fheb_mlimb_add_batch(a, b, r, count, (uint32_t)q_.size(), q_.data(), s));
+    }
+    void mod_sub_neon(const uint64_t* a, const uint64_t* b, uint64_t* r, size_t count, void* s = nullptr) const {
+        check(fheb_mlimb_sub_batch(a, b, r, count, (uint32_t)q_.size(), q_.data(), s));
+    }
+
+   private:
+    std::vector<uint64_t> q_, consts_;
+};
+
+class BootstrapEngine {
+   public:
+    // bsk = [n][(k+1)*level][k+1][N] coefficient-form words as generate_bootstrap_key produces them
+    BootstrapEngine(uint32_t poly_degree, uint64_t modulus, uint32_t lwe_dimension, uint32_t glwe_dimension,
+                    uint32_t decomp_base_log, uint32_t decomp_level, const uint64_t* bsk)
+        : ntt_(poly_degree, modulus), n_(lwe_dimension), k_(glwe_dimension) {
+        const fheb_boot_params p{lwe_dimension, glwe_dimension, decomp_base_log, decomp_level};
+        check(fheb_boot_key_create(ntt_.handle(), &p, bsk, &key_));
+    }
+    ~BootstrapEngine() { fheb_boot_key_destroy(key_); }
+    BootstrapEngine(const BootstrapEngine&) = delete;
+    BootstrapEngine& operator=(const BootstrapEngine&) = delete;
+
+    void set_key_switch_key(const uint64_t* ksk, size_t entries, uint32_t n_out, uint32_t base_log, uint32_t level) {
+        check(fheb_boot_key_set_ksk(key_, ksk, entries, n_out, base_log, level));
+    }
+    void external_product(const uint64_t* glwe, uint32_t index, uint64_t* out, size_t batch = 1, void* s = nullptr) const {
+        check(fheb_external_product_batch(key_, index, glwe, out, batch, s));
+    }
+    void cmux(uint32_t index, const uint64_t* ct0, const uint64_t* ct1, uint64_t* out, size_t batch = 1, void* s = nullptr) const {
+        check(fheb_cmux_batch(key_, index, ct0, ct1, out, batch, s));
+    }
+    void blind_rotate(const uint64_t* lwe, const uint64_t* test_poly, uint64_t* out, size_t batch = 1, void* s = nullptr) const {
+        check(fheb_blind_rotate_batch(key_, lwe, test_poly, out, batch, s));
+    }
+    void sample_extract(const uint64_t* glwe, uint64_t* out, size_t batch = 1, void* s = nullptr) const {
+        check(fheb_sample_extract_batch(key_, glwe, out, batch, s));
+    }
+    void key_switch(const uint64_t* lwe, uint64_t* out, size_t batch = 1, void* s = nullptr) const {
+        check(fheb_key_switch_batch(key_, lwe, out, batch, s));
+    }
+    void bootstrap_with_test_poly(const uint64_t* lwe, const uint64_t* test_poly, uint64_t* out, size_t batch = 1, void* s = nullptr) const {
+        check(fheb_bootstrap_batch(key_, lwe, test_poly, out, batch, s));
+    }
+    std::vector<uint64_t> get_default_test_poly(uint64_t plaintext_modulus = 4) const { return lut(3, plaintext_modulus, 0); }
+    std::vector<uint64_t> create_identity_lut(uint64_t modulus) const { return lut(0, modulus, 0); }
+    std::vector<uint64_t> create_negation_lut(uint64_t modulus) const { return lut(1, modulus, 0); }
+    std::vector<uint64_t> create_threshold_lut(uint64_t threshold, uint64_t modulus) const { return lut(2, threshold, modulus); }
+
+   private:
+    std::vector<uint64_t> lut(int kind, uint64_t a0, uint64_t a1) const {
+        std::vector<uint64_t> out(ntt_.get_degree());
+        check(fheb_make_test_poly(ntt_.handle(), kind, a0, a1, out.data()));
+        return out;
+    }
+    NTTProcessor ntt_;
+    fheb_boot_key* key_ = nullptr;
+    uint32_t n_, k_;
+};
+
+// EncryptionEngine::batch_add / tally_votes words: cts = [count][2][N] -> out = [2][N]
+inline void tally_votes(const uint64_t* cts, size_t count, uint32_t degree, uint64_t modulus, uint64_t* out, void* s = nullptr) {
+    check(fheb_tally(cts, count, degree, modulus, out, s));
+}
+
+}  // namespace fheb200

@@ -71,6 +71,24 @@ __global__ void __launch_bounds__(TALLY_THREADS) tally_kernel(const uint64_t* __
     if (pair) out[1] = fold128(hi1, lo1, m);
 }
 
+// Transform-domain tensor product of EncryptionEngine::multiply (cpp/src/encryption.cpp:760-785) for a whole
+// batch in one launch: t = [batch][4][N] holds T(a0), T(a1), T(b0), T(b1); out = [batch][3][N] gets
+// a0.b0, a0.b1 + a1.b0, a1.b1 (canonical words).
+__global__ void __launch_bounds__(256) tensor_pointwise_kernel(const uint64_t* __restrict__ ta, const uint64_t* __restrict__ tb,
+                                                               uint64_t* __restrict__ out, size_t batch, uint32_t N, const ModQ m) {
+    const size_t total = batch * N;
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+        const size_t ct = i / N, j = i - ct * N;
+        const uint64_t a0 = ta[(ct * 2) * N + j], a1 = ta[(ct * 2 + 1) * N + j];
+        const uint64_t b0 = tb[(ct * 2) * N + j], b1 = tb[(ct * 2 + 1) * N + j];
+        uint64_t* o = out + ct * 3 * N + j;
+        o[0] = mulmod(a0, b0, m);
+        o[N] = addmod_canon(mulmod(a0, b1, m), mulmod(a1, b0, m), m.q);
+        o[2 * (size_t)N] = mulmod(a1, b1, m);
+    }
+}
+
 // splitmix64 (public-domain constants) - counter-based, reproducible on the CPU
 __device__ __forceinline__ uint64_t splitmix64(uint64_t x) {
     x += 0x9E3779B97F4A7C15ULL;
@@ -187,28 +205,22 @@ int fheb_tensor_multiply_batch(const fheb_ntt_plan* plan, const uint64_t* ct1, c
     FHEB_REQUIRE(ct1 != nullptr && ct2 != nullptr && out != nullptr, "ciphertext pointers must not be null");
     const NttPlan* p = reinterpret_cast<const NttPlan*>(plan);
     const size_t N = p->degree;
-    const uint64_t q = p->modulus;
     cudaStream_t s = (cudaStream_t)stream;
     Staged s1, s2, so;
     FHEB_TRY(s1.bind(ct1, batch * 2 * N * 8, true, false, s));
     FHEB_TRY(s2.bind(ct2, batch * 2 * N * 8, true, false, s));
     FHEB_TRY(so.bind(out, batch * 3 * N * 8, false, true, s));
-    uint64_t* work = nullptr;  // [batch][2][N] x 2 transformed operands + 2 product temporaries per ct
-    FHEB_CUDA(cudaMallocAsync(&work, batch * 6 * N * 8, s));
-    uint64_t* ta = work;                   // T(ct1): [batch][2][N]
-    uint64_t* tb = work + batch * 2 * N;   // T(ct2)
-    uint64_t* tmp = work + batch * 4 * N;  // [batch][2][N] scratch
+    uint64_t* work = nullptr;  // T(ct1), T(ct2): [batch][2][N] each
+    FHEB_CUDA(cudaMallocAsync(&work, batch * 4 * N * 8, s));
+    uint64_t* ta = work;
+    uint64_t* tb = work + batch * 2 * N;
     int rc = ntt_forward_device(p, s1.ptr<const uint64_t>(), ta, batch * 2, s);
     if (rc == FHEB_OK) rc = ntt_forward_device(p, s2.ptr<const uint64_t>(), tb, batch * 2, s);
     uint64_t* o = so.ptr<uint64_t>();
-    for (size_t i = 0; i < batch && rc == FHEB_OK; ++i) {
-        const uint64_t *a0 = ta + i * 2 * N, *a1 = a0 + N, *b0 = tb + i * 2 * N, *b1 = b0 + N;
-        uint64_t *c0 = o + i * 3 * N, *c1 = c0 + N, *c2 = c1 + N, *x = tmp + i * 2 * N, *y = x + N;
-        rc = elementwise_device(2, a0, b0, 0, c0, N, q, s);
-        if (rc == FHEB_OK) rc = elementwise_device(2, a0, b1, 0, x, N, q, s);
-        if (rc == FHEB_OK) rc = elementwise_device(2, a1, b0, 0, y, N, q, s);
-        if (rc == FHEB_OK) rc = elementwise_device(0, x, y, 0, c1, N, q, s);
-        if (rc == FHEB_OK) rc = elementwise_device(2, a1, b1, 0, c2, N, q, s);
+    if (rc == FHEB_OK) {
+        tensor_pointwise_kernel<<<stream_grid(batch * N, 256, 8), 256, 0, s>>>(ta, tb, o, batch, (uint32_t)N, p->mod);
+        if (cudaGetLastError() != cudaSuccess) rc = set_error(FHEB_ERR_NATIVE, "tensor_pointwise_kernel launch failed");
+        count_launch();
     }
     if (rc == FHEB_OK) rc = ntt_inverse_device(p, o, o, batch * 3, s);
     cudaFreeAsync(work, s);

@@ -349,3 +349,17 @@ def test_host_buffers_are_pipelined_in_chunks_and_match_device_path(fhe, torch, 
     # tally of host ballots: chunk partials folded at the end
     cts = rng.integers(0, QT, size=(3001, 2, 1024), dtype=np.uint64)
     eq(fhe.tally_votes(cts, 1024, QT), oracle.tally(cts, QT))
+
+
+def test_tensor_multiply_batch_matches_oracle(fhe, torch, oracle):
+    """EncryptionEngine::multiply tensor product over a batch (one fused pointwise launch)."""
+    for n, q in [(1024, QT), (4096, Q62)]:
+        fwd, inv, _, _, inv_n = oracle.twiddles(n, q)
+        rng = np.random.default_rng(n)
+        ct1 = rng.integers(0, q, size=(9, 2, n), dtype=np.uint64)
+        ct2 = rng.integers(0, q, size=(9, 2, n), dtype=np.uint64)
+        ring = fhe.PolynomialRing(n, q)
+        got = host(ring.tensor_multiply(dev(torch, ct1), dev(torch, ct2)))
+        exp = np.stack([oracle.tensor_multiply(ct1[i], ct2[i], q, fwd, inv, inv_n) for i in range(9)])
+        eq(got, exp)
+        eq(ring.tensor_multiply(ct1[:2], ct2[:2]), exp[:2])  # host buffers
