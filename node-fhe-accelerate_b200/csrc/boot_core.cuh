@@ -23,12 +23,13 @@ struct BootStep {          // block-uniform description of one step
     uint64_t* acc;         // smem [KP1][N], natural index: ct0 / running accumulator
     uint64_t* work;        // smem [max(rows, KP1)][N], swizzled index
     const uint64_t* diff;  // smem [KP1][N] natural index: precomputed ct1 - ct0 (or the GLWE itself); null = rotate acc
-    const Tw* ggsw;        // global [rows][KP1][E][N/E] (position u*E + e at [e][u], E = width of the last pass): (value, Shoup companion) pairs, or doubles in DP mode
+    const Tw* ggsw;        // global [rows][E][N/E][KP1] (position u*E + e, component j at [e][u][j]; E = width of the last pass), times N^-1: (value, Shoup companion) pairs, or doubles in DP mode
     uint64_t* gout;        // when non-null the final pass stores here ([KP1][N], global) instead of acc
     uint32_t rot;          // normalised rotation in [0, 2N) (used when diff == null)
     uint32_t levels;
     uint32_t base_log;
     uint32_t add_acc;      // 1: result = acc + product (cmux); 0: product only (external product)
+    uint32_t maybe_raw;    // 1: acc may still hold unreduced caller words (>= q); cleared after the first executed step
 };
 
 // normalisation of rotate_polynomial (cpp/src/bootstrap_engine.cpp:127-128), int32 arithmetic as written
@@ -79,8 +80,8 @@ FHEB_HD void boot_first_pass(uint32_t tid, uint32_t nthreads, const BootStep& s,
             for (int e = 0; e < E; ++e) d[e] = src[u | ((uint32_t)e << EB)];
         } else {
             // X^rot * acc - acc.  After the first executed step every accumulator word is canonical; only
-            // the words of a caller's test polynomial can be unreduced.  One test per item (not per word)
-            // picks between the plain formulas and the reference's exact unsigned wrap-around ones.
+            // the words of a caller's test polynomial can be unreduced (s.maybe_raw).  Then one test per
+            // item picks between the plain formulas and the reference's exact unsigned wrap-around ones.
             const uint64_t* a = s.acc + (size_t)c * N;
             uint64_t ct0[E], src[E];
             bool raw = false;
@@ -90,7 +91,10 @@ FHEB_HD void boot_first_pass(uint32_t tid, uint32_t nthreads, const BootStep& s,
                 const uint32_t sidx = (pos + 2u * N - s.rot) & (2u * N - 1u);
                 ct0[e] = a[pos];
                 src[e] = a[sidx & (N - 1u)];
-                raw = raw || ct0[e] >= m.q || src[e] >= m.q;
+            }
+            if (s.maybe_raw) {  // block-uniform: only before the first executed step of a blind rotation
+#pragma unroll
+                for (int e = 0; e < E; ++e) raw = raw || ct0[e] >= m.q || src[e] >= m.q;
             }
             if (!raw) {
 #pragma unroll
@@ -149,24 +153,40 @@ FHEB_HD void boot_mid_pass(uint32_t tid, uint32_t nthreads, const BootStep& s, c
         for (int j = 0; j < KP1; ++j)
 #pragma unroll
             for (int e = 0; e < E; ++e) out[j][e] = 0;
+        Tw wf[E - 1];  // this item's forward twiddles: the same for every digit row
+        load_item_tw<R, S0, DP>(twf, TB, wf);
         for (uint32_t row = 0; row < rows; ++row) {
             const uint64_t* src = s.work + (size_t)row * N;
             uint64_t x[E];
 #pragma unroll
             for (int e = 0; e < E; ++e) x[e] = src[pb ^ swz((uint32_t)e)];
-            fwd_stages<R, S0, KIN, DP, false>(x, twf, TB, m);
-            // key element (row, j, position u*E + e) lives at ((row*KP1 + j)*E + e)*ITEMS + u: lanes
-            // (consecutive u) read consecutive entries with every load
+            fwd_stages<R, S0, KIN, DP, false, 0, true>(x, wf, 0u, m);
+            // key element (row, position u*E + e, component j) lives at ((row*E + e)*ITEMS + u)*KP1 + j: lanes
+            // (consecutive u) read consecutive entries, and the k+1 components of one position are adjacent
 #pragma unroll
-            for (int j = 0; j < KP1; ++j) {
+            for (int e = 0; e < E; ++e) {
+                const uint32_t g0 = ((row * E + (uint32_t)e) * ITEMS + u) * (uint32_t)KP1;
+                Tw w[KP1];
+                if constexpr (DP && KP1 == 2) {  // one 16-byte load for both components
+#if defined(__CUDA_ARCH__)
+                    const ulonglong2 v2 = __ldg(reinterpret_cast<const ulonglong2*>(s.ggsw) + (g0 >> 1));
+                    w[0].w = v2.x;
+                    w[1].w = v2.y;
+#else
+                    w[0] = load_tw<DP>(s.ggsw, g0);
+                    w[1] = load_tw<DP>(s.ggsw, g0 + 1);
+#endif
+                } else {
 #pragma unroll
-                for (int e = 0; e < E; ++e) {
-                    const Tw w = load_tw<DP>(s.ggsw, ((row * (uint32_t)KP1 + (uint32_t)j) * E + (uint32_t)e) * ITEMS + u);
+                    for (int j = 0; j < KP1; ++j) w[j] = load_tw<DP>(s.ggsw, g0 + (uint32_t)j);
+                }
+#pragma unroll
+                for (int j = 0; j < KP1; ++j) {
                     if constexpr (DP) {  // |t| < q: plain sums (rows <= CAP_DP checked at key upload)
-                        const double t = dp_mulmod(bits_to_double(x[e]), bits_to_double(w.w), m);
+                        const double t = dp_mulmod(bits_to_double(x[e]), bits_to_double(w[j].w), m);
                         out[j][e] = double_to_bits(dp_add(bits_to_double(out[j][e]), t));
                     } else {  // t in [0, 2q) for any x; keep the running sum in [0, 2q)
-                        out[j][e] = csub(out[j][e] + shoup_lazy(x[e], w.w, w.wp, m.q), m.q2);
+                        out[j][e] = csub(out[j][e] + shoup_lazy(x[e], w[j].w, w[j].wp, m.q), m.q2);
                     }
                 }
             }
@@ -193,6 +213,7 @@ FHEB_HD void boot_final_pass(uint32_t tid, uint32_t nthreads, const BootStep& s,
     constexpr int E = 1 << R;
     constexpr int EB = L - R;
     constexpr int KIN = plan_inv_kin<L, DP, 0>();
+    constexpr int KFIN = inv_pass_k(KIN, R, DP);
     constexpr uint32_t N = 1u << L;
     constexpr uint32_t ITEMS = N >> R;
     for (uint32_t U = tid; U < (uint32_t)KP1 * ITEMS; U += nthreads) {
@@ -210,9 +231,12 @@ FHEB_HD void boot_final_pass(uint32_t tid, uint32_t nthreads, const BootStep& s,
         bool raw = false;
 #pragma unroll
         for (int e = 0; e < E; ++e) {
-            v[e] = scale_word<DP>(x[e], ninv, m);
+            v[e] = canon_k<KFIN, DP>(x[e], m);  // N^-1 is folded into the uploaded key (the transform is linear)
             a0[e] = s.add_acc ? a[u | ((uint32_t)e << EB)] : 0;
-            raw = raw || a0[e] >= m.q;
+        }
+        if (s.maybe_raw) {
+#pragma unroll
+            for (int e = 0; e < E; ++e) raw = raw || a0[e] >= m.q;
         }
         if (raw) {  // unreduced ct0 words (caller data): PolynomialRing::add reduces them first
 #pragma unroll

@@ -85,6 +85,7 @@ __global__ void __launch_bounds__(BootGeometry<L>::MAX_THREADS, 1) boot_kernel(c
         s.diff = nullptr;
         s.add_acc = 1;
         s.gout = nullptr;
+        s.maybe_raw = (a.mode == BOOT_BLIND) ? 1u : 0u;  // CMUX loads ct0 reduced (PolynomialRing::add reduces it anyway)
         uint64_t* gout = a.out + ct * GW;
         uint32_t nsteps = 1;
         if (a.mode == BOOT_BLIND) {
@@ -105,8 +106,9 @@ __global__ void __launch_bounds__(BootGeometry<L>::MAX_THREADS, 1) boot_kernel(c
                 const uint64_t* g1 = a.in1 + ct * GW;
                 for (uint32_t i = tid; i < GW; i += TPC) {
                     const uint64_t c0 = g0[i];
-                    acc[i] = c0;
-                    diff[i] = submod_canon(canon_any(g1[i], a.m), canon_any(c0, a.m), a.m.q);
+                    const uint64_t c0r = canon_any(c0, a.m);
+                    acc[i] = c0r;
+                    diff[i] = submod_canon(canon_any(g1[i], a.m), c0r, a.m.q);
                 }
             } else {
                 for (uint32_t i = tid; i < GW; i += TPC) diff[i] = g0[i];
@@ -126,6 +128,7 @@ __global__ void __launch_bounds__(BootGeometry<L>::MAX_THREADS, 1) boot_kernel(c
                 s.ggsw = reinterpret_cast<const Tw*>(reinterpret_cast<const char*>(a.bsk) + (size_t)i * ggsw_words * (DP ? 8 : 16));
             }
             boot_run_step<L, DP, KP1>(active, tid, TPC, s, a);
+            if (active) s.maybe_raw = 0;  // every accumulator word is now the output of a modular addition
         }
         if (a.mode == BOOT_BLIND && valid) {
             for (uint32_t i = tid; i < GW; i += TPC) gout[i] = acc[i];

@@ -21,26 +21,33 @@ struct BootKey {
 };
 
 // ---- key preparation --------------------------------------------------------------------
-// in: transforms in the reference's output order (index p of the permuted array); out: the value of
-// position u * 2^rlast + e (i.e. index bitrev(position)) at [e][u] of its polynomial, with its Shoup
-// companion floor(w * 2^64 / q), or as a double in DP mode.
+// in: transforms y = [ggsw][row][j][N] in the reference's output order (index p of the permuted array).
+// out, per GGSW: element (row, e, u, j) = y[row][j][bitrev(u * 2^rlast + e)] * N^-1 mod q, stored at
+// ((row * E + e) * ITEMS + u) * KP1 + j with its Shoup companion floor(w * 2^64 / q), or as a double in DP mode.
+// N^-1 is folded in here because the transform is linear: T^-1(sum D.G) = unscaled network of sum D.(G N^-1).
 __global__ void __launch_bounds__(256) bsk_pack_kernel(const uint64_t* __restrict__ y, Tw* __restrict__ g, size_t words,
-                                                       uint32_t logn, uint32_t rlast, uint64_t q, int dp) {
+                                                       uint32_t logn, uint32_t rlast, uint32_t kp1, uint32_t rows,
+                                                       const ModQ m, uint64_t ninv, int dp) {
     const size_t stride = (size_t)gridDim.x * blockDim.x;
-    const uint32_t nmask = (1u << logn) - 1u;
-    const uint32_t items_log = logn - rlast;  // out index within a polynomial = e * (N >> rlast) + u  <->  position u * 2^rlast + e
+    const uint32_t N = 1u << logn, E = 1u << rlast, items = N >> rlast;
+    const size_t ggsw_words = (size_t)rows * kp1 * N;
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < words; i += stride) {
-        const uint32_t rem = (uint32_t)i & nmask;
-        const uint32_t e = rem >> items_log, u = rem & ((1u << items_log) - 1u);
+        const size_t gidx = i / ggsw_words;
+        uint32_t rem = (uint32_t)(i - gidx * ggsw_words);
+        const uint32_t j = rem % kp1;
+        rem /= kp1;
+        const uint32_t u = rem % items;
+        rem /= items;
+        const uint32_t e = rem % E, row = rem / E;
         const uint32_t pos = (u << rlast) | e;
-        const size_t src = (i - rem) + bitrev_rt(pos, (int)logn);
-        const uint64_t w = y[src];
+        const size_t src = gidx * ggsw_words + ((size_t)row * kp1 + j) * N + bitrev_rt(pos, (int)logn);
+        const uint64_t w = mulmod(y[src], ninv, m);
         if (dp) {  // FP64 mode: the value as a double, 8 bytes per entry
             reinterpret_cast<uint64_t*>(g)[i] = double_to_bits((double)w);
         } else {
             Tw t;
             t.w = w;
-            t.wp = (uint64_t)((((u128)w) << 64) / q);
+            t.wp = (uint64_t)((((u128)w) << 64) / m.q);
             g[i] = t;
         }
     }
@@ -247,7 +254,8 @@ int fheb_boot_key_create(const fheb_ntt_plan* plan, const fheb_boot_params* para
         // T(row polynomial) once, here, instead of on every external product (bootstrap_engine.cpp:478-487)
         if (rc == FHEB_OK) rc = ntt_forward_device(p, in.ptr<const uint64_t>(), tmp, polys, s);
         if (rc == FHEB_OK) {
-            bsk_pack_kernel<<<stream_grid(words, 256, 8), 256, 0, s>>>(tmp, key->d_bsk, words, p->logn, last_pass_width(p->logn), p->modulus, (int)p->mod.dp);
+            bsk_pack_kernel<<<stream_grid(words, 256, 8), 256, 0, s>>>(tmp, key->d_bsk, words, p->logn, last_pass_width(p->logn), key->k + 1,
+                                                                          (key->k + 1) * key->levels, p->mod, p->inv_n % p->modulus, (int)p->mod.dp);
             if (cudaGetLastError() != cudaSuccess) rc = set_error(FHEB_ERR_NATIVE, "bsk_pack_kernel launch failed");
             count_launch();
         }

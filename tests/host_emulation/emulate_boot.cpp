@@ -65,13 +65,15 @@ static int check(uint32_t threads, uint32_t levels, uint32_t base_log, uint32_t 
     std::vector<uint64_t> g(bsk.size() * GE);
     {
         std::vector<uint64_t> t(N);
-        for (size_t poly = 0; poly < bsk.size() / N; ++poly) {
+        const uint32_t rl = last_pass_width(L), E = 1u << rl, items = N >> rl;
+        for (size_t poly = 0; poly < bsk.size() / N; ++poly) {  // poly = (ggsw, row, j)
             std::memcpy(t.data(), bsk.data() + poly * N, N * 8);
             orc_forward_ntt(t.data(), N, q, fwd.data());
-            const uint32_t rl = last_pass_width(L), items = N >> rl;
+            const size_t gi = poly / ((size_t)rows * KP1), row = (poly / KP1) % rows, j = poly % KP1;
             for (uint32_t pos = 0; pos < N; ++pos) {
-                const uint64_t w = t[bitrev_c(pos, L)];
-                const size_t at = poly * N + (size_t)(pos & ((1u << rl) - 1u)) * items + (pos >> rl);  // [e][u]
+                const uint64_t w = mulmod(t[bitrev_c(pos, L)], sc[2], m);  // times N^-1
+                const uint32_t e = pos & (E - 1), u = pos >> rl;
+                const size_t at = gi * ggsw_w + ((row * E + e) * items + u) * KP1 + j;
                 if (DP) g[at] = double_to_bits((double)w);
                 else { g[2 * at] = w; g[2 * at + 1] = shoup_companion(w, q); }
             }
@@ -96,10 +98,11 @@ static int check(uint32_t threads, uint32_t levels, uint32_t base_log, uint32_t 
     diff = ct0;
     s.diff = diff.data();
     s.add_acc = 0;
+    s.maybe_raw = 0;
     run_step<L, DP, KP1>(threads, s, hf, hi, ninv, m);
     orc_external_product(&p, ct0.data(), bsk.data() + gi * ggsw_w, ref.data());
     if (out != ref) { std::printf("L=%d dp=%d kp1=%d levels=%u: EXTERNAL PRODUCT mismatch\n", L, DP, KP1, levels); ++bad; }
-    acc = ct0;
+    for (size_t i = 0; i < gw; ++i) acc[i] = canon_any(ct0[i], m);  // the kernel loads ct0 reduced
     for (size_t i = 0; i < gw; ++i) diff[i] = submod_canon(canon_any(ct1[i], m), canon_any(ct0[i], m), q);
     s.add_acc = 1;
     run_step<L, DP, KP1>(threads, s, hf, hi, ninv, m);
@@ -120,12 +123,14 @@ static int check(uint32_t threads, uint32_t levels, uint32_t base_log, uint32_t 
         s.diff = nullptr;
         s.add_acc = 1;
         s.gout = nullptr;
+        s.maybe_raw = 1;
         for (uint32_t i = 0; i < n; ++i) {
             const uint32_t rot = lwe_rotation(lwe[i], false, N, q);
             if (rot == 0) continue;
             s.rot = rot;
             s.ggsw = reinterpret_cast<const Tw*>(g.data() + (size_t)i * ggsw_w * GE);
             run_step<L, DP, KP1>(threads, s, hf, hi, ninv, m);
+            s.maybe_raw = 0;
         }
         if (acc != ref) { std::printf("L=%d dp=%d kp1=%d levels=%u trial=%d: BLIND ROTATE mismatch\n", L, DP, KP1, levels, trial); ++bad; }
         // sample extraction
