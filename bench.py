@@ -232,8 +232,17 @@ def run_ours(args):
     algo_bytes = 16.0 * BATCH * N_DEG
     achieved = algo_bytes / (fwd_ms * 1e-3) / 1e9
     roofline = {"bound": "hbm", "kernel": "ntt_forward_kernel<14>", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
-                "algorithmic_bytes_per_launch": algo_bytes, "avg_launch_ms": fwd_ms}
+                "frac": achieved / peak, "traffic": 210.0e6, "traffic_source": "profiles/r01_ntt_n16384_q62_ncu_summary.txt",
+                "peak_source": peak_src, "algorithmic_bytes_per_launch": algo_bytes, "avg_launch_ms": fwd_ms}
+
+    # The transform is integer-multiply bound before it is HBM bound: a Shoup butterfly is
+    # 6 IMAD.WIDE (4 FMA-heavy-pipe cycles per warp each, measured by tools/microbench/pipes.cu) + ~8.1 narrow
+    # IMAD (2 cycles) = ~40.2 pipe cycles per warp-butterfly, so one SM sustains at most 4 * 32 / 40.2 = 3.18
+    # butterflies per clock.  The live figure below uses the measured launch time and the nominal 1965 MHz.
+    bfly = BATCH * (N_DEG // 2) * 14
+    bfly_per_clk_sm = bfly / (fwd_ms * 1e-3) / (148 * 1.965e9)
+    roofline["integer_pipe"] = {"butterflies_per_clk_per_sm": bfly_per_clk_sm, "ceiling": 3.18, "frac": bfly_per_clk_sm / 3.18,
+                                "ncu_fmaheavy_pct": 53.9, "source": "profiles/README.md"}
 
     # ---- end to end: pinned host buffers through the C ABI, copies inside the timed region
     hx = torch.empty((BATCH, N_DEG), dtype=torch.int64).pin_memory()

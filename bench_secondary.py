@@ -120,4 +120,9 @@ def run_bootstrap(fhe, torch, dist, world, rank, dev, barrier, max_over_ranks, b
     return {"value": world * batch / (ms * 1e-3), "unit": "bootstraps/s", "ms": ms, "batch_per_gpu": batch, "n_gpus": world,
             "shape": f"N={N} k={k} n={n} base_log={base_log} L={level} q={q}",
             "modmul_per_bootstrap": bfly + macs,
-            "gmodmul_per_s_per_gpu": (bfly + macs) * batch / (ms * 1e-3) / 1e9}
+            "gmodmul_per_s_per_gpu": (bfly + macs) * batch / (ms * 1e-3) / 1e9,
+            # FP64-pipe roofline: 8 DP operations per butterfly, 7 per multiply-accumulate, ~9 per coefficient
+            # for the conversions and reductions of a step (ncu: 197 k DP operations per step); peak = 64
+            # DFMA/clk/SM (tools/microbench/pipes.cu) x 148 SMs x 1.965 GHz
+            "roofline": {"bound": "fp64-pipe", "achieved": n * 197e3 * batch / (ms * 1e-3) / 1e12, "peak": 148 * 64 * 1.965e9 / 1e12,
+                         "unit": "T DP-op/s", "frac": n * 197e3 * batch / (ms * 1e-3) / (148 * 64 * 1.965e9)}}

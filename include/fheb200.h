@@ -236,6 +236,19 @@ FHEB_API int fheb_tally(const uint64_t* cts, size_t count, uint32_t degree, uint
  * e.g. the result of an NCCL all-gather of per-GPU fheb_tally outputs) into out = [2][N]. */
 FHEB_API int fheb_tally_combine(const uint64_t* partials, size_t parts, uint32_t degree, uint64_t modulus,
                                 uint64_t* out, void* stream);
+/* Streaming tally: replaces the running accumulator of
+ * CiphertextStreamProcessor::stream_add (cpp/src/streaming_processor.cpp:460-526) and the accumulate path
+ * of ChunkedCiphertextProcessor: ballots arrive in chunks, the running total stays on the device.
+ * Semantics follow stream_add: the first ciphertext becomes the accumulator untouched; every later one is
+ * folded with EncryptionEngine::add, so after >= 2 ballots the total is canonical.  add() accepts host or
+ * device chunks ([count][2][N]); total() writes the running total ([2][N]) and may be called at any time. */
+typedef struct fheb_tally_stream fheb_tally_stream;
+FHEB_API int fheb_tally_stream_create(uint32_t degree, uint64_t modulus, fheb_tally_stream** out);
+FHEB_API int fheb_tally_stream_add(fheb_tally_stream* ts, const uint64_t* cts, size_t count, void* stream);
+FHEB_API int fheb_tally_stream_total(const fheb_tally_stream* ts, uint64_t* out, void* stream);
+FHEB_API uint64_t fheb_tally_stream_count(const fheb_tally_stream* ts);
+FHEB_API int fheb_tally_stream_destroy(fheb_tally_stream* ts);
+
 /* replaces EncryptionEngine::multiply (tensor product): cpp/src/encryption.cpp:737-798.
  * ct1, ct2 = [batch][2][N]; out = [batch][3][N]. */
 FHEB_API int fheb_tensor_multiply_batch(const fheb_ntt_plan* plan, const uint64_t* ct1, const uint64_t* ct2,

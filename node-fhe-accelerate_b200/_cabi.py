@@ -88,6 +88,11 @@ SIGNATURES = {
     "fheb_make_test_poly": ([p, i, u64, u64, p], i),
     "fheb_tally": ([p, sz, u32, u64, p, p], i),
     "fheb_tally_combine": ([p, sz, u32, u64, p, p], i),
+    "fheb_tally_stream_create": ([u32, u64, p], i),
+    "fheb_tally_stream_add": ([p, p, sz, p], i),
+    "fheb_tally_stream_total": ([p, p, p], i),
+    "fheb_tally_stream_count": ([p], u64),
+    "fheb_tally_stream_destroy": ([p], i),
     "fheb_tensor_multiply_batch": ([p, p, p, p, sz, p], i),
     "fheb_synth_ballots": ([p, sz, sz, u32, u64, u64, p], i),
     "fheb_launch_count": ([i], u64),

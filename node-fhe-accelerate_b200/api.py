@@ -424,6 +424,38 @@ def synth_ballots(cts_device, first_ballot: int, count: int, degree: int, modulu
     return cts_device
 
 
+class CiphertextStreamAccumulator:
+    """Running tally kept on the device: the accumulator of CiphertextStreamProcessor::stream_add
+    (cpp/src/streaming_processor.cpp:460-526).  add() folds a chunk [count][2][N] (host or device);
+    total() returns the running total [2][N]."""
+
+    def __init__(self, degree: int, modulus: int):
+        self.degree, self.modulus = degree, modulus
+        self._h = C.c_void_p()
+        self._destroy = lib().fheb_tally_stream_destroy
+        check(lib().fheb_tally_stream_create(degree, modulus, C.byref(self._h)))
+
+    def __del__(self):
+        h, self._h = getattr(self, "_h", None), None
+        if h and self._destroy is not None:
+            self._destroy(h)
+
+    def add(self, cts):
+        cts = as_words(cts)
+        count = _words(cts) // (2 * self.degree)
+        check(lib().fheb_tally_stream_add(self._h, _ptr(cts), count, _stream(cts)))
+        return self
+
+    @property
+    def count(self) -> int:
+        return int(lib().fheb_tally_stream_count(self._h))
+
+    def total(self, out=None):
+        out = np.empty((2, self.degree), np.uint64) if out is None else out
+        check(lib().fheb_tally_stream_total(self._h, _ptr(out), _stream(out)))
+        return out
+
+
 def tally_noise_budget(budgets: Sequence[float], variant: str = "linear") -> float:
     """noise_budget metadata of the reference's tally variants (host-side):
     linear = min - log2(count) (encryption.cpp:1359-1360); tree = min - 1 per level (:1413,1437)."""

@@ -195,6 +195,77 @@ int fheb_tally_combine(const uint64_t* partials, size_t parts, uint32_t degree, 
     return tally_entry(partials, parts, degree, modulus, out, true, stream);
 }
 
+// ---- streaming accumulator ------------------------------------------------------------------
+struct TallyStream {
+    uint32_t degree = 0;
+    uint64_t modulus = 0;
+    uint64_t count = 0;        // ballots folded so far
+    uint64_t* d_total = nullptr;   // [2][N]: raw words of the only ballot while count == 1, canonical sums afterwards
+    uint64_t* d_part = nullptr;    // [2][N] scratch
+};
+
+int fheb_tally_stream_create(uint32_t degree, uint64_t modulus, fheb_tally_stream** out) {
+    FHEB_REQUIRE(out != nullptr, "out must not be null");
+    *out = nullptr;
+    FHEB_TRY(ensure_ready());
+    FHEB_REQUIRE(degree > 0 && (degree & (degree - 1)) == 0, "Polynomial degree must be a power of 2");
+    FHEB_REQUIRE(modulus >= 2, "Modulus must be at least 2");
+    TallyStream* t = new TallyStream();
+    t->degree = degree;
+    t->modulus = modulus;
+    const size_t bytes = (size_t)2 * degree * 8;
+    if (cudaMalloc(&t->d_total, bytes) != cudaSuccess || cudaMalloc(&t->d_part, bytes) != cudaSuccess) {
+        fheb_tally_stream_destroy(reinterpret_cast<fheb_tally_stream*>(t));
+        return set_error(FHEB_ERR_OUT_OF_MEMORY, "cudaMalloc of the tally accumulator failed");
+    }
+    *out = reinterpret_cast<fheb_tally_stream*>(t);
+    return FHEB_OK;
+}
+
+int fheb_tally_stream_add(fheb_tally_stream* ts, const uint64_t* cts, size_t count, void* stream) {
+    FHEB_TRY(ensure_ready());
+    FHEB_REQUIRE(ts != nullptr, "tally stream must not be null");
+    if (count == 0) return FHEB_OK;
+    FHEB_REQUIRE(cts != nullptr, "ciphertext pointer must not be null");
+    TallyStream* t = reinterpret_cast<TallyStream*>(ts);
+    cudaStream_t s = (cudaStream_t)stream;
+    const uint32_t width = 2 * t->degree;
+    // first ballot ever: it becomes the accumulator as it is (stream_add, :482-484)
+    uint64_t* dst = (t->count == 0) ? t->d_total : t->d_part;
+    const bool raw_single = (t->count == 0 && count == 1);
+    if (is_device_pointer(cts)) {
+        FHEB_TRY(tally_device(cts, count, width, t->modulus, dst, raw_single, s));
+    } else {  // host chunk: reuse the one-shot entry point's staging / pipelining into a device result
+        FHEB_TRY(tally_entry(cts, count, t->degree, t->modulus, dst, raw_single, stream));
+    }
+    if (t->count != 0) FHEB_TRY(elementwise_device(0 /* add: reduces both inputs first */, t->d_total, t->d_part, 0, t->d_total, width, t->modulus, s));
+    t->count += count;
+    return FHEB_OK;
+}
+
+int fheb_tally_stream_total(const fheb_tally_stream* ts, uint64_t* out, void* stream) {
+    FHEB_TRY(ensure_ready());
+    FHEB_REQUIRE(ts != nullptr && out != nullptr, "tally stream and out must not be null");
+    const TallyStream* t = reinterpret_cast<const TallyStream*>(ts);
+    // message follows EncryptionEngine::batch_add on an empty input, cpp/src/encryption.cpp:1328-1330
+    FHEB_REQUIRE(t->count != 0, "Cannot add empty vector of ciphertexts");
+    cudaStream_t s = (cudaStream_t)stream;
+    FHEB_CUDA(cudaMemcpyAsync(out, t->d_total, (size_t)2 * t->degree * 8, cudaMemcpyDefault, s));
+    if (!is_device_pointer(out)) FHEB_CUDA(cudaStreamSynchronize(s));
+    return FHEB_OK;
+}
+
+uint64_t fheb_tally_stream_count(const fheb_tally_stream* ts) { return ts ? reinterpret_cast<const TallyStream*>(ts)->count : 0; }
+
+int fheb_tally_stream_destroy(fheb_tally_stream* ts) {
+    TallyStream* t = reinterpret_cast<TallyStream*>(ts);
+    if (!t) return FHEB_OK;
+    if (t->d_total) cudaFree(t->d_total);
+    if (t->d_part) cudaFree(t->d_part);
+    delete t;
+    return FHEB_OK;
+}
+
 int fheb_tensor_multiply_batch(const fheb_ntt_plan* plan, const uint64_t* ct1, const uint64_t* ct2, uint64_t* out,
                                size_t batch, void* stream) {
     // EncryptionEngine::multiply, cpp/src/encryption.cpp:737-798: T on the four operand

@@ -363,3 +363,26 @@ def test_tensor_multiply_batch_matches_oracle(fhe, torch, oracle):
         exp = np.stack([oracle.tensor_multiply(ct1[i], ct2[i], q, fwd, inv, inv_n) for i in range(9)])
         eq(got, exp)
         eq(ring.tensor_multiply(ct1[:2], ct2[:2]), exp[:2])  # host buffers
+
+
+def test_streaming_tally_accumulator(fhe, torch, oracle):
+    """Running device-resident tally (stream_add semantics): chunks of ballots, host and device, any sizes."""
+    n, q = 1024, QT
+    rng = np.random.default_rng(9)
+    cts = rng.integers(0, q, size=(1500, 2, n), dtype=np.uint64)
+    cts[0] = rng.integers(0, 2**64, size=(2, n), dtype=np.uint64)  # the first ballot may hold unreduced words
+    acc = fhe.CiphertextStreamAccumulator(n, q)
+    with pytest.raises(fhe.FheError):
+        acc.total()  # nothing added yet
+    acc.add(cts[0:1])
+    eq(acc.total(), cts[0])  # first ciphertext becomes the accumulator untouched
+    done = 1
+    for size, on_device in [(1, False), (2, True), (61, False), (700, True), (735, False)]:
+        chunk = cts[done:done + size]
+        acc.add(dev(torch, chunk) if on_device else chunk)
+        done += size
+        assert acc.count == done
+        eq(acc.total(), oracle.tally(cts[:done], q))
+    out = torch.empty((2, n), dtype=torch.int64, device="cuda")
+    acc.total(out=out)
+    eq(host(out), oracle.tally(cts, q))
