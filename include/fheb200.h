@@ -80,6 +80,22 @@ typedef struct fheb_device_info {
 } fheb_device_info;
 FHEB_API int fheb_device_info_get(fheb_device_info* out);
 
+/* The scalar class the reference's addon exports today: ModularArithmetic::{new, montgomery_mul, mod_add,
+ * mod_sub, to_montgomery, from_montgomery, get_modulus} (src/native/lib.rs:44-120, cpp/src/modular_arithmetic.cpp:
+ * 52-165).  One scalar per call: host-side integer code with no GPU value, kept so that the
+ * addon's existing surface has a home behind this boundary.  It repeats the reference word for word,
+ * INCLUDING its Montgomery constant q_inv = -(q^-1 mod (2^64 - 1)) (mathematically not a Montgomery
+ * constant) with AArch64 division semantics (x / 0 = 0, x % 0 = x).  Not used by any kernel. */
+typedef struct fheb_modarith fheb_modarith;
+FHEB_API int fheb_modarith_create(uint64_t modulus, fheb_modarith** out);
+FHEB_API int fheb_modarith_destroy(fheb_modarith* m);
+FHEB_API uint64_t fheb_modarith_montgomery_mul(const fheb_modarith* m, uint64_t a, uint64_t b);
+FHEB_API uint64_t fheb_modarith_mod_add(const fheb_modarith* m, uint64_t a, uint64_t b);
+FHEB_API uint64_t fheb_modarith_mod_sub(const fheb_modarith* m, uint64_t a, uint64_t b);
+FHEB_API uint64_t fheb_modarith_to_montgomery(const fheb_modarith* m, uint64_t a);
+FHEB_API uint64_t fheb_modarith_from_montgomery(const fheb_modarith* m, uint64_t a);
+FHEB_API uint64_t fheb_modarith_get_modulus(const fheb_modarith* m);
+
 /* Buffer helpers; replace MetalComputeContext::create_buffer / release_buffer /
  * copy_to_buffer / copy_from_buffer / synchronize: cpp/include/metal_compute.h:46-50,79. */
 FHEB_API int fheb_device_alloc(void** out, size_t bytes);

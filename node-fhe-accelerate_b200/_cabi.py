@@ -56,6 +56,14 @@ SIGNATURES = {
     "fheb_host_alloc": ([p, sz], i),
     "fheb_host_free": ([p], i),
     "fheb_copy": ([p, p, sz, p], i),
+    "fheb_modarith_create": ([u64, p], i),
+    "fheb_modarith_destroy": ([p], i),
+    "fheb_modarith_montgomery_mul": ([p, u64, u64], u64),
+    "fheb_modarith_mod_add": ([p, u64, u64], u64),
+    "fheb_modarith_mod_sub": ([p, u64, u64], u64),
+    "fheb_modarith_to_montgomery": ([p, u64], u64),
+    "fheb_modarith_from_montgomery": ([p, u64], u64),
+    "fheb_modarith_get_modulus": ([p], u64),
     "fheb_synchronize": ([p], i),
     "fheb_ntt_plan_create": ([u32, u64, p], i),
     "fheb_ntt_plan_create_with_tables": ([u32, u64, p, p, u64, p], i),

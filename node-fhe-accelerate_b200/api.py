@@ -100,6 +100,52 @@ def synchronize() -> None:
     check(lib().fheb_synchronize(None))
 
 
+# --------------------------------------------------------------------- ModularArithmetic --
+class ModularArithmetic:
+    """The scalar class of the reference's addon (src/native/lib.rs:44-120): host-side, one value per call,
+    word-for-word the reference's arithmetic including its Montgomery-constant quirk."""
+
+    def __init__(self, modulus: int):
+        if modulus <= 0:
+            raise FheError(_cabi.INVALID_PARAMETERS, "Modulus must be positive")  # lib.rs:53-55
+        self._h = C.c_void_p()
+        self._destroy = lib().fheb_modarith_destroy
+        check(lib().fheb_modarith_create(modulus, C.byref(self._h)))
+
+    def __del__(self):
+        h, self._h = getattr(self, "_h", None), None
+        if h and self._destroy is not None:
+            self._destroy(h)
+
+    @staticmethod
+    def _nonneg(*vals):
+        if any(v < 0 for v in vals):
+            raise FheError(_cabi.INVALID_PARAMETERS, "Inputs must be non-negative")  # lib.rs:64-66
+
+    def montgomery_mul(self, a: int, b: int) -> int:
+        self._nonneg(a, b)
+        return int(lib().fheb_modarith_montgomery_mul(self._h, a, b))
+
+    def mod_add(self, a: int, b: int) -> int:
+        self._nonneg(a, b)
+        return int(lib().fheb_modarith_mod_add(self._h, a, b))
+
+    def mod_sub(self, a: int, b: int) -> int:
+        self._nonneg(a, b)
+        return int(lib().fheb_modarith_mod_sub(self._h, a, b))
+
+    def to_montgomery(self, a: int) -> int:
+        self._nonneg(a)
+        return int(lib().fheb_modarith_to_montgomery(self._h, a))
+
+    def from_montgomery(self, a: int) -> int:
+        self._nonneg(a)
+        return int(lib().fheb_modarith_from_montgomery(self._h, a))
+
+    def get_modulus(self) -> int:
+        return int(lib().fheb_modarith_get_modulus(self._h))
+
+
 # ------------------------------------------------------------------------- NTTProcessor --
 class NTTProcessor:
     """cpp/include/ntt_processor.h:49-303."""

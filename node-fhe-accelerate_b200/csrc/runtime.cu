@@ -318,6 +318,81 @@ int fheb_synchronize(void* stream) {
     return FHEB_OK;
 }
 
+// ---- scalar ModularArithmetic (the addon's existing surface; host-side, see include/fheb200.h) ------
+struct ScalarModArith {
+    uint64_t modulus, r2_mod_q, q_inv;
+};
+typedef unsigned __int128 u128_t;
+
+static uint64_t scalar_mod_inverse(uint64_t a, uint64_t m) {  // cpp/src/modular_arithmetic.cpp:8-31, AArch64 division
+    if (m == 0) return 0;
+    int64_t m0 = (int64_t)m, x0 = 0, x1 = 1;
+    if (m == 1) return 0;
+    while (a > 1) {
+        const int64_t quo = (m != 0) ? (int64_t)(a / m) : 0;
+        int64_t t = (int64_t)m;
+        m = (m != 0) ? (a % m) : a;
+        a = (uint64_t)t;
+        t = x0;
+        x0 = x1 - quo * x0;
+        x1 = t;
+    }
+    if (x1 < 0) x1 += m0;
+    return (uint64_t)x1;
+}
+
+static uint64_t scalar_montgomery_reduce(const ScalarModArith* c, uint64_t hi, uint64_t lo) {  // :84-110
+    const uint64_t m = lo * c->q_inv;
+    const u128_t mq = (u128_t)m * c->modulus;
+    const u128_t sum = ((u128_t)hi << 64) + lo + mq;  // wraps modulo 2^128 exactly as the reference's sum does
+    uint64_t t = (uint64_t)(sum >> 64);
+    if (t >= c->modulus) t -= c->modulus;
+    return t;
+}
+
+int fheb_modarith_create(uint64_t modulus, fheb_modarith** out) {
+    FHEB_REQUIRE(out != nullptr, "out must not be null");
+    *out = nullptr;
+    // message follows MontgomeryConstants::MontgomeryConstants, cpp/src/modular_arithmetic.cpp:53-55
+    FHEB_REQUIRE(modulus != 0 && (modulus & 1) != 0, "Modulus must be odd and non-zero for Montgomery arithmetic");
+    ScalarModArith* c = new ScalarModArith();
+    c->modulus = modulus;
+    const uint64_t r_mod_q = (uint64_t)((((u128_t)1) << 64) % modulus);
+    c->r2_mod_q = (uint64_t)(((u128_t)r_mod_q * r_mod_q) % modulus);
+    c->q_inv = (~scalar_mod_inverse(modulus, UINT64_MAX)) + 1;  // :69-70
+    *out = reinterpret_cast<fheb_modarith*>(c);
+    return FHEB_OK;
+}
+int fheb_modarith_destroy(fheb_modarith* m) {
+    delete reinterpret_cast<ScalarModArith*>(m);
+    return FHEB_OK;
+}
+uint64_t fheb_modarith_montgomery_mul(const fheb_modarith* m, uint64_t a, uint64_t b) {  // :112-120
+    const u128_t p = (u128_t)a * b;
+    return scalar_montgomery_reduce(reinterpret_cast<const ScalarModArith*>(m), (uint64_t)(p >> 64), (uint64_t)p);
+}
+uint64_t fheb_modarith_mod_add(const fheb_modarith* m, uint64_t a, uint64_t b) {  // :122-136
+    const uint64_t q = reinterpret_cast<const ScalarModArith*>(m)->modulus;
+    a %= q;
+    b %= q;
+    uint64_t s = a + b;
+    if (s < a || s >= q) s -= q;
+    return s;
+}
+uint64_t fheb_modarith_mod_sub(const fheb_modarith* m, uint64_t a, uint64_t b) {  // :138-153
+    const uint64_t q = reinterpret_cast<const ScalarModArith*>(m)->modulus;
+    a %= q;
+    b %= q;
+    return a >= b ? a - b : q - (b - a);
+}
+uint64_t fheb_modarith_to_montgomery(const fheb_modarith* m, uint64_t a) {  // :155-159
+    return fheb_modarith_montgomery_mul(m, a, reinterpret_cast<const ScalarModArith*>(m)->r2_mod_q);
+}
+uint64_t fheb_modarith_from_montgomery(const fheb_modarith* m, uint64_t a) {  // :161-165
+    return scalar_montgomery_reduce(reinterpret_cast<const ScalarModArith*>(m), 0, a);
+}
+uint64_t fheb_modarith_get_modulus(const fheb_modarith* m) { return reinterpret_cast<const ScalarModArith*>(m)->modulus; }
+
 uint64_t fheb_launch_count(int reset) {
     uint64_t v = g_launches.load();
     if (reset) g_launches.store(0);

@@ -246,6 +246,27 @@ int ref_tensor_multiply(void* h, const uint64_t* ct1, const uint64_t* ct2, uint6
     REF_CATCH
 }
 
+/* ------------------------------------------------- scalar ModularArithmetic - */
+/* the class behind the reference's N-API addon (src/native/lib.rs:44-120)      */
+int ref_scalar_create(uint64_t modulus, void** out) {
+    REF_TRY
+    *out = new ModularArithmetic(modulus);
+    REF_CATCH
+}
+void ref_scalar_destroy(void* h) { delete static_cast<ModularArithmetic*>(h); }
+/* op: 0 montgomery_mul, 1 mod_add, 2 mod_sub, 3 to_montgomery, 4 from_montgomery, 5 get_modulus */
+uint64_t ref_scalar_op(void* h, int op, uint64_t a, uint64_t b) {
+    auto* m = static_cast<ModularArithmetic*>(h);
+    switch (op) {
+        case 0: return m->montgomery_mul(a, b);
+        case 1: return m->mod_add(a, b);
+        case 2: return m->mod_sub(a, b);
+        case 3: return m->to_montgomery(a);
+        case 4: return m->from_montgomery(a);
+        default: return m->get_modulus();
+    }
+}
+
 /* ------------------------------------------------------------ multi-limb - */
 /* MultiLimbModularArithmetic: cpp/src/modular_arithmetic.cpp:471-693        */
 int ref_mlimb_create(const uint64_t* q_limbs, size_t limbs, void** out) {

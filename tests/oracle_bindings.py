@@ -343,6 +343,9 @@ class RefOracle:
             "tally_linear": b("ref_tally_linear", "p p sz p"),
             "tally_tree": b("ref_tally_tree", "p p sz p"),
             "tensor": b("ref_tensor_multiply", "p p p p"),
+            "scalar_create": b("ref_scalar_create", "u64 p"),
+            "scalar_destroy": b("ref_scalar_destroy", "p", None),
+            "scalar_op": b("ref_scalar_op", "p int u64 u64", C.c_uint64),
             "ml_create": b("ref_mlimb_create", "p sz p"),
             "ml_destroy": b("ref_mlimb_destroy", "p", None),
             "ml_consts": b("ref_mlimb_constants", "p p"),
@@ -448,6 +451,20 @@ class RefOracle:
         out = np.zeros((3, ct1.shape[-1]), np.uint64)
         self.call("tensor", h, ct1, ct2, out)
         return out
+
+    # -- scalar ModularArithmetic (the reference addon's class)
+    SCALAR_OPS = {"montgomery_mul": 0, "mod_add": 1, "mod_sub": 2, "to_montgomery": 3, "from_montgomery": 4, "get_modulus": 5}
+
+    def scalar_create(self, modulus):
+        h = C.c_void_p()
+        self._ck(self._f["scalar_create"](modulus, C.addressof(h)))
+        return h
+
+    def scalar_destroy(self, h):
+        self._f["scalar_destroy"](h)
+
+    def scalar_op(self, h, op, a=0, b=0):
+        return int(self._f["scalar_op"](h, self.SCALAR_OPS[op], a, b))
 
     # -- MultiLimbModularArithmetic
     def mlimb_create(self, q_limbs):

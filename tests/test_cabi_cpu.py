@@ -138,3 +138,29 @@ def test_sharded_tally_exchange_gloo_world2(fhe, tmp_path):
     outs = [p.communicate(timeout=180)[0] for p in procs]
     for r, (p, o) in enumerate(zip(procs, outs)):
         assert p.returncode == 0 and f"ok {r}" in o, o
+
+
+def test_scalar_modular_arithmetic_matches_reference(fhe, ref):
+    """The addon's existing scalar class (src/native/lib.rs:44-120): host-side code, word-for-word the
+    reference's - including its (mathematically wrong) Montgomery constant."""
+    rng = np.random.default_rng(17)
+    for q in (17, 97, 132120577, 1099511678977, 4611686018326724609, 0xFFFFFFFFFFFFFFC5):
+        h = ref.scalar_create(q)
+        m = fhe.ModularArithmetic(q)
+        try:
+            assert m.get_modulus() == ref.scalar_op(h, "get_modulus") == q
+            vals = [0, 1, q - 1, q, q + 1] + [int(v) for v in rng.integers(0, 2**63, size=200, dtype=np.uint64)]
+            for a, b in zip(vals, reversed(vals)):
+                for op in ("montgomery_mul", "mod_add", "mod_sub"):
+                    assert getattr(m, op)(a, b) == ref.scalar_op(h, op, a, b), (q, op, a, b)
+                for op in ("to_montgomery", "from_montgomery"):
+                    assert getattr(m, op)(a) == ref.scalar_op(h, op, a), (q, op, a)
+        finally:
+            ref.scalar_destroy(h)
+    for bad in (0, 16):
+        with pytest.raises(fhe.FheError) as e:
+            fhe.ModularArithmetic(bad)
+        assert "Modulus must be" in str(e.value)
+    with pytest.raises(fhe.FheError) as e:
+        fhe.ModularArithmetic(17).mod_add(-1, 2)
+    assert "non-negative" in str(e.value)
