@@ -9,8 +9,7 @@
 // So the network can run on the data where it lies (no permutation): distance N/2 first,
 // distance 1 last, one twiddle per contiguous block of N/2^s positions, and the result for
 // permuted entry p ends up at position bitrev(p).  The device twiddle table is therefore
-// stored block-ordered as a binary heap: entry (2^s + b) holds table[bitrev_s(b) << (L-1-s)],
-// and the children of the twiddle used at one stage are the two twiddles of the next.
+// stored block-ordered: block b of stage s uses table[bitrev_s(b) << (L-1-s)] (layout: tw_index).
 // The inverse (ntt_processor.cpp:325-380) is the same pairs walked backwards with
 // (A,B) <- (A + B, (A - B)*w), then the bit-reversal (which brings entry p back to position
 // bitrev(bitrev(i)) = i, i.e. nothing to move) and the scaling by N^-1.
