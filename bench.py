@@ -38,6 +38,7 @@ BATCH = 1024
 Q62 = 4611686018326724609
 QT = 1099511678977  # substitute prime for the tfhe-128-fast shape (preset modulus 2^40+1 is composite)
 METRIC = "ntt_coeffs_per_sec_n16384_batched"
+WORKLOAD = f"forward+inverse transform, N={N_DEG}, batch {BATCH} per GPU, q={Q62}"
 UNIT = "coeff/s"
 
 
@@ -157,7 +158,7 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "u64", "data": "synthetic",
-        "config": {"workload": f"forward+inverse transform, N={N_DEG}, batch {BATCH}, q={Q62} (CPU: bounded sample)"},
+        "config": {"workload": WORKLOAD, "note": "reference arm: each step is a bounded sample of the workload (cpu_baseline.sample)"},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": used, "kind": kind, "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -285,7 +286,7 @@ def run_ours(args):
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64",
             "data": "synthetic",
-            "config": {"workload": f"forward+inverse transform, N={N_DEG}, batch {BATCH} per GPU, q={Q62}",
+            "config": {"workload": WORKLOAD,
                        "l2": f"{NSETS} rotating input sets of 134 MB + 2 output buffers: larger than the 126 MB L2",
                        "sharding": "batch split across ranks, no collective"},
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches),

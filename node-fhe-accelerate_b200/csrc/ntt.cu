@@ -99,7 +99,11 @@ static int plan_finish(NttPlan* p) {
 template <int L, bool DP>
 struct Geometry {  // threads per block, polynomials per block
     static constexpr int PPC = (L <= 9) ? (1024 >> L) : (L == 10 ? 2 : 1);
+#if defined(FHEB_EXP_R3)
+    static constexpr int THREADS = (L <= 11) ? 128 : (L == 12 ? 256 : 1024);
+#else
     static constexpr int THREADS = (L <= 11) ? 128 : (L == 12 ? 256 : 512);
+#endif
     static constexpr size_t SMEM = (Plan<L>::P > 1) ? (size_t)PPC * (1u << L) * 8 : 0;
 };
 

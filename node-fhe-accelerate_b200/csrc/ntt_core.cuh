@@ -318,26 +318,31 @@ FHEB_HD uint64_t scale_word(uint64_t x, const Tw& ninv, const ModQ& m) {
 }
 
 // ---- pass plans: how the L stages are split into register passes ----------------------
-// plan<L>::R[p] = stages in pass p (forward order); at most 4 passes, each of 1..4 stages.
+// plan<L>::R[p] = stages in pass p (forward order); at most 5 passes, each of 1..4 stages.
 template <int L> struct Plan;
 #define FHEB_PLAN(L_, P_, ...)                         \
     template <> struct Plan<L_> {                      \
         static constexpr int P = P_;                   \
-        static constexpr int R[4] = {__VA_ARGS__};     \
+        static constexpr int R[5] = {__VA_ARGS__};     \
     };
-FHEB_PLAN(2, 1, 2, 0, 0, 0)
-FHEB_PLAN(3, 1, 3, 0, 0, 0)
-FHEB_PLAN(4, 1, 4, 0, 0, 0)
-FHEB_PLAN(5, 2, 3, 2, 0, 0)
-FHEB_PLAN(6, 2, 3, 3, 0, 0)
-FHEB_PLAN(7, 2, 4, 3, 0, 0)
-FHEB_PLAN(8, 2, 4, 4, 0, 0)
-FHEB_PLAN(9, 3, 3, 3, 3, 0)
-FHEB_PLAN(10, 3, 4, 3, 3, 0)
-FHEB_PLAN(11, 3, 4, 4, 3, 0)
-FHEB_PLAN(12, 3, 4, 4, 4, 0)
-FHEB_PLAN(13, 4, 4, 3, 3, 3)
-FHEB_PLAN(14, 4, 4, 4, 3, 3)
+FHEB_PLAN(2, 1, 2, 0, 0, 0, 0)
+FHEB_PLAN(3, 1, 3, 0, 0, 0, 0)
+FHEB_PLAN(4, 1, 4, 0, 0, 0, 0)
+FHEB_PLAN(5, 2, 3, 2, 0, 0, 0)
+FHEB_PLAN(6, 2, 3, 3, 0, 0, 0)
+FHEB_PLAN(7, 2, 4, 3, 0, 0, 0)
+FHEB_PLAN(8, 2, 4, 4, 0, 0, 0)
+FHEB_PLAN(9, 3, 3, 3, 3, 0, 0)
+FHEB_PLAN(10, 3, 4, 3, 3, 0, 0)
+FHEB_PLAN(11, 3, 4, 4, 3, 0, 0)
+FHEB_PLAN(12, 3, 4, 4, 4, 0, 0)
+#if defined(FHEB_EXP_R3)  // experiment: 8-value passes only (fewer registers, more warps)
+FHEB_PLAN(13, 5, 3, 3, 3, 2, 2)
+FHEB_PLAN(14, 5, 3, 3, 3, 3, 2)
+#else
+FHEB_PLAN(13, 4, 4, 3, 3, 3, 0)
+FHEB_PLAN(14, 4, 4, 4, 3, 3, 0)
+#endif
 #undef FHEB_PLAN
 
 template <int L, int PASS>
@@ -357,14 +362,14 @@ constexpr uint32_t plan_tw_offset() {  // first table entry of pass PASS: sum ov
     return off;
 }
 // runtime view of the plan for the host-side table builders
-inline void plan_runtime(int L, int& P, int (&R)[4]) {
+inline void plan_runtime(int L, int& P, int (&R)[5]) {
     P = 0;
-    R[0] = R[1] = R[2] = R[3] = 0;
+    R[0] = R[1] = R[2] = R[3] = R[4] = 0;
     switch (L) {
 #define FHEB_PLAN_RT(L_)                                          \
     case L_:                                                      \
         P = Plan<L_>::P;                                          \
-        for (int i = 0; i < 4; ++i) R[i] = Plan<L_>::R[i];        \
+        for (int i = 0; i < 5; ++i) R[i] = Plan<L_>::R[i];        \
         break;
         FHEB_PLAN_RT(2) FHEB_PLAN_RT(3) FHEB_PLAN_RT(4) FHEB_PLAN_RT(5) FHEB_PLAN_RT(6) FHEB_PLAN_RT(7) FHEB_PLAN_RT(8)
         FHEB_PLAN_RT(9) FHEB_PLAN_RT(10) FHEB_PLAN_RT(11) FHEB_PLAN_RT(12) FHEB_PLAN_RT(13) FHEB_PLAN_RT(14)

@@ -25,7 +25,7 @@ inline uint32_t log2_exact(uint32_t n) {
 // b = (blk << a) + g at stage s = S0 + a is table[bitrev_s(b) << (L-1-s)].  N - 1 entries, padded to N.
 template <class Put>
 inline void for_each_twiddle(uint32_t L, Put put) {
-    int P, R[4];
+    int P, R[5];
     plan_runtime((int)L, P, R);
     uint32_t idx = 0;
     int s0 = 0;
@@ -61,7 +61,7 @@ inline std::vector<uint64_t> build_heap_table_dp(const uint64_t* table, uint32_t
 
 // width (log2) of the last register pass: the bootstrapping key is stored [..][e][u] for position u*2^R + e
 inline uint32_t last_pass_width(uint32_t L) {
-    int P, R[4];
+    int P, R[5];
     plan_runtime((int)L, P, R);
     return (uint32_t)R[P - 1];
 }
