@@ -165,8 +165,13 @@ int run_host_pipeline(size_t items, std::vector<PipeArg> args, const PipeFn& fn,
             }
         if (args[i].stride > max_stride) max_stride = args[i].stride;
     }
-    // ~8 MB per buffer per chunk: long enough for PCIe efficiency, short enough to pipeline
-    size_t chunk = chunk_items ? chunk_items : (8u << 20) / max_stride;
+    // ~16 MB per buffer per chunk: long enough for PCIe efficiency, short enough to pipeline
+    static const size_t chunk_bytes = [] {  // FHEB_PIPE_CHUNK_MB: tuning knob
+        const char* e = getenv("FHEB_PIPE_CHUNK_MB");
+        const long mb = e ? atol(e) : 0;
+        return (size_t)(mb > 0 ? mb : 16) << 20;  // 16 MB measured best on PCIe Gen5 (tools/prof_e2e.py)
+    }();
+    size_t chunk = chunk_items ? chunk_items : chunk_bytes / max_stride;
     if (chunk < 1) chunk = 1;
     if (chunk > items) chunk = items;
     const size_t nchunks = (items + chunk - 1) / chunk;

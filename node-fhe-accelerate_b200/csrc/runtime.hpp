@@ -104,6 +104,6 @@ struct PipeArg {
 };
 using PipeFn = std::function<int(void* const* dev, size_t first_item, size_t n_items, cudaStream_t s)>;
 bool all_host(std::initializer_list<const void*> ptrs);  // true when no non-null pointer is device memory
-int run_host_pipeline(size_t items, std::vector<PipeArg> args, const PipeFn& fn, size_t chunk_items = 0 /* 0: ~8 MB per buffer */);
+int run_host_pipeline(size_t items, std::vector<PipeArg> args, const PipeFn& fn, size_t chunk_items = 0 /* 0: ~16 MB per buffer */);
 
 }  // namespace fheb

@@ -161,7 +161,8 @@ static int tally_entry(const uint64_t* cts, size_t count, uint32_t degree, uint6
         int rc = run_host_pipeline(count, {{cts, row, 0, true, false}},
                                    [&](void* const* d, size_t first, size_t n, cudaStream_t ps) {
                                        return tally_device(static_cast<const uint64_t*>(d[0]), n, width, q, partial + (first / chunk) * width, false, ps);
-                                   });
+                                   },
+                                   chunk);
         uint64_t* dout = nullptr;
         if (rc == FHEB_OK && cudaMalloc(&dout, row) != cudaSuccess) rc = set_error(FHEB_ERR_OUT_OF_MEMORY, "cudaMalloc failed");
         if (rc == FHEB_OK) rc = tally_device(partial, nchunks, width, q, dout, false, s);
