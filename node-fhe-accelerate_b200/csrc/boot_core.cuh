@@ -57,6 +57,13 @@ FHEB_HD uint64_t gadget_digit(uint64_t c, uint32_t shift, uint64_t mask, uint64_
 template <int L>
 constexpr int boot_phases() { return 2 * Plan<L>::P - 1; }
 
+// Bound (in units of q) on the multiply-accumulate sums that enter the inverse network: the integer path
+// keeps its running sum in [0, 2q); the FP64 path adds |t| < q per gadget row and reduces only when more
+// than BOOT_DP_ROWS_LAZY rows were summed (block-uniform), so the common 2-row case skips the reduction.
+constexpr int BOOT_DP_ROWS_LAZY = 2;
+template <bool DP>
+constexpr int boot_kacc() { return 2; }
+
 // ---- phase 0: difference, decomposition and the first forward pass ------------------------
 template <int L, bool DP, int KP1>
 FHEB_HD void boot_first_pass(uint32_t tid, uint32_t nthreads, const BootStep& s, const Tw* __restrict__ tw,
@@ -193,11 +200,13 @@ FHEB_HD void boot_mid_pass(uint32_t tid, uint32_t nthreads, const BootStep& s, c
         }
 #pragma unroll
         for (int j = 0; j < KP1; ++j) {
-            if constexpr (DP) {  // back to |v| <= q/2 + 1 so that the inverse passes' static bounds hold
+            if constexpr (DP) {  // more rows than the static bound covers: back to |v| <= q/2 + 1
+                if (rows > (uint32_t)BOOT_DP_ROWS_LAZY) {
 #pragma unroll
-                for (int e = 0; e < E; ++e) out[j][e] = double_to_bits(dp_reduce(bits_to_double(out[j][e]), m));
+                    for (int e = 0; e < E; ++e) out[j][e] = double_to_bits(dp_reduce(bits_to_double(out[j][e]), m));
+                }
             }
-            inv_stages<R, S0, DP ? 1 : 2, DP, false>(out[j], twi, TB, m);
+            inv_stages<R, S0, boot_kacc<DP>(), DP, false>(out[j], twi, TB, m);
             uint64_t* dst = s.work + (size_t)j * N;
 #pragma unroll
             for (int e = 0; e < E; ++e) dst[pb ^ swz((uint32_t)e)] = out[j][e];
@@ -212,7 +221,7 @@ FHEB_HD void boot_final_pass(uint32_t tid, uint32_t nthreads, const BootStep& s,
     constexpr int R = Plan<L>::R[0];
     constexpr int E = 1 << R;
     constexpr int EB = L - R;
-    constexpr int KIN = plan_inv_kin<L, DP, 0>();
+    constexpr int KIN = plan_inv_kin<L, DP, 0, boot_kacc<DP>()>();
     constexpr int KFIN = inv_pass_k(KIN, R, DP);
     constexpr uint32_t N = 1u << L;
     constexpr uint32_t ITEMS = N >> R;
@@ -261,7 +270,7 @@ FHEB_HD void boot_phase(uint32_t tid, uint32_t nthreads, const BootStep& s, cons
     } else if constexpr (PH == P - 1) {
         boot_mid_pass<L, DP, KP1>(tid, nthreads, s, twf, twi, m);
     } else if constexpr (PH < 2 * P - 2) {
-        inv_pass<L, DP, 2 * P - 2 - PH, IO_SMEM, IO_SMEM>(tid, nthreads, (uint32_t)KP1, nullptr, nullptr, s.work, twi, ninv, m);
+        inv_pass<L, DP, 2 * P - 2 - PH, IO_SMEM, IO_SMEM, true, 0, boot_kacc<DP>()>(tid, nthreads, (uint32_t)KP1, nullptr, nullptr, s.work, twi, ninv, m);
     } else {
         boot_final_pass<L, DP, KP1>(tid, nthreads, s, twi, ninv, m);
     }

@@ -383,9 +383,9 @@ constexpr int plan_fwd_kin() {  // bound on values entering forward pass PASS (i
     for (int p = 0; p < PASS; ++p) K = fwd_pass_k(K, Plan<L>::R[p], p == 0, DP);
     return K;
 }
-template <int L, bool DP, int PASS>
-constexpr int plan_inv_kin() {  // bound entering inverse pass PASS (run order P-1 .. 0), inputs < kin0*q
-    int K = 1;
+template <int L, bool DP, int PASS, int KSTART = 1>
+constexpr int plan_inv_kin() {  // bound entering inverse pass PASS (run order P-1 .. 0), first executed pass fed values < KSTART*q
+    int K = KSTART;
     for (int p = Plan<L>::P - 1; p > PASS; --p) K = inv_pass_k(K, Plan<L>::R[p], DP);
     return K;
 }
@@ -558,14 +558,14 @@ FHEB_HD void polymul_mid_pass(uint32_t tid, uint32_t nthreads, uint32_t polys, c
 // may read the reference's input order (bit-reversed positions) from global memory; the
 // last one executed (PASS == 0) multiplies by N^-1 (`ninv`, Shoup pair) and stores canonical
 // values in natural order.
-template <int L, bool DP, int PASS, int IN, int OUT, bool BITREV_IN = true, int IPT = 0>
+template <int L, bool DP, int PASS, int IN, int OUT, bool BITREV_IN = true, int IPT = 0, int KSTART = 1>
 FHEB_HD void inv_pass(uint32_t tid, uint32_t nthreads, uint32_t polys, const uint64_t* gin, uint64_t* gout,
                       uint64_t* smem, const Tw* __restrict__ tw, const Tw ninv, const ModQ& m) {
     constexpr int R = Plan<L>::R[PASS];
     constexpr int E = 1 << R;
     constexpr int S0 = plan_s0<L, PASS>();
     constexpr int EB = L - S0 - R;
-    constexpr int KIN = plan_inv_kin<L, DP, PASS>();
+    constexpr int KIN = plan_inv_kin<L, DP, PASS, KSTART>();
     constexpr bool FIRST = (PASS == Plan<L>::P - 1);
     constexpr uint32_t N = 1u << L;
     constexpr uint32_t ITEMS = N >> R;
