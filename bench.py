@@ -67,12 +67,12 @@ class ClockSampler:
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index: int):
-        self.index, self.samples, self.proc = index, [], None
+        self.index, self.samples, self.proc, self.t_mark = index, [], None, 0.0
 
     def __enter__(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "20"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
@@ -82,7 +82,11 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.samples.append([s.strip() for s in line.split(",")])
+            self.samples.append((time.perf_counter(), [s.strip() for s in line.split(",")]))
+
+    def mark(self):
+        """Samples taken before this call (idle GPU, nvidia-smi start-up) are not part of the summary."""
+        self.t_mark = time.perf_counter()
 
     def __exit__(self, *a):
         if self.proc:
@@ -93,7 +97,9 @@ class ClockSampler:
     def summary(self):
         sm, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for s in self.samples:
+        for t, s in self.samples:
+            if t < self.t_mark:
+                continue
             try:
                 sm.append(float(s[0]))
                 mx.append(float(s[1]))
@@ -206,16 +212,24 @@ def run_ours(args):
         ntt.forward_ntt(xs[i % NSETS], out=y)
         ntt.inverse_ntt(y, out=z)
 
-    for i in range(args.warmup):
-        step(i)
-    torch.cuda.synchronize()
-    assert torch.equal(z, xs[(args.warmup - 1) % NSETS]) if args.warmup else True  # round trip is exact
-
-    fheb200.launch_count(reset=True)
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    fwd_ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
-    barrier()
+    # the clock sampler (nvidia-smi, 20 ms period) runs from the warm-up to the end of the timed region: the timed
+    # region of a short run is only a few milliseconds, the warm-up keeps the same load on the GPU before it
     with ClockSampler(local) as clk:
+        time.sleep(0.25)  # nvidia-smi start-up
+        for i in range(max(args.warmup, 3)):
+            step(i)
+        torch.cuda.synchronize()
+        assert torch.equal(z, xs[(max(args.warmup, 3) - 1) % NSETS])  # round trip is exact
+        clk.mark()
+        t_load = time.perf_counter()
+        while time.perf_counter() - t_load < 0.3:  # untimed: hold the load long enough to be sampled
+            step(0)
+        torch.cuda.synchronize()
+
+        fheb200.launch_count(reset=True)
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        fwd_ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+        barrier()
         ev0.record()
         for i in range(args.steps):
             fwd_ev[i][0].record()
@@ -304,7 +318,7 @@ def main():
     os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-secondary", action="store_true")

@@ -37,6 +37,24 @@ def run(fhe, torch, dist, world, rank, dev, barrier, max_over_ranks, peak):
     out = {}
     gen = torch.Generator(device=dev).manual_seed(99 + rank)
 
+    # ---- the published M4 Max rows use q = 132120577 at every size: same transform, FP64-pipe arithmetic (q < 2^42)
+    for n, q, tag in ((16384, Q27, "q132120577"), (1024, QT, "q1099511678977")):
+        ntt = fhe.NTTProcessor(n, q)
+        batch = 1024 if n == 16384 else 16384
+        sets = 4
+        xs = [torch.randint(0, q, (batch, n), dtype=torch.int64, device=dev, generator=gen) for _ in range(sets)]
+        y = torch.empty_like(xs[0])
+        z = torch.empty_like(xs[0])
+
+        def fwd_inv(i, ntt=ntt, xs=xs, y=y, z=z):
+            ntt.forward_ntt(xs[i % sets], out=y)
+            ntt.inverse_ntt(y, out=z)
+
+        ms = _time(torch, fwd_inv, 10)
+        out[f"ntt_n{n}_{tag}_b{batch}"] = {"value": 2.0 * batch * n / (ms * 1e-3), "unit": "coeff/s", "ms": ms,
+                                            "roofline": _hbm(peak, 32.0 * n * batch, ms)}
+        del xs, y, z
+
     # ---- C2: fused polynomial multiplication, batch 1024
     for n in (4096, 16384):
         ring = fhe.PolynomialRing(n, Q62)
