@@ -386,3 +386,70 @@ def test_streaming_tally_accumulator(fhe, torch, oracle):
     out = torch.empty((2, n), dtype=torch.int64, device="cuda")
     acc.total(out=out)
     eq(host(out), oracle.tally(cts, q))
+
+
+# ---------------------------------------------------------------------------- edge cases --
+def test_edge_cases_empty_aliased_unaligned(fhe, torch, oracle):
+    n, q = 256, QT
+    ring = fhe.PolynomialRing(n, q)
+    fwd, inv, _, _, inv_n = oracle.twiddles(n, q)
+    rng = np.random.default_rng(3)
+    # empty batches are no-ops everywhere
+    e = np.zeros((0, n), np.uint64)
+    assert ring.to_ntt(e).shape == ring.from_ntt(e).shape == ring.multiply(e, e).shape == ring.add(e, e).shape == (0, n)
+    assert host(ring.multiply(dev(torch, e), dev(torch, e))).shape == (0, n)
+    # product written over either operand, device and host
+    a = rng.integers(0, q, size=(7, n), dtype=np.uint64)
+    b = rng.integers(0, q, size=(7, n), dtype=np.uint64)
+    exp = oracle.multiply(a, b, q, fwd, inv, inv_n)
+    ad, bd = dev(torch, a), dev(torch, b)
+    ring.multiply(ad, bd, out=ad)
+    eq(host(ad), exp)
+    ad = dev(torch, a)
+    ring.multiply(ad, bd, out=bd)
+    eq(host(bd), exp)
+    ah = a.copy()
+    ring.multiply(ah, b, out=ah)
+    eq(ah, exp)
+    sq = oracle.multiply(a, a, q, fwd, inv, inv_n)
+    ad = dev(torch, a)
+    eq(host(ring.multiply(ad, ad)), sq)
+    # 8-byte aligned but not 16-byte aligned device pointers (vector path must not be taken)
+    buf = dev(torch, np.concatenate([[np.uint64(0)], a.reshape(-1)]))
+    bufb = dev(torch, np.concatenate([[np.uint64(0)], b.reshape(-1)]))
+    va, vb = buf[1:], bufb[1:]
+    eq(host(fhe.modmul_batch(va, vb, q)), oracle.pointwise(a.reshape(-1), b.reshape(-1), q))
+    eq(host(ring.to_ntt(va.view(7, n))), oracle.forward(a, q, fwd))
+    cts = rng.integers(0, q, size=(33, 2, n), dtype=np.uint64)
+    odd = dev(torch, np.concatenate([[np.uint64(0)], cts.reshape(-1)]))[1:].view(33, 2, n)
+    eq(host(fhe.tally_votes(odd, n, q)), oracle.tally(cts, q))
+    # all-zero and all-(q-1) polynomials, single polynomial batches
+    for v in (0, q - 1):
+        x = np.full((1, n), v, np.uint64)
+        eq(ring.to_ntt(x), oracle.forward(x, q, fwd))
+        eq(ring.multiply(x, x), oracle.multiply(x, x, q, fwd, inv, inv_n))
+
+
+def test_randomised_shapes_match_oracle(fhe, torch, oracle):
+    """Property-style sweep (fixed seed): random degree, modulus class, batch, value class."""
+    rng = np.random.default_rng(2026)
+    primes = {False: [Q62, 1152921504606584833, Q50], True: [QT, Q27, 97 * 0 + 1099511592961]}
+    for trial in range(24):
+        dp = bool(trial & 1)
+        logn = int(rng.integers(2, 13))
+        n = 1 << logn
+        cands = [p for p in primes[dp] if (p - 1) % (2 * n) == 0]
+        if not cands:
+            continue
+        q = cands[int(rng.integers(0, len(cands)))]
+        batch = int(rng.integers(1, 40))
+        fwd, inv, _, _, inv_n = oracle.twiddles(n, q)
+        ring = fhe.PolynomialRing(n, q)
+        hi = 2**64 if trial % 3 == 0 else q
+        a = rng.integers(0, hi, size=(batch, n), dtype=np.uint64)
+        b = rng.integers(0, hi, size=(batch, n), dtype=np.uint64)
+        ad, bd = dev(torch, a), dev(torch, b)
+        eq(host(ring.to_ntt(ad)), oracle.forward(a, q, fwd))
+        eq(host(ring.from_ntt(ad)), oracle.inverse(a, q, inv, inv_n))
+        eq(host(ring.multiply(ad, bd)), oracle.multiply(a, b, q, fwd, inv, inv_n))
+        eq(host(ring.subtract(ad, bd)), oracle.sub(a, b, q))
