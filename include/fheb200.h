@@ -111,7 +111,8 @@ FHEB_API int fheb_synchronize(void* stream);
  * 134-160,168-208.  Finds the same primitive 2N-th root as find_primitive_root (:92-128:
  * smallest g >= 2) and builds the same tables.  Errors mirror the constructor's
  * (":141-153": degree not a power of two / outside [4, 65536] / even modulus; ":103-105":
- * modulus not NTT-friendly).  Supported on this backend: N <= 16384, q < 2^62. */
+ * modulus not NTT-friendly).  Supported on this backend: the reference's full range N = 4 .. 65536 (one
+ * launch up to 16384, two launches above), q < 2^62; bootstrap kernels N = 32 .. 4096. */
 FHEB_API int fheb_ntt_plan_create(uint32_t degree, uint64_t modulus, fheb_ntt_plan** out);
 
 /* Caller-supplied tables, the shape of MetalComputeContext::batch_ntt_forward(..., twiddles)

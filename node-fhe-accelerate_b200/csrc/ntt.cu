@@ -16,6 +16,8 @@
 
 namespace fheb {
 
+int elementwise_device(int op, const uint64_t* a, const uint64_t* b, uint64_t scalar, uint64_t* r, size_t count, uint64_t q, cudaStream_t s);
+
 // ---- host-side plan maths (mirrors the reference's constructor) --------------------------
 static uint64_t h_mod_pow(uint64_t base, uint64_t exp, uint64_t mod) {  // ntt_processor.cpp:47-62
     uint64_t result = 1;
@@ -66,7 +68,6 @@ static int validate_degree_modulus(uint32_t degree, uint64_t modulus) {
     FHEB_REQUIRE(degree > 0 && (degree & (degree - 1)) == 0, "Polynomial degree must be a power of 2");
     FHEB_REQUIRE(degree >= 4 && degree <= 65536, "Polynomial degree must be between 4 and 65536");
     FHEB_REQUIRE((modulus & 1) != 0, "Modulus must be odd");
-    FHEB_REQUIRE(degree <= 16384, "degree %u is above this backend's limit of 16384", degree);
     FHEB_REQUIRE(modulus > 2 && modulus < (1ULL << 62), "modulus must be below 2^62 on this backend");
     return FHEB_OK;
 }
@@ -85,6 +86,23 @@ static int plan_finish(NttPlan* p) {
     p->ninv = p->mod.dp ? Tw{double_to_bits((double)(p->inv_n % q)), 0} : Tw{p->inv_n % q, shoup_companion(p->inv_n % q, q)};
     p->unit_first = (p->fwd_table[0] % q == 1) && (p->inv_table[0] % q == 1);
     FHEB_REQUIRE(p->unit_first, "twiddle tables must start with 1 (root^0)");
+    p->one = p->mod.dp ? Tw{double_to_bits(1.0), 0} : Tw{1, shoup_companion(1, q)};
+    if (p->logn > 14) {  // sub-block tables + top-stage tables (ntt_device.cuh, degrees above 2^14)
+        const uint32_t L = p->logn, D = L - 14;
+        const bool dp = p->mod.dp != 0;
+        const size_t epw = dp ? 1 : 2, sub = (size_t)1 << 14;
+        p->top = D;
+        for (int dir = 0; dir < 2; ++dir) {
+            const uint64_t* table = dir ? p->inv_table.data() : p->fwd_table.data();
+            std::vector<uint64_t> words(((size_t)sub << D) * epw, 0), topw(8 * epw, 0);
+            for (uint32_t h = 0; h < (1u << D); ++h)
+                for_each_sub_twiddle(L, D, h, [&](uint32_t at, uint32_t e) { put_twiddle(words, (size_t)h * sub + at, table[e] % q, q, dp); });
+            for_each_top_twiddle(L, D, [&](uint32_t at, uint32_t e) { put_twiddle(topw, at, table[e] % q, q, dp); });
+            FHEB_TRY(upload_heap(words, dir ? &p->d_inv : &p->d_fwd));
+            FHEB_TRY(upload_heap(topw, dir ? &p->d_top_inv : &p->d_top_fwd));
+        }
+        return FHEB_OK;
+    }
     if (p->mod.dp) {  // FP64 mode: one double per twiddle
         FHEB_TRY(upload_heap(build_heap_table_dp(p->fwd_table.data(), p->logn, q), &p->d_fwd));
         FHEB_TRY(upload_heap(build_heap_table_dp(p->inv_table.data(), p->logn, q), &p->d_inv));
@@ -115,6 +133,12 @@ static int configure(K kernel, size_t smem, int threads, int* blocks_per_sm) {
     FHEB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, kernel, threads, smem));
     if (*blocks_per_sm < 1) return set_error(FHEB_ERR_NATIVE, "kernel does not fit on an SM (smem %zu)", smem);
     return FHEB_OK;
+}
+
+static unsigned stream_grid_for(size_t work_items, int threads, int blocks_per_sm) {
+    const size_t want = (work_items + threads - 1) / threads;
+    const size_t cap = (size_t)ctx().sm_count * blocks_per_sm;
+    return (unsigned)(want < cap ? (want ? want : 1) : cap);
 }
 
 static unsigned persistent_grid(size_t work_groups, int blocks_per_sm) {
@@ -170,6 +194,55 @@ static int launch_polymul(const NttPlan* p, const uint64_t* a, const uint64_t* b
     return FHEB_OK;
 }
 
+// Degrees 2^15 and 2^16: top stages + 2^D sub-transforms of 2^14 (two launches, one scratch pass).
+template <bool DP>
+static int launch_transform_big(const NttPlan* p, int dir, const uint64_t* in, uint64_t* out, size_t batch, cudaStream_t s) {
+    constexpr int LS = 14;
+    using G = Geometry<LS, DP>;
+    const uint32_t D = p->top;
+    FHEB_REQUIRE(dir != DIR_INV_FWDNET, "the forward-network inverse is limited to degrees up to 16384 on this backend");
+    const size_t N = (size_t)1 << p->logn, subs = batch << D;
+    uint64_t* tmp = nullptr;
+    FHEB_CUDA(cudaMallocAsync(&tmp, batch * N * 8, s));
+    const unsigned top_grid = stream_grid_for(batch * (N >> D), 256, 8);
+    int bps = 0;
+    int rc = FHEB_OK;
+    if (dir == DIR_FWD) {
+        if (D == 1) ntt_top_kernel<1, DP, false><<<top_grid, 256, 0, s>>>(in, tmp, batch, p->logn, p->d_top_fwd, p->ninv, p->mod);
+        else ntt_top_kernel<2, DP, false><<<top_grid, 256, 0, s>>>(in, tmp, batch, p->logn, p->d_top_fwd, p->ninv, p->mod);
+        auto k = ntt_forward_sub_kernel<LS, DP, G::THREADS, false>;
+        rc = configure(k, G::SMEM, G::THREADS, &bps);
+        if (rc == FHEB_OK) k<<<persistent_grid(subs, bps), G::THREADS, G::SMEM, s>>>(tmp, out, subs, D, p->d_fwd, p->ninv, p->mod);
+    } else {
+        auto k = ntt_inverse_sub_kernel<LS, DP, G::THREADS>;
+        rc = configure(k, G::SMEM, G::THREADS, &bps);
+        if (rc == FHEB_OK) {
+            k<<<persistent_grid(subs, bps), G::THREADS, G::SMEM, s>>>(in, tmp, subs, D, p->d_inv, p->one, p->mod);
+            if (D == 1) ntt_top_kernel<1, DP, true><<<top_grid, 256, 0, s>>>(tmp, out, batch, p->logn, p->d_top_inv, p->ninv, p->mod);
+            else ntt_top_kernel<2, DP, true><<<top_grid, 256, 0, s>>>(tmp, out, batch, p->logn, p->d_top_inv, p->ninv, p->mod);
+        }
+    }
+    if (rc == FHEB_OK && cudaGetLastError() != cudaSuccess) rc = set_error(FHEB_ERR_NATIVE, "large-degree transform launch failed");
+    count_launch(2);
+    cudaFreeAsync(tmp, s);
+    return rc;
+}
+
+// Product for degrees above 2^14: T(a), T(b), pointwise, T^-1 as separate launches.
+template <bool DP>
+static int launch_polymul_big(const NttPlan* p, const uint64_t* a, const uint64_t* b, uint64_t* c, size_t batch, cudaStream_t s) {
+    const size_t words = batch << p->logn;
+    uint64_t* ta = nullptr;
+    FHEB_CUDA(cudaMallocAsync(&ta, 2 * words * 8, s));
+    uint64_t* tb = ta + words;
+    int rc = launch_transform_big<DP>(p, DIR_FWD, a, ta, batch, s);
+    if (rc == FHEB_OK) rc = launch_transform_big<DP>(p, DIR_FWD, b, tb, batch, s);
+    if (rc == FHEB_OK) rc = elementwise_device(2 /* mul */, ta, tb, 0, ta, words, p->modulus, s);
+    if (rc == FHEB_OK) rc = launch_transform_big<DP>(p, DIR_INV, ta, c, batch, s);
+    cudaFreeAsync(ta, s);
+    return rc;
+}
+
 #define FHEB_DISPATCH_L(FN, L_, ...)                                         \
     case L_:                                                                 \
         return dp ? FN<L_, true>(__VA_ARGS__) : FN<L_, false>(__VA_ARGS__);
@@ -190,6 +263,8 @@ static int dispatch_transform(const NttPlan* p, int dir, const uint64_t* in, uin
         FHEB_DISPATCH_L(launch_transform, 12, p, dir, in, out, batch, s)
         FHEB_DISPATCH_L(launch_transform, 13, p, dir, in, out, batch, s)
         FHEB_DISPATCH_L(launch_transform, 14, p, dir, in, out, batch, s)
+        case 15:
+        case 16: return dp ? launch_transform_big<true>(p, dir, in, out, batch, s) : launch_transform_big<false>(p, dir, in, out, batch, s);
     }
     return set_error(FHEB_ERR_INVALID_PARAMETERS, "unsupported degree 2^%u", p->logn);
 }
@@ -210,6 +285,8 @@ static int dispatch_polymul(const NttPlan* p, const uint64_t* a, const uint64_t*
         FHEB_DISPATCH_L(launch_polymul, 12, p, a, b, c, batch, s)
         FHEB_DISPATCH_L(launch_polymul, 13, p, a, b, c, batch, s)
         FHEB_DISPATCH_L(launch_polymul, 14, p, a, b, c, batch, s)
+        case 15:
+        case 16: return dp ? launch_polymul_big<true>(p, a, b, c, batch, s) : launch_polymul_big<false>(p, a, b, c, batch, s);
     }
     return set_error(FHEB_ERR_INVALID_PARAMETERS, "unsupported degree 2^%u", p->logn);
 }
@@ -312,6 +389,8 @@ int fheb_ntt_plan_destroy(fheb_ntt_plan* plan) {
     if (!p) return FHEB_OK;
     if (p->d_fwd) cudaFree(p->d_fwd);
     if (p->d_inv) cudaFree(p->d_inv);
+    if (p->d_top_fwd) cudaFree(p->d_top_fwd);
+    if (p->d_top_inv) cudaFree(p->d_top_inv);
     delete p;
     return FHEB_OK;
 }

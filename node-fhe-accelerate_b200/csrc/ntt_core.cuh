@@ -377,12 +377,20 @@ inline void plan_runtime(int L, int& P, int (&R)[5]) {
     }
 }
 
-template <int L, bool DP, int PASS>
+// SUB: the L stages are the tail of a larger transform (degrees above 2^14, see ntt_device.cuh): the first
+// pass has no unit twiddles then.
+template <int L, bool DP, int PASS, bool SUB = false>
 constexpr int plan_fwd_kin() {  // bound on values entering forward pass PASS (inputs canonical)
     int K = 1;
-    for (int p = 0; p < PASS; ++p) K = fwd_pass_k(K, Plan<L>::R[p], p == 0, DP);
+    for (int p = 0; p < PASS; ++p) K = fwd_pass_k(K, Plan<L>::R[p], p == 0 && !SUB, DP);
     return K;
 }
+
+// SUB kernels address caller memory through this map: word i of the sub-transform's reference-order
+// side lives at global index (i << shift) | low of its polynomial.
+struct GlobalMap {
+    uint32_t shift, low;
+};
 template <int L, bool DP, int PASS, int KSTART = 1>
 constexpr int plan_inv_kin() {  // bound entering inverse pass PASS (run order P-1 .. 0), first executed pass fed values < KSTART*q
     int K = KSTART;
@@ -409,15 +417,17 @@ enum {
 //   SCALE      : multiply the outputs by `ninv` (fast_ntt_inverse semantics)
 // OUT == IO_STASH_*: the finished transform is parked (position order, no bit reversal) in
 // `gout` for the fused polynomial product; canonical words in integer mode, lazy doubles (|v| < KOUT*q) in DP mode.
-template <int L, bool DP, int PASS, int IN, int OUT, bool BITREV_OUT = true, bool SCALE = false, int IPT = 0>
+template <int L, bool DP, int PASS, int IN, int OUT, bool BITREV_OUT = true, bool SCALE = false, int IPT = 0, bool SUB = false>
 FHEB_HD void fwd_pass(uint32_t tid, uint32_t nthreads, uint32_t polys, const uint64_t* gin, uint64_t* gout,
-                      uint64_t* smem, const Tw* __restrict__ tw, const ModQ& m, const Tw ninv = Tw{0, 0}) {
+                      uint64_t* smem, const Tw* __restrict__ tw, const ModQ& m, const Tw ninv = Tw{0, 0},
+                      const GlobalMap map = GlobalMap{0, 0}) {
     constexpr int R = Plan<L>::R[PASS];
     constexpr int E = 1 << R;
     constexpr int S0 = plan_s0<L, PASS>();
     constexpr int EB = L - S0 - R;  // lowest position bit handled by this pass
-    constexpr int KIN = plan_fwd_kin<L, DP, PASS>();
-    constexpr int KOUT = fwd_pass_k(KIN, R, PASS == 0, DP);
+    constexpr bool UNIT = (PASS == 0 && !SUB);
+    constexpr int KIN = plan_fwd_kin<L, DP, PASS, SUB>();
+    constexpr int KOUT = fwd_pass_k(KIN, R, UNIT, DP);
     constexpr bool LAST = (PASS == Plan<L>::P - 1);
     constexpr uint32_t N = 1u << L;
     constexpr uint32_t ITEMS = N >> R;  // per polynomial
@@ -467,14 +477,15 @@ FHEB_HD void fwd_pass(uint32_t tid, uint32_t nthreads, uint32_t polys, const uin
             for (int c = 0; c < E; ++c) x[c] = src[pb ^ swz((uint32_t)c << EB)];
         }
         const uint32_t TB = plan_tw_offset<L, PASS>() + (S0 ? (base >> (L - S0)) : 0u);
-        if constexpr (IPT > 0) fwd_stages<R, S0, KIN, DP, PASS == 0, 0, true>(x, wall[k], 0u, m);
-        else fwd_stages<R, S0, KIN, DP, PASS == 0>(x, tw, TB, m);
+        if constexpr (IPT > 0) fwd_stages<R, S0, KIN, DP, UNIT, 0, true>(x, wall[k], 0u, m);
+        else fwd_stages<R, S0, KIN, DP, UNIT>(x, tw, TB, m);
         if (OUT == IO_GLOBAL) {
             uint64_t* dst = gout + (size_t)poly * N;
 #pragma unroll
             for (int c = 0; c < E; ++c) {
                 const uint64_t v = SCALE ? scale_word<DP>(x[c], ninv, m) : canon_k<KOUT, DP>(x[c], m);
-                if (BITREV_OUT) stream_store(dst + ((bitrev_c((uint32_t)c, R) << (L - R)) | t), v);
+                if (SUB) stream_store(dst + ((((bitrev_c((uint32_t)c, R) << (L - R)) | t) << map.shift) | map.low), v);
+                else if (BITREV_OUT) stream_store(dst + ((bitrev_c((uint32_t)c, R) << (L - R)) | t), v);
                 else stream_store(dst + (base | ((uint32_t)c << EB)), v);
             }
         } else if (OUT == IO_STASH_GLOBAL) {
@@ -558,9 +569,10 @@ FHEB_HD void polymul_mid_pass(uint32_t tid, uint32_t nthreads, uint32_t polys, c
 // may read the reference's input order (bit-reversed positions) from global memory; the
 // last one executed (PASS == 0) multiplies by N^-1 (`ninv`, Shoup pair) and stores canonical
 // values in natural order.
-template <int L, bool DP, int PASS, int IN, int OUT, bool BITREV_IN = true, int IPT = 0, int KSTART = 1>
+template <int L, bool DP, int PASS, int IN, int OUT, bool BITREV_IN = true, int IPT = 0, int KSTART = 1, bool SUB = false>
 FHEB_HD void inv_pass(uint32_t tid, uint32_t nthreads, uint32_t polys, const uint64_t* gin, uint64_t* gout,
-                      uint64_t* smem, const Tw* __restrict__ tw, const Tw ninv, const ModQ& m) {
+                      uint64_t* smem, const Tw* __restrict__ tw, const Tw ninv, const ModQ& m,
+                      const GlobalMap map = GlobalMap{0, 0}) {
     constexpr int R = Plan<L>::R[PASS];
     constexpr int E = 1 << R;
     constexpr int S0 = plan_s0<L, PASS>();
@@ -600,7 +612,10 @@ FHEB_HD void inv_pass(uint32_t tid, uint32_t nthreads, uint32_t polys, const uin
         uint64_t x[E];
         if (IN == IO_GLOBAL) {
             const uint64_t* src = gin + (size_t)poly * N;
-            if (BITREV_IN) {
+            if (SUB && BITREV_IN) {
+#pragma unroll
+                for (int c = 0; c < E; ++c) x[c] = stream_load(src + ((((bitrev_c((uint32_t)c, R) << (L - R)) | t) << map.shift) | map.low));
+            } else if (BITREV_IN) {
 #pragma unroll
                 for (int c = 0; c < E; ++c) x[c] = stream_load(src + ((bitrev_c((uint32_t)c, R) << (L - R)) | t));
             } else {
@@ -615,8 +630,8 @@ FHEB_HD void inv_pass(uint32_t tid, uint32_t nthreads, uint32_t polys, const uin
             for (int c = 0; c < E; ++c) x[c] = src[pb ^ swz((uint32_t)c << EB)];
         }
         const uint32_t TB = plan_tw_offset<L, PASS>() + (S0 ? (base >> (L - S0)) : 0u);
-        if constexpr (IPT > 0) inv_stages<R, S0, KIN, DP, PASS == 0, R - 1, true>(x, wall[k], 0u, m);
-        else inv_stages<R, S0, KIN, DP, PASS == 0>(x, tw, TB, m);
+        if constexpr (IPT > 0) inv_stages<R, S0, KIN, DP, (PASS == 0 && !SUB), R - 1, true>(x, wall[k], 0u, m);
+        else inv_stages<R, S0, KIN, DP, (PASS == 0 && !SUB)>(x, tw, TB, m);
         if (OUT == IO_GLOBAL) {
             uint64_t* dst = gout + (size_t)poly * N;
 #pragma unroll

@@ -14,23 +14,23 @@ __device__ __forceinline__ void prefetch_l2_bulk(const void* p, uint32_t bytes) 
         asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
 }
 
-template <int L, bool DP, int PASS>
+template <int L, bool DP, int PASS, bool SUB = false>
 __device__ __forceinline__ void fwd_middle(uint32_t tid, uint32_t nthreads, uint32_t polys, uint64_t* smem,
                                            const Tw* __restrict__ tw, const ModQ& m) {
     if constexpr (PASS < Plan<L>::P - 1) {
-        fwd_pass<L, DP, PASS, IO_SMEM, IO_SMEM>(tid, nthreads, polys, nullptr, nullptr, smem, tw, m);
+        fwd_pass<L, DP, PASS, IO_SMEM, IO_SMEM, true, false, 0, SUB>(tid, nthreads, polys, nullptr, nullptr, smem, tw, m);
         __syncthreads();
-        fwd_middle<L, DP, PASS + 1>(tid, nthreads, polys, smem, tw, m);
+        fwd_middle<L, DP, PASS + 1, SUB>(tid, nthreads, polys, smem, tw, m);
     }
 }
 
-template <int L, bool DP, int PASS>
+template <int L, bool DP, int PASS, bool SUB = false>
 __device__ __forceinline__ void inv_middle(uint32_t tid, uint32_t nthreads, uint32_t polys, uint64_t* smem,
                                            const Tw* __restrict__ tw, const Tw ninv, const ModQ& m) {
     if constexpr (PASS > 0) {
-        inv_pass<L, DP, PASS, IO_SMEM, IO_SMEM>(tid, nthreads, polys, nullptr, nullptr, smem, tw, ninv, m);
+        inv_pass<L, DP, PASS, IO_SMEM, IO_SMEM, true, 0, 1, SUB>(tid, nthreads, polys, nullptr, nullptr, smem, tw, ninv, m);
         __syncthreads();
-        inv_middle<L, DP, PASS - 1>(tid, nthreads, polys, smem, tw, ninv, m);
+        inv_middle<L, DP, PASS - 1, SUB>(tid, nthreads, polys, smem, tw, ninv, m);
     }
 }
 
@@ -95,6 +95,85 @@ __global__ void __launch_bounds__(THREADS) ntt_inverse_kernel(const uint64_t* in
             inv_pass<L, DP, 0, IO_SMEM, IO_GLOBAL>(tid, THREADS, polys, gin, gout, smem, tw, ninv, m);
             __syncthreads();
         }
+    }
+}
+
+// ---- degrees above 2^14 (one polynomial no longer fits the shared memory of an SM) ----------------
+// The first D = L - 14 stages pair positions N/2, N/4 apart; after them the 2^D contiguous sub-blocks
+// of 2^14 positions are independent.  So: a streaming kernel runs the top D stages in registers
+// (global -> scratch), then the 14-stage shared-memory kernel transforms every sub-block with its own
+// twiddle table (the tail of the big network: no unit twiddles) and scatters the results into the
+// reference's output order, index (r << D) | bitrev_D(h) for word r of sub-block h.  The inverse runs
+// the same two kernels backwards.
+template <int D, bool DP, bool INVERSE>
+__global__ void __launch_bounds__(256) ntt_top_kernel(const uint64_t* in, uint64_t* out, size_t batch, uint32_t L,
+                                                      const Tw* __restrict__ tw, const Tw ninv, const ModQ m) {
+    constexpr int E = 1 << D;
+    const size_t N = (size_t)1 << L, items = N >> D;
+    const size_t total = batch * items;
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+        const size_t poly = i / items, j = i - poly * items;
+        const uint64_t* src = in + poly * N + j;
+        uint64_t* dst = out + poly * N + j;
+        uint64_t x[E];
+#pragma unroll
+        for (int c = 0; c < E; ++c) x[c] = stream_load(src + (size_t)c * items);
+        load_words<DP, E>(x, m);
+        if constexpr (INVERSE) {
+            inv_stages<D, 0, 1, DP, true>(x, tw, 0u, m);
+#pragma unroll
+            for (int c = 0; c < E; ++c) stream_store(dst + (size_t)c * items, scale_word<DP>(x[c], ninv, m));
+        } else {
+            fwd_stages<D, 0, 1, DP, true>(x, tw, 0u, m);
+            constexpr int KOUT = fwd_pass_k(1, D, true, DP);
+#pragma unroll
+            for (int c = 0; c < E; ++c) dst[(size_t)c * items] = canon_k<KOUT, DP>(x[c], m);  // re-read soon: keep in L2
+        }
+    }
+}
+
+// 14-stage tail of a larger forward transform: sub-block g of `tmp` (natural positions, canonical)
+// -> caller memory in the reference's order.  tables = 2^D consecutive twiddle tables.
+template <int L, bool DP, int THREADS, bool SCALE>
+__global__ void __launch_bounds__(THREADS) ntt_forward_sub_kernel(const uint64_t* tmp, uint64_t* out, size_t subs, uint32_t D,
+                                                                  const Tw* __restrict__ tables, const Tw ninv, const ModQ m) {
+    extern __shared__ __align__(16) uint64_t smem[];
+    constexpr int P = Plan<L>::P;
+    constexpr size_t N = (size_t)1 << L;
+    const uint32_t tid = threadIdx.x;
+    for (size_t g = blockIdx.x; g < subs; g += gridDim.x) {
+        const size_t poly = g >> D;
+        const uint32_t h = (uint32_t)(g & ((1u << D) - 1u));
+        const Tw* tw = reinterpret_cast<const Tw*>(reinterpret_cast<const char*>(tables) + (size_t)h * N * (DP ? 8 : 16));
+        const GlobalMap map{D, bitrev_rt(h, (int)D)};
+        fwd_pass<L, DP, 0, IO_GLOBAL, IO_SMEM, true, false, 0, true>(tid, THREADS, 1, tmp + g * N, nullptr, smem, tw, m);
+        __syncthreads();
+        fwd_middle<L, DP, 1, true>(tid, THREADS, 1, smem, tw, m);
+        fwd_pass<L, DP, P - 1, IO_SMEM, IO_GLOBAL, true, SCALE, 0, true>(tid, THREADS, 1, nullptr, out + (poly << (L + D)), smem, tw, m, ninv, map);
+        __syncthreads();
+    }
+}
+
+// 14-stage head of a larger inverse transform: caller memory (reference order) -> `tmp` (natural
+// positions, canonical, unscaled); the top D stages and the scaling follow in ntt_top_kernel.
+template <int L, bool DP, int THREADS>
+__global__ void __launch_bounds__(THREADS) ntt_inverse_sub_kernel(const uint64_t* in, uint64_t* tmp, size_t subs, uint32_t D,
+                                                                  const Tw* __restrict__ tables, const Tw one, const ModQ m) {
+    extern __shared__ __align__(16) uint64_t smem[];
+    constexpr int P = Plan<L>::P;
+    constexpr size_t N = (size_t)1 << L;
+    const uint32_t tid = threadIdx.x;
+    for (size_t g = blockIdx.x; g < subs; g += gridDim.x) {
+        const size_t poly = g >> D;
+        const uint32_t h = (uint32_t)(g & ((1u << D) - 1u));
+        const Tw* tw = reinterpret_cast<const Tw*>(reinterpret_cast<const char*>(tables) + (size_t)h * N * (DP ? 8 : 16));
+        const GlobalMap map{D, bitrev_rt(h, (int)D)};
+        inv_pass<L, DP, P - 1, IO_GLOBAL, IO_SMEM, true, 0, 1, true>(tid, THREADS, 1, in + (poly << (L + D)), nullptr, smem, tw, one, m, map);
+        __syncthreads();
+        inv_middle<L, DP, P - 2, true>(tid, THREADS, 1, smem, tw, one, m);
+        inv_pass<L, DP, 0, IO_SMEM, IO_GLOBAL, true, 0, 1, true>(tid, THREADS, 1, nullptr, tmp + g * N, smem, tw, one, m);
+        __syncthreads();
     }
 }
 

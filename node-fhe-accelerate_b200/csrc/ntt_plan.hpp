@@ -59,6 +59,45 @@ inline std::vector<uint64_t> build_heap_table_dp(const uint64_t* table, uint32_t
     return out;
 }
 
+// ---- degrees above 2^14: tables of the 2^D sub-blocks and of the top D stages (ntt_device.cuh) -------
+// Sub-block h runs stages D..L-1 of the big network; its stage s' = s - D has blocks b' whose big-network
+// block is b = (h << s') + b', i.e. twiddle table[bitrev_s(b) << (L-1-s)].  Same entry order as above.
+template <class Put>
+inline void for_each_sub_twiddle(uint32_t L, uint32_t D, uint32_t h, Put put) {
+    const uint32_t LS = L - D;
+    int P, R[5];
+    plan_runtime((int)LS, P, R);
+    uint32_t idx = 0;
+    int s0 = 0;
+    for (int p = 0; p < P; ++p) {
+        for (int a = 0; a < R[p]; ++a) {
+            const int sp = s0 + a, s = sp + (int)D;
+            for (uint32_t g = 0; g < (1u << a); ++g)
+                for (uint32_t blk = 0; blk < (1u << s0); ++blk) {
+                    const uint32_t b = (h << sp) + (blk << a) + g;
+                    put(idx + ((((1u << a) - 1u) + g) << s0) + blk, bitrev_c(b, s) << (L - 1 - s));
+                }
+        }
+        idx += ((1u << R[p]) - 1u) << s0;
+        s0 += R[p];
+    }
+}
+// top D stages as one register pass (S0 = 0): entry ((1 << a) - 1) + g = table[bitrev_a(g) << (L-1-a)]
+template <class Put>
+inline void for_each_top_twiddle(uint32_t L, uint32_t D, Put put) {
+    for (uint32_t a = 0; a < D; ++a)
+        for (uint32_t g = 0; g < (1u << a); ++g) put(((1u << a) - 1u) + g, bitrev_c(g, (int)a) << (L - 1 - a));
+}
+
+// raw words of a device table: (w, w') pairs or doubles
+inline void put_twiddle(std::vector<uint64_t>& words, size_t at, uint64_t w, uint64_t q, bool dp) {
+    if (dp) words[at] = double_to_bits((double)w);
+    else {
+        words[2 * at] = w;
+        words[2 * at + 1] = shoup_companion(w, q);
+    }
+}
+
 // width (log2) of the last register pass: the bootstrapping key is stored [..][e][u] for position u*2^R + e
 inline uint32_t last_pass_width(uint32_t L) {
     int P, R[5];

@@ -21,6 +21,12 @@ struct NttPlan {
     Tw ninv{};
     Tw* d_fwd = nullptr;  // heap-ordered twiddles, N entries: (w, w') pairs, or doubles when mod.dp
     Tw* d_inv = nullptr;
+    // degrees above 2^14 (top = log2 N - 14 > 0): d_fwd / d_inv hold 2^top consecutive sub-block tables
+    // of 2^14 entries, d_top_* the few twiddles of the first `top` stages, `one` the multiplicand 1
+    uint32_t top = 0;
+    Tw* d_top_fwd = nullptr;
+    Tw* d_top_inv = nullptr;
+    Tw one{};
 };
 
 // device-pointer entry points shared between translation units

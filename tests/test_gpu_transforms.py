@@ -453,3 +453,27 @@ def test_randomised_shapes_match_oracle(fhe, torch, oracle):
         eq(host(ring.from_ntt(ad)), oracle.inverse(a, q, inv, inv_n))
         eq(host(ring.multiply(ad, bd)), oracle.multiply(a, b, q, fwd, inv, inv_n))
         eq(host(ring.subtract(ad, bd)), oracle.sub(a, b, q))
+
+
+@pytest.mark.parametrize("q", [Q62, Q27], ids=["q62", "q27-fp64"])
+@pytest.mark.parametrize("logn", [15, 16])
+def test_large_degrees_two_launch_path(fhe, torch, oracle, logn, q):
+    """Degrees above 2^14 (the reference accepts up to 65536): top stages + 2^14 sub-transforms."""
+    n = 1 << logn
+    ring = fhe.PolynomialRing(n, q)
+    fwd, inv, psi, psi_inv, inv_n = oracle.twiddles(n, q)
+    assert ring.ntt.get_twiddles()[2:] == (psi, psi_inv, inv_n)
+    rng = np.random.default_rng(logn)
+    x = rng.integers(0, q, size=(3, n), dtype=np.uint64)
+    x[2] = rng.integers(0, 2**64, size=n, dtype=np.uint64)  # unreduced words
+    xd = dev(torch, x)
+    y = ring.to_ntt(xd)
+    eq(host(y), oracle.forward(x, q, fwd))
+    eq(host(ring.from_ntt(xd)), oracle.inverse(x, q, inv, inv_n))
+    back = ring.from_ntt(y)
+    eq(host(back), x % np.uint64(q))
+    ring.to_ntt(xd, out=xd)  # in place
+    eq(host(xd), oracle.forward(x, q, fwd))
+    a, b = x[:2], x[1:3]
+    eq(host(ring.multiply(dev(torch, a), dev(torch, b))), oracle.multiply(a, b, q, fwd, inv, inv_n))
+    eq(ring.multiply(a, b), oracle.multiply(a, b, q, fwd, inv, inv_n))  # host buffers
