@@ -22,7 +22,8 @@ namespace fheb {
 struct BootStep {          // block-uniform description of one step
     uint64_t* acc;         // smem [KP1][N], natural index: ct0 / running accumulator
     uint64_t* work;        // smem [max(rows, KP1)][N], swizzled index
-    const uint64_t* diff;  // smem [KP1][N] natural index: precomputed ct1 - ct0 (or the GLWE itself); null = rotate acc
+    const uint64_t* diff;  // [KP1][N] natural index: precomputed ct1 - ct0 / the GLWE itself (shared or global); null = rotate acc
+    const uint64_t* diff_sub;  // when non-null: the digits come from diff - diff_sub (both reduced first), read from global memory
     const Tw* ggsw;        // global [rows][E][N/E][KP1] (position u*E + e, component j at [e][u][j]; E = width of the last pass), times N^-1: (value, Shoup companion) pairs, or doubles in DP mode
     uint64_t* gout;        // when non-null the final pass stores here ([KP1][N], global) instead of acc
     uint32_t rot;          // normalised rotation in [0, 2N) (used when diff == null)
@@ -85,6 +86,11 @@ FHEB_HD void boot_first_pass(uint32_t tid, uint32_t nthreads, const BootStep& s,
             const uint64_t* src = s.diff + (size_t)c * N;
 #pragma unroll
             for (int e = 0; e < E; ++e) d[e] = src[u | ((uint32_t)e << EB)];
+            if (s.diff_sub) {  // PolynomialRing::subtract(ct1, ct0) on the fly (large shapes: no staging buffer)
+                const uint64_t* sub = s.diff_sub + (size_t)c * N;
+#pragma unroll
+                for (int e = 0; e < E; ++e) d[e] = submod_canon(canon_any(d[e], m), canon_any(sub[u | ((uint32_t)e << EB)], m), m.q);
+            }
         } else {
             // X^rot * acc - acc.  After the first executed step every accumulator word is canonical; only
             // the words of a caller's test polynomial can be unreduced (s.maybe_raw).  Then one test per

@@ -21,6 +21,7 @@ struct BootLaunch {
     uint32_t n;              // LWE dimension (BLIND)
     uint32_t levels, base_log;
     int mode;
+    int acc_global;          // 1: the accumulator lives in the output buffer (global memory, L2) instead of shared memory
     const Tw* twf;
     const Tw* twi;
     Tw ninv;
@@ -38,9 +39,9 @@ struct BootGeometry {
 };
 
 // shared-memory bytes per ciphertext: acc [KP1][N] | work [rows][N] | (CMUX/EXT) diff [KP1][N] | (BLIND) rotations [n] (u32)
-inline size_t boot_smem_bytes(int mode, uint32_t N, uint32_t kp1, uint32_t levels, uint32_t n) {
-    size_t words = (size_t)kp1 * N + (size_t)kp1 * levels * N;
-    if (mode != BOOT_BLIND) words += (size_t)kp1 * N;
+inline size_t boot_smem_bytes(int mode, uint32_t N, uint32_t kp1, uint32_t levels, uint32_t n, bool acc_global = false) {
+    size_t words = (acc_global ? 0 : (size_t)kp1 * N) + (size_t)kp1 * levels * N;
+    if (mode != BOOT_BLIND && !acc_global) words += (size_t)kp1 * N;
     size_t bytes = words * 8;
     if (mode == BOOT_BLIND) bytes += ((size_t)n * 4 + 15) & ~(size_t)15;
     return bytes;
@@ -66,8 +67,10 @@ __global__ void __launch_bounds__(BootGeometry<L>::MAX_THREADS, 1) boot_kernel(c
     const uint32_t groups = blockDim.x / TPC;
     const uint32_t tid = threadIdx.x % TPC;
     const uint32_t rows = (uint32_t)KP1 * a.levels;
-    uint64_t* acc = smem + (size_t)group * (ct_bytes / 8);
-    uint64_t* work = acc + GW;
+    // large shapes (e.g. tfhe-256-secure: N=4096, three levels): the working rows alone nearly fill the SM, so
+    // the accumulator is kept in the output GLWE in global memory (L2 resident, touched twice per step)
+    uint64_t* sm_acc = smem + (size_t)group * (ct_bytes / 8);
+    uint64_t* work = sm_acc + (a.acc_global ? 0 : GW);
     uint64_t* diff = work + (size_t)rows * N;                   // CMUX / EXT only
     uint32_t* rots = reinterpret_cast<uint32_t*>(work + (size_t)rows * N);  // BLIND only
     const size_t ggsw_words = (size_t)rows * KP1 * N;
@@ -75,6 +78,10 @@ __global__ void __launch_bounds__(BootGeometry<L>::MAX_THREADS, 1) boot_kernel(c
     for (size_t ct0 = (size_t)blockIdx.x * groups; ct0 < a.batch; ct0 += (size_t)gridDim.x * groups) {
         const size_t ct = ct0 + group;
         const bool valid = ct < a.batch;
+        uint64_t* gout = a.out + (valid ? ct : 0) * GW;
+        // accumulator: shared memory, or (acc_global) the output GLWE itself / the caller's ct0 for a single CMux
+        uint64_t* acc = !a.acc_global ? sm_acc
+                        : (a.mode == BOOT_CMUX ? const_cast<uint64_t*>(a.in0 + (valid ? ct : 0) * GW) : gout);
         BootStep s;
         s.acc = acc;
         s.work = work;
@@ -83,10 +90,10 @@ __global__ void __launch_bounds__(BootGeometry<L>::MAX_THREADS, 1) boot_kernel(c
         s.rot = 0;
         s.ggsw = a.bsk;
         s.diff = nullptr;
+        s.diff_sub = nullptr;
         s.add_acc = 1;
         s.gout = nullptr;
-        s.maybe_raw = (a.mode == BOOT_BLIND) ? 1u : 0u;  // CMUX loads ct0 reduced (PolynomialRing::add reduces it anyway)
-        uint64_t* gout = a.out + ct * GW;
+        s.maybe_raw = (a.mode == BOOT_BLIND || a.acc_global) ? 1u : 0u;  // CMUX loads ct0 reduced into shared memory
         uint32_t nsteps = 1;
         if (a.mode == BOOT_BLIND) {
             if (valid) {
@@ -102,18 +109,23 @@ __global__ void __launch_bounds__(BootGeometry<L>::MAX_THREADS, 1) boot_kernel(c
             nsteps = a.n;
         } else if (valid) {
             const uint64_t* g0 = a.in0 + ct * GW;
-            if (a.mode == BOOT_CMUX) {
-                const uint64_t* g1 = a.in1 + ct * GW;
-                for (uint32_t i = tid; i < GW; i += TPC) {
-                    const uint64_t c0 = g0[i];
-                    const uint64_t c0r = canon_any(c0, a.m);
-                    acc[i] = c0r;
-                    diff[i] = submod_canon(canon_any(g1[i], a.m), c0r, a.m.q);
-                }
+            if (a.acc_global) {  // no staging: the first pass reads the operands from global memory
+                s.diff = (a.mode == BOOT_CMUX) ? a.in1 + ct * GW : g0;
+                s.diff_sub = (a.mode == BOOT_CMUX) ? g0 : nullptr;
             } else {
-                for (uint32_t i = tid; i < GW; i += TPC) diff[i] = g0[i];
+                if (a.mode == BOOT_CMUX) {
+                    const uint64_t* g1 = a.in1 + ct * GW;
+                    for (uint32_t i = tid; i < GW; i += TPC) {
+                        const uint64_t c0 = g0[i];
+                        const uint64_t c0r = canon_any(c0, a.m);
+                        acc[i] = c0r;
+                        diff[i] = submod_canon(canon_any(g1[i], a.m), c0r, a.m.q);
+                    }
+                } else {
+                    for (uint32_t i = tid; i < GW; i += TPC) diff[i] = g0[i];
+                }
+                s.diff = diff;
             }
-            s.diff = diff;
             s.add_acc = (a.mode == BOOT_CMUX) ? 1 : 0;
             s.gout = gout;
         }
@@ -130,7 +142,7 @@ __global__ void __launch_bounds__(BootGeometry<L>::MAX_THREADS, 1) boot_kernel(c
             boot_run_step<L, DP, KP1>(active, tid, TPC, s, a);
             if (active) s.maybe_raw = 0;  // every accumulator word is now the output of a modular addition
         }
-        if (a.mode == BOOT_BLIND && valid) {
+        if (a.mode == BOOT_BLIND && valid && !a.acc_global) {
             for (uint32_t i = tid; i < GW; i += TPC) gout[i] = acc[i];
         }
         __syncthreads();  // the next ciphertexts overwrite acc / rots / diff
@@ -138,11 +150,17 @@ __global__ void __launch_bounds__(BootGeometry<L>::MAX_THREADS, 1) boot_kernel(c
 }
 
 template <int L, bool DP, int KP1>
-int boot_launch_one(const BootLaunch& a, cudaStream_t stream) {
+int boot_launch_one(const BootLaunch& a_in, cudaStream_t stream) {
     using G = BootGeometry<L>;
-    const size_t ct_bytes = boot_smem_bytes(a.mode, 1u << L, KP1, a.levels, a.n);
+    BootLaunch a = a_in;
+    size_t ct_bytes = boot_smem_bytes(a.mode, 1u << L, KP1, a.levels, a.n);
     const size_t cap = (size_t)ctx().prop.sharedMemPerBlockOptin;
     auto k = boot_kernel<L, DP, KP1>;
+    a.acc_global = 0;
+    if (ct_bytes > cap) {  // keep the accumulator in the output buffer instead
+        a.acc_global = 1;
+        ct_bytes = boot_smem_bytes(a.mode, 1u << L, KP1, a.levels, a.n, true);
+    }
     if (ct_bytes > cap)
         return set_error(FHEB_ERR_INVALID_PARAMETERS,
                          "bootstrap working set (%zu bytes) exceeds the shared memory of one SM; reduce N, k or the level count",

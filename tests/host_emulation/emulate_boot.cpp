@@ -82,6 +82,7 @@ static int check(uint32_t threads, uint32_t levels, uint32_t base_log, uint32_t 
     int bad = 0;
     std::vector<uint64_t> acc(gw), work((size_t)rows * N), diff(gw), out(gw), ref(gw);
     BootStep s{};
+    s.diff_sub = nullptr;
     s.acc = acc.data();
     s.work = work.data();
     s.levels = levels;

@@ -87,6 +87,9 @@ SHAPES = [  # N, q, n, k, base_log, level, batch
     (1024, QT, 12, 1, 23, 1, 300),   # tfhe-128-fast shape (short key), more ciphertexts than resident blocks
     (2048, Q27, 3, 1, 9, 2, 3),
     (4096, Q62, 2, 1, 30, 1, 2),
+    (2048, 1125899906826241, 3, 1, 15, 2, 3),      # tfhe-128-balanced shape (Q_50_1), short key
+    (4096, 1152921504606584833, 2, 1, 10, 3, 3),   # tfhe-256-secure shape (Q_60_1): accumulator kept in global memory
+    (4096, Q27, 2, 1, 9, 3, 2),                    # the same working set in FP64 mode
 ]
 
 
