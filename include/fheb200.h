@@ -198,7 +198,9 @@ typedef struct fheb_boot_params { /* the TFHE fields of ParameterSet: cpp/includ
 /* replaces ExtendedBootstrapKey.bsk (cpp/include/bootstrap_engine.h:139-158) as produced by
  * BootstrapEngine::generate_bootstrap_key / encrypt_ggsw (cpp/src/bootstrap_engine.cpp:
  * 268-364).  bsk = [n][(k+1)*L rows][k+1 polys (k mask, then body)][N] coefficient-form words
- * (host or device).  The key is transformed ONCE here and kept resident in HBM. */
+ * (host or device).  The key is transformed ONCE here and kept resident in HBM.  Supported: N = 32 .. 4096,
+ * k = 1 .. 3, any level count whose working rows fit one SM's shared memory (all three TFHE presets of
+ * cpp/src/parameter_set.cpp:108-190 do).  The plan must outlive the key. */
 FHEB_API int fheb_boot_key_create(const fheb_ntt_plan* plan, const fheb_boot_params* params, const uint64_t* bsk,
                                   fheb_boot_key** out);
 /* replaces ExtendedBootstrapKey.ksk / KeySwitchKey (cpp/include/key_manager.h:92-99):

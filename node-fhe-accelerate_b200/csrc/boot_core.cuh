@@ -62,6 +62,9 @@ constexpr int boot_phases() { return 2 * Plan<L>::P - 1; }
 // keeps its running sum in [0, 2q); the FP64 path adds |t| < q per gadget row and reduces only when more
 // than BOOT_DP_ROWS_LAZY rows were summed (block-uniform), so the common 2-row case skips the reduction.
 constexpr int BOOT_DP_ROWS_LAZY = 2;
+// Degrees from 2^11 up may keep the accumulator / operands in global memory when the working rows fill the SM
+// (boot_kernel.cuh); the smaller, hot kernels are compiled without that path.
+constexpr int BOOT_GLOBAL_MIN_L = 11;
 template <bool DP>
 constexpr int boot_kacc() { return 2; }
 
@@ -86,7 +89,7 @@ FHEB_HD void boot_first_pass(uint32_t tid, uint32_t nthreads, const BootStep& s,
             const uint64_t* src = s.diff + (size_t)c * N;
 #pragma unroll
             for (int e = 0; e < E; ++e) d[e] = src[u | ((uint32_t)e << EB)];
-            if (s.diff_sub) {  // PolynomialRing::subtract(ct1, ct0) on the fly (large shapes: no staging buffer)
+            if (L >= BOOT_GLOBAL_MIN_L && s.diff_sub) {  // PolynomialRing::subtract(ct1, ct0) on the fly (large shapes: no staging buffer)
                 const uint64_t* sub = s.diff_sub + (size_t)c * N;
 #pragma unroll
                 for (int e = 0; e < E; ++e) d[e] = submod_canon(canon_any(d[e], m), canon_any(sub[u | ((uint32_t)e << EB)], m), m.q);

@@ -69,8 +69,9 @@ __global__ void __launch_bounds__(BootGeometry<L>::MAX_THREADS, 1) boot_kernel(c
     const uint32_t rows = (uint32_t)KP1 * a.levels;
     // large shapes (e.g. tfhe-256-secure: N=4096, three levels): the working rows alone nearly fill the SM, so
     // the accumulator is kept in the output GLWE in global memory (L2 resident, touched twice per step)
+    const bool acc_global = (L >= BOOT_GLOBAL_MIN_L) && a.acc_global;
     uint64_t* sm_acc = smem + (size_t)group * (ct_bytes / 8);
-    uint64_t* work = sm_acc + (a.acc_global ? 0 : GW);
+    uint64_t* work = sm_acc + (acc_global ? 0 : GW);
     uint64_t* diff = work + (size_t)rows * N;                   // CMUX / EXT only
     uint32_t* rots = reinterpret_cast<uint32_t*>(work + (size_t)rows * N);  // BLIND only
     const size_t ggsw_words = (size_t)rows * KP1 * N;
@@ -80,7 +81,7 @@ __global__ void __launch_bounds__(BootGeometry<L>::MAX_THREADS, 1) boot_kernel(c
         const bool valid = ct < a.batch;
         uint64_t* gout = a.out + (valid ? ct : 0) * GW;
         // accumulator: shared memory, or (acc_global) the output GLWE itself / the caller's ct0 for a single CMux
-        uint64_t* acc = !a.acc_global ? sm_acc
+        uint64_t* acc = !acc_global ? sm_acc
                         : (a.mode == BOOT_CMUX ? const_cast<uint64_t*>(a.in0 + (valid ? ct : 0) * GW) : gout);
         BootStep s;
         s.acc = acc;
@@ -93,7 +94,7 @@ __global__ void __launch_bounds__(BootGeometry<L>::MAX_THREADS, 1) boot_kernel(c
         s.diff_sub = nullptr;
         s.add_acc = 1;
         s.gout = nullptr;
-        s.maybe_raw = (a.mode == BOOT_BLIND || a.acc_global) ? 1u : 0u;  // CMUX loads ct0 reduced into shared memory
+        s.maybe_raw = (a.mode == BOOT_BLIND || acc_global) ? 1u : 0u;  // CMUX loads ct0 reduced into shared memory
         uint32_t nsteps = 1;
         if (a.mode == BOOT_BLIND) {
             if (valid) {
@@ -109,7 +110,7 @@ __global__ void __launch_bounds__(BootGeometry<L>::MAX_THREADS, 1) boot_kernel(c
             nsteps = a.n;
         } else if (valid) {
             const uint64_t* g0 = a.in0 + ct * GW;
-            if (a.acc_global) {  // no staging: the first pass reads the operands from global memory
+            if (acc_global) {  // no staging: the first pass reads the operands from global memory
                 s.diff = (a.mode == BOOT_CMUX) ? a.in1 + ct * GW : g0;
                 s.diff_sub = (a.mode == BOOT_CMUX) ? g0 : nullptr;
             } else {
@@ -142,7 +143,7 @@ __global__ void __launch_bounds__(BootGeometry<L>::MAX_THREADS, 1) boot_kernel(c
             boot_run_step<L, DP, KP1>(active, tid, TPC, s, a);
             if (active) s.maybe_raw = 0;  // every accumulator word is now the output of a modular addition
         }
-        if (a.mode == BOOT_BLIND && valid && !a.acc_global) {
+        if (a.mode == BOOT_BLIND && valid && !acc_global) {
             for (uint32_t i = tid; i < GW; i += TPC) gout[i] = acc[i];
         }
         __syncthreads();  // the next ciphertexts overwrite acc / rots / diff
@@ -157,7 +158,7 @@ int boot_launch_one(const BootLaunch& a_in, cudaStream_t stream) {
     const size_t cap = (size_t)ctx().prop.sharedMemPerBlockOptin;
     auto k = boot_kernel<L, DP, KP1>;
     a.acc_global = 0;
-    if (ct_bytes > cap) {  // keep the accumulator in the output buffer instead
+    if (ct_bytes > cap && L >= BOOT_GLOBAL_MIN_L) {  // keep the accumulator in the output buffer instead
         a.acc_global = 1;
         ct_bytes = boot_smem_bytes(a.mode, 1u << L, KP1, a.levels, a.n, true);
     }
