@@ -2,7 +2,8 @@
 
 Run in the build container (needs oracle/_ref/libref_oracle.so, i.e. /root/reference):
 
-    python tests/golden/make_golden.py
+    python tests/golden/make_golden.py                 # everything (keys are random: every file changes)
+    python tests/golden/make_golden.py boot_tfhe256    # only the files whose name starts with the given prefix
 
 The reference ships no known-answer vectors for this path, so these files
 are outputs of the reference itself (oracle/ref_harness.cpp -> NTTProcessor, PolynomialRing,
@@ -40,6 +41,18 @@ def ntt_case(r, n, q, seed, polys):
                 x=x, forward=y, inverse=z, product=prod)
 
 
+ONLY = sys.argv[1] if len(sys.argv) > 1 else ""
+
+
+def want(name):
+    return name.startswith(ONLY)
+
+
+def save(name, **arrays):
+    if want(name):
+        np.savez_compressed(os.path.join(HERE, name + ".npz"), **arrays)
+
+
 def main():
     r = RefOracle()
     rng = np.random.default_rng(20261018)
@@ -47,7 +60,8 @@ def main():
     # --- transforms + polymul (C1, C2 shapes and the reference's own small configs)
     for n, q, seed, polys in [(8, 17, 42, 4), (8, 97, 42, 4), (16, 97, 42, 4), (1024, Q27, 42, 4),
                               (1024, QT, 7, 2), (4096, Q62, 42, 2), (16384, Q62, 123, 2)]:
-        np.savez_compressed(os.path.join(HERE, f"ntt_n{n}_q{q}.npz"), **ntt_case(r, n, q, seed, polys))
+        if want(f"ntt_n{n}_q{q}"):
+            save(f"ntt_n{n}_q{q}", **ntt_case(r, n, q, seed, polys))
 
     # --- multi-limb (C3 modulus, cpp/tests/test_multi_limb.cpp:143)
     ql = np.array([0xFFFFFFFFFFFFFF43, 1], np.uint64)
@@ -58,27 +72,34 @@ def main():
     vals[:6] = [0, 1, qint - 1, qint - 2, (1 << 64) - 1, 1 << 64]
     ab = np.array([[v & (2**64 - 1), v >> 64] for v in vals], np.uint64)
     a, b = ab[:256], ab[256:]
-    np.savez_compressed(os.path.join(HERE, "mlimb_q65.npz"), q=ql, q_inv=np.uint64(q_inv), r_mod_q=r1, r2_mod_q=r2,
+    save("mlimb_q65", q=ql, q_inv=np.uint64(q_inv), r_mod_q=r1, r2_mod_q=r2,
                         a=a, b=b, montmul=r.mlimb_op(h, "montmul", a, b), add=r.mlimb_op(h, "add", a, b),
                         sub=r.mlimb_op(h, "sub", a, b), to_mont=r.mlimb_op(h, "to_mont", a),
                         from_mont=r.mlimb_op(h, "from_mont", a))
     r.mlimb_destroy(h)
 
     # --- bootstrap: two small shapes with keys drawn by the reference's own generators
-    for tag, (N, n, k, base_log, level, with_ksk) in {
-        "n128_l3": (128, 8, 1, 4, 3, True),          # engine defaults base_log 4 / level 3; n power of two -> KSK works
-        "tfhe_shape_small_n": (1024, 6, 1, 23, 1, False),  # tfhe-128-fast gadget (23,1) at N=1024, short LWE key
+    Q60 = 1152921504606584833  # primes::Q_60_1, cpp/src/parameter_set.cpp:24
+    for tag, (N, QB, n, k, base_log, level, with_ksk) in {
+        "n128_l3": (128, QT, 8, 1, 4, 3, True),          # engine defaults base_log 4 / level 3; n power of two -> KSK works
+        "tfhe_shape_small_n": (1024, QT, 6, 1, 23, 1, False),  # tfhe-128-fast gadget (23,1) at N=1024, short LWE key
+        # tfhe-256-secure (parameter_set.cpp:166-190: N=4096, Q_60_1, base_log 10, 3 levels) - the one TFHE preset
+        # the reference can instantiate end to end (prime modulus, power-of-two LWE dimension) - with a 4-word LWE key
+        "tfhe256_shape_small_n": (4096, Q60, 4, 1, 10, 3, True),
     }.items():
-        h = r.boot_create(N, QT, n, k, base_log, level, 4)
+        if not want(f"boot_{tag}"):
+            continue
+        QT_ = QB
+        h = r.boot_create(N, QB, n, k, base_log, level, 4)
         sk = r.boot_keygen(h, with_ksk)
         bsk = r.boot_export_bsk(h)
         lwe = r.boot_encrypt_lwe(h, np.array([0, 1, 2, 3], np.uint64), sk)
         lwe[3, 0] = 0            # exercises the rotation == 0 skip (bootstrap_engine.cpp:566)
-        lwe[2, 1] = QT - 1       # rotation == 2N (not skipped, identity rotation)
+        lwe[2, 1] = QT_ - 1      # rotation == 2N (not skipped, identity rotation)
         tp = r.boot_default_test_poly(h)
         acc = r.boot_blind_rotate(h, lwe, tp)
-        glwe = rng.integers(0, QT, size=(k + 1, N), dtype=np.uint64)
-        out = dict(N=N, n=n, k=k, base_log=base_log, level=level, q=np.uint64(QT), t=4, lwe_sk=sk, bsk=bsk, lwe=lwe,
+        glwe = rng.integers(0, QT_, size=(k + 1, N), dtype=np.uint64)
+        out = dict(N=N, n=n, k=k, base_log=base_log, level=level, q=np.uint64(QT_), t=4, lwe_sk=sk, bsk=bsk, lwe=lwe,
                    test_poly=tp, blind_rotate=acc, glwe=glwe, external_product=r.boot_external_product(h, glwe, 1),
                    cmux=r.boot_cmux(h, 2, glwe, acc[0]), sample_extract=r.boot_sample_extract(h, acc),
                    decompose=r.boot_decompose(h, glwe[0], base_log, level), rotate_5=r.boot_rotate(h, glwe[0], 5),
@@ -88,7 +109,7 @@ def main():
             ksk = r.boot_export_ksk(h)
             out.update(ksk=ksk, key_switch=r.boot_key_switch(h, r.boot_sample_extract(h, acc), n),
                        bootstrap=r.boot_bootstrap(h, lwe, tp, n))
-        np.savez_compressed(os.path.join(HERE, f"boot_{tag}.npz"), **out)
+        save(f"boot_{tag}", **out)
         r.boot_destroy(h)
 
     # --- tally + tensor product (C5 shape scaled down)
@@ -96,7 +117,7 @@ def main():
         ring = r.ring_create(n, q)
         cts = rng.integers(0, q, size=(m, 2, n), dtype=np.uint64)
         cts[1, 0, :4] = [q, q + 1, 2**64 - 1, 0]  # unreduced words: mod_add reduces inputs first
-        np.savez_compressed(os.path.join(HERE, f"tally_n{n}_m{m}.npz"), n=n, q=np.uint64(q), cts=cts,
+        save(f"tally_n{n}_m{m}", n=n, q=np.uint64(q), cts=cts,
                             linear=r.tally(ring, cts), tree=r.tally(ring, cts, tree=True), single=r.tally(ring, cts[1:2]),
                             tensor=r.tensor_multiply(ring, cts[0], cts[2]))
         r.ring_destroy(ring)

@@ -52,7 +52,7 @@ def host(t):
     return t.cpu().numpy().view(np.uint64)
 
 
-@pytest.mark.parametrize("tag", ["n128_l3", "tfhe_shape_small_n"])
+@pytest.mark.parametrize("tag", ["n128_l3", "tfhe_shape_small_n", "tfhe256_shape_small_n"])
 def test_golden_bootstrap(fhe, torch, tag):
     g = np.load(os.path.join(GOLDEN, f"boot_{tag}.npz"))
     N, n, k, base_log, level, q, t = (int(g[x]) for x in ("N", "n", "k", "base_log", "level", "q", "t"))

@@ -92,7 +92,7 @@ def test_golden_multi_limb(oracle):
     assert exp == got
 
 
-@pytest.mark.parametrize("tag", ["n128_l3", "tfhe_shape_small_n"])
+@pytest.mark.parametrize("tag", ["n128_l3", "tfhe_shape_small_n", "tfhe256_shape_small_n"])
 def test_golden_bootstrap(oracle, tag):
     g = np.load(os.path.join(GOLDEN, f"boot_{tag}.npz"))
     N, n, k, base_log, level, q, t = (int(g[x]) for x in ("N", "n", "k", "base_log", "level", "q", "t"))
