@@ -5,6 +5,8 @@
 #pragma once
 #include <cuda_runtime.h>
 
+#include <cstdlib>
+
 #include "boot_core.cuh"
 #include "runtime.hpp"
 
@@ -36,6 +38,14 @@ struct BootGeometry {
     static constexpr int TPC = (L <= 6) ? 32 : (L <= 8) ? 64 : (L <= 10) ? 128 : (L == 11) ? 256 : 512;
     static constexpr int MAX_THREADS = 512;
     static constexpr int MAX_GROUPS = MAX_THREADS / TPC;
+    // N = 1024 (the tfhe-128-fast shape): one ciphertext per 128-thread block and five blocks per SM (96
+    // registers) measured 7 % faster than four ciphertexts in lockstep in one 512-thread block - the blocks
+    // drift out of phase, so one block's FP64 bursts overlap another's loads, digit extraction and barriers.
+#if !defined(FHEB_EXP_BOOT_LB_BLOCKS)
+#define FHEB_EXP_BOOT_LB_BLOCKS 5
+#endif
+    static constexpr int LB_THREADS = (L == 10) ? TPC : MAX_THREADS;
+    static constexpr int LB_BLOCKS = (L == 10) ? FHEB_EXP_BOOT_LB_BLOCKS : 1;
 };
 
 // shared-memory bytes per ciphertext: acc [KP1][N] | work [rows][N] | (CMUX/EXT) diff [KP1][N] | (BLIND) rotations [n] (u32)
@@ -58,7 +68,7 @@ __device__ __forceinline__ void boot_run_step(bool active, uint32_t tid, uint32_
 }
 
 template <int L, bool DP, int KP1>
-__global__ void __launch_bounds__(BootGeometry<L>::MAX_THREADS, 1) boot_kernel(const BootLaunch a, const uint32_t ct_bytes) {
+__global__ void __launch_bounds__(BootGeometry<L>::LB_THREADS, BootGeometry<L>::LB_BLOCKS) boot_kernel(const BootLaunch a, const uint32_t ct_bytes) {
     extern __shared__ __align__(16) uint64_t smem[];
     constexpr uint32_t N = 1u << L;
     constexpr uint32_t TPC = BootGeometry<L>::TPC;
@@ -168,7 +178,12 @@ int boot_launch_one(const BootLaunch& a_in, cudaStream_t stream) {
                          ct_bytes);
     size_t groups = cap / ct_bytes;  // ciphertexts per block: as many as fit, at most 512 threads' worth
     if (groups > (size_t)G::MAX_GROUPS) groups = G::MAX_GROUPS;
+    if (groups > (size_t)(G::LB_THREADS / G::TPC)) groups = G::LB_THREADS / G::TPC;
     if (groups > a.batch) groups = a.batch;
+    if (const char* e = getenv("FHEB_BOOT_GROUPS")) {  // experiment knob: ciphertexts per block
+        const size_t g = (size_t)atoi(e);
+        if (g >= 1 && g < groups) groups = g;
+    }
     const size_t smem = groups * ct_bytes;
     const int threads = (int)groups * G::TPC;
     if (smem > 48 * 1024) FHEB_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
