@@ -56,6 +56,7 @@ typedef enum fheb_status {
 
 typedef struct fheb_ntt_plan fheb_ntt_plan; /* replaces NTTProcessor / PolynomialRing state   */
 typedef struct fheb_boot_key fheb_boot_key; /* replaces ExtendedBootstrapKey (device resident) */
+typedef struct fheb_relin_key fheb_relin_key; /* replaces EvaluationKey.relin_key (device resident, pre-transformed) */
 
 /* ---- library / device ---------------------------------------------------------------- */
 
@@ -272,6 +273,25 @@ FHEB_API int fheb_tally_stream_destroy(fheb_tally_stream* ts);
  * ct1, ct2 = [batch][2][N]; out = [batch][3][N]. */
 FHEB_API int fheb_tensor_multiply_batch(const fheb_ntt_plan* plan, const uint64_t* ct1, const uint64_t* ct2,
                                         uint64_t* out, size_t batch, void* stream);
+
+/* replaces EvaluationKey / KeySwitchKey as produced by KeyManager::generate_eval_key (cpp/include/key_manager.h:
+ * 92-111, cpp/src/key_manager.cpp:266-331) for EncryptionEngine::relinearize.  keys = [key_count][2][N]
+ * coefficient-form words, (a, b) of every pair in generation order (host or device).  decomp_base_log /
+ * decomp_level are the KeySwitchKey fields; zero values fall back as the reference does (base_log 4,
+ * ceil(64 / base_log) levels: cpp/src/encryption.cpp:935-939) and min(levels, key_count) levels are applied.
+ * Both key polynomials of every level are transformed ONCE here (the reference re-transforms them on every
+ * call).  Shift amounts of 64 bits or more are undefined in the reference and rejected here.  The plan must
+ * outlive the key. */
+FHEB_API int fheb_relin_key_create(const fheb_ntt_plan* plan, const uint64_t* keys, uint32_t key_count,
+                                   uint32_t decomp_base_log, uint32_t decomp_level, uint64_t key_id, fheb_relin_key** out);
+FHEB_API int fheb_relin_key_destroy(fheb_relin_key* key);
+FHEB_API uint32_t fheb_relin_key_levels(const fheb_relin_key* key); /* levels actually applied */
+/* replaces EncryptionEngine::relinearize / relinearize_inplace on degree-2 ciphertexts: cpp/src/encryption.cpp:
+ * 904-1003.  cts = [batch][3][N] (c0, c1, c2), coefficient form, e.g. the output of fheb_tensor_multiply_batch;
+ * out = [batch][2][N].  ct_key_id must equal the key's id (FHEB_ERR_KEY_MISMATCH, the reference's message).
+ * With no key pairs c0 and c1 are returned untouched, as the reference does (:980-989). */
+FHEB_API int fheb_relinearize_batch(const fheb_relin_key* key, const uint64_t* cts, uint64_t ct_key_id, uint64_t* out,
+                                    size_t batch, void* stream);
 
 /* Synthetic ballots generated ON DEVICE (bench / scaling runs: 16 GB never crosses PCIe).
  * word(ballot, comp, j) = splitmix64(seed + (ballot*2 + comp)*N + j) % modulus, reproducible on

@@ -140,6 +140,29 @@ class PolynomialRing {
     NTTProcessor ntt_;
 };
 
+// EvaluationKey.relin_key on the device (cpp/include/key_manager.h:92-111), pre-transformed once.
+class RelinearizationKey {
+   public:
+    // keys = [key_count][2][N]: (a, b) of every pair in generation order (KeyManager::generate_eval_key)
+    RelinearizationKey(const PolynomialRing& ring, const uint64_t* keys, uint32_t key_count, uint32_t decomp_base_log,
+                       uint32_t decomp_level, uint64_t key_id = 0)
+        : key_id_(key_id) {
+        check(fheb_relin_key_create(ring.ntt().handle(), keys, key_count, decomp_base_log, decomp_level, key_id, &key_));
+    }
+    ~RelinearizationKey() { fheb_relin_key_destroy(key_); }
+    RelinearizationKey(const RelinearizationKey&) = delete;
+    RelinearizationKey& operator=(const RelinearizationKey&) = delete;
+    uint32_t levels() const { return fheb_relin_key_levels(key_); }
+    // EncryptionEngine::relinearize (encryption.cpp:904-993): [batch][3][N] -> [batch][2][N]
+    void relinearize(const uint64_t* cts, uint64_t* out, size_t batch = 1, void* s = nullptr) const {
+        check(fheb_relinearize_batch(key_, cts, key_id_, out, batch, s));
+    }
+
+   private:
+    fheb_relin_key* key_ = nullptr;
+    uint64_t key_id_;
+};
+
 class MultiLimbModularArithmetic {
    public:
     explicit MultiLimbModularArithmetic(const std::vector<uint64_t>& q) : q_(q), consts_(1 + 2 * q.size()) {

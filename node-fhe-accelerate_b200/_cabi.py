@@ -102,6 +102,10 @@ SIGNATURES = {
     "fheb_tally_stream_count": ([p], u64),
     "fheb_tally_stream_destroy": ([p], i),
     "fheb_tensor_multiply_batch": ([p, p, p, p, sz, p], i),
+    "fheb_relin_key_create": ([p, p, u32, u32, u32, u64, p], i),
+    "fheb_relin_key_destroy": ([p], i),
+    "fheb_relin_key_levels": ([p], u32),
+    "fheb_relinearize_batch": ([p, p, u64, p, sz, p], i),
     "fheb_synth_ballots": ([p, sz, sz, u32, u64, u64, p], i),
     "fheb_launch_count": ([i], u64),
 }

@@ -285,6 +285,39 @@ class PolynomialRing:
         return out
 
 
+class RelinearizationKey:
+    """EvaluationKey.relin_key (cpp/include/key_manager.h:92-111) resident on the device, both polynomials of every
+    level pre-transformed.  keys = [key_count][2][N]: (a, b) of every pair in generation order."""
+
+    def __init__(self, ring: "PolynomialRing", keys, decomp_base_log: int = 0, decomp_level: int = 0, key_id: int = 0):
+        self.ring, self.key_id = ring, key_id
+        keys = np.ascontiguousarray(as_words(keys)) if not _is_torch(keys) else as_words(keys)
+        count = _words(keys) // (2 * ring.degree)
+        h = C.c_void_p()
+        check(lib().fheb_relin_key_create(ring.ntt._h, _ptr(keys) if count else None, count, decomp_base_log, decomp_level,
+                                          key_id, C.byref(h)))
+        self._h = h
+        self.levels = int(lib().fheb_relin_key_levels(h))
+
+    def relinearize(self, cts, ct_key_id: Optional[int] = None, out=None):
+        """EncryptionEngine::relinearize (cpp/src/encryption.cpp:904-993): [batch][3][N] -> [batch][2][N]."""
+        cts = as_words(cts)
+        n = self.ring.degree
+        batch = _words(cts) // (3 * n)
+        out = _like(cts, tuple(cts.shape[:-2]) + (2, n)) if out is None else out
+        check(lib().fheb_relinearize_batch(self._h, _ptr(cts), self.key_id if ct_key_id is None else ct_key_id, _ptr(out),
+                                           batch, _stream(cts, out)))
+        return out
+
+    def __del__(self):
+        h, self._h = getattr(self, "_h", None), None
+        if h:
+            try:
+                lib().fheb_relin_key_destroy(h)
+            except Exception:
+                pass
+
+
 # ----------------------------------------------------------- MultiLimbModularArithmetic --
 class MultiLimbModularArithmetic:
     """cpp/include/modular_arithmetic.h:124-194; integers are [count][limbs] little-endian words."""

@@ -658,3 +658,32 @@ void orc_tensor_multiply(const uint64_t* ct1, const uint64_t* ct2, uint64_t* out
     orc_inverse_ntt(out + 2 * n, n, q, inv_table, inv_n);
     free(w);
 }
+/* src/encryption.cpp:904-993 (relinearize).  ct = [3][n]; keys = [key_count][2][n], (a, b) per pair; out = [2][n].
+ * Level l takes the raw bits (c2 >> l*base_log) & (base-1) (:948-955), transforms the digit polynomial and both key
+ * polynomials (:957-963), and adds T^-1 of the pointwise products to c0 (with b) and c1 (with a) (:965-978). */
+void orc_relinearize(const uint64_t* ct, const uint64_t* keys, uint32_t key_count, uint32_t key_base_log, uint32_t key_level,
+                     uint64_t* out, size_t n, uint64_t q, const uint64_t* fwd_table, const uint64_t* inv_table, uint64_t inv_n) {
+    const uint32_t base_log = key_base_log > 0 ? key_base_log : 4;                       /* :936 */
+    const uint64_t base = 1ULL << base_log;
+    const uint32_t num_levels = key_level > 0 ? key_level : (64 + base_log - 1) / base_log; /* :938-939 */
+    uint64_t* w = (uint64_t*)malloc(4 * n * 8);
+    uint64_t *dig = w, *ka = w + n, *kb = w + 2 * n, *prod = w + 3 * n;
+    const uint64_t* c2 = ct + 2 * n;
+    memcpy(out, ct, 2 * n * 8); /* clones of c0 and c1 (:942-943) */
+    for (uint32_t level = 0; level < num_levels && level < key_count; ++level) {
+        const uint64_t shift = (uint64_t)level * base_log, mask = base - 1;
+        for (size_t i = 0; i < n; ++i) dig[i] = (c2[i] >> shift) & mask;
+        memcpy(ka, keys + ((size_t)level * 2) * n, n * 8);
+        memcpy(kb, keys + ((size_t)level * 2 + 1) * n, n * 8);
+        orc_forward_ntt(dig, n, q, fwd_table);
+        orc_forward_ntt(ka, n, q, fwd_table);
+        orc_forward_ntt(kb, n, q, fwd_table);
+        orc_poly_pointwise(dig, kb, prod, n, q);
+        orc_inverse_ntt(prod, n, q, inv_table, inv_n);
+        orc_poly_add(out, prod, out, n, q);
+        orc_poly_pointwise(dig, ka, prod, n, q);
+        orc_inverse_ntt(prod, n, q, inv_table, inv_n);
+        orc_poly_add(out + n, prod, out + n, n, q);
+    }
+    free(w);
+}

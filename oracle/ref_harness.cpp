@@ -246,6 +246,45 @@ int ref_tensor_multiply(void* h, const uint64_t* ct1, const uint64_t* ct2, uint6
     REF_CATCH
 }
 
+/* Relinearisation: EncryptionEngine::relinearize, cpp/src/encryption.cpp:904-993, composed from the same
+ * unmodified PolynomialRing calls in the same order (clone, to_ntt on the digit polynomial AND on both key
+ * polynomials every level, pointwise_multiply, from_ntt, add_inplace).  ct = [3][N] (c0, c1, c2);
+ * keys = [key_count][2][N] ((a, b) per pair); base_log / level = the KeySwitchKey fields; out = [2][N]. */
+int ref_relinearize(void* h, const uint64_t* ct, const uint64_t* keys, uint32_t key_count, uint32_t key_base_log,
+                    uint32_t key_level, uint64_t* out) {
+    REF_TRY
+    auto* ring = static_cast<PolynomialRing*>(h);
+    uint32_t degree = ring->degree();
+    uint64_t modulus = ring->modulus();
+    uint32_t decomp_base_log = key_base_log > 0 ? key_base_log : 4;
+    uint64_t decomp_base = 1ULL << decomp_base_log;
+    uint32_t num_levels = key_level > 0 ? key_level : static_cast<uint32_t>((64 + decomp_base_log - 1) / decomp_base_log);
+    Polynomial result_c0 = make_poly(ct, degree, modulus, false);
+    Polynomial result_c1 = make_poly(ct + degree, degree, modulus, false);
+    const uint64_t* c2 = ct + 2 * (size_t)degree;
+    for (uint32_t level = 0; level < num_levels && level < key_count; ++level) {
+        Polynomial c2_digit(degree, modulus);
+        uint64_t shift = level * decomp_base_log;
+        uint64_t mask = decomp_base - 1;
+        for (uint32_t i = 0; i < degree; ++i) c2_digit[i] = (c2[i] >> shift) & mask;
+        Polynomial rlk_a_ntt = make_poly(keys + ((size_t)level * 2) * degree, degree, modulus, false);
+        Polynomial rlk_b_ntt = make_poly(keys + ((size_t)level * 2 + 1) * degree, degree, modulus, false);
+        Polynomial c2_digit_ntt = c2_digit.clone();
+        ring->to_ntt(c2_digit_ntt);
+        ring->to_ntt(rlk_a_ntt);
+        ring->to_ntt(rlk_b_ntt);
+        Polynomial prod_b = ring->pointwise_multiply(c2_digit_ntt, rlk_b_ntt);
+        ring->from_ntt(prod_b);
+        ring->add_inplace(result_c0, prod_b);
+        Polynomial prod_a = ring->pointwise_multiply(c2_digit_ntt, rlk_a_ntt);
+        ring->from_ntt(prod_a);
+        ring->add_inplace(result_c1, prod_a);
+    }
+    std::memcpy(out, result_c0.data(), (size_t)degree * 8);
+    std::memcpy(out + degree, result_c1.data(), (size_t)degree * 8);
+    REF_CATCH
+}
+
 /* ------------------------------------------------- scalar ModularArithmetic - */
 /* the class behind the reference's N-API addon (src/native/lib.rs:44-120)      */
 int ref_scalar_create(uint64_t modulus, void** out) {

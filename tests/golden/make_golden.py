@@ -121,6 +121,21 @@ def main():
                             linear=r.tally(ring, cts), tree=r.tally(ring, cts, tree=True), single=r.tally(ring, cts[1:2]),
                             tensor=r.tensor_multiply(ring, cts[0], cts[2]))
         r.ring_destroy(ring)
+    # --- relinearisation: EncryptionEngine::relinearize composed from the reference's PolynomialRing
+    # calls (ref_harness.cpp: ref_relinearize).  Keys are uniform words: the arithmetic does not care how they were made.
+    rrng = np.random.default_rng(904)
+    for n, q, key_count, base_log, level in [(64, Q27, 3, 8, 3), (1024, QT, 16, 0, 0), (4096, Q62, 4, 16, 4), (8, 17, 5, 6, 0)]:
+        if not want(f"relin_n{n}"):
+            continue
+        ring = r.ring_create(n, q)
+        ct = rrng.integers(0, q, size=(2, 3, n), dtype=np.uint64)
+        ct[1, 0, :3] = [q, 2**64 - 1, q + 5]   # unreduced c0 words: add_inplace reduces both sides
+        ct[1, 2, :2] = [2**64 - 1, 2**63 + 12345]  # c2 is only ever read through shifts and masks
+        keys = rrng.integers(0, q, size=(key_count, 2, n), dtype=np.uint64)
+        out = np.stack([r.relinearize(ring, ct[i], keys, base_log, level) for i in range(2)])
+        nokey = r.relinearize(ring, ct[1], keys[:0], base_log, level)
+        save(f"relin_n{n}", n=n, q=np.uint64(q), ct=ct, keys=keys, base_log=base_log, level=level, out=out, nokey=nokey)
+        r.ring_destroy(ring)
     print("golden vectors written to", HERE)
 
 

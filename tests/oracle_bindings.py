@@ -110,6 +110,7 @@ class Oracle:
             "tally_linear": _bind(L, "orc_tally_linear", "p sz sz u64 p"),
             "tally_tree": _bind(L, "orc_tally_tree", "p sz sz u64 p"),
             "tensor": _bind(L, "orc_tensor_multiply", "p p p sz u64 p p u64", None),
+            "relin": _bind(L, "orc_relinearize", "p p u32 u32 u32 p sz u64 p p u64", None),
         }
 
     # -- scalars
@@ -309,6 +310,14 @@ class Oracle:
         self._f["tensor"](_ptr(ct1), _ptr(ct2), _ptr(out), n, q, _ptr(fwd), _ptr(inv), inv_n)
         return out
 
+    def relinearize(self, ct, keys, key_base_log, key_level, q, fwd, inv, inv_n):
+        ct, keys = u64(ct), u64(keys)
+        n = ct.shape[-1]
+        out = np.zeros((2, n), np.uint64)
+        self._f["relin"](_ptr(ct), _ptr(keys), keys.shape[0] if keys.size else 0, key_base_log, key_level, _ptr(out), n, q,
+                         _ptr(fwd), _ptr(inv), inv_n)
+        return out
+
 
 def ref_available():
     return os.path.exists(REF_SO)
@@ -343,6 +352,7 @@ class RefOracle:
             "tally_linear": b("ref_tally_linear", "p p sz p"),
             "tally_tree": b("ref_tally_tree", "p p sz p"),
             "tensor": b("ref_tensor_multiply", "p p p p"),
+            "relin": b("ref_relinearize", "p p p u32 u32 u32 p"),
             "scalar_create": b("ref_scalar_create", "u64 p"),
             "scalar_destroy": b("ref_scalar_destroy", "p", None),
             "scalar_op": b("ref_scalar_op", "p int u64 u64", C.c_uint64),
@@ -450,6 +460,12 @@ class RefOracle:
         ct1, ct2 = u64(ct1), u64(ct2)
         out = np.zeros((3, ct1.shape[-1]), np.uint64)
         self.call("tensor", h, ct1, ct2, out)
+        return out
+
+    def relinearize(self, h, ct, keys, key_base_log, key_level):
+        ct, keys = u64(ct), u64(keys)
+        out = np.zeros((2, ct.shape[-1]), np.uint64)
+        self.call("relin", h, ct, keys, keys.shape[0] if keys.size else 0, key_base_log, key_level, out)
         return out
 
     # -- scalar ModularArithmetic (the reference addon's class)

@@ -279,6 +279,44 @@ def test_golden_tally(fhe, torch, name):
     eq(ring.tensor_multiply(cts[0:1], cts[2:3])[0], g["tensor"])
 
 
+# ----------------------------------------------------------------------- relinearisation --
+@pytest.mark.parametrize("name", ["relin_n64.npz", "relin_n1024.npz", "relin_n4096.npz"])
+def test_golden_relinearize(fhe, torch, name):
+    """EncryptionEngine::relinearize (SURVEY 8f N4) against outputs of the reference's own code."""
+    g = np.load(os.path.join(GOLDEN, name))
+    n, q, bl, lv = int(g["n"]), int(g["q"]), int(g["base_log"]), int(g["level"])
+    ring = fhe.PolynomialRing(n, q)
+    key = fhe.RelinearizationKey(ring, g["keys"], bl, lv, key_id=7)
+    eq(key.relinearize(g["ct"]), g["out"])                        # host buffers (pipelined staging)
+    eq(host(key.relinearize(dev(torch, g["ct"]))), g["out"])      # device buffers
+    eq(host(key.relinearize(dev(torch, g["ct"][1:2])))[0], g["out"][1])
+    nokey = fhe.RelinearizationKey(ring, g["keys"][:0], bl, lv)
+    assert nokey.levels == 0
+    eq(host(nokey.relinearize(dev(torch, g["ct"][1:2])))[0], g["nokey"])
+    with pytest.raises(fhe.FheError) as e:
+        key.relinearize(g["ct"], ct_key_id=8)
+    assert e.value.code == 2 and "Evaluation key does not match ciphertext key" in str(e.value)
+    with pytest.raises(fhe.FheError):
+        fhe.RelinearizationKey(ring, g["keys"], 40, 3)  # third shift would reach 80 bits
+
+
+@pytest.mark.parametrize("n,q,key_count,bl,lv,batch", [(256, Q27, 16, 0, 0, 5), (2048, 1125899906826241, 3, 17, 3, 9),
+                                                       (8192, Q62, 2, 31, 2, 3), (1024, QT, 6, 7, 6, 33)])
+def test_relinearize_matches_oracle(fhe, torch, oracle, n, q, key_count, bl, lv, batch):
+    rng = np.random.default_rng(n + batch)
+    fwd, inv, _, _, inv_n = oracle.twiddles(n, q)
+    ring = fhe.PolynomialRing(n, q)
+    a = rng.integers(0, q, size=(batch, 2, n), dtype=np.uint64)
+    b = rng.integers(0, q, size=(batch, 2, n), dtype=np.uint64)
+    ct3 = ring.tensor_multiply(dev(torch, a), dev(torch, b))      # multiply -> relinearize, the reference's chain
+    keys = rng.integers(0, q, size=(key_count, 2, n), dtype=np.uint64)
+    key = fhe.RelinearizationKey(ring, dev(torch, keys), bl, lv)
+    got = host(key.relinearize(ct3))
+    ct3h = host(ct3)
+    for i in range(batch):
+        eq(got[i], oracle.relinearize(ct3h[i], keys, bl, lv, q, fwd, inv, inv_n))
+
+
 @pytest.mark.parametrize("count", [2, 3, 63, 64, 65, 1000, 20000])
 def test_tally_matches_oracle(fhe, torch, oracle, count):
     n, q = 1024, QT

@@ -133,6 +133,20 @@ def test_golden_tally(oracle, name):
     eq(oracle.tensor_multiply(cts[0], cts[2], q, fwd, inv, inv_n), g["tensor"])
 
 
+RELIN_GOLDEN = ["relin_n8.npz", "relin_n64.npz", "relin_n1024.npz", "relin_n4096.npz"]
+
+
+@pytest.mark.parametrize("name", RELIN_GOLDEN)
+def test_golden_relinearize(oracle, name):
+    g = np.load(os.path.join(GOLDEN, name))
+    n, q, bl, lv = int(g["n"]), int(g["q"]), int(g["base_log"]), int(g["level"])
+    fwd, inv, _, _, inv_n = oracle.twiddles(n, q)
+    for i in range(2):
+        eq(oracle.relinearize(g["ct"][i], g["keys"], bl, lv, q, fwd, inv, inv_n), g["out"][i])
+    eq(oracle.relinearize(g["ct"][1], g["keys"][:0], bl, lv, q, fwd, inv, inv_n), g["nokey"])
+    eq(g["nokey"], g["ct"][1, :2])  # no key pairs: c0 and c1 come back untouched, unreduced words included
+
+
 # ----------------------------------------------------- reference, run live --
 @pytest.mark.parametrize("n,q", [(4, 17), (8, 17), (16, 97), (64, QT), (512, Q27), (1024, Q27), (2048, 1125899906826241),
                                  (4096, Q62), (8192, Q62)])
@@ -189,6 +203,11 @@ def test_ring_ops_match_reference(oracle, ref, n, q):
         eq(oracle.tally(cts, q), ref.tally(ring, cts))
         eq(oracle.tally(cts, q, tree=True), ref.tally(ring, cts, tree=True))
         eq(oracle.tensor_multiply(cts[0], cts[1], q, fwd, inv, inv_n), ref.tensor_multiply(ring, cts[0], cts[1]))
+        # relinearisation of a tensor product, default and explicit gadgets, fewer keys than levels
+        ct3 = ref.tensor_multiply(ring, cts[0], cts[1])
+        for key_count, bl, lv in [(16, 0, 0), (3, 0, 0), (2, 20, 2), (4, 7, 6)]:
+            keys = rng.integers(0, q, size=(key_count, 2, n), dtype=np.uint64)
+            eq(oracle.relinearize(ct3, keys, bl, lv, q, fwd, inv, inv_n), ref.relinearize(ring, ct3, keys, bl, lv))
     finally:
         ref.ring_destroy(ring)
 
