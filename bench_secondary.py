@@ -106,6 +106,44 @@ def run(fhe, torch, dist, world, rank, dev, barrier, max_over_ranks, peak):
                           "roofline": _hbm(peak, 16384.0 * per_rank, ms),
                           "checksum": int(res[0].view(-1)[:4].sum().item() & 0xFFFFFFFF)}
     del cts
+
+    # ---- N4: multiply -> relinearize chain (tensor product + relinearisation with a pre-transformed key)
+    n, levels, base_log = 4096, 4, 16
+    ring = fhe.PolynomialRing(n, Q62)
+    keys = torch.randint(0, Q62, (levels, 2, n), dtype=torch.int64, device=dev, generator=gen)
+    rk = fhe.RelinearizationKey(ring, keys, base_log, levels)
+    batch = 2048  # 201 MB of degree-2 ciphertexts per set
+    ct3 = [torch.randint(0, Q62, (batch, 3, n), dtype=torch.int64, device=dev, generator=gen) for _ in range(2)]
+    o2 = torch.empty((batch, 2, n), dtype=torch.int64, device=dev)
+    ms = _time(torch, lambda i: rk.relinearize(ct3[i % 2], out=o2), 10)
+    # algorithmic bytes: read 3 polynomials, write 2; integer work: `levels` forward + 2 inverse transforms
+    out[f"relinearize_n{n}_L{levels}_b{batch}"] = {"value": batch / (ms * 1e-3), "unit": "ciphertexts/s", "ms": ms,
+                                                     "transforms_per_ct": levels + 2,
+                                                     "coeff_transforms_per_s": (levels + 2) * n * batch / (ms * 1e-3),
+                                                     "roofline": _hbm(peak, 40.0 * n * batch, ms)}
+    del ct3, o2, keys
+
+    # ---- N3: FHEV ballot records -> device ingest (checksum + realign), wire bytes already in HBM
+    n, cnt = 1024, 32768
+    one = np.random.default_rng(3).integers(0, QT, size=(64, 1, 2, n), dtype=np.uint64)
+    recs = [fhe.serialize_ballot(one[i], QT, i) for i in range(64)]
+    blob = b"".join(recs) * (cnt // 64)
+    pad = (-len(blob)) % 8
+    wire = torch.from_numpy(np.frombuffer(blob + b"\0" * pad, dtype=np.uint8).copy()).to(dev)
+    offs = np.arange(cnt + 1, dtype=np.uint64) * np.uint64(len(recs[0]))
+    ing = torch.empty((cnt, 1, 2, n), dtype=torch.int64, device=dev)
+    status = [None]
+
+    def ingest(i):
+        status[0] = fhe.ingest_ballots(wire, cnt, 1, n, QT, offsets=offs, out=ing)[1]
+
+    ms = _time(torch, ingest, 5, warm=2)
+    assert not status[0].any()
+    out["ballot_ingest_n1024"] = {"value": cnt / (ms * 1e-3), "unit": "ballots/s", "ms": ms, "ballots": cnt,
+                                  "note": "includes the per-call status copy and synchronisation",
+                                  # validate reads the record once, unpack reads it again and writes the aligned words
+                                  "roofline": _hbm(peak, (2.0 * len(recs[0]) + 16384.0) * cnt, ms)}
+    del wire, ing
     out["bootstrap_tfhe128fast_shape"] = run_bootstrap(fhe, torch, dist, world, rank, dev, barrier, max_over_ranks)
     return out
 

@@ -293,6 +293,66 @@ FHEB_API uint32_t fheb_relin_key_levels(const fheb_relin_key* key); /* levels ac
 FHEB_API int fheb_relinearize_batch(const fheb_relin_key* key, const uint64_t* cts, uint64_t ct_key_id, uint64_t* out,
                                     size_t batch, void* stream);
 
+/* ---- wire formats ----------------------------------------------------------------- */
+
+/* SerializationHeader as written by KeySerializer::write_header (cpp/include/key_serializer.h:59-84, cpp/src/
+ * key_serializer.cpp:96-108): 49 packed little-endian bytes in front of data_size payload bytes. */
+typedef struct fheb_wire_header {
+    uint32_t magic;         /* FHES / FHEP / FHEE / FHEB / FHEV: key_serializer.h:33-37 */
+    uint32_t version;
+    uint32_t key_type;      /* 0 secret, 1 public, 2 eval, 3 bootstrap, 4 ballot */
+    uint64_t key_id;        /* ballots: the timestamp */
+    uint32_t poly_degree;
+    uint64_t modulus;
+    uint32_t data_size;
+    uint8_t checksum_type;  /* ChecksumType: 0 none, 1 CRC32, 2 "SHA256" (the reference falls back to its CRC32) */
+    uint8_t compression;    /* CompressionType; the reference never compresses */
+    uint32_t checksum;
+} fheb_wire_header;
+FHEB_API int fheb_wire_header_read(const void* bytes, size_t len, fheb_wire_header* out); /* KeySerializer::read_header, :623-641 */
+/* replaces KeySerializer::compute_crc32 (:34-40) INCLUDING its table as shipped: only the first 60 of the 256
+ * IEEE 802.3 entries are initialised (:21-32), so this is not the standard CRC-32.  Host-side. */
+FHEB_API uint32_t fheb_wire_crc32(const void* data, size_t len);
+
+/* replaces BallotSerializer::serialize_ballot (:709-774) for one record: choices = [num_choices][2][degree] host
+ * words.  *written receives the record size (also when the buffer is too small); fheb_ballot_wire_size is
+ * estimate_ballot_size's exact counterpart (:848-854 counts sizeof(SerializationHeader) = 64 instead of the 49
+ * bytes actually written). */
+FHEB_API size_t fheb_ballot_wire_size(uint32_t num_choices, uint32_t degree);
+FHEB_API int fheb_ballot_serialize(const uint64_t* choices, uint32_t num_choices, uint32_t degree, uint64_t modulus,
+                                   uint64_t timestamp, void* out, size_t capacity, size_t* written);
+
+/* Per-record result of fheb_ballots_ingest.  1..3 are the three rejections of BallotSerializer::deserialize_ballot
+ * (:781-783 "Input too small", :800-802 "Invalid magic bytes for ballot", :808-811 "Checksum verification failed");
+ * 4 is this bulk path's own: the record is well formed but not num_choices ciphertexts of the given degree/modulus. */
+enum {
+    FHEB_WIRE_OK = 0,
+    FHEB_WIRE_TOO_SMALL = 1,
+    FHEB_WIRE_BAD_MAGIC = 2,
+    FHEB_WIRE_BAD_CHECKSUM = 3,
+    FHEB_WIRE_SHAPE_MISMATCH = 4
+};
+/* replaces a loop of BallotSerializer::deserialize_ballot (:776-846) over `count` FHEV records, validated and
+ * unpacked ON THE DEVICE straight into the layout fheb_tally reads.  wire = the records' bytes (host, or 8-byte
+ * aligned device memory); offsets = count + 1 host entries, record r = bytes [offsets[r], offsets[r+1]) - or
+ * NULL (host wire only): records are back to back and their extents are walked from the headers.
+ * cts = [count][num_choices][2][degree] (host or device): accepted records' words exactly as stored; REJECTED
+ * records become all-zero ciphertexts, the additive identity, so the buffer can be tallied as a whole.
+ * status = [count] host bytes (FHEB_WIRE_*); timestamps = [count] host words or NULL; *accepted (optional) =
+ * number of FHEB_WIRE_OK records.  Returns after the results are in place. */
+FHEB_API int fheb_ballots_ingest(const void* wire, size_t wire_bytes, const uint64_t* offsets, size_t count,
+                                 uint32_t num_choices, uint32_t degree, uint64_t modulus, uint64_t* cts, uint8_t* status,
+                                 uint64_t* timestamps, size_t* accepted, void* stream);
+
+/* replace KeySerializer::deserialize_eval_key (:414-466) / deserialize_bootstrap_key (:545-615) followed by the
+ * device key constructors above.  Errors carry the reference's messages ("Failed to read header", "Invalid magic
+ * bytes", "Checksum verification failed", "Polynomial degree mismatch").  FHEB containers: glwe_dimension 1 only
+ * (the container stores polynomial pairs); the KeyManager-style key-switching pairs at its end are skipped -
+ * BootstrapEngine::key_switch consumes a different structure (fheb_boot_key_set_ksk). */
+FHEB_API int fheb_relin_key_from_wire(const fheb_ntt_plan* plan, const void* bytes, size_t len, fheb_relin_key** out);
+FHEB_API int fheb_boot_key_from_wire(const fheb_ntt_plan* plan, const fheb_boot_params* params, const void* bytes,
+                                     size_t len, fheb_boot_key** out);
+
 /* Synthetic ballots generated ON DEVICE (bench / scaling runs: 16 GB never crosses PCIe).
  * word(ballot, comp, j) = splitmix64(seed + (ballot*2 + comp)*N + j) % modulus, reproducible on
  * the CPU (tests/ restate it).  Not part of the reference; test/bench support only. */

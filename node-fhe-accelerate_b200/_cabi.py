@@ -37,6 +37,13 @@ class DeviceInfo(C.Structure):
     ]
 
 
+class WireHeader(C.Structure):
+    """fheb_wire_header: SerializationHeader of cpp/include/key_serializer.h:59-84."""
+    _fields_ = [("magic", C.c_uint32), ("version", C.c_uint32), ("key_type", C.c_uint32), ("key_id", C.c_uint64),
+                ("poly_degree", C.c_uint32), ("modulus", C.c_uint64), ("data_size", C.c_uint32), ("checksum_type", C.c_uint8),
+                ("compression", C.c_uint8), ("checksum", C.c_uint32)]
+
+
 class BootParams(C.Structure):
     _fields_ = [("lwe_dimension", C.c_uint32), ("glwe_dimension", C.c_uint32), ("decomp_base_log", C.c_uint32),
                 ("decomp_level", C.c_uint32)]
@@ -106,6 +113,13 @@ SIGNATURES = {
     "fheb_relin_key_destroy": ([p], i),
     "fheb_relin_key_levels": ([p], u32),
     "fheb_relinearize_batch": ([p, p, u64, p, sz, p], i),
+    "fheb_wire_header_read": ([p, sz, p], i),
+    "fheb_wire_crc32": ([p, sz], u32),
+    "fheb_ballot_wire_size": ([u32, u32], sz),
+    "fheb_ballot_serialize": ([p, u32, u32, u64, u64, p, sz, p], i),
+    "fheb_ballots_ingest": ([p, sz, p, sz, u32, u32, u64, p, p, p, p, p], i),
+    "fheb_relin_key_from_wire": ([p, p, sz, p], i),
+    "fheb_boot_key_from_wire": ([p, p, p, sz, p], i),
     "fheb_synth_ballots": ([p, sz, sz, u32, u64, u64, p], i),
     "fheb_launch_count": ([i], u64),
 }

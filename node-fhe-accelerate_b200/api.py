@@ -19,7 +19,7 @@ from typing import Optional, Sequence
 import numpy as np
 
 from . import _cabi
-from ._cabi import BootParams, DeviceInfo, FheError, check, lib
+from ._cabi import BootParams, DeviceInfo, FheError, WireHeader, check, lib
 
 try:  # torch is plumbing only (device tensors / streams); numpy-only use works without it
     import torch
@@ -52,6 +52,11 @@ def _like(x, shape=None):
     if _is_torch(x):
         return torch.empty(x.shape if shape is None else shape, dtype=x.dtype, device=x.device)
     return np.empty(x.shape if shape is None else shape, dtype=np.uint64)
+
+
+def _raw(a):
+    """pointer to a host ndarray of any dtype (byte buffers, status arrays)"""
+    return None if a is None or a.size == 0 else a.ctypes.data_as(C.c_void_p)
 
 
 def _stream(*xs) -> Optional[int]:
@@ -111,6 +116,23 @@ class ModularArithmetic:
         self._h = C.c_void_p()
         self._destroy = lib().fheb_modarith_destroy
         check(lib().fheb_modarith_create(modulus, C.byref(self._h)))
+
+    @classmethod
+    def from_wire(cls, data: bytes, lwe_dimension: int, decomp_base_log: int, decomp_level: int, plaintext_modulus: int = 4):
+        """KeySerializer::deserialize_bootstrap_key (key_serializer.cpp:545-615) straight into a device key
+        (glwe_dimension 1; degree and modulus come from the container's header)."""
+        hdr = wire_header(data)
+        self = cls.__new__(cls)
+        self.N, self.q, self.n, self.k = hdr.poly_degree, hdr.modulus, lwe_dimension, 1
+        self.base_log, self.level, self.t = decomp_base_log, decomp_level, plaintext_modulus
+        self.ntt = NTTProcessor(self.N, self.q)
+        self._h = C.c_void_p()
+        self._destroy = lib().fheb_boot_key_destroy
+        buf = np.frombuffer(bytes(data), dtype=np.uint8)
+        params = BootParams(self.n, self.k, self.base_log, self.level)
+        check(lib().fheb_boot_key_from_wire(self.ntt._h, C.byref(params), _raw(buf), buf.size, C.byref(self._h)))
+        self.n_out = None
+        return self
 
     def __del__(self):
         h, self._h = getattr(self, "_h", None), None
@@ -298,6 +320,19 @@ class RelinearizationKey:
                                           key_id, C.byref(h)))
         self._h = h
         self.levels = int(lib().fheb_relin_key_levels(h))
+
+    @classmethod
+    def from_wire(cls, ring: "PolynomialRing", data: bytes):
+        """KeySerializer::deserialize_eval_key (key_serializer.cpp:414-466) straight into a device key."""
+        self = cls.__new__(cls)
+        self.ring = ring
+        buf = np.frombuffer(bytes(data), dtype=np.uint8)
+        h = C.c_void_p()
+        check(lib().fheb_relin_key_from_wire(ring.ntt._h, _raw(buf), buf.size, C.byref(h)))
+        self._h = h
+        self.key_id = wire_header(data).key_id
+        self.levels = int(lib().fheb_relin_key_levels(h))
+        return self
 
     def relinearize(self, cts, ct_key_id: Optional[int] = None, out=None):
         """EncryptionEngine::relinearize (cpp/src/encryption.cpp:904-993): [batch][3][N] -> [batch][2][N]."""
@@ -488,6 +523,59 @@ def tally_votes(cts, degree: int, modulus: int, out=None):
 
 
 batch_add = tally_votes
+
+
+# ------------------------------------------------------------------------- wire formats --
+WIRE_OK, WIRE_TOO_SMALL, WIRE_BAD_MAGIC, WIRE_BAD_CHECKSUM, WIRE_SHAPE_MISMATCH = range(5)
+
+
+def wire_crc32(data: bytes) -> int:
+    """KeySerializer::compute_crc32 with the reference's table as shipped (key_serializer.cpp:21-40)."""
+    buf = np.frombuffer(bytes(data), dtype=np.uint8)
+    return int(lib().fheb_wire_crc32(_raw(buf), buf.size))
+
+
+def wire_header(data: bytes) -> WireHeader:
+    buf = np.frombuffer(bytes(data[:49]), dtype=np.uint8)
+    h = WireHeader()
+    check(lib().fheb_wire_header_read(_raw(buf), buf.size, C.byref(h)))
+    return h
+
+
+def serialize_ballot(choices, modulus: int, timestamp: int) -> bytes:
+    """BallotSerializer::serialize_ballot (key_serializer.cpp:709-774): choices = [num_choices][2][N] host words."""
+    choices = np.ascontiguousarray(as_words(choices))
+    num, _, n = choices.shape if choices.size else (0, 2, 0)
+    size = int(lib().fheb_ballot_wire_size(num, n))
+    out = np.zeros(size, np.uint8)
+    written = C.c_size_t()
+    check(lib().fheb_ballot_serialize(_ptr(choices) if choices.size else None, num, n, modulus, timestamp, _raw(out), size,
+                                      C.byref(written)))
+    return out[:written.value].tobytes()
+
+
+def ingest_ballots(wire, count: int, num_choices: int, degree: int, modulus: int, offsets=None, out=None, device=None):
+    """A loop of BallotSerializer::deserialize_ballot (key_serializer.cpp:776-846) over `count` FHEV records, validated
+    and unpacked on the device.  wire: bytes / uint8 ndarray (host) or a torch uint8 CUDA tensor.  Returns
+    (cts [count][num_choices][2][N], status [count] uint8, timestamps [count] uint64); cts is a CUDA tensor when
+    `device` is given (or wire / out are CUDA tensors), else a host array.  Rejected records are zero ciphertexts."""
+    if isinstance(wire, (bytes, bytearray, memoryview)):
+        wire = np.frombuffer(bytes(wire), dtype=np.uint8)
+    nbytes = int(wire.numel()) if _is_torch(wire) else int(wire.size)
+    if out is None:
+        shape = (count, num_choices, 2, degree)
+        if _is_torch(wire) or device is not None:
+            out = torch.empty(shape, dtype=torch.int64, device=wire.device if _is_torch(wire) else device)
+        else:
+            out = np.empty(shape, np.uint64)
+    status = np.zeros(count, np.uint8)
+    stamps = np.zeros(count, np.uint64)
+    offs = None if offsets is None else np.ascontiguousarray(offsets, dtype=np.uint64)
+    accepted = C.c_size_t()
+    wptr = C.c_void_p(wire.data_ptr()) if _is_torch(wire) else _raw(np.ascontiguousarray(wire))
+    check(lib().fheb_ballots_ingest(wptr, nbytes, None if offs is None else _ptr(offs), count, num_choices, degree, modulus,
+                                    _ptr(out), _raw(status), _ptr(stamps), C.byref(accepted), _stream(out)))
+    return out, status, stamps
 
 
 def tally_combine(partials, degree: int, modulus: int, out=None):

@@ -14,6 +14,8 @@
 #       gets AArch64 divide-by-zero semantics (q/0 = 0, a%0 = a) instead of
 #       SIGFPE on x86.  It only affects the single-limb Montgomery q_inv, which
 #       the NTT / polynomial / bootstrap path never uses.
+#   P6  key_serializer.cpp (wire formats) is compiled with `-include cstring`:
+#       key_serializer.h uses std::memset without including <cstring>.
 # encryption.cpp is NOT compiled (it does not compile as shipped);
 # the tally and tensor-product wrappers compose unmodified PolynomialRing calls.
 set -euo pipefail
@@ -50,7 +52,9 @@ for f in ntt_processor polynomial_ring parameter_set key_manager bootstrap_engin
     compile "$REF/cpp/src/$f.cpp" "$TMP/$f.o" &
     pids+=($!)
 done
-compile "$HERE/ref_harness.cpp" "$TMP/ref_harness.o" &
+"$CXX" "${FLAGS[@]}" -include cstring -c "$REF/cpp/src/key_serializer.cpp" -o "$TMP/key_serializer.o" &
+pids+=($!)
+"$CXX" "${FLAGS[@]}" -include cstring -c "$HERE/ref_harness.cpp" -o "$TMP/ref_harness.o" &
 pids+=($!)
 for p in "${pids[@]}"; do wait "$p"; done
 

@@ -687,3 +687,59 @@ void orc_relinearize(const uint64_t* ct, const uint64_t* keys, uint32_t key_coun
     }
     free(w);
 }
+
+/* ---- wire formats: src/key_serializer.cpp ------------------------------------------------------------ */
+/* compute_crc32 (:34-40) over the table AS SHIPPED (:21-32): the initialiser list stops after 60 entries, the other
+ * 196 are zero.  Entry i < 60 is the reflected IEEE 802.3 value (polynomial 0xEDB88320). */
+static uint32_t orc_crc_entry(uint32_t i) {
+    if (i >= 60) return 0;
+    uint32_t c = i;
+    for (int k = 0; k < 8; ++k) c = (c & 1) ? (0xEDB88320u ^ (c >> 1)) : (c >> 1);
+    return c;
+}
+uint32_t orc_crc32(const uint8_t* data, size_t len) {
+    uint32_t crc = 0xFFFFFFFFu;
+    for (size_t i = 0; i < len; ++i) crc = orc_crc_entry((crc ^ data[i]) & 0xFF) ^ (crc >> 8);
+    return crc ^ 0xFFFFFFFFu;
+}
+static uint64_t orc_le(const uint8_t* p, int bytes) {
+    uint64_t v = 0;
+    for (int i = 0; i < bytes; ++i) v |= (uint64_t)p[i] << (8 * i);
+    return v;
+}
+/* BallotSerializer::deserialize_ballot (:776-846) on one record of `len` bytes, then the shape test of the bulk
+ * ingest path.  Returns 0 ok, 1 "Input too small" (:781: len < sizeof(SerializationHeader) = 64), 2 "Invalid magic
+ * bytes for ballot" (:800), 3 "Checksum verification failed" (:808; payload read into a zero-filled buffer of
+ * data_size bytes), 4 not `choices` ciphertexts of degree n over q.  out = [choices][2][n], zeroed unless 0. */
+int orc_ballot_parse(const uint8_t* rec, size_t len, uint32_t choices, size_t n, uint64_t q, uint64_t* out, uint64_t* timestamp) {
+    memset(out, 0, (size_t)choices * 2 * n * 8);
+    *timestamp = 0;
+    if (len < 64) return 1;
+    if ((uint32_t)orc_le(rec, 4) != 0x46484556u) return 2;
+    const uint32_t data_size = (uint32_t)orc_le(rec + 32, 4);
+    const uint32_t checksum = (uint32_t)orc_le(rec + 45, 4);
+    uint8_t* data = (uint8_t*)calloc(data_size ? data_size : 1, 1);
+    const size_t avail = len - 49;
+    memcpy(data, rec + 49, data_size < avail ? data_size : avail);
+    const uint32_t crc = orc_crc32(data, data_size);
+    int rc = 0;
+    if (crc != checksum) {
+        rc = 3;
+    } else if (data_size > avail || data_size != 12 + (uint64_t)choices * (12 + 16 * n) || (uint32_t)orc_le(data + 8, 4) != choices) {
+        rc = 4;
+    } else {
+        for (uint32_t c = 0; c < choices && rc == 0; ++c) {
+            const uint8_t* ch = data + 12 + (size_t)c * (12 + 16 * n);
+            if (orc_le(ch, 4) != n || orc_le(ch + 4, 8) != q) rc = 4;
+        }
+        if (rc == 0) {
+            *timestamp = orc_le(data, 8);
+            for (uint32_t c = 0; c < choices; ++c) {
+                const uint8_t* ch = data + 12 + (size_t)c * (12 + 16 * n) + 12;
+                for (size_t j = 0; j < 2 * n; ++j) out[(size_t)c * 2 * n + j] = orc_le(ch + 8 * j, 8);
+            }
+        }
+    }
+    free(data);
+    return rc;
+}

@@ -20,6 +20,7 @@
 #undef private
 #include "adaptive_dispatcher.h"
 #include "key_manager.h"
+#include "key_serializer.h"
 #include "modular_arithmetic.h"
 #include "ntt_processor.h"
 #include "parameter_set.h"
@@ -282,6 +283,120 @@ int ref_relinearize(void* h, const uint64_t* ct, const uint64_t* keys, uint32_t 
     }
     std::memcpy(out, result_c0.data(), (size_t)degree * 8);
     std::memcpy(out + degree, result_c1.data(), (size_t)degree * 8);
+    REF_CATCH
+}
+
+/* ------------------------------------------------------------ wire formats - */
+/* KeySerializer / BallotSerializer, cpp/src/key_serializer.cpp (compiled unmodified). */
+uint32_t ref_crc32(const uint8_t* data, size_t len) { return KeySerializer::compute_crc32(data, len); }
+
+static int copy_out(const std::vector<uint8_t>& bytes, uint8_t* out, size_t cap, size_t* len) {
+    *len = bytes.size();
+    if (bytes.size() > cap) {
+        g_err = "output buffer too small";
+        return -1;
+    }
+    std::memcpy(out, bytes.data(), bytes.size());
+    return 0;
+}
+
+/* BallotSerializer::serialize_ballot (:709-774): choices = [num_choices][2][n] */
+int ref_serialize_ballot(const uint64_t* choices, uint32_t num_choices, uint32_t n, uint64_t q, uint64_t timestamp,
+                         uint8_t* out, size_t cap, size_t* len) {
+    REF_TRY
+    std::vector<std::pair<Polynomial, Polynomial>> enc;
+    for (uint32_t c = 0; c < num_choices; ++c)
+        enc.emplace_back(make_poly(choices + ((size_t)c * 2) * n, n, q, false), make_poly(choices + ((size_t)c * 2 + 1) * n, n, q, false));
+    BallotSerializer bs;
+    std::vector<uint8_t> bytes;
+    auto r = bs.serialize_ballot(enc, timestamp, bytes);
+    if (!r.success) throw std::runtime_error(r.error_message);
+    if (copy_out(bytes, out, cap, len) != 0) return -1;
+    REF_CATCH
+}
+
+/* BallotSerializer::deserialize_ballot (:776-846): out = [max_choices][2][n]; returns -1 with the reference's
+ * error message when it rejects the record */
+int ref_deserialize_ballot(const uint8_t* in, size_t len, uint32_t n, uint64_t q, uint64_t* out, uint32_t max_choices,
+                           uint32_t* num_choices, uint64_t* timestamp) {
+    REF_TRY
+    BallotSerializer bs;
+    auto r = bs.deserialize_ballot(std::vector<uint8_t>(in, in + len), n, q);
+    if (!r.success) throw std::runtime_error(r.error_message);
+    *num_choices = (uint32_t)r.value->encrypted_choices.size();
+    *timestamp = r.value->timestamp;
+    for (uint32_t c = 0; c < *num_choices && c < max_choices; ++c) {
+        const auto& ch = r.value->encrypted_choices[c];
+        if (ch.first.degree() != n) throw std::runtime_error("choice degree differs from n");
+        std::memcpy(out + ((size_t)c * 2) * n, ch.first.data(), (size_t)n * 8);
+        std::memcpy(out + ((size_t)c * 2 + 1) * n, ch.second.data(), (size_t)n * 8);
+    }
+    REF_CATCH
+}
+
+/* KeySerializer::serialize_eval_key (:353-412): keys = [count][2][n] ((a, b) per pair) */
+int ref_serialize_eval_key(const uint64_t* keys, uint32_t count, uint32_t n, uint64_t q, uint32_t base_log, uint32_t level,
+                           uint64_t key_id, uint8_t* out, size_t cap, size_t* len) {
+    REF_TRY
+    EvaluationKey ek;
+    ek.key_id = key_id;
+    ek.relin_key.decomp_base_log = base_log;
+    ek.relin_key.decomp_level = level;
+    ek.relin_key.key_id = key_id;
+    for (uint32_t i = 0; i < count; ++i)
+        ek.relin_key.keys.emplace_back(make_poly(keys + ((size_t)i * 2) * n, n, q, false), make_poly(keys + ((size_t)i * 2 + 1) * n, n, q, false));
+    KeySerializer ks;
+    std::vector<uint8_t> bytes;
+    auto r = ks.serialize_eval_key(ek, bytes);
+    if (!r.success) throw std::runtime_error(r.error_message);
+    if (copy_out(bytes, out, cap, len) != 0) return -1;
+    REF_CATCH
+}
+
+/* KeySerializer::deserialize_eval_key (:414-466): keys_out = [max_count][2][n]; meta = {count, base_log, level} */
+int ref_deserialize_eval_key(const uint8_t* in, size_t len, uint32_t n, uint64_t* keys_out, uint32_t max_count, uint32_t meta[3],
+                             uint64_t* key_id) {
+    REF_TRY
+    KeySerializer ks;
+    auto r = ks.deserialize_eval_key(std::vector<uint8_t>(in, in + len));
+    if (!r.success) throw std::runtime_error(r.error_message);
+    const auto& rk = r.value->relin_key;
+    meta[0] = (uint32_t)rk.keys.size();
+    meta[1] = rk.decomp_base_log;
+    meta[2] = rk.decomp_level;
+    *key_id = r.value->key_id;
+    for (uint32_t i = 0; i < meta[0] && i < max_count; ++i) {
+        std::memcpy(keys_out + ((size_t)i * 2) * n, rk.keys[i].first.data(), (size_t)n * 8);
+        std::memcpy(keys_out + ((size_t)i * 2 + 1) * n, rk.keys[i].second.data(), (size_t)n * 8);
+    }
+    REF_CATCH
+}
+
+/* KeySerializer::serialize_bootstrap_key (:472-543): bsk = [n_lwe][rows][2][n]; ksk = [ksk_count][2][n] */
+int ref_serialize_bootstrap_key(const uint64_t* bsk, uint32_t n_lwe, uint32_t rows, const uint64_t* ksk, uint32_t ksk_count,
+                                uint32_t ksk_base_log, uint32_t ksk_level, uint32_t n, uint64_t q, uint64_t key_id,
+                                uint8_t* out, size_t cap, size_t* len) {
+    REF_TRY
+    BootstrapKey bk;
+    bk.key_id = key_id;
+    bk.lwe_dimension = n_lwe;
+    for (uint32_t i = 0; i < n_lwe; ++i) {
+        std::vector<std::pair<Polynomial, Polynomial>> row;
+        for (uint32_t j = 0; j < rows; ++j) {
+            const uint64_t* p = bsk + (((size_t)i * rows + j) * 2) * n;
+            row.emplace_back(make_poly(p, n, q, false), make_poly(p + n, n, q, false));
+        }
+        bk.bsk.push_back(std::move(row));
+    }
+    bk.ksk.decomp_base_log = ksk_base_log;
+    bk.ksk.decomp_level = ksk_level;
+    for (uint32_t i = 0; i < ksk_count; ++i)
+        bk.ksk.keys.emplace_back(make_poly(ksk + ((size_t)i * 2) * n, n, q, false), make_poly(ksk + ((size_t)i * 2 + 1) * n, n, q, false));
+    KeySerializer ks;
+    std::vector<uint8_t> bytes;
+    auto r = ks.serialize_bootstrap_key(bk, bytes);
+    if (!r.success) throw std::runtime_error(r.error_message);
+    if (copy_out(bytes, out, cap, len) != 0) return -1;
     REF_CATCH
 }
 

@@ -136,6 +136,22 @@ def main():
         nokey = r.relinearize(ring, ct[1], keys[:0], base_log, level)
         save(f"relin_n{n}", n=n, q=np.uint64(q), ct=ct, keys=keys, base_log=base_log, level=level, out=out, nokey=nokey)
         r.ring_destroy(ring)
+    # --- wire formats: records written by the reference's own BallotSerializer / KeySerializer
+    if want("wire_"):
+        wrng = np.random.default_rng(709)
+        n, q, choices = 64, QT, 2
+        ballots = wrng.integers(0, q, size=(6, choices, 2, n), dtype=np.uint64)
+        records = [r.serialize_ballot(ballots[i], q, 1_700_000_000 + i) for i in range(6)]
+        sizes = np.array([len(x) for x in records], np.uint64)
+        keys = wrng.integers(0, q, size=(3, 2, n), dtype=np.uint64)
+        eval_key = r.serialize_eval_key(keys, q, 12, 3, 0xABCDEF)
+        probe = bytes(wrng.integers(0, 256, size=1000, dtype=np.uint8))
+        bsk = wrng.integers(0, q, size=(6, 4, 2, n), dtype=np.uint64)       # 6 GGSWs, (k+1)*L = 4 rows, k = 1
+        kskp = wrng.integers(0, q, size=(2, 2, n), dtype=np.uint64)         # KeyManager-style pairs (skipped on ingest)
+        boot_key = r.serialize_bootstrap_key(bsk, kskp, 4, 2, q, 0x5EED)
+        save("wire_n64", n=n, q=np.uint64(q), choices=choices, ballots=ballots, sizes=sizes,
+             records=np.frombuffer(b"".join(records), np.uint8), keys=keys, eval_key=np.frombuffer(eval_key, np.uint8),
+             bsk=bsk, boot_key=np.frombuffer(boot_key, np.uint8), probe=np.frombuffer(probe, np.uint8), probe_crc=np.uint32(r.crc32(probe)), empty_crc=np.uint32(r.crc32(b"")))
     print("golden vectors written to", HERE)
 
 

@@ -111,6 +111,8 @@ class Oracle:
             "tally_tree": _bind(L, "orc_tally_tree", "p sz sz u64 p"),
             "tensor": _bind(L, "orc_tensor_multiply", "p p p sz u64 p p u64", None),
             "relin": _bind(L, "orc_relinearize", "p p u32 u32 u32 p sz u64 p p u64", None),
+            "crc32": _bind(L, "orc_crc32", "p sz", C.c_uint32),
+            "ballot_parse": _bind(L, "orc_ballot_parse", "p sz u32 sz u64 p p"),
         }
 
     # -- scalars
@@ -318,6 +320,18 @@ class Oracle:
                          _ptr(fwd), _ptr(inv), inv_n)
         return out
 
+    def crc32(self, data: bytes):
+        buf = np.frombuffer(bytes(data), dtype=np.uint8)
+        return int(self._f["crc32"](_ptr(buf) if buf.size else None, buf.size))
+
+    def ballot_parse(self, record: bytes, choices, n, q):
+        """-> (status, cts [choices][2][n], timestamp)"""
+        buf = np.frombuffer(bytes(record), dtype=np.uint8)
+        out = np.zeros((choices, 2, n), np.uint64)
+        ts = C.c_uint64()
+        rc = self._f["ballot_parse"](_ptr(buf) if buf.size else None, buf.size, choices, n, q, _ptr(out), C.addressof(ts))
+        return rc, out, int(ts.value)
+
 
 def ref_available():
     return os.path.exists(REF_SO)
@@ -353,6 +367,12 @@ class RefOracle:
             "tally_tree": b("ref_tally_tree", "p p sz p"),
             "tensor": b("ref_tensor_multiply", "p p p p"),
             "relin": b("ref_relinearize", "p p p u32 u32 u32 p"),
+            "crc32": b("ref_crc32", "p sz", C.c_uint32),
+            "ser_ballot": b("ref_serialize_ballot", "p u32 u32 u64 u64 p sz p"),
+            "de_ballot": b("ref_deserialize_ballot", "p sz u32 u64 p u32 p p"),
+            "ser_eval": b("ref_serialize_eval_key", "p u32 u32 u64 u32 u32 u64 p sz p"),
+            "de_eval": b("ref_deserialize_eval_key", "p sz u32 p u32 p p"),
+            "ser_boot": b("ref_serialize_bootstrap_key", "p u32 u32 p u32 u32 u32 u32 u64 u64 p sz p"),
             "scalar_create": b("ref_scalar_create", "u64 p"),
             "scalar_destroy": b("ref_scalar_destroy", "p", None),
             "scalar_op": b("ref_scalar_op", "p int u64 u64", C.c_uint64),
@@ -467,6 +487,49 @@ class RefOracle:
         out = np.zeros((2, ct.shape[-1]), np.uint64)
         self.call("relin", h, ct, keys, keys.shape[0] if keys.size else 0, key_base_log, key_level, out)
         return out
+
+    # -- wire formats (KeySerializer / BallotSerializer)
+    def crc32(self, data: bytes):
+        buf = np.frombuffer(bytes(data), dtype=np.uint8)
+        return int(self._f["crc32"](_ptr(buf) if buf.size else None, buf.size))
+
+    def _ser(self, name, cap, *args):
+        out = np.zeros(cap, np.uint8)
+        n = C.c_size_t()
+        self.call(name, *args, out, cap, C.addressof(n))
+        return out[:n.value].tobytes()
+
+    def serialize_ballot(self, choices, q, timestamp):
+        choices = u64(choices)
+        num, _, n = choices.shape
+        return self._ser("ser_ballot", 64 + 12 + num * (12 + 16 * n), choices, num, n, q, timestamp)
+
+    def deserialize_ballot(self, record: bytes, n, q, max_choices=8):
+        """-> (cts [num_choices][2][n], timestamp); raises RefError with the reference's message"""
+        buf = np.frombuffer(bytes(record), dtype=np.uint8)
+        out = np.zeros((max_choices, 2, n), np.uint64)
+        num, ts = C.c_uint32(), C.c_uint64()
+        self.call("de_ballot", buf if buf.size else None, buf.size, n, q, out, max_choices, C.addressof(num), C.addressof(ts))
+        return out[:num.value], int(ts.value)
+
+    def serialize_eval_key(self, keys, q, base_log, level, key_id):
+        keys = u64(keys)
+        count, _, n = keys.shape
+        return self._ser("ser_eval", 64 + 12 + count * 2 * (4 + 8 * n), keys, count, n, q, base_log, level, key_id)
+
+    def deserialize_eval_key(self, data: bytes, n, max_count=64):
+        buf = np.frombuffer(bytes(data), dtype=np.uint8)
+        out = np.zeros((max_count, 2, n), np.uint64)
+        meta = np.zeros(3, np.uint32)
+        kid = C.c_uint64()
+        self.call("de_eval", buf, buf.size, n, out, max_count, meta, C.addressof(kid))
+        return out[:int(meta[0])], int(meta[1]), int(meta[2]), int(kid.value)
+
+    def serialize_bootstrap_key(self, bsk, ksk, ksk_base_log, ksk_level, q, key_id):
+        bsk, ksk = u64(bsk), u64(ksk)
+        n_lwe, rows, _, n = bsk.shape
+        cap = 64 + 8 + n_lwe * (4 + rows * 2 * (4 + 8 * n)) + 12 + ksk.shape[0] * 2 * (4 + 8 * n)
+        return self._ser("ser_boot", cap, bsk, n_lwe, rows, ksk if ksk.size else None, ksk.shape[0], ksk_base_log, ksk_level, n, q, key_id)
 
     # -- scalar ModularArithmetic (the reference addon's class)
     SCALAR_OPS = {"montgomery_mul": 0, "mod_add": 1, "mod_sub": 2, "to_montgomery": 3, "from_montgomery": 4, "get_modulus": 5}

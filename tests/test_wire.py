@@ -1,0 +1,237 @@
+"""Wire formats: the reference's FHEV ballot / FHEE eval-key / FHEB bootstrap-key containers
+(cpp/src/key_serializer.cpp).  CPU tests pin the C restatement and the host-side C-ABI functions to the reference's
+own serializer (compiled under oracle/_ref) and to records it wrote (tests/golden/wire_n64.npz); the GPU tests run
+the device ingest path against both."""
+import os
+
+import numpy as np
+import pytest
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+QT = 1099511678977
+Q62 = 4611686018326724609
+
+
+def eq(a, b):
+    a, b = np.asarray(a), np.asarray(b)
+    assert a.shape == b.shape, (a.shape, b.shape)
+    assert np.array_equal(a, b)
+
+
+@pytest.fixture(scope="module")
+def wire():
+    g = np.load(os.path.join(GOLDEN, "wire_n64.npz"))
+    blob = g["records"].tobytes()
+    offs = np.concatenate([[0], np.cumsum(g["sizes"])]).astype(np.uint64)
+    recs = [blob[int(offs[i]):int(offs[i + 1])] for i in range(len(g["sizes"]))]
+    return g, recs
+
+
+def corruptions(rec):
+    """(label, bytes, expected status or None) - the three rejections of deserialize_ballot.  None: whatever the
+    reference's checksum makes of it.  With 196 of its 256 table entries zero the CRC state decays to the last few
+    payload bytes, so a damaged payload is usually NOT detected (the reference accepts it too); parity, not
+    detection, is what is tested for those."""
+    flip = bytearray(rec)
+    flip[200] ^= 0x40
+    tail = bytearray(rec)
+    tail[-1] ^= 0x01
+    magic = bytearray(rec)
+    magic[0] ^= 1
+    crc = bytearray(rec)
+    crc[47] ^= 0x80
+    return [("ok", rec, 0), ("payload bit flipped", bytes(flip), None), ("last byte flipped", bytes(tail), None),
+            ("bad magic", bytes(magic), 2), ("checksum field", bytes(crc), 3), ("truncated", rec[:-5], None),
+            ("too small", rec[:63], 1), ("empty", b"", 1)]
+
+
+# ------------------------------------------------------------------------------- CPU --
+def test_crc_is_the_references_not_ieee(oracle, wire):
+    import zlib
+
+    g, _ = wire
+    probe = g["probe"].tobytes()
+    assert oracle.crc32(probe) == int(g["probe_crc"])
+    assert oracle.crc32(b"") == int(g["empty_crc"]) == 0
+    assert oracle.crc32(probe) != zlib.crc32(probe)  # only 60 table entries are initialised (key_serializer.cpp:21-32)
+
+
+def test_oracle_parses_reference_records(oracle, wire):
+    g, recs = wire
+    n, q, ch = int(g["n"]), int(g["q"]), int(g["choices"])
+    for i, rec in enumerate(recs):
+        st, cts, ts = oracle.ballot_parse(rec, ch, n, q)
+        assert st == 0 and ts == 1_700_000_000 + i
+        eq(cts, g["ballots"][i])
+    for label, bad, want in corruptions(recs[1]):
+        st, cts, _ = oracle.ballot_parse(bad, ch, n, q)
+        assert want is None or st == want, label
+        if st:
+            assert not cts.any()
+    assert oracle.ballot_parse(recs[0], ch + 1, n, q)[0] == 4
+    assert oracle.ballot_parse(recs[0], ch, n, q + 2)[0] == 4
+
+
+def test_oracle_matches_reference_live(oracle, ref):
+    rng = np.random.default_rng(5)
+    for n, q, ch in [(8, 17, 1), (64, QT, 3), (1024, Q62, 1)]:
+        cts = rng.integers(0, q, size=(ch, 2, n), dtype=np.uint64)
+        rec = ref.serialize_ballot(cts, q, 42)
+        got, ts = ref.deserialize_ballot(rec, n, q)
+        eq(got, cts)
+        st, mine, ts2 = oracle.ballot_parse(rec, ch, n, q)
+        assert st == 0 and ts == ts2 == 42
+        eq(mine, cts)
+        messages = {1: "Input too small", 2: "Invalid magic bytes for ballot", 3: "Checksum verification failed"}
+        from oracle_bindings import RefError
+
+        for label, bad, want in corruptions(rec):
+            st, mine, _ = oracle.ballot_parse(bad, ch, n, q)
+            assert want is None or st == want, label
+            if st in messages:
+                with pytest.raises(RefError) as e:
+                    ref.deserialize_ballot(bad, n, q)
+                assert messages[st] in str(e.value), label
+            elif st == 0:  # accepted by both, damaged words included
+                eq(ref.deserialize_ballot(bad, n, q)[0], mine)
+        for size in (0, 1, 59, 60, 61, 255, 4096):
+            blob = bytes(rng.integers(0, 256, size=size, dtype=np.uint8))
+            assert oracle.crc32(blob) == ref.crc32(blob)
+
+
+def test_cabi_host_side_wire_functions(oracle, wire):
+    """fheb_wire_crc32 / fheb_wire_header_read / fheb_ballot_serialize are host code: no GPU needed."""
+    import fheb200
+
+    g, recs = wire
+    n, q, ch = int(g["n"]), int(g["q"]), int(g["choices"])
+    assert fheb200.wire_crc32(g["probe"].tobytes()) == int(g["probe_crc"])
+    for i, rec in enumerate(recs):
+        assert fheb200.serialize_ballot(g["ballots"][i], q, 1_700_000_000 + i) == rec  # byte-identical to the reference's record
+        h = fheb200.wire_header(rec)
+        assert (h.magic, h.version, h.key_type, h.key_id) == (0x46484556, 1, 4, 1_700_000_000 + i)
+        assert (h.poly_degree, h.modulus, h.data_size, h.checksum_type, h.compression) == (n, q, len(rec) - 49, 1, 0)
+        assert h.checksum == oracle.crc32(rec[49:])
+    h = fheb200.wire_header(g["eval_key"].tobytes())
+    assert (h.magic, h.key_type, h.key_id, h.poly_degree, h.modulus) == (0x46484545, 2, 0xABCDEF, n, q)
+    with pytest.raises(fheb200.FheError) as e:
+        fheb200.wire_header(recs[0][:20])
+    assert "Failed to read header" in str(e.value)
+
+
+# ------------------------------------------------------------------------------- GPU --
+@pytest.fixture(scope="module")
+def fhe():
+    import fheb200
+
+    fheb200.initialize()
+    return fheb200
+
+
+def host(t):
+    return t.cpu().numpy().view(np.uint64) if hasattr(t, "cpu") else np.asarray(t)
+
+
+@pytest.mark.gpu
+def test_ingest_golden_records(fhe, wire, oracle):
+    import torch
+
+    g, recs = wire
+    n, q, ch = int(g["n"]), int(g["q"]), int(g["choices"])
+    # clean stream, self-describing (no offsets), host output
+    cts, status, stamps = fhe.ingest_ballots(b"".join(recs), len(recs), ch, n, q)
+    assert not status.any()
+    eq(cts, g["ballots"])
+    eq(stamps, 1_700_000_000 + np.arange(len(recs), dtype=np.uint64))
+    # every rejection, explicit extents, device output; rejected records are zero ciphertexts
+    mixed = [b for _, b, _ in corruptions(recs[1])] + [recs[3]]
+    want = [oracle.ballot_parse(b, ch, n, q)[0] for b in mixed]
+    assert {1, 2, 3} <= set(want) and want[0] == 0 and want[-1] == 0
+    offs = np.concatenate([[0], np.cumsum([len(b) for b in mixed])]).astype(np.uint64)
+    cts, status, stamps = fhe.ingest_ballots(b"".join(mixed), len(mixed), ch, n, q, offsets=offs, device="cuda")
+    eq(status, np.array(want, np.uint8))
+    got = host(cts)
+    for i, rec in enumerate(mixed):
+        st, exp, ts = oracle.ballot_parse(rec, ch, n, q)
+        assert st == want[i]
+        eq(got[i], exp)
+        assert int(stamps[i]) == ts
+    # wire bytes already on the device (8-byte aligned), unaligned records inside
+    blob = np.frombuffer(b"".join(mixed), np.uint8)
+    dcts, status2, _ = fhe.ingest_ballots(torch.from_numpy(blob.copy()).cuda(), len(mixed), ch, n, q, offsets=offs)
+    eq(status2, status)
+    eq(host(dcts), got)
+    # wrong expected shape
+    _, status3, _ = fhe.ingest_ballots(b"".join(recs), len(recs), ch, n, q + 2)
+    assert (status3 == 4).all()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("n,q,ch,count", [(1024, QT, 1, 300), (256, 132120577, 3, 77), (4096, Q62, 1, 9)])
+def test_ingest_then_tally_matches_oracle(fhe, oracle, n, q, ch, count):
+    """The production chain either side of C5: wire records -> device ingest -> tally, with damaged ballots dropped."""
+    rng = np.random.default_rng(count)
+    ballots = rng.integers(0, q, size=(count, ch, 2, n), dtype=np.uint64)
+    recs = [fhe.serialize_ballot(ballots[i], q, i) for i in range(count)]
+    damaged = [int(x) for x in rng.choice(count, size=count // 4, replace=False)]
+    for k, i in enumerate(damaged):
+        b = bytearray(recs[i])
+        if k % 3 == 0:
+            b[45 + k % 4] ^= 0x10  # the checksum field: always rejected
+        elif k % 3 == 1:
+            b[len(b) - 1 - k % 6] ^= 1 << (k % 8)  # the payload's tail: sometimes caught by the reference's CRC
+        else:
+            b[49 + int(rng.integers(0, len(b) - 49))] ^= 1 << int(rng.integers(0, 8))  # anywhere: usually not caught
+        recs[i] = bytes(b)
+    cts, status, _ = fhe.ingest_ballots(b"".join(recs), count, ch, n, q, device="cuda")
+    got = host(cts)
+    parsed = np.zeros_like(ballots)
+    for i in range(count):  # record by record against the restated deserialize_ballot
+        st, parsed[i], _ = oracle.ballot_parse(recs[i], ch, n, q)
+        assert status[i] == st
+        eq(got[i], parsed[i])
+    good = [i for i in range(count) if status[i] == 0]
+    assert 0 < len(good) < count and set(status) <= {0, 3}
+    for c in range(ch):  # tally over the whole ingested buffer == oracle tally of the accepted ballots
+        eq(host(fhe.tally_votes(cts[:, c].contiguous(), n, q)), oracle.tally(parsed[good][:, c], q))
+
+
+@pytest.mark.gpu
+def test_keys_from_wire(fhe, wire, oracle):
+    import torch
+
+    g, _ = wire
+    n, q = int(g["n"]), int(g["q"])
+    ring = fhe.PolynomialRing(n, q)
+    key = fhe.RelinearizationKey.from_wire(ring, g["eval_key"].tobytes())
+    assert key.key_id == 0xABCDEF and key.levels == 3
+    fwd, inv, _, _, inv_n = oracle.twiddles(n, q)
+    ct3 = np.random.default_rng(3).integers(0, q, size=(4, 3, n), dtype=np.uint64)
+    got = key.relinearize(ct3)
+    for i in range(4):
+        eq(got[i], oracle.relinearize(ct3[i], g["keys"], 12, 3, q, fwd, inv, inv_n))
+    bad = bytearray(g["eval_key"].tobytes())
+    bad[46] ^= 2  # the checksum field (a damaged payload usually passes the reference's CRC, see corruptions())
+    with pytest.raises(fhe.FheError) as e:
+        fhe.RelinearizationKey.from_wire(ring, bytes(bad))
+    assert "Checksum verification failed" in str(e.value)
+    with pytest.raises(fhe.FheError) as e:
+        fhe.RelinearizationKey.from_wire(ring, g["records"].tobytes())
+    assert "Invalid magic bytes" in str(e.value)
+    # FHEB container -> device bootstrap key: same external products as a key made from the raw words
+    blob = g["boot_key"].tobytes()
+    h = fhe.wire_header(blob)
+    assert (h.magic, h.key_type, h.key_id, h.poly_degree, h.modulus) == (0x46484542, 3, 0x5EED, n, q)
+    eng_w = fhe.BootstrapEngine.from_wire(blob, lwe_dimension=6, decomp_base_log=9, decomp_level=2)
+    eng_r = fhe.BootstrapEngine(n, q, 6, 1, 9, 2, g["bsk"])
+    glwe = np.random.default_rng(4).integers(0, q, size=(3, 2, n), dtype=np.uint64)
+    p = oracle.boot_params(n, q, 6, 1, 9, 2, 4, fwd, inv, inv_n)
+    for idx in (0, 5):
+        a = eng_w.external_product(glwe, idx)
+        eq(a, eng_r.external_product(glwe, idx))
+        for i in range(3):
+            eq(a[i], oracle.external_product(p, glwe[i], g["bsk"][idx]))
+    with pytest.raises(fhe.FheError):
+        fhe.BootstrapEngine.from_wire(blob, lwe_dimension=7, decomp_base_log=9, decomp_level=2)
+    with pytest.raises(fhe.FheError):
+        fhe.BootstrapEngine.from_wire(blob, lwe_dimension=6, decomp_base_log=9, decomp_level=3)
