@@ -117,23 +117,6 @@ class ModularArithmetic:
         self._destroy = lib().fheb_modarith_destroy
         check(lib().fheb_modarith_create(modulus, C.byref(self._h)))
 
-    @classmethod
-    def from_wire(cls, data: bytes, lwe_dimension: int, decomp_base_log: int, decomp_level: int, plaintext_modulus: int = 4):
-        """KeySerializer::deserialize_bootstrap_key (key_serializer.cpp:545-615) straight into a device key
-        (glwe_dimension 1; degree and modulus come from the container's header)."""
-        hdr = wire_header(data)
-        self = cls.__new__(cls)
-        self.N, self.q, self.n, self.k = hdr.poly_degree, hdr.modulus, lwe_dimension, 1
-        self.base_log, self.level, self.t = decomp_base_log, decomp_level, plaintext_modulus
-        self.ntt = NTTProcessor(self.N, self.q)
-        self._h = C.c_void_p()
-        self._destroy = lib().fheb_boot_key_destroy
-        buf = np.frombuffer(bytes(data), dtype=np.uint8)
-        params = BootParams(self.n, self.k, self.base_log, self.level)
-        check(lib().fheb_boot_key_from_wire(self.ntt._h, C.byref(params), _raw(buf), buf.size, C.byref(self._h)))
-        self.n_out = None
-        return self
-
     def __del__(self):
         h, self._h = getattr(self, "_h", None), None
         if h and self._destroy is not None:
@@ -429,6 +412,23 @@ class BootstrapEngine:
         params = BootParams(self.n, self.k, self.base_log, self.level)
         check(lib().fheb_boot_key_create(self.ntt._h, C.byref(params), _ptr(bsk), C.byref(self._h)))
         self.n_out = None
+
+    @classmethod
+    def from_wire(cls, data: bytes, lwe_dimension: int, decomp_base_log: int, decomp_level: int, plaintext_modulus: int = 4):
+        """KeySerializer::deserialize_bootstrap_key (key_serializer.cpp:545-615) straight into a device key
+        (glwe_dimension 1; degree and modulus come from the container's header)."""
+        hdr = wire_header(data)
+        self = cls.__new__(cls)
+        self.N, self.q, self.n, self.k = hdr.poly_degree, hdr.modulus, lwe_dimension, 1
+        self.base_log, self.level, self.t = decomp_base_log, decomp_level, plaintext_modulus
+        self.ntt = NTTProcessor(self.N, self.q)
+        self._h = C.c_void_p()
+        self._destroy = lib().fheb_boot_key_destroy
+        buf = np.frombuffer(bytes(data), dtype=np.uint8)
+        params = BootParams(self.n, self.k, self.base_log, self.level)
+        check(lib().fheb_boot_key_from_wire(self.ntt._h, C.byref(params), _raw(buf), buf.size, C.byref(self._h)))
+        self.n_out = None
+        return self
 
     def __del__(self):
         h, self._h = getattr(self, "_h", None), None

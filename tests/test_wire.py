@@ -235,3 +235,34 @@ def test_keys_from_wire(fhe, wire, oracle):
         fhe.BootstrapEngine.from_wire(blob, lwe_dimension=7, decomp_base_log=9, decomp_level=2)
     with pytest.raises(fhe.FheError):
         fhe.BootstrapEngine.from_wire(blob, lwe_dimension=6, decomp_base_log=9, decomp_level=3)
+
+
+@pytest.mark.gpu
+def test_checksum_repair_rounds_are_exact():
+    """FHEB_WIRE_WARMUP=0 makes every lane's start-state guess wrong, so the warp-parallel checksum has to repair
+    all 31 slices; the statuses must still be the serial checksum's (run in a subprocess: the knob is read once)."""
+    import subprocess
+    import sys
+
+    code = r'''
+import sys, numpy as np
+sys.path.insert(0, "tests")
+import fheb200
+from oracle_bindings import Oracle
+fheb200.initialize(); orc = Oracle()
+n, q, count = 1024, 4611686018326724609, 40
+rng = np.random.default_rng(11)
+ballots = rng.integers(0, q, size=(count, 1, 2, n), dtype=np.uint64)
+recs = [fheb200.serialize_ballot(ballots[i], q, i) for i in range(count)]
+for i in range(0, count, 3):
+    b = bytearray(recs[i]); b[len(b) - 1 - i % 5] ^= 1 << (i % 8); recs[i] = bytes(b)
+cts, status, _ = fheb200.ingest_ballots(b"".join(recs), count, 1, n, q)
+want = [orc.ballot_parse(r, 1, n, q)[0] for r in recs]
+assert list(status) == want, (list(status), want)
+assert 0 in want and 3 in want
+print("ok")
+'''
+    env = dict(os.environ, FHEB_WIRE_WARMUP="0")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "-c", code], cwd=root, env=env, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and "ok" in r.stdout, r.stderr[-2000:]
