@@ -69,7 +69,9 @@ template <bool DP>
 constexpr int boot_kacc() { return 2; }
 
 // ---- phase 0: difference, decomposition and the first forward pass ------------------------
-template <int L, bool DP, int KP1>
+// RAWOK = false compiles the handling of unreduced accumulator words out (the lean blind-rotation kernel, used when
+// the caller's test polynomial is canonical - the only source of such words).
+template <int L, bool DP, int KP1, bool RAWOK = true>
 FHEB_HD void boot_first_pass(uint32_t tid, uint32_t nthreads, const BootStep& s, const Tw* __restrict__ tw,
                              const ModQ& m) {
     constexpr int R = Plan<L>::R[0];
@@ -108,7 +110,7 @@ FHEB_HD void boot_first_pass(uint32_t tid, uint32_t nthreads, const BootStep& s,
                 ct0[e] = a[pos];
                 src[e] = a[sidx & (N - 1u)];
             }
-            if (s.maybe_raw) {  // block-uniform: only before the first executed step of a blind rotation
+            if ((RAWOK && s.maybe_raw)) {  // block-uniform: only before the first executed step of a blind rotation
 #pragma unroll
                 for (int e = 0; e < E; ++e) raw = raw || ct0[e] >= m.q || src[e] >= m.q;
             }
@@ -224,7 +226,7 @@ FHEB_HD void boot_mid_pass(uint32_t tid, uint32_t nthreads, const BootStep& s, c
 }
 
 // ---- last phase: final inverse pass, scaling by N^-1, `+ ct0` ------------------------------------
-template <int L, bool DP, int KP1>
+template <int L, bool DP, int KP1, bool RAWOK = true>
 FHEB_HD void boot_final_pass(uint32_t tid, uint32_t nthreads, const BootStep& s, const Tw* __restrict__ twi,
                              const Tw ninv, const ModQ& m) {
     constexpr int R = Plan<L>::R[0];
@@ -252,7 +254,7 @@ FHEB_HD void boot_final_pass(uint32_t tid, uint32_t nthreads, const BootStep& s,
             v[e] = canon_k<KFIN, DP>(x[e], m);  // N^-1 is folded into the uploaded key (the transform is linear)
             a0[e] = s.add_acc ? a[u | ((uint32_t)e << EB)] : 0;
         }
-        if (s.maybe_raw) {
+        if ((RAWOK && s.maybe_raw)) {
 #pragma unroll
             for (int e = 0; e < E; ++e) raw = raw || a0[e] >= m.q;
         }
@@ -267,13 +269,13 @@ FHEB_HD void boot_final_pass(uint32_t tid, uint32_t nthreads, const BootStep& s,
 }
 
 // Phase PH of a step; the caller puts a block barrier after every phase.
-template <int L, bool DP, int KP1, int PH>
+template <int L, bool DP, int KP1, int PH, bool RAWOK = true>
 FHEB_HD void boot_phase(uint32_t tid, uint32_t nthreads, const BootStep& s, const Tw* __restrict__ twf,
                         const Tw* __restrict__ twi, const Tw ninv, const ModQ& m) {
     constexpr int P = Plan<L>::P;
     static_assert(PH >= 0 && PH < 2 * P - 1, "phase out of range");
     if constexpr (PH == 0) {
-        boot_first_pass<L, DP, KP1>(tid, nthreads, s, twf, m);
+        boot_first_pass<L, DP, KP1, RAWOK>(tid, nthreads, s, twf, m);
     } else if constexpr (PH < P - 1) {
         fwd_pass<L, DP, PH, IO_SMEM, IO_SMEM>(tid, nthreads, (uint32_t)KP1 * s.levels, nullptr, nullptr, s.work, twf, m);
     } else if constexpr (PH == P - 1) {
@@ -281,7 +283,7 @@ FHEB_HD void boot_phase(uint32_t tid, uint32_t nthreads, const BootStep& s, cons
     } else if constexpr (PH < 2 * P - 2) {
         inv_pass<L, DP, 2 * P - 2 - PH, IO_SMEM, IO_SMEM, true, 0, boot_kacc<DP>()>(tid, nthreads, (uint32_t)KP1, nullptr, nullptr, s.work, twi, ninv, m);
     } else {
-        boot_final_pass<L, DP, KP1>(tid, nthreads, s, twi, ninv, m);
+        boot_final_pass<L, DP, KP1, RAWOK>(tid, nthreads, s, twi, ninv, m);
     }
 }
 

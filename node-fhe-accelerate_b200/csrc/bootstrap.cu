@@ -18,6 +18,7 @@ struct BootKey {
     uint64_t* d_ksk = nullptr;      // [entries][n_out + 1] raw words
     size_t ksk_entries = 0;
     uint32_t ksk_n_out = 0, ksk_base_log = 0, ksk_levels = 0;
+    int* d_raw_flag = nullptr;      // "the test polynomial of the running blind rotation has words >= q" (lean / general kernel choice)
 };
 
 // ---- key preparation --------------------------------------------------------------------
@@ -153,6 +154,14 @@ static size_t ggsw_words(const BootKey* key) {
     return ((size_t)key->k + 1) * key->levels * ((size_t)key->k + 1) * key->plan->degree;
 }
 
+// flag = 1 when any word of the test polynomial is unreduced (>= q)
+__global__ void __launch_bounds__(256) test_poly_raw_kernel(const uint64_t* __restrict__ tp, uint32_t N, uint64_t q, int* flag) {
+    int raw = 0;
+    for (uint32_t i = threadIdx.x; i < N; i += 256) raw |= (tp[i] >= q) ? 1 : 0;
+    raw = __syncthreads_or(raw);
+    if (threadIdx.x == 0) *flag = raw;
+}
+
 // device-pointer stages of the chain
 static int blind_rotate_device(const BootKey* key, const uint64_t* lwe, const uint64_t* test_poly, uint64_t* out,
                                size_t batch, cudaStream_t s) {
@@ -163,6 +172,12 @@ static int blind_rotate_device(const BootKey* key, const uint64_t* lwe, const ui
     a.in1 = test_poly;
     a.out = out;
     a.batch = batch;
+    if (key->d_raw_flag && key->k == 1) {
+        test_poly_raw_kernel<<<1, 256, 0, s>>>(test_poly, key->plan->degree, key->plan->mod.q, key->d_raw_flag);
+        FHEB_CHECK_LAUNCH();
+        count_launch();
+        a.raw_flag = key->d_raw_flag;
+    }
     return boot_dispatch(key, a, s);
 }
 
@@ -241,6 +256,10 @@ int fheb_boot_key_create(const fheb_ntt_plan* plan, const fheb_boot_params* para
     key->k = params->glwe_dimension;
     key->base_log = params->decomp_base_log;
     key->levels = params->decomp_level;
+    if (cudaMalloc(&key->d_raw_flag, sizeof(int)) != cudaSuccess) {  // without it only the general kernel runs
+        cudaGetLastError();
+        key->d_raw_flag = nullptr;
+    }
     const size_t words = (size_t)key->n * ggsw_words(key);
     const size_t polys = words / p->degree;
     cudaStream_t s = nullptr;
@@ -297,6 +316,7 @@ int fheb_boot_key_destroy(fheb_boot_key* key_) {
     if (!key) return FHEB_OK;
     if (key->d_bsk) cudaFree(key->d_bsk);
     if (key->d_ksk) cudaFree(key->d_ksk);
+    if (key->d_raw_flag) cudaFree(key->d_raw_flag);
     delete key;
     return FHEB_OK;
 }
