@@ -39,14 +39,15 @@ struct BootGeometry {
     static constexpr int TPC = (L <= 6) ? 32 : (L <= 8) ? 64 : (L <= 10) ? 128 : (L == 11) ? 256 : 512;
     static constexpr int MAX_THREADS = 512;
     static constexpr int MAX_GROUPS = MAX_THREADS / TPC;
-    // N = 1024 (the tfhe-128-fast shape): one ciphertext per 128-thread block and five blocks per SM (96
-    // registers) measured 7 % faster than four ciphertexts in lockstep in one 512-thread block - the blocks
-    // drift out of phase, so one block's FP64 bursts overlap another's loads, digit extraction and barriers.
+    // N = 1024 (the tfhe-128-fast shape) and N = 512: one ciphertext per 128-thread block and five blocks per SM
+    // (96 registers) measured 7 % (N = 1024) and 21 % (N = 512) faster than four ciphertexts in lockstep in one
+    // 512-thread block - the blocks drift out of phase, so one block's FP64 bursts overlap another's loads, digit
+    // extraction and barriers.  N = 2048 measured the same either way and keeps the lockstep pair.
 #if !defined(FHEB_EXP_BOOT_LB_BLOCKS)
 #define FHEB_EXP_BOOT_LB_BLOCKS 5
 #endif
-    static constexpr int LB_THREADS = (L == 10) ? TPC : MAX_THREADS;
-    static constexpr int LB_BLOCKS = (L == 10) ? FHEB_EXP_BOOT_LB_BLOCKS : 1;
+    static constexpr int LB_THREADS = (L == 9 || L == 10) ? TPC : MAX_THREADS;
+    static constexpr int LB_BLOCKS = (L == 9 || L == 10) ? FHEB_EXP_BOOT_LB_BLOCKS : 1;
 };
 
 // shared-memory bytes per ciphertext: acc [KP1][N] | work [rows][N] | (CMUX/EXT) diff [KP1][N] | (BLIND) rotations [n] (u32)

@@ -182,3 +182,25 @@ def test_full_batch_tfhe_shape_properties(fhe, torch, oracle):
     perm = torch.randperm(batch, device="cuda")
     acc_p = eng.blind_rotate(lwe_d[perm].contiguous(), dev(torch, test_poly))
     assert torch.equal(acc_p, acc[perm])
+
+
+@pytest.mark.parametrize("N,q,n,base_log,level", [(1024, QT, 6, 23, 1), (128, Q62, 5, 9, 2)])
+def test_blind_rotation_with_unreduced_test_polynomial(fhe, torch, oracle, N, q, n, base_log, level):
+    """A caller's test polynomial may hold words >= q; the reference's rotate / subtract / add treat them with their
+    unsigned wrap-around formulas until the first executed step.  A device flag routes such calls to the general
+    kernel (the lean one has that handling compiled out); both must reproduce the oracle."""
+    rng = np.random.default_rng(N)
+    fwd, inv, _, _, inv_n = oracle.twiddles(N, q)
+    p = oracle.boot_params(N, q, n, 1, base_log, level, 4, fwd, inv, inv_n)
+    bsk = rng.integers(0, q, size=(n, 2 * level, 2, N), dtype=np.uint64)
+    eng = fhe.BootstrapEngine(N, q, n, 1, base_log, level, bsk)
+    lwe = rng.integers(0, q, size=(5, n + 1), dtype=np.uint64)
+    lwe[0, :] = 0     # no step executes: the raw words pass through the initial rotation only
+    lwe[1, :2] = 0    # the first executed step comes late
+    clean = oracle.default_test_poly(p)
+    raw = clean.copy()
+    raw[::7] += np.uint64(q)                          # same residues, unreduced
+    raw[3], raw[N - 1] = np.uint64(2**64 - 1), np.uint64(q)
+    for tp in (raw, clean, raw):                      # alternate: the flag is recomputed on every call
+        eq(host(eng.blind_rotate(dev(torch, lwe), dev(torch, tp))), oracle.blind_rotate(p, lwe, bsk, tp))
+    eq(eng.blind_rotate(lwe, raw), oracle.blind_rotate(p, lwe, bsk, raw))  # host buffers
