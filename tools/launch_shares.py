@@ -1,0 +1,25 @@
+"""Aggregate an `ncu --metrics gpu__time_duration.sum --csv` launch list per kernel: python tools/launch_shares.py <csv>."""
+import csv
+import re
+import sys
+from collections import defaultdict
+
+rows = [r for r in csv.reader(open(sys.argv[1], errors="replace")) if len(r) > 5]
+hdr = next(r for r in rows if "Kernel Name" in r)
+ki, vi, ui = hdr.index("Kernel Name"), hdr.index("Metric Value"), hdr.index("Metric Unit")
+tot = defaultdict(lambda: [0, 0.0])
+for r in rows:
+    if r is hdr or len(r) <= vi or r[ki] == "Kernel Name":
+        continue
+    try:
+        v = float(r[vi].replace(",", ""))
+    except ValueError:
+        continue
+    scale = {"ns": 1e-3, "us": 1.0, "ms": 1e3, "s": 1e6}.get(r[ui], 1.0)
+    name = re.sub(r"\(.*", "", r[ki]).strip()
+    tot[name][0] += 1
+    tot[name][1] += v * scale
+total = sum(v[1] for v in tot.values())
+print("kernel, launches, total_us, share_of_profiled_time")
+for k, (n, us) in sorted(tot.items(), key=lambda kv: -kv[1][1]):
+    print(f"{k}, {n}, {us:.1f}, {100.0 * us / total:.1f}%")
