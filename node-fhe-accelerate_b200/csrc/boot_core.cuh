@@ -264,7 +264,7 @@ FHEB_HD void boot_final_pass(uint32_t tid, uint32_t nthreads, const BootStep& s,
         }
 #pragma unroll
         for (int e = 0; e < E; ++e)
-            dst[u | ((uint32_t)e << EB)] = s.add_acc ? addmod_canon(v[e], a0[e], m.q) : v[e];  // PolynomialRing::add(result, ct0), :533-537
+            dst[u | ((uint32_t)e << EB)] = s.add_acc ? csub(v[e] + a0[e], m.q) : v[e];  // both canonical, q < 2^62  // PolynomialRing::add(result, ct0), :533-537
     }
 }
 
