@@ -55,6 +55,20 @@ def run(fhe, torch, dist, world, rank, dev, barrier, max_over_ranks, peak):
                                             "roofline": _hbm(peak, 32.0 * n * batch, ms)}
         del xs, y, z
 
+    # ---- C1: the reference's own CPU-runnable case (test_ntt_processor): N = 1024, q = 132120577, batch 1 - latency only
+    ntt1 = fhe.NTTProcessor(1024, Q27)
+    x1 = torch.randint(0, Q27, (1, 1024), dtype=torch.int64, device=dev, generator=gen)
+    y1, z1 = torch.empty_like(x1), torch.empty_like(x1)
+
+    def one(i):
+        ntt1.forward_ntt(x1, out=y1)
+        ntt1.inverse_ntt(y1, out=z1)
+
+    ms = _time(torch, one, 50)
+    assert torch.equal(z1, x1)
+    out["ntt_n1024_q132120577_b1_latency"] = {"value": ms * 1e3, "unit": "us per forward+inverse (two launches, device buffers)", "ms": ms,
+                                              "roofline": {"bound": "latency", "achieved": None, "peak": None, "unit": None, "frac": None}}
+
     # ---- C2: fused polynomial multiplication, batch 1024
     for n in (4096, 16384):
         ring = fhe.PolynomialRing(n, Q62)

@@ -164,3 +164,25 @@ def test_scalar_modular_arithmetic_matches_reference(fhe, ref):
     with pytest.raises(fhe.FheError) as e:
         fhe.ModularArithmetic(17).mod_add(-1, 2)
     assert "non-negative" in str(e.value)
+
+
+def test_node_addon_source_type_checks_and_links(fhe, tmp_path):
+    """the Node-API addon cannot be built for real here (no Node toolchain).  It is type-checked against
+    the stand-in declarations in addon/stub/node_api.h and linked against libfheb200.so: every symbol it leaves
+    undefined must be an N-API function (resolved by the node binary at load time) or come from the C/C++ runtime."""
+    src = os.path.join(ROOT, "addon", "fheb_addon.cc")
+    out = str(tmp_path / "addon.node")
+    cmd = ["g++", "-std=c++17", "-Wall", "-Wextra", "-Werror", "-fPIC", "-shared", "-I", os.path.join(ROOT, "addon", "stub"),
+           "-I", os.path.join(ROOT, "include"), src, "-o", out, "-L", os.path.dirname(fhe.LIB_PATH), "-lfheb200"]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    nm = subprocess.run(["nm", "-D", "--undefined-only", out], capture_output=True, text=True).stdout
+    undefined = set(re.findall(r"\bU (\w+)", nm))
+    napi = {s for s in undefined if s.startswith("napi_")}
+    fheb = {s for s in undefined if s.startswith("fheb_")}
+    assert napi and fheb
+    assert fheb <= set(declared_symbols())          # only declared C-ABI entry points
+    stub = open(os.path.join(ROOT, "addon", "stub", "node_api.h")).read()
+    assert all(re.search(rf"\b{s}\(", stub) for s in napi)
+    defined = subprocess.run(["nm", "-D", "--defined-only", out], capture_output=True, text=True).stdout
+    assert "napi_register_module_v1" in defined     # the entry point node looks up

@@ -37,5 +37,28 @@ fheb200.tally_votes(cts, 1024, 1099511678977)
 acc = fheb200.CiphertextStreamAccumulator(1024, 1099511678977)
 acc.add(cts[:1]); acc.add(cts[1:300]); acc.total()
 fheb200.tally_votes(rng.integers(0, 97, size=(1200, 2, 1024), dtype=np.uint64), 1024, 97)  # host pipeline (19 MB)
+# relinearisation, wire formats, unreduced test polynomial (general blind-rotation kernel)
+q62 = 4611686018326724609
+ring = fheb200.PolynomialRing(4096, q62)
+rk = fheb200.RelinearizationKey(ring, rng.integers(0, q62, size=(3, 2, 4096), dtype=np.uint64), 20, 3)
+rk.relinearize(dev(rng.integers(0, q62, size=(5, 3, 4096), dtype=np.uint64)))
+rk.relinearize(rng.integers(0, q62, size=(2, 3, 4096), dtype=np.uint64))
+qt = 1099511678977
+ballots = rng.integers(0, qt, size=(67, 2, 2, 1024), dtype=np.uint64)
+recs = [fheb200.serialize_ballot(ballots[i], qt, i) for i in range(67)]
+recs[3] = recs[3][:-9]
+recs[5] = recs[5][:40]
+offs = np.concatenate([[0], np.cumsum([len(r) for r in recs])]).astype(np.uint64)
+blob = b"".join(recs)
+fheb200.ingest_ballots(blob, 67, 2, 1024, qt, offsets=offs)
+wire = torch.from_numpy(np.frombuffer(blob + b"\0" * ((-len(blob)) % 8), dtype=np.uint8).copy()).cuda()
+fheb200.ingest_ballots(wire[: len(blob)], 67, 2, 1024, qt, offsets=offs)
+small = [fheb200.serialize_ballot(ballots[i, :1, :, :16].copy(), qt, i) for i in range(9)]
+fheb200.ingest_ballots(b"".join(small), 9, 1, 16, qt)
+bsk = rng.integers(0, qt, size=(4, 2, 2, 1024), dtype=np.uint64)
+eng = fheb200.BootstrapEngine(1024, qt, 4, 1, 23, 1, bsk)
+tp = eng.get_default_test_poly().copy()
+tp[::5] += np.uint64(qt)
+eng.blind_rotate(dev(rng.integers(0, qt, size=(6, 5), dtype=np.uint64)), dev(tp))
 torch.cuda.synchronize()
 print("sanitize smoke done,", fheb200.launch_count(), "launches")
