@@ -94,9 +94,13 @@ static int plan_finish(NttPlan* p) {
         p->top = D;
         for (int dir = 0; dir < 2; ++dir) {
             const uint64_t* table = dir ? p->inv_table.data() : p->fwd_table.data();
-            std::vector<uint64_t> words(((size_t)sub << D) * epw, 0), topw(8 * epw, 0);
-            for (uint32_t h = 0; h < (1u << D); ++h)
-                for_each_sub_twiddle(L, D, h, [&](uint32_t at, uint32_t e) { put_twiddle(words, (size_t)h * sub + at, table[e] % q, q, dp); });
+            // per sub-block: `sub` entries pass by pass + `sub` entries holding the last pass again with the block
+            // index bit-reversed (append_bitrev_last_pass: coalesced twiddle loads in the bit-reversed last pass)
+            std::vector<uint64_t> words(((size_t)(2 * sub) << D) * epw, 0), topw(8 * epw, 0);
+            for (uint32_t h = 0; h < (1u << D); ++h) {
+                for_each_sub_twiddle(L, D, h, [&](uint32_t at, uint32_t e) { put_twiddle(words, (size_t)h * 2 * sub + at, table[e] % q, q, dp); });
+                append_bitrev_last_pass_words(words.data() + (size_t)h * 2 * sub * epw, 14, epw);
+            }
             for_each_top_twiddle(L, D, [&](uint32_t at, uint32_t e) { put_twiddle(topw, at, table[e] % q, q, dp); });
             FHEB_TRY(upload_heap(words, dir ? &p->d_inv : &p->d_fwd));
             FHEB_TRY(upload_heap(topw, dir ? &p->d_top_inv : &p->d_top_fwd));

@@ -431,6 +431,10 @@ FHEB_HD void fwd_pass(uint32_t tid, uint32_t nthreads, uint32_t polys, const uin
     constexpr bool LAST = (PASS == Plan<L>::P - 1);
     constexpr uint32_t N = 1u << L;
     constexpr uint32_t ITEMS = N >> R;  // per polynomial
+    // BRTW: items are walked in bit-reversed order (u = bitrev(t)); the table's second copy of this pass (offset N,
+    // block index bit-reversed: ntt_plan.hpp) is indexed by t, so consecutive lanes read consecutive twiddles
+    constexpr bool BRTW = LAST && OUT == IO_GLOBAL && BITREV_OUT && S0 > 0;
+    static_assert(!BRTW || (EB == 0 && S0 == L - R), "the last pass covers the lowest position bits");
     static_assert(IN == IO_SMEM || PASS == 0, "only the first pass reads global memory");
     static_assert(OUT == IO_SMEM || LAST, "only the last pass writes outside the work buffer");
 
@@ -445,10 +449,11 @@ FHEB_HD void fwd_pass(uint32_t tid, uint32_t nthreads, uint32_t polys, const uin
         for (int k = 0; k < IPT; ++k) {
             const uint32_t U = tid + (uint32_t)k * nthreads;
             if (U < polys * ITEMS) {
-                uint32_t u = U & (ITEMS - 1);
+                const uint32_t t0 = U & (ITEMS - 1);
+                uint32_t u = t0;
                 if (OUT == IO_GLOBAL && BITREV_OUT) u = bitrev_rt(u, L - R);
                 const uint32_t base = ((u >> EB) << (EB + R)) | (u & ((1u << EB) - 1u));
-                load_item_tw<R, S0, DP>(tw, plan_tw_offset<L, PASS>() + (S0 ? (base >> (L - S0)) : 0u), wall[k]);
+                load_item_tw<R, S0, DP>(tw, BRTW ? (N + t0) : plan_tw_offset<L, PASS>() + (S0 ? (base >> (L - S0)) : 0u), wall[k]);
             }
         }
     }
@@ -476,7 +481,7 @@ FHEB_HD void fwd_pass(uint32_t tid, uint32_t nthreads, uint32_t polys, const uin
 #pragma unroll
             for (int c = 0; c < E; ++c) x[c] = src[pb ^ swz((uint32_t)c << EB)];
         }
-        const uint32_t TB = plan_tw_offset<L, PASS>() + (S0 ? (base >> (L - S0)) : 0u);
+        const uint32_t TB = BRTW ? (N + t) : plan_tw_offset<L, PASS>() + (S0 ? (base >> (L - S0)) : 0u);
         if constexpr (IPT > 0) fwd_stages<R, S0, KIN, DP, UNIT, 0, true>(x, wall[k], 0u, m);
         else fwd_stages<R, S0, KIN, DP, UNIT>(x, tw, TB, m);
         if (OUT == IO_GLOBAL) {
@@ -581,6 +586,8 @@ FHEB_HD void inv_pass(uint32_t tid, uint32_t nthreads, uint32_t polys, const uin
     constexpr bool FIRST = (PASS == Plan<L>::P - 1);
     constexpr uint32_t N = 1u << L;
     constexpr uint32_t ITEMS = N >> R;
+    constexpr bool BRTW = FIRST && IN == IO_GLOBAL && BITREV_IN && S0 > 0;  // see fwd_pass
+    static_assert(!BRTW || (EB == 0 && S0 == L - R), "the last pass covers the lowest position bits");
     static_assert(IN == IO_SMEM || FIRST, "only the first executed pass reads global memory");
     static_assert(OUT == IO_SMEM || PASS == 0, "only the last executed pass writes global memory");
 
@@ -592,10 +599,11 @@ FHEB_HD void inv_pass(uint32_t tid, uint32_t nthreads, uint32_t polys, const uin
         for (int k = 0; k < IPT; ++k) {
             const uint32_t U = tid + (uint32_t)k * nthreads;
             if (U < polys * ITEMS) {
-                uint32_t u = U & (ITEMS - 1);
+                const uint32_t t0 = U & (ITEMS - 1);
+                uint32_t u = t0;
                 if (FIRST && IN == IO_GLOBAL && BITREV_IN) u = bitrev_rt(u, L - R);
                 const uint32_t base = ((u >> EB) << (EB + R)) | (u & ((1u << EB) - 1u));
-                load_item_tw<R, S0, DP>(tw, plan_tw_offset<L, PASS>() + (S0 ? (base >> (L - S0)) : 0u), wall[k]);
+                load_item_tw<R, S0, DP>(tw, BRTW ? (N + t0) : plan_tw_offset<L, PASS>() + (S0 ? (base >> (L - S0)) : 0u), wall[k]);
             }
         }
     }
@@ -629,7 +637,7 @@ FHEB_HD void inv_pass(uint32_t tid, uint32_t nthreads, uint32_t polys, const uin
 #pragma unroll
             for (int c = 0; c < E; ++c) x[c] = src[pb ^ swz((uint32_t)c << EB)];
         }
-        const uint32_t TB = plan_tw_offset<L, PASS>() + (S0 ? (base >> (L - S0)) : 0u);
+        const uint32_t TB = BRTW ? (N + t) : plan_tw_offset<L, PASS>() + (S0 ? (base >> (L - S0)) : 0u);
         if constexpr (IPT > 0) inv_stages<R, S0, KIN, DP, (PASS == 0 && !SUB), R - 1, true>(x, wall[k], 0u, m);
         else inv_stages<R, S0, KIN, DP, (PASS == 0 && !SUB)>(x, tw, TB, m);
         if (OUT == IO_GLOBAL) {

@@ -102,7 +102,7 @@ __global__ void __launch_bounds__(THREADS) ntt_inverse_kernel(const uint64_t* in
 // The first D = L - 14 stages pair positions N/2, N/4 apart; after them the 2^D contiguous sub-blocks
 // of 2^14 positions are independent.  So: a streaming kernel runs the top D stages in registers
 // (global -> scratch), then the 14-stage shared-memory kernel transforms every sub-block with its own
-// twiddle table (the tail of the big network: no unit twiddles) and scatters the results into the
+// twiddle table (the tail of the big network: no unit twiddles; 2 * 2^14 entries each, see ntt_plan.hpp) and scatters the results into the
 // reference's output order, index (r << D) | bitrev_D(h) for word r of sub-block h.  The inverse runs
 // the same two kernels backwards.
 template <int D, bool DP, bool INVERSE>
@@ -145,7 +145,7 @@ __global__ void __launch_bounds__(THREADS) ntt_forward_sub_kernel(const uint64_t
     for (size_t g = blockIdx.x; g < subs; g += gridDim.x) {
         const size_t poly = g >> D;
         const uint32_t h = (uint32_t)(g & ((1u << D) - 1u));
-        const Tw* tw = reinterpret_cast<const Tw*>(reinterpret_cast<const char*>(tables) + (size_t)h * N * (DP ? 8 : 16));
+        const Tw* tw = reinterpret_cast<const Tw*>(reinterpret_cast<const char*>(tables) + (size_t)h * 2 * N * (DP ? 8 : 16));
         const GlobalMap map{D, bitrev_rt(h, (int)D)};
         fwd_pass<L, DP, 0, IO_GLOBAL, IO_SMEM, true, false, 0, true>(tid, THREADS, 1, tmp + g * N, nullptr, smem, tw, m);
         __syncthreads();
@@ -167,7 +167,7 @@ __global__ void __launch_bounds__(THREADS) ntt_inverse_sub_kernel(const uint64_t
     for (size_t g = blockIdx.x; g < subs; g += gridDim.x) {
         const size_t poly = g >> D;
         const uint32_t h = (uint32_t)(g & ((1u << D) - 1u));
-        const Tw* tw = reinterpret_cast<const Tw*>(reinterpret_cast<const char*>(tables) + (size_t)h * N * (DP ? 8 : 16));
+        const Tw* tw = reinterpret_cast<const Tw*>(reinterpret_cast<const char*>(tables) + (size_t)h * 2 * N * (DP ? 8 : 16));
         const GlobalMap map{D, bitrev_rt(h, (int)D)};
         inv_pass<L, DP, P - 1, IO_GLOBAL, IO_SMEM, true, 0, 1, true>(tid, THREADS, 1, in + (poly << (L + D)), nullptr, smem, tw, one, m, map);
         __syncthreads();

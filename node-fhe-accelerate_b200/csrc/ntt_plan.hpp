@@ -43,12 +43,56 @@ inline void for_each_twiddle(uint32_t L, Put put) {
     }
 }
 
+// Second copy of the LAST pass's entries, from offset N on, with the block index bit-reversed:
+// entry N + (slot << S0) + bitrev_S0(blk) = entry off_last + (slot << S0) + blk.  The transform kernels walk the last
+// pass's items in bit-reversed order (so that the reference-order stores / loads are coalesced); with this copy
+// consecutive lanes read consecutive twiddles there too, instead of one 32-byte sector per lane (ntt_core.cuh:
+// fwd_pass / inv_pass, BRTW).  The first N entries are unchanged (fused product and bootstrap kernels use them).
+template <class T>
+inline void append_bitrev_last_pass(std::vector<T>& out, uint32_t L) {
+    int P, R[5];
+    plan_runtime((int)L, P, R);
+    const size_t N = (size_t)1 << L;
+    out.resize(2 * N, T{});
+    uint32_t off = 0;
+    int s0 = 0;
+    for (int p = 0; p + 1 < P; ++p) {
+        off += ((1u << R[p]) - 1u) << s0;
+        s0 += R[p];
+    }
+    if (s0 == 0) return;  // single-pass plans: one block per stage, nothing to reorder
+    const uint32_t slots = (1u << R[P - 1]) - 1u;
+    for (uint32_t slot = 0; slot < slots; ++slot)
+        for (uint32_t blk = 0; blk < (1u << s0); ++blk)
+            out[N + ((size_t)slot << s0) + bitrev_c(blk, s0)] = out[off + ((size_t)slot << s0) + blk];
+}
+
+// the same on raw table words (epw words per entry) of one sub-block table with room for 2 * 2^L entries
+inline void append_bitrev_last_pass_words(uint64_t* words, uint32_t L, size_t epw) {
+    int P, R[5];
+    plan_runtime((int)L, P, R);
+    const size_t N = (size_t)1 << L;
+    uint32_t off = 0;
+    int s0 = 0;
+    for (int p = 0; p + 1 < P; ++p) {
+        off += ((1u << R[p]) - 1u) << s0;
+        s0 += R[p];
+    }
+    if (s0 == 0) return;
+    const uint32_t slots = (1u << R[P - 1]) - 1u;
+    for (uint32_t slot = 0; slot < slots; ++slot)
+        for (uint32_t blk = 0; blk < (1u << s0); ++blk)
+            for (size_t w = 0; w < epw; ++w)
+                words[(N + ((size_t)slot << s0) + bitrev_c(blk, s0)) * epw + w] = words[(off + ((size_t)slot << s0) + blk) * epw + w];
+}
+
 inline std::vector<Tw> build_heap_table(const uint64_t* table, uint32_t L, uint64_t q) {
     std::vector<Tw> out((size_t)1 << L, Tw{0, 0});
     for_each_twiddle(L, [&](uint32_t at, uint32_t e) {
         const uint64_t w = table[e] % q;
         out[at] = Tw{w, shoup_companion(w, q)};
     });
+    append_bitrev_last_pass(out, L);
     return out;
 }
 
@@ -56,6 +100,7 @@ inline std::vector<Tw> build_heap_table(const uint64_t* table, uint32_t L, uint6
 inline std::vector<uint64_t> build_heap_table_dp(const uint64_t* table, uint32_t L, uint64_t q) {
     std::vector<uint64_t> out((size_t)1 << L, 0);
     for_each_twiddle(L, [&](uint32_t at, uint32_t e) { out[at] = double_to_bits((double)(table[e] % q)); });
+    append_bitrev_last_pass(out, L);
     return out;
 }
 
