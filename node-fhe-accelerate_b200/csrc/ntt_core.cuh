@@ -417,7 +417,7 @@ enum {
 //   SCALE      : multiply the outputs by `ninv` (fast_ntt_inverse semantics)
 // OUT == IO_STASH_*: the finished transform is parked (position order, no bit reversal) in
 // `gout` for the fused polynomial product; canonical words in integer mode, lazy doubles (|v| < KOUT*q) in DP mode.
-template <int L, bool DP, int PASS, int IN, int OUT, bool BITREV_OUT = true, bool SCALE = false, int IPT = 0, bool SUB = false>
+template <int L, bool DP, int PASS, int IN, int OUT, bool BITREV_OUT = true, bool SCALE = false, int IPT = 0, bool SUB = false, bool PIPE = false>
 FHEB_HD void fwd_pass(uint32_t tid, uint32_t nthreads, uint32_t polys, const uint64_t* gin, uint64_t* gout,
                       uint64_t* smem, const Tw* __restrict__ tw, const ModQ& m, const Tw ninv = Tw{0, 0},
                       const GlobalMap map = GlobalMap{0, 0}) {
@@ -457,6 +457,12 @@ FHEB_HD void fwd_pass(uint32_t tid, uint32_t nthreads, uint32_t polys, const uin
             }
         }
     }
+    // PIPE (chosen by the kernel): software-pipelined global loads of a multi-pass plan's first pass, for the
+    // degrees where a thread has several items.  +1 % (integer) / +5 % (FP64 mode) in the plain transform at
+    // N = 16384; the fused product kernel loses 7 % with it (register pressure) and does not ask for it.
+    constexpr bool PIPE_IN = PIPE && IN == IO_GLOBAL && OUT == IO_SMEM && IPT == 0;
+    uint64_t xnext[PIPE_IN ? E : 1];
+    bool have_next = false;
     for (uint32_t U0 = tid; U0 < (IPT > 0 ? tid + 1 : polys * ITEMS); U0 += nthreads) {
 #pragma unroll
       for (int k = 0; k < TRIPS; ++k) {
@@ -471,9 +477,31 @@ FHEB_HD void fwd_pass(uint32_t tid, uint32_t nthreads, uint32_t polys, const uin
         const uint32_t base = ((u >> EB) << (EB + R)) | (u & ((1u << EB) - 1u));
         uint64_t x[E];
         if (IN == IO_GLOBAL) {
-            const uint64_t* src = gin + (size_t)poly * N;
+            if constexpr (PIPE_IN) {
+                // the words of this item were requested one trip ago; request the next item's now, so that the
+                // global-memory latency of the first pass is paid once per polynomial instead of once per item
+                if (have_next) {
 #pragma unroll
-            for (int c = 0; c < E; ++c) x[c] = stream_load(src + (base | ((uint32_t)c << EB)));
+                    for (int c = 0; c < E; ++c) x[c] = xnext[c];
+                } else {
+                    const uint64_t* src = gin + (size_t)poly * N;
+#pragma unroll
+                    for (int c = 0; c < E; ++c) x[c] = stream_load(src + (base | ((uint32_t)c << EB)));
+                }
+                const uint32_t Un = U + nthreads;
+                have_next = Un < polys * ITEMS;
+                if (have_next) {
+                    const uint32_t un = Un & (ITEMS - 1);
+                    const uint32_t basen = ((un >> EB) << (EB + R)) | (un & ((1u << EB) - 1u));
+                    const uint64_t* srcn = gin + (size_t)(Un >> (L - R)) * N;
+#pragma unroll
+                    for (int c = 0; c < E; ++c) xnext[c] = stream_load(srcn + (basen | ((uint32_t)c << EB)));
+                }
+            } else {
+                const uint64_t* src = gin + (size_t)poly * N;
+#pragma unroll
+                for (int c = 0; c < E; ++c) x[c] = stream_load(src + (base | ((uint32_t)c << EB)));
+            }
             load_words<DP, E>(x, m);
         } else {
             const uint64_t* src = smem + (size_t)poly * N;
@@ -574,7 +602,7 @@ FHEB_HD void polymul_mid_pass(uint32_t tid, uint32_t nthreads, uint32_t polys, c
 // may read the reference's input order (bit-reversed positions) from global memory; the
 // last one executed (PASS == 0) multiplies by N^-1 (`ninv`, Shoup pair) and stores canonical
 // values in natural order.
-template <int L, bool DP, int PASS, int IN, int OUT, bool BITREV_IN = true, int IPT = 0, int KSTART = 1, bool SUB = false>
+template <int L, bool DP, int PASS, int IN, int OUT, bool BITREV_IN = true, int IPT = 0, int KSTART = 1, bool SUB = false, bool PIPE = false>
 FHEB_HD void inv_pass(uint32_t tid, uint32_t nthreads, uint32_t polys, const uint64_t* gin, uint64_t* gout,
                       uint64_t* smem, const Tw* __restrict__ tw, const Tw ninv, const ModQ& m,
                       const GlobalMap map = GlobalMap{0, 0}) {
@@ -607,6 +635,9 @@ FHEB_HD void inv_pass(uint32_t tid, uint32_t nthreads, uint32_t polys, const uin
             }
         }
     }
+    constexpr bool PIPE_IN = PIPE && FIRST && IN == IO_GLOBAL && BITREV_IN && !SUB && IPT == 0;  // see fwd_pass
+    uint64_t xnext[PIPE_IN ? E : 1];
+    bool have_next = false;
     for (uint32_t U0 = tid; U0 < (IPT > 0 ? tid + 1 : polys * ITEMS); U0 += nthreads) {
 #pragma unroll
       for (int k = 0; k < TRIPS; ++k) {
@@ -618,7 +649,25 @@ FHEB_HD void inv_pass(uint32_t tid, uint32_t nthreads, uint32_t polys, const uin
         if (FIRST && IN == IO_GLOBAL && BITREV_IN) u = bitrev_rt(t, L - R);
         const uint32_t base = ((u >> EB) << (EB + R)) | (u & ((1u << EB) - 1u));
         uint64_t x[E];
-        if (IN == IO_GLOBAL) {
+        if constexpr (PIPE_IN) {  // plain transform, reference-order input: this item's words were requested one trip ago
+            if (have_next) {
+#pragma unroll
+                for (int c = 0; c < E; ++c) x[c] = xnext[c];
+            } else {
+                const uint64_t* src = gin + (size_t)poly * N;
+#pragma unroll
+                for (int c = 0; c < E; ++c) x[c] = stream_load(src + ((bitrev_c((uint32_t)c, R) << (L - R)) | t));
+            }
+            const uint32_t Un = U + nthreads;
+            have_next = Un < polys * ITEMS;
+            if (have_next) {
+                const uint64_t* srcn = gin + (size_t)(Un >> (L - R)) * N;
+                const uint32_t tn = Un & (ITEMS - 1);
+#pragma unroll
+                for (int c = 0; c < E; ++c) xnext[c] = stream_load(srcn + ((bitrev_c((uint32_t)c, R) << (L - R)) | tn));
+            }
+            load_words<DP, E>(x, m);
+        } else if (IN == IO_GLOBAL) {
             const uint64_t* src = gin + (size_t)poly * N;
             if (SUB && BITREV_IN) {
 #pragma unroll

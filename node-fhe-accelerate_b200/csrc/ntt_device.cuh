@@ -57,7 +57,7 @@ __global__ void __launch_bounds__(THREADS) ntt_forward_kernel(const uint64_t* in
         if constexpr (P == 1) {
             fwd_pass<L, DP, 0, IO_GLOBAL, IO_GLOBAL, true, SCALE>(tid, THREADS, polys, gin, gout, smem, tw, m, ninv);
         } else {
-            fwd_pass<L, DP, 0, IO_GLOBAL, IO_SMEM>(tid, THREADS, polys, gin, gout, smem, tw, m);
+            fwd_pass<L, DP, 0, IO_GLOBAL, IO_SMEM, true, false, 0, false, (L >= 13)>(tid, THREADS, polys, gin, gout, smem, tw, m);
             __syncthreads();
             fwd_middle<L, DP, 1>(tid, THREADS, polys, smem, tw, m);
             fwd_pass<L, DP, P - 1, IO_SMEM, IO_GLOBAL, true, SCALE>(tid, THREADS, polys, gin, gout, smem, tw, m, ninv);
@@ -89,7 +89,7 @@ __global__ void __launch_bounds__(THREADS) ntt_inverse_kernel(const uint64_t* in
         if constexpr (P == 1) {
             inv_pass<L, DP, 0, IO_GLOBAL, IO_GLOBAL>(tid, THREADS, polys, gin, gout, smem, tw, ninv, m);
         } else {
-            inv_pass<L, DP, P - 1, IO_GLOBAL, IO_SMEM>(tid, THREADS, polys, gin, gout, smem, tw, ninv, m);
+            inv_pass<L, DP, P - 1, IO_GLOBAL, IO_SMEM, true, 0, 1, false, (L >= 14)>(tid, THREADS, polys, gin, gout, smem, tw, ninv, m);
             __syncthreads();
             inv_middle<L, DP, P - 2>(tid, THREADS, polys, smem, tw, ninv, m);
             inv_pass<L, DP, 0, IO_SMEM, IO_GLOBAL>(tid, THREADS, polys, gin, gout, smem, tw, ninv, m);
