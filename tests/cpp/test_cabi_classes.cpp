@@ -102,6 +102,27 @@ static void test_polynomial_ring() {
     ring.tensor_multiply(a.data(), b.data(), ten.data(), 1);
     orc_tensor_multiply(a.data(), b.data(), ten_ref.data(), n, q, fwd.data(), inv.data(), sc[2]);
     EXPECT(ten == ten_ref, "tensor product vs oracle");
+    // multiply -> relinearize (EncryptionEngine::relinearize, encryption.cpp:904-993) with a pre-transformed device key
+    const uint32_t key_count = 3, base_log = 20, level = 3;
+    std::vector<uint64_t> keys((size_t)key_count * 2 * n), rel(2 * n), rel_ref(2 * n);
+    for (auto& v : keys) v = r.next_coefficient(q);
+    fheb200::RelinearizationKey rk(ring, keys.data(), key_count, base_log, level, 99);
+    EXPECT(rk.levels() == 3, "relinearisation levels");
+    rk.relinearize(ten.data(), rel.data(), 1);
+    orc_relinearize(ten.data(), keys.data(), key_count, base_log, level, rel_ref.data(), n, q, fwd.data(), inv.data(), sc[2]);
+    EXPECT(rel == rel_ref, "relinearize vs oracle");
+    // wire format: a record written here parses with the restated deserialize_ballot and survives the device ingest
+    std::vector<uint8_t> rec(fheb_ballot_wire_size(1, n));
+    size_t written = 0;
+    EXPECT(fheb_ballot_serialize(a.data(), 1, n, q, 1234, rec.data(), rec.size(), &written) == 0 && written == rec.size(), "ballot serialize");
+    std::vector<uint64_t> parsed(2 * n), ingested(2 * n);
+    uint64_t stamp = 0, stamps[1] = {0};
+    EXPECT(orc_ballot_parse(rec.data(), rec.size(), 1, n, q, parsed.data(), &stamp) == 0 && stamp == 1234, "oracle parses the record");
+    EXPECT(std::memcmp(parsed.data(), a.data(), 2 * n * 8) == 0, "record payload");
+    uint8_t status[1] = {9};
+    size_t accepted = 0;
+    EXPECT(fheb_ballots_ingest(rec.data(), rec.size(), nullptr, 1, 1, n, q, ingested.data(), status, stamps, &accepted, nullptr) == 0, "ingest");
+    EXPECT(status[0] == FHEB_WIRE_OK && accepted == 1 && stamps[0] == 1234 && ingested == parsed, "device ingest vs oracle");
 }
 
 static void test_multi_limb() {
