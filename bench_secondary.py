@@ -157,7 +157,12 @@ def run(fhe, torch, dist, world, rank, dev, barrier, max_over_ranks, peak):
                                   "note": "includes the per-call status copy and synchronisation",
                                   # validate reads the record once, unpack reads it again and writes the aligned words
                                   "roofline": _hbm(peak, (2.0 * len(recs[0]) + 16384.0) * cnt, ms)}
-    del wire, ing
+    res = torch.empty((1, 2, n), dtype=torch.int64, device=dev)
+    ms = _time(torch, lambda i: fhe.tally_wire(wire, cnt, 1, n, QT, offsets=offs, out=res), 5, warm=2)
+    out["tally_wire_n1024"] = {"value": cnt / (ms * 1e-3), "unit": "ballots/s", "ms": ms, "ballots": cnt,
+                               "note": "checksum validation + tally straight from the wire bytes (no unpacked ciphertexts)",
+                               "roofline": _hbm(peak, 2.0 * len(recs[0]) * cnt, ms)}  # the wire is read twice
+    del wire, ing, res
     out["bootstrap_tfhe128fast_shape"] = run_bootstrap(fhe, torch, dist, world, rank, dev, barrier, max_over_ranks)
     return out
 

@@ -344,6 +344,15 @@ FHEB_API int fheb_ballots_ingest(const void* wire, size_t wire_bytes, const uint
                                  uint32_t num_choices, uint32_t degree, uint64_t modulus, uint64_t* cts, uint8_t* status,
                                  uint64_t* timestamps, size_t* accepted, void* stream);
 
+/* The receive-and-count path in one call: fheb_ballots_ingest's validation followed by EncryptionEngine::tally_votes
+ * (cpp/src/encryption.cpp:1061-1067,1327-1364) over every choice of the ACCEPTED records, summed straight out of the
+ * wire bytes (the ciphertexts are never materialised: the wire is read once for the checksums and once for the sum).
+ * out = [num_choices][2][degree] (host or device), choice c = the tally of ciphertext c of every accepted ballot.
+ * wire / offsets / status / accepted as in fheb_ballots_ingest.  No accepted record fails with the reference's
+ * "Cannot add empty vector of ciphertexts"; a single accepted record is returned untouched, as batch_add does. */
+FHEB_API int fheb_tally_wire(const void* wire, size_t wire_bytes, const uint64_t* offsets, size_t count, uint32_t num_choices,
+                             uint32_t degree, uint64_t modulus, uint64_t* out, uint8_t* status, size_t* accepted, void* stream);
+
 /* replace KeySerializer::deserialize_eval_key (:414-466) / deserialize_bootstrap_key (:545-615) followed by the
  * device key constructors above.  Errors carry the reference's messages ("Failed to read header", "Invalid magic
  * bytes", "Checksum verification failed", "Polynomial degree mismatch").  FHEB containers: glwe_dimension 1 only

@@ -118,6 +118,7 @@ SIGNATURES = {
     "fheb_ballot_wire_size": ([u32, u32], sz),
     "fheb_ballot_serialize": ([p, u32, u32, u64, u64, p, sz, p], i),
     "fheb_ballots_ingest": ([p, sz, p, sz, u32, u32, u64, p, p, p, p, p], i),
+    "fheb_tally_wire": ([p, sz, p, sz, u32, u32, u64, p, p, p, p], i),
     "fheb_relin_key_from_wire": ([p, p, sz, p], i),
     "fheb_boot_key_from_wire": ([p, p, p, sz, p], i),
     "fheb_synth_ballots": ([p, sz, sz, u32, u64, u64, p], i),

@@ -633,3 +633,24 @@ def tally_noise_budget(budgets: Sequence[float], variant: str = "linear") -> flo
     if variant == "linear":
         return lo - math.log2(count)
     return lo - math.ceil(math.log2(count))
+
+
+def tally_wire(wire, count: int, num_choices: int, degree: int, modulus: int, offsets=None, out=None, device=None):
+    """Validate `count` FHEV records and tally every choice of the accepted ones straight from the wire bytes
+    (deserialize_ballot per record + tally_votes per choice).  Returns (tallies [num_choices][2][N], status [count])."""
+    if isinstance(wire, (bytes, bytearray, memoryview)):
+        wire = np.frombuffer(bytes(wire), dtype=np.uint8)
+    nbytes = int(wire.numel()) if _is_torch(wire) else int(wire.size)
+    if out is None:
+        shape = (num_choices, 2, degree)
+        if _is_torch(wire) or device is not None:
+            out = torch.empty(shape, dtype=torch.int64, device=wire.device if _is_torch(wire) else device)
+        else:
+            out = np.empty(shape, np.uint64)
+    status = np.zeros(max(count, 1), np.uint8)
+    offs = None if offsets is None else np.ascontiguousarray(offsets, dtype=np.uint64)
+    accepted = C.c_size_t()
+    wptr = C.c_void_p(wire.data_ptr()) if _is_torch(wire) else _raw(np.ascontiguousarray(wire))
+    check(lib().fheb_tally_wire(wptr, nbytes, None if offs is None else _ptr(offs), count, num_choices, degree, modulus, _ptr(out),
+                                _raw(status), C.byref(accepted), _stream(out)))
+    return out, status[:count]

@@ -140,6 +140,15 @@ FHEB_HD uint64_t canon_any(uint64_t x, const ModQ& m) {  // x % q for any x
     return x >= m.q ? reduce64(x, m) : x;
 }
 
+// 128-bit running sum of raw words (exact for any count below 2^64) and its reduction
+FHEB_HD void acc128(uint64_t& lo, uint64_t& hi, uint64_t v) {
+    lo += v;
+    hi += (lo < v) ? 1 : 0;
+}
+FHEB_HD uint64_t fold128(uint64_t hi, uint64_t lo, const ModQ& m) {
+    return reduce128(canon_any(hi, m), lo, m);  // hi reduced first so that (hi:lo) < q * 2^64
+}
+
 // ---- exact modular arithmetic on the FP64 pipe (moduli below 2^42) ------------------------
 // On B200 a DFMA issues at 64 lanes/clk/SM, the same rate as a 32-bit IMAD, while the 64-bit
 // Shoup product needs six IMAD.WIDE (half rate) plus four IMAD (tools/microbench/pipes.cu).  For

@@ -16,14 +16,6 @@
 
 namespace fheb {
 
-__device__ __forceinline__ void acc128(uint64_t& lo, uint64_t& hi, uint64_t v) {
-    lo += v;
-    hi += (lo < v) ? 1 : 0;
-}
-
-__device__ __forceinline__ uint64_t fold128(uint64_t hi, uint64_t lo, const ModQ& m) {
-    return reduce128(canon_any(hi, m), lo, m);  // hi reduced first so that (hi:lo) < q * 2^64
-}
 
 // grid = (column chunks, slabs).  Block: 256 threads x 2 columns.  Slab y sums ballots
 // [y*per_slab, min(count, (y+1)*per_slab)) and writes canonical partial sums to
@@ -137,6 +129,11 @@ static int tally_device(const uint64_t* cts, size_t count, uint32_t width, uint6
     count_launch(2);
     FHEB_CUDA(cudaFreeAsync(partial, s));
     return FHEB_OK;
+}
+
+// device rows -> one row (any count, canonical result); used by the wire-format tally (wire.cu)
+int tally_rows_device(const uint64_t* rows, size_t count, uint32_t width, uint64_t q, uint64_t* out, cudaStream_t s) {
+    return tally_device(rows, count, width, q, out, false, s);
 }
 
 static int tally_entry(const uint64_t* cts, size_t count, uint32_t degree, uint64_t q, uint64_t* out, bool single_raw,

@@ -265,8 +265,75 @@ __global__ void __launch_bounds__(256) ballot_unpack_kernel(const uint8_t* __res
     }
 }
 
-int ballots_ingest_device(const uint8_t* wire, size_t wire_bytes, const uint64_t* offsets, size_t count, uint32_t choices, uint32_t N, uint64_t q,
-                          uint64_t* cts, uint8_t* status, uint64_t* timestamps, cudaStream_t s) {
+// Tally straight from the wire bytes: column pair (2 words) per thread, one slab of records per blockIdx.y, raw words
+// of the ACCEPTED records summed in 128-bit counters and reduced once (the words of batch_add / tally_votes for any
+// grouping, see tally.cu).  The payload is never 8-byte aligned: the thread reads the three aligned words that cover
+// its 16 bytes and funnel-shifts by the record's misalignment (uniform across the block).  width = choices * 2N.
+constexpr int WTALLY_THREADS = 256;
+constexpr int WTALLY_UNROLL = 4;
+
+__global__ void __launch_bounds__(WTALLY_THREADS) tally_wire_kernel(const uint8_t* __restrict__ wire, const uint8_t* wire_end,
+                                                                    const uint64_t* __restrict__ offsets, const uint8_t* __restrict__ status,
+                                                                    size_t count, size_t per_slab, uint32_t words_per_choice,
+                                                                    uint32_t width, uint64_t* __restrict__ partial, const ModQ m) {
+    const uint32_t col = (blockIdx.x * WTALLY_THREADS + threadIdx.x) * 2;  // words_per_choice is even: a pair never straddles choices
+    if (col >= width) return;
+    const uint32_t c = col / words_per_choice, j = col - c * words_per_choice;
+    const size_t rel = WIRE_HEADER_BYTES + 12 + (size_t)c * (12 + 8 * (size_t)words_per_choice) + 12 + 8 * (size_t)j;
+    const size_t first = (size_t)blockIdx.y * per_slab;
+    size_t last = first + per_slab;
+    if (last > count) last = count;
+    uint64_t lo0 = 0, hi0 = 0, lo1 = 0, hi1 = 0;
+    auto fetch = [&](size_t r, uint64_t (&w)[3], uint32_t& sh, bool& ok) {
+        ok = status[r] == FHEB_WIRE_OK;
+        sh = 0;
+        w[0] = w[1] = w[2] = 0;
+        if (!ok) return;
+        const uint8_t* src = wire + offsets[r] + rel;
+        const uintptr_t a = (uintptr_t)src;
+        const uint64_t* al = reinterpret_cast<const uint64_t*>(a & ~(uintptr_t)7);
+        sh = (uint32_t)(a & 7) * 8;
+        if (reinterpret_cast<const uint8_t*>(al + 3) <= wire_end) {
+            w[0] = __ldcs(al);
+            w[1] = __ldcs(al + 1);
+            w[2] = sh ? __ldcs(al + 2) : 0;
+        } else {  // the very end of the buffer: no read past it
+            w[0] = load_le<uint64_t>(src);
+            w[1] = load_le<uint64_t>(src + 8);
+            sh = 0;
+        }
+    };
+    auto add = [&](const uint64_t (&w)[3], uint32_t sh, bool ok) {
+        if (!ok) return;
+        const uint64_t v0 = sh ? (w[0] >> sh) | (w[1] << (64 - sh)) : w[0];
+        const uint64_t v1 = sh ? (w[1] >> sh) | (w[2] << (64 - sh)) : w[1];
+        acc128(lo0, hi0, v0);
+        acc128(lo1, hi1, v1);
+    };
+    size_t r = first;
+    for (; r + WTALLY_UNROLL <= last; r += WTALLY_UNROLL) {
+        uint64_t w[WTALLY_UNROLL][3];
+        uint32_t sh[WTALLY_UNROLL];
+        bool ok[WTALLY_UNROLL];
+#pragma unroll
+        for (int u = 0; u < WTALLY_UNROLL; ++u) fetch(r + u, w[u], sh[u], ok[u]);
+#pragma unroll
+        for (int u = 0; u < WTALLY_UNROLL; ++u) add(w[u], sh[u], ok[u]);
+    }
+    for (; r < last; ++r) {
+        uint64_t w[3];
+        uint32_t sh;
+        bool ok;
+        fetch(r, w, sh, ok);
+        add(w, sh, ok);
+    }
+    uint64_t* out = partial + (size_t)blockIdx.y * width + col;
+    out[0] = fold128(hi0, lo0, m);
+    out[1] = fold128(hi1, lo1, m);
+}
+
+int ballots_validate_device(const uint8_t* wire, const uint64_t* offsets, size_t count, uint32_t choices, uint32_t N, uint64_t q,
+                            uint8_t* status, uint64_t* timestamps, cudaStream_t s) {
     // FHEB_WIRE_WARMUP: test knob - 0 makes every start-state guess wrong, which exercises the repair rounds
     static const uint32_t warmup = [] {
         const char* e = getenv("FHEB_WIRE_WARMUP");
@@ -281,6 +348,12 @@ int ballots_ingest_device(const uint8_t* wire, size_t wire_bytes, const uint64_t
                                                                                                   status, timestamps, warmup);
     FHEB_CHECK_LAUNCH();
     count_launch();
+    return FHEB_OK;
+}
+
+int ballots_ingest_device(const uint8_t* wire, size_t wire_bytes, const uint64_t* offsets, size_t count, uint32_t choices, uint32_t N, uint64_t q,
+                          uint64_t* cts, uint8_t* status, uint64_t* timestamps, cudaStream_t s) {
+    FHEB_TRY(ballots_validate_device(wire, offsets, count, choices, N, q, status, timestamps, s));
     const size_t cap = (size_t)ctx().sm_count * 8;
     ballot_unpack_kernel<<<(unsigned)(count < cap ? count : cap), 256, 0, s>>>(wire, wire + wire_bytes, offsets, status, count, choices, N, cts);
     FHEB_CHECK_LAUNCH();
@@ -462,6 +535,104 @@ int fheb_ballots_ingest(const void* wire, size_t wire_bytes, const uint64_t* off
         *accepted = ok;
     }
     return FHEB_OK;
+}
+
+int fheb_tally_wire(const void* wire, size_t wire_bytes, const uint64_t* offsets, size_t count, uint32_t num_choices,
+                    uint32_t degree, uint64_t modulus, uint64_t* out, uint8_t* status, size_t* accepted, void* stream) {
+    // BallotSerializer::deserialize_ballot per record (:776-846) + EncryptionEngine::tally_votes per choice
+    // (encryption.cpp:1061-1067,1327-1364) without materialising the ciphertexts: validate, then sum the accepted
+    // records' words straight out of the wire bytes.
+    FHEB_TRY(ensure_ready());
+    if (accepted) *accepted = 0;
+    FHEB_REQUIRE(count != 0, "Cannot add empty vector of ciphertexts");  // encryption.cpp:1328-1330
+    FHEB_REQUIRE(wire != nullptr && out != nullptr && status != nullptr, "wire, out and status must not be null");
+    FHEB_REQUIRE(degree >= 1 && num_choices >= 1, "degree and num_choices must be positive");
+    FHEB_REQUIRE(modulus >= 2, "Modulus must be at least 2");
+    FHEB_REQUIRE(!is_device_pointer(status) && (offsets == nullptr || !is_device_pointer(offsets)), "status and offsets are host arrays");
+    const uint8_t* w = static_cast<const uint8_t*>(wire);
+    const bool wire_on_device = is_device_pointer(wire);
+    std::vector<uint64_t> walked;
+    if (!offsets) {
+        FHEB_REQUIRE(!wire_on_device, "offsets are required when the wire buffer is device memory");
+        walked.resize(count + 1);
+        size_t pos = 0;
+        for (size_t r = 0; r < count; ++r) {
+            walked[r] = pos;
+            FHEB_REQUIRE(wire_bytes - pos >= WIRE_HEADER_BYTES, "wire buffer ends inside record %zu", r);
+            const size_t next = pos + WIRE_HEADER_BYTES + load_le<uint32_t>(w + pos + 32);
+            pos = next < wire_bytes ? next : wire_bytes;
+        }
+        walked[count] = pos;
+        offsets = walked.data();
+    }
+    for (size_t r = 0; r < count; ++r)
+        FHEB_REQUIRE(offsets[r] <= offsets[r + 1] && offsets[r + 1] <= wire_bytes, "record %zu lies outside the wire buffer", r);
+    cudaStream_t s = (cudaStream_t)stream;
+    const uint32_t wpc = 2 * degree, width = num_choices * wpc;
+    Staged so;
+    FHEB_TRY(so.bind(out, (size_t)width * 8, false, true, s));
+    uint8_t* d_wire = nullptr;
+    uint64_t* d_off = nullptr;
+    uint8_t* d_status = nullptr;
+    uint64_t* partial = nullptr;
+    int rc = FHEB_OK;
+    auto cuda_ok = [&](cudaError_t e, const char* what) {
+        if (e != cudaSuccess && rc == FHEB_OK) rc = set_error(FHEB_ERR_NATIVE, "%s failed: %s", what, cudaGetErrorString(e));
+        return e == cudaSuccess;
+    };
+    if (wire_on_device) {
+        if (((uintptr_t)w & 7) != 0) rc = set_error(FHEB_ERR_INVALID_PARAMETERS, "a device wire buffer must be 8-byte aligned");
+        d_wire = const_cast<uint8_t*>(w);
+    } else if (cuda_ok(cudaMallocAsync(&d_wire, wire_bytes, s), "cudaMallocAsync")) {
+        cuda_ok(cudaMemcpyAsync(d_wire, w, wire_bytes, cudaMemcpyHostToDevice, s), "cudaMemcpyAsync");
+    }
+    if (rc == FHEB_OK) cuda_ok(cudaMallocAsync(&d_off, (count + 1) * 8, s), "cudaMallocAsync");
+    if (rc == FHEB_OK) cuda_ok(cudaMallocAsync(&d_status, count, s), "cudaMallocAsync");
+    if (rc == FHEB_OK) cuda_ok(cudaMemcpyAsync(d_off, offsets, (count + 1) * 8, cudaMemcpyHostToDevice, s), "cudaMemcpyAsync");
+    if (rc == FHEB_OK) rc = ballots_validate_device(d_wire, d_off, count, num_choices, degree, modulus, d_status, nullptr, s);
+    if (rc == FHEB_OK) cuda_ok(cudaMemcpyAsync(status, d_status, count, cudaMemcpyDeviceToHost, s), "cudaMemcpyAsync");
+    if (rc == FHEB_OK) cuda_ok(cudaStreamSynchronize(s), "cudaStreamSynchronize");  // the number of accepted records picks the path
+    size_t ok = 0, lone = 0;
+    if (rc == FHEB_OK) {
+        for (size_t r = 0; r < count; ++r)
+            if (status[r] == FHEB_WIRE_OK) {
+                ++ok;
+                lone = r;
+            }
+        if (accepted) *accepted = ok;
+        if (ok == 0) rc = set_error(FHEB_ERR_INVALID_PARAMETERS, "Cannot add empty vector of ciphertexts");
+    }
+    if (rc == FHEB_OK && ok == 1) {
+        // a single ciphertext is returned untouched, unreduced words included (encryption.cpp:1332-1334)
+        const size_t cap = 1;
+        ballot_unpack_kernel<<<(unsigned)cap, 256, 0, s>>>(d_wire, d_wire + wire_bytes, d_off + lone, d_status + lone, 1, num_choices, degree,
+                                                           so.ptr<uint64_t>());
+        if (cudaGetLastError() != cudaSuccess) rc = set_error(FHEB_ERR_NATIVE, "ballot_unpack_kernel launch failed");
+        count_launch();
+    } else if (rc == FHEB_OK) {
+        const unsigned chunks = (width + 2 * WTALLY_THREADS - 1) / (2 * WTALLY_THREADS);
+        size_t slabs = ((size_t)ctx().sm_count * 4 + chunks - 1) / chunks;
+        const size_t max_slabs = (count + 63) / 64;
+        if (slabs > max_slabs) slabs = max_slabs;
+        if (slabs < 1) slabs = 1;
+        const size_t per_slab = (count + slabs - 1) / slabs;
+        slabs = (count + per_slab - 1) / per_slab;
+        if (cuda_ok(cudaMallocAsync(&partial, slabs * (size_t)width * 8, s), "cudaMallocAsync")) {
+            tally_wire_kernel<<<dim3(chunks, (unsigned)slabs), WTALLY_THREADS, 0, s>>>(d_wire, d_wire + wire_bytes, d_off, d_status, count, per_slab,
+                                                                                 wpc, width, partial, make_modq(modulus));
+            if (cudaGetLastError() != cudaSuccess) rc = set_error(FHEB_ERR_NATIVE, "tally_wire_kernel launch failed");
+            count_launch();
+            // fold the slab partials; with two or more accepted ballots every word is the output of a modular addition
+            if (rc == FHEB_OK) rc = tally_rows_device(partial, slabs, width, modulus, so.ptr<uint64_t>(), s);
+        }
+    }
+    if (rc == FHEB_OK) rc = so.finish();
+    if (rc == FHEB_OK && so.staged()) cuda_ok(cudaStreamSynchronize(s), "cudaStreamSynchronize");
+    if (partial) cudaFreeAsync(partial, s);
+    if (d_off) cudaFreeAsync(d_off, s);
+    if (d_status) cudaFreeAsync(d_status, s);
+    if (!wire_on_device && d_wire) cudaFreeAsync(d_wire, s);
+    return rc;
 }
 
 int fheb_relin_key_from_wire(const fheb_ntt_plan* plan, const void* bytes, size_t len, fheb_relin_key** out) {

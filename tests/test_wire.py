@@ -266,3 +266,55 @@ print("ok")
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     r = subprocess.run([sys.executable, "-c", code], cwd=root, env=env, capture_output=True, text=True, timeout=600)
     assert r.returncode == 0 and "ok" in r.stdout, r.stderr[-2000:]
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("n,q,ch,count", [(1024, QT, 1, 500), (64, 132120577, 2, 333), (4096, Q62, 1, 70)])
+def test_tally_straight_from_the_wire(fhe, oracle, n, q, ch, count):
+    """fheb_tally_wire == deserialize_ballot per record + tally_votes per choice over the accepted ones."""
+    import torch
+
+    rng = np.random.default_rng(n + count)
+    ballots = rng.integers(0, q, size=(count, ch, 2, n), dtype=np.uint64)
+    ballots[:3, 0, 0, :3] = [q, q + 7, 2**64 - 1]  # unreduced words: add reduces them, a lone ballot keeps them
+    recs = [fhe.serialize_ballot(ballots[i], q, i) for i in range(count)]
+    for k, i in enumerate(int(x) for x in rng.choice(count, size=count // 5, replace=False)):
+        b = bytearray(recs[i])
+        if k % 2:
+            b[45 + k % 4] ^= 0x21              # checksum field: rejected
+        else:
+            b[int(rng.integers(49, len(b)))] ^= 4  # payload: usually accepted by the reference's CRC, damaged words and all
+        recs[i] = bytes(b)
+    offs = np.concatenate([[0], np.cumsum([len(r) for r in recs])]).astype(np.uint64)
+    parsed = np.zeros_like(ballots)
+    want = np.zeros(count, np.uint8)
+    for i in range(count):
+        want[i], parsed[i], _ = oracle.ballot_parse(recs[i], ch, n, q)
+    good = np.flatnonzero(want == 0)
+    assert 0 < len(good) < count
+    exp = np.stack([oracle.tally(parsed[good][:, c], q) for c in range(ch)])
+    blob = b"".join(recs)
+    got, status = fhe.tally_wire(blob, count, ch, n, q)                       # host wire, self-describing records
+    eq(status, want)
+    eq(got, exp)
+    got2, status2 = fhe.tally_wire(blob, count, ch, n, q, offsets=offs, device="cuda")  # explicit extents, device result
+    eq(status2, want)
+    eq(host(got2), exp)
+    dwire = torch.from_numpy(np.frombuffer(blob + b"\0" * ((-len(blob)) % 8), np.uint8).copy()).cuda()[: len(blob)]
+    got3, status3 = fhe.tally_wire(dwire, count, ch, n, q, offsets=offs)      # wire bytes already in HBM
+    eq(status3, want)
+    eq(host(got3), exp)
+    # the same numbers through ingest + tally_votes
+    cts, _, _ = fhe.ingest_ballots(blob, count, ch, n, q, device="cuda")
+    for c in range(ch):
+        eq(host(fhe.tally_votes(cts[:, c].contiguous(), n, q)), exp[c])
+    # one accepted record: returned untouched (unreduced words included); none: the reference's error
+    li = int(good[0])
+    bad3 = [bytes(bytearray(recs[i][:45]) + bytes([recs[i][45] ^ 1]) + bytearray(recs[i][46:])) for i in good[1:4]]
+    lone = [recs[li]] + bad3
+    got4, status4 = fhe.tally_wire(b"".join(lone), 4, ch, n, q)
+    eq(status4, np.array([0, 3, 3, 3], np.uint8))
+    eq(got4, parsed[li])
+    with pytest.raises(fhe.FheError) as e:
+        fhe.tally_wire(b"".join(lone[1:]), 3, ch, n, q)
+    assert "Cannot add empty vector of ciphertexts" in str(e.value)
