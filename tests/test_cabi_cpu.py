@@ -69,7 +69,9 @@ def test_no_cpu_fallback_without_gpu(fhe):
     for call in (lambda: fhe.NTTProcessor(8, 97), lambda: fhe.modadd_batch(x, x, 97),
                  lambda: fhe.tally_votes(np.zeros((2, 2, 8), np.uint64), 8, 97),
                  lambda: fhe.MultiLimbModularArithmetic([0xFFFFFFFFFFFFFF43, 1]).mod_add(np.zeros((1, 2), np.uint64),
-                                                                                         np.zeros((1, 2), np.uint64))):
+                                                                                         np.zeros((1, 2), np.uint64)),
+                 lambda: fhe.ingest_ballots(fhe.serialize_ballot(np.zeros((1, 2, 8), np.uint64), 97, 1), 1, 1, 8, 97),
+                 lambda: fhe.tally_wire(fhe.serialize_ballot(np.zeros((1, 2, 8), np.uint64), 97, 1) * 2, 2, 1, 8, 97)):
         with pytest.raises(fhe.FheError) as e:
             call()
         assert e.value.code_name == "HARDWARE_UNAVAILABLE", e.value
