@@ -9,6 +9,8 @@
 //
 // C-ABI entry points here (include/fheb200.h): fheb_tally, fheb_tally_combine,
 // fheb_tensor_multiply_batch, fheb_synth_ballots.
+#include <cstdlib>
+
 #include "elementwise.hpp"
 #include "modarith.cuh"
 #include "plan.hpp"
@@ -25,15 +27,17 @@ constexpr int TALLY_UNROLL = 8;
 
 __global__ void __launch_bounds__(TALLY_THREADS) tally_kernel(const uint64_t* __restrict__ cts, size_t count,
                                                               size_t per_slab, uint32_t width /* 2N words */,
-                                                              uint64_t* __restrict__ partial, const ModQ m, int vec_ok) {
+                                                              uint64_t* partial, const ModQ m, int vec_ok,
+                                                              unsigned* done = nullptr, uint64_t* final_out = nullptr) {
     const uint32_t col = (blockIdx.x * TALLY_THREADS + threadIdx.x) * 2;
-    if (col >= width) return;
+    const bool live = col < width;  // (threads past the row's end still take part in the barriers below)
     const size_t first = (size_t)blockIdx.y * per_slab;
     size_t last = first + per_slab;
     if (last > count) last = count;
     uint64_t lo0 = 0, hi0 = 0, lo1 = 0, hi1 = 0;
     const bool pair = (col + 1 < width);
-    if (vec_ok && pair) {
+    if (!live) {
+    } else if (vec_ok && pair) {
         const ulonglong2* base = reinterpret_cast<const ulonglong2*>(cts + col);
         const size_t row = width / 2;  // ulonglong2 per ballot
         size_t i = first;
@@ -58,9 +62,48 @@ __global__ void __launch_bounds__(TALLY_THREADS) tally_kernel(const uint64_t* __
             if (pair) acc128(lo1, hi1, cts[i * width + col + 1]);
         }
     }
-    uint64_t* out = partial + (size_t)blockIdx.y * width + col;
-    out[0] = fold128(hi0, lo0, m);
-    if (pair) out[1] = fold128(hi1, lo1, m);
+    if (live) {
+        uint64_t* out = partial + (size_t)blockIdx.y * width + col;
+        out[0] = fold128(hi0, lo0, m);
+        if (pair) out[1] = fold128(hi1, lo1, m);
+    }
+    if (done == nullptr) return;
+    // Second stage without a second launch (a 4-block fold kernel between two 0.3 ms launches costs ~25 us of drain,
+    // launch and ramp-up): the LAST block of a column chunk to finish folds that chunk's slab partials.
+    __shared__ bool is_last;
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) is_last = atomicAdd(done + blockIdx.x, 1u) == gridDim.y - 1;
+    __syncthreads();
+    if (!is_last) return;
+    __threadfence();
+    if (live) {
+        lo0 = hi0 = lo1 = hi1 = 0;
+        const uint64_t* p = partial + col;  // written by other SMs: read through L2, many loads in flight
+        constexpr unsigned FOLD_UNROLL = 16;
+        unsigned y = 0;
+        if (pair && (width % 2 == 0)) {  // partial rows are 16-byte aligned (stream-ordered allocation, even width, even col)
+            const ulonglong2* p2 = reinterpret_cast<const ulonglong2*>(p);
+            const size_t row = width / 2;
+            for (; y + FOLD_UNROLL <= gridDim.y; y += FOLD_UNROLL) {
+                ulonglong2 v[FOLD_UNROLL];
+#pragma unroll
+                for (unsigned u = 0; u < FOLD_UNROLL; ++u) v[u] = __ldcg(p2 + (size_t)(y + u) * row);
+#pragma unroll
+                for (unsigned u = 0; u < FOLD_UNROLL; ++u) {
+                    acc128(lo0, hi0, v[u].x);
+                    acc128(lo1, hi1, v[u].y);
+                }
+            }
+        }
+        for (; y < gridDim.y; ++y) {
+            acc128(lo0, hi0, __ldcg(p + (size_t)y * width));
+            if (pair) acc128(lo1, hi1, __ldcg(p + (size_t)y * width + 1));
+        }
+        final_out[col] = fold128(hi0, lo0, m);
+        if (pair) final_out[col + 1] = fold128(hi1, lo1, m);
+    }
+    if (threadIdx.x == 0) done[blockIdx.x] = 0;  // ready for the next call that draws this counter slot
 }
 
 // Transform-domain tensor product of EncryptionEngine::multiply (cpp/src/encryption.cpp:760-785) for a whole
@@ -96,6 +139,28 @@ __global__ void __launch_bounds__(256) synth_ballots_kernel(uint64_t* out, size_
         out[i] = reduce64(splitmix64(seed + first_word + i), m);
 }
 
+// "Blocks done" counters of the in-kernel second stage: TALLY_SLOTS sets of TALLY_MAX_CHUNKS counters, all zero between
+// calls (the folding block resets its own).  Calls draw sets round-robin, so up to TALLY_SLOTS tallies may be in flight
+// on different streams at once.
+constexpr unsigned TALLY_SLOTS = 64, TALLY_MAX_CHUNKS = 256;
+static unsigned* tally_counters() {
+    static unsigned* pool = nullptr;
+    static std::atomic<unsigned> next{0};
+    static std::mutex mu;
+    {
+        std::lock_guard<std::mutex> lock(mu);
+        if (!pool) {
+            if (cudaMalloc(&pool, (size_t)TALLY_SLOTS * TALLY_MAX_CHUNKS * sizeof(unsigned)) != cudaSuccess ||
+                cudaMemset(pool, 0, (size_t)TALLY_SLOTS * TALLY_MAX_CHUNKS * sizeof(unsigned)) != cudaSuccess) {
+                cudaGetLastError();
+                pool = nullptr;
+                return nullptr;  // falls back to the two-launch form
+            }
+        }
+    }
+    return pool + (size_t)(next.fetch_add(1) % TALLY_SLOTS) * TALLY_MAX_CHUNKS;
+}
+
 // Sums `count` rows of `width` words; out = [width].  single_raw: a lone row is copied verbatim
 // (EncryptionEngine::batch_add returns the ciphertext untouched for size 1, encryption.cpp:1332-1334).
 static int tally_device(const uint64_t* cts, size_t count, uint32_t width, uint64_t q, uint64_t* out, bool single_raw,
@@ -107,7 +172,8 @@ static int tally_device(const uint64_t* cts, size_t count, uint32_t width, uint6
     const ModQ m = make_modq(q);
     const unsigned chunks = (width + 2 * TALLY_THREADS - 1) / (2 * TALLY_THREADS);
     // enough slabs to put ~4 blocks on every SM, but at least 64 ballots per slab
-    size_t slabs = ((size_t)ctx().sm_count * 4 + chunks - 1) / chunks;
+    static const int bpsm = getenv("FHEB_EXP_TALLY_BPSM") ? atoi(getenv("FHEB_EXP_TALLY_BPSM")) : 4;  // tuning knob
+    size_t slabs = ((size_t)ctx().sm_count * bpsm + chunks - 1) / chunks;
     const size_t max_slabs = (count + 63) / 64;
     if (slabs > max_slabs) slabs = max_slabs;
     if (slabs < 1) slabs = 1;
@@ -122,11 +188,18 @@ static int tally_device(const uint64_t* cts, size_t count, uint32_t width, uint6
     }
     uint64_t* partial = nullptr;
     FHEB_CUDA(cudaMallocAsync(&partial, slabs * (size_t)width * 8, s));
-    tally_kernel<<<dim3(chunks, (unsigned)slabs), TALLY_THREADS, 0, s>>>(cts, count, per_slab, width, partial, m, vec_ok);
-    FHEB_CHECK_LAUNCH();
-    tally_kernel<<<dim3(chunks, 1), TALLY_THREADS, 0, s>>>(partial, slabs, slabs, width, out, m, 1);
-    FHEB_CHECK_LAUNCH();
-    count_launch(2);
+    unsigned* done = chunks <= TALLY_MAX_CHUNKS ? tally_counters() : nullptr;
+    if (done) {
+        tally_kernel<<<dim3(chunks, (unsigned)slabs), TALLY_THREADS, 0, s>>>(cts, count, per_slab, width, partial, m, vec_ok, done, out);
+        FHEB_CHECK_LAUNCH();
+        count_launch();
+    } else {
+        tally_kernel<<<dim3(chunks, (unsigned)slabs), TALLY_THREADS, 0, s>>>(cts, count, per_slab, width, partial, m, vec_ok);
+        FHEB_CHECK_LAUNCH();
+        tally_kernel<<<dim3(chunks, 1), TALLY_THREADS, 0, s>>>(partial, slabs, slabs, width, out, m, 1);
+        FHEB_CHECK_LAUNCH();
+        count_launch(2);
+    }
     FHEB_CUDA(cudaFreeAsync(partial, s));
     return FHEB_OK;
 }

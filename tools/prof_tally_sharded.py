@@ -1,0 +1,45 @@
+"""Phase timing of the sharded tally (local fold / all-gather / combine) with CUDA events:
+    python -m torch.distributed.run --nproc-per-node N --master-addr 127.0.0.1 tools/prof_tally_sharded.py [ballots_total]"""
+import os
+import sys
+
+import torch
+import torch.distributed as dist
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import fheb200  # noqa: E402
+
+rank, world = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
+torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", 0)))
+if world > 1:
+    dist.init_process_group("nccl")
+total = int(sys.argv[1]) if len(sys.argv) > 1 else 1 << 20
+n, q = 1024, 1099511678977
+per = total // world
+cts = torch.empty((per, 2, n), dtype=torch.int64, device="cuda")
+fheb200.synth_ballots(cts, rank * per, per, n, q, 0xB200)
+st = fheb200.ShardedTally(n, q)
+gathered = torch.empty(world * 2 * n, dtype=torch.int64, device="cuda")
+for _ in range(5):
+    st.tally(cts)
+torch.cuda.synchronize()
+iters = 30
+ev = [[torch.cuda.Event(enable_timing=True) for _ in range(4)] for _ in range(iters)]
+if world > 1:
+    dist.barrier()
+for i in range(iters):
+    ev[i][0].record()
+    part = fheb200.tally_votes(cts, n, q)
+    ev[i][1].record()
+    if world > 1:
+        dist.all_gather_into_tensor(gathered, part.view(-1))
+    ev[i][2].record()
+    res = fheb200.tally_combine(gathered.view(world, 2, n), n, q) if world > 1 else part
+    ev[i][3].record()
+torch.cuda.synchronize()
+loc = sum(e[0].elapsed_time(e[1]) for e in ev) / iters
+gat = sum(e[1].elapsed_time(e[2]) for e in ev) / iters
+com = sum(e[2].elapsed_time(e[3]) for e in ev) / iters
+whole = ev[0][0].elapsed_time(ev[-1][3]) / iters
+print(f"rank {rank}/{world}: {per} ballots/rank  local {loc * 1e3:.1f} us  all-gather {gat * 1e3:.1f} us  combine {com * 1e3:.1f} us  "
+      f"iteration {whole * 1e3:.1f} us -> {total / whole / 1e3:.1f} M ballots/s")
