@@ -256,6 +256,23 @@ FHEB_API int fheb_tally(const uint64_t* cts, size_t count, uint32_t degree, uint
  * e.g. the result of an NCCL all-gather of per-GPU fheb_tally outputs) into out = [2][N]. */
 FHEB_API int fheb_tally_combine(const uint64_t* partials, size_t parts, uint32_t degree, uint64_t modulus,
                                 uint64_t* out, void* stream);
+/* Sharded tally with the cross-GPU step FUSED into the tally kernel (one process per GPU of one box).  Same result
+ * words as fheb_tally on every rank + an all-gather + fheb_tally_combine, in ONE launch per rank: the block that
+ * finishes a column chunk stores its words into every peer's inbox over NVLink (CUDA IPC peer memory), publishes a
+ * flag, waits for the peers' flags and sums the rows.  Set-up: every rank creates its handle (which exports a
+ * 64-byte IPC handle), the ranks exchange those bytes by any means (the Python mirror uses one torch.distributed
+ * all-gather), then connect.  run() must be called by all ranks the same number of times (each call is one
+ * epoch); a rank that never arrives makes its peers give up after ~3 s and sets the status flag. */
+typedef struct fheb_tally_peers fheb_tally_peers;
+#define FHEB_PEER_HANDLE_BYTES 64
+FHEB_API int fheb_tally_peers_create(uint32_t degree, uint64_t modulus, uint32_t world, uint32_t rank, fheb_tally_peers** out,
+                                     uint8_t* handle_out /* [FHEB_PEER_HANDLE_BYTES] */);
+FHEB_API int fheb_tally_peers_connect(fheb_tally_peers* peers, const uint8_t* handles /* [world][FHEB_PEER_HANDLE_BYTES], rank order */);
+/* cts = this rank's ballots [count][2][N] (device), out = [2][N] (device): the GLOBAL tally, on every rank */
+FHEB_API int fheb_tally_peers_run(fheb_tally_peers* peers, const uint64_t* cts, size_t count, uint64_t* out, void* stream);
+FHEB_API int fheb_tally_peers_status(const fheb_tally_peers* peers, int* timed_out); /* synchronises */
+FHEB_API int fheb_tally_peers_destroy(fheb_tally_peers* peers);
+
 /* Streaming tally: replaces the running accumulator of
  * CiphertextStreamProcessor::stream_add (cpp/src/streaming_processor.cpp:460-526) and the accumulate path
  * of ChunkedCiphertextProcessor: ballots arrive in chunks, the running total stays on the device.

@@ -103,6 +103,11 @@ SIGNATURES = {
     "fheb_make_test_poly": ([p, i, u64, u64, p], i),
     "fheb_tally": ([p, sz, u32, u64, p, p], i),
     "fheb_tally_combine": ([p, sz, u32, u64, p, p], i),
+    "fheb_tally_peers_create": ([u32, u64, u32, u32, p, p], i),
+    "fheb_tally_peers_connect": ([p, p], i),
+    "fheb_tally_peers_run": ([p, p, sz, p, p], i),
+    "fheb_tally_peers_status": ([p, p], i),
+    "fheb_tally_peers_destroy": ([p], i),
     "fheb_tally_stream_create": ([u32, u64, p], i),
     "fheb_tally_stream_add": ([p, p, sz, p], i),
     "fheb_tally_stream_total": ([p, p, p], i),

@@ -24,11 +24,40 @@ namespace fheb {
 // partial[y][width].
 constexpr int TALLY_THREADS = 256;
 constexpr int TALLY_UNROLL = 8;
+constexpr uint32_t TALLY_MAX_PEERS = 16;
+
+// Cross-GPU stage of the sharded tally, fused into the tally kernel (peer memory over NVLink instead of an
+// all-gather + a combine kernel): the block that folds a column chunk stores its 512 words into row `rank` of EVERY
+// peer's inbox, publishes a per-(rank, chunk) flag with the call's epoch (release, system scope), waits for the same
+// flag from every peer in its own inbox (acquire), and sums the `world` rows.  Inboxes are double-buffered by epoch
+// parity: a peer can be at most one call ahead (it needs this rank's flag of call k+1 to finish call k+1, and this
+// rank sends that only after its call k has completed on its stream).
+struct TallyPeerArgs {
+    uint64_t* inbox[TALLY_MAX_PEERS];   // peer p's inbox of this epoch's parity: [world][width] words
+    unsigned* flags[TALLY_MAX_PEERS];   // peer p's flags: [world][chunks]
+    unsigned* status;                   // local: set to 1 when a wait timed out
+    uint32_t world, rank, epoch;
+};
+
+__device__ __forceinline__ void st_release_sys(unsigned* p, unsigned v) {
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ unsigned ld_acquire_sys(const unsigned* p) {
+    unsigned v;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ uint64_t ld_relaxed_sys(const uint64_t* p) {
+    uint64_t v;
+    asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
 
 __global__ void __launch_bounds__(TALLY_THREADS) tally_kernel(const uint64_t* __restrict__ cts, size_t count,
                                                               size_t per_slab, uint32_t width /* 2N words */,
                                                               uint64_t* partial, const ModQ m, int vec_ok,
-                                                              unsigned* done = nullptr, uint64_t* final_out = nullptr) {
+                                                              unsigned* done = nullptr, uint64_t* final_out = nullptr,
+                                                              const int use_peers = 0, const TallyPeerArgs pa = TallyPeerArgs{}) {
     const uint32_t col = (blockIdx.x * TALLY_THREADS + threadIdx.x) * 2;
     const bool live = col < width;  // (threads past the row's end still take part in the barriers below)
     const size_t first = (size_t)blockIdx.y * per_slab;
@@ -100,10 +129,48 @@ __global__ void __launch_bounds__(TALLY_THREADS) tally_kernel(const uint64_t* __
             acc128(lo0, hi0, __ldcg(p + (size_t)y * width));
             if (pair) acc128(lo1, hi1, __ldcg(p + (size_t)y * width + 1));
         }
+        if (!use_peers) {
+            final_out[col] = fold128(hi0, lo0, m);
+            if (pair) final_out[col + 1] = fold128(hi1, lo1, m);
+        }
+    }
+    if (threadIdx.x == 0) done[blockIdx.x] = 0;  // ready for the next call that draws this counter slot
+    if (!use_peers) return;
+
+    // ---- fused exchange + combine over peer memory ------------------------------------------------
+    const uint32_t chunks = gridDim.x;
+    if (live) {
+        const uint64_t v0 = fold128(hi0, lo0, m), v1 = pair ? fold128(hi1, lo1, m) : 0;
+        for (uint32_t p = 0; p < pa.world; ++p) {  // NVLink stores into every inbox (the own one included)
+            uint64_t* dst = pa.inbox[p] + (size_t)pa.rank * width + col;
+            dst[0] = v0;
+            if (pair) dst[1] = v1;
+        }
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x < pa.world) {
+        st_release_sys(pa.flags[threadIdx.x] + (size_t)pa.rank * chunks + blockIdx.x, pa.epoch);
+        const unsigned* mine = pa.flags[pa.rank] + (size_t)threadIdx.x * chunks + blockIdx.x;
+        const long long t0 = clock64();
+        while (ld_acquire_sys(mine) != pa.epoch) {
+            if (clock64() - t0 > (5ll << 30)) {  // ~2.7 s at 2 GHz: a peer never arrived
+                *pa.status = 1;
+                break;
+            }
+        }
+    }
+    __syncthreads();
+    if (live) {
+        lo0 = hi0 = lo1 = hi1 = 0;
+        const uint64_t* row = pa.inbox[pa.rank] + col;
+        for (uint32_t r = 0; r < pa.world; ++r) {
+            acc128(lo0, hi0, ld_relaxed_sys(row + (size_t)r * width));
+            if (pair) acc128(lo1, hi1, ld_relaxed_sys(row + (size_t)r * width + 1));
+        }
         final_out[col] = fold128(hi0, lo0, m);
         if (pair) final_out[col + 1] = fold128(hi1, lo1, m);
     }
-    if (threadIdx.x == 0) done[blockIdx.x] = 0;  // ready for the next call that draws this counter slot
 }
 
 // Transform-domain tensor product of EncryptionEngine::multiply (cpp/src/encryption.cpp:760-785) for a whole
@@ -209,6 +276,51 @@ int tally_rows_device(const uint64_t* rows, size_t count, uint32_t width, uint64
     return tally_device(rows, count, width, q, out, false, s);
 }
 
+// ---- sharded tally with the exchange fused into the kernel (peer memory) --------------------------------
+struct TallyPeers {
+    uint32_t degree = 0, world = 0, rank = 0, chunks = 0, epoch = 0;
+    uint64_t modulus = 0;
+    void* local = nullptr;                 // this rank's exported allocation: inbox[2][world][width] | flags[world][chunks] | status
+    void* peer[TALLY_MAX_PEERS] = {};      // opened allocations of the peers (peer[rank] == local)
+    bool connected = false;
+    size_t inbox_bytes() const { return (size_t)world * 2 * degree * 8; }
+    size_t flags_offset() const { return 2 * inbox_bytes(); }
+    size_t status_offset() const { return flags_offset() + (((size_t)world * chunks * 4 + 15) & ~(size_t)15); }
+    size_t total_bytes() const { return status_offset() + 16; }
+};
+
+static int tally_peers_run_device(TallyPeers* tp, const uint64_t* cts, size_t count, uint64_t* out, cudaStream_t s) {
+    const uint32_t width = 2 * tp->degree;
+    const ModQ m = make_modq(tp->modulus);
+    const unsigned chunks = tp->chunks;
+    size_t slabs = ((size_t)ctx().sm_count * 4 + chunks - 1) / chunks;
+    const size_t max_slabs = (count + 63) / 64;
+    if (slabs > max_slabs) slabs = max_slabs;
+    if (slabs < 1) slabs = 1;
+    const size_t per_slab = count ? (count + slabs - 1) / slabs : 1;
+    slabs = count ? (count + per_slab - 1) / per_slab : 1;
+    unsigned* done = tally_counters();
+    FHEB_REQUIRE(done != nullptr, "tally counters unavailable");
+    TallyPeerArgs pa{};
+    pa.world = tp->world;
+    pa.rank = tp->rank;
+    pa.epoch = ++tp->epoch;
+    const size_t parity = (pa.epoch & 1u) * tp->inbox_bytes();
+    for (uint32_t p = 0; p < tp->world; ++p) {
+        pa.inbox[p] = reinterpret_cast<uint64_t*>(static_cast<char*>(tp->peer[p]) + parity);
+        pa.flags[p] = reinterpret_cast<unsigned*>(static_cast<char*>(tp->peer[p]) + tp->flags_offset());
+    }
+    pa.status = reinterpret_cast<unsigned*>(static_cast<char*>(tp->local) + tp->status_offset());
+    uint64_t* partial = nullptr;
+    FHEB_CUDA(cudaMallocAsync(&partial, slabs * (size_t)width * 8, s));
+    const int vec_ok = ((reinterpret_cast<uintptr_t>(cts) & 15u) == 0);
+    tally_kernel<<<dim3(chunks, (unsigned)slabs), TALLY_THREADS, 0, s>>>(cts, count, per_slab, width, partial, m, vec_ok, done, out, 1, pa);
+    FHEB_CHECK_LAUNCH();
+    count_launch();
+    FHEB_CUDA(cudaFreeAsync(partial, s));
+    return FHEB_OK;
+}
+
 static int tally_entry(const uint64_t* cts, size_t count, uint32_t degree, uint64_t q, uint64_t* out, bool single_raw,
                        void* stream) {
     FHEB_TRY(ensure_ready());
@@ -264,6 +376,88 @@ int fheb_tally(const uint64_t* cts, size_t count, uint32_t degree, uint64_t modu
 int fheb_tally_combine(const uint64_t* partials, size_t parts, uint32_t degree, uint64_t modulus, uint64_t* out,
                        void* stream) {
     return tally_entry(partials, parts, degree, modulus, out, true, stream);
+}
+
+int fheb_tally_peers_create(uint32_t degree, uint64_t modulus, uint32_t world, uint32_t rank, fheb_tally_peers** out,
+                            uint8_t* handle_out) {
+    FHEB_TRY(ensure_ready());
+    FHEB_REQUIRE(out != nullptr && handle_out != nullptr, "out and handle_out must not be null");
+    FHEB_REQUIRE(degree > 0 && (degree & (degree - 1)) == 0, "Polynomial degree must be a power of 2");
+    FHEB_REQUIRE(modulus >= 2, "Modulus must be at least 2");
+    FHEB_REQUIRE(world >= 2 && world <= TALLY_MAX_PEERS && rank < world, "world must be 2..%u and rank below it", TALLY_MAX_PEERS);
+    static_assert(sizeof(cudaIpcMemHandle_t) == FHEB_PEER_HANDLE_BYTES, "IPC handle size");
+    TallyPeers* tp = new TallyPeers();
+    tp->degree = degree;
+    tp->modulus = modulus;
+    tp->world = world;
+    tp->rank = rank;
+    tp->chunks = (2 * degree + 2 * TALLY_THREADS - 1) / (2 * TALLY_THREADS);
+    if (tp->chunks > TALLY_MAX_CHUNKS) {
+        delete tp;
+        return set_error(FHEB_ERR_INVALID_PARAMETERS, "degree too large for the fused sharded tally");
+    }
+    cudaIpcMemHandle_t h;
+    if (cudaMalloc(&tp->local, tp->total_bytes()) != cudaSuccess || cudaMemset(tp->local, 0, tp->total_bytes()) != cudaSuccess ||
+        cudaIpcGetMemHandle(&h, tp->local) != cudaSuccess) {
+        const cudaError_t e = cudaGetLastError();
+        if (tp->local) cudaFree(tp->local);
+        delete tp;
+        return set_error(FHEB_ERR_NATIVE, "peer buffer set-up failed: %s", cudaGetErrorString(e));
+    }
+    cudaDeviceSynchronize();
+    std::memcpy(handle_out, &h, sizeof(h));
+    tp->peer[rank] = tp->local;
+    *out = reinterpret_cast<fheb_tally_peers*>(tp);
+    return FHEB_OK;
+}
+
+int fheb_tally_peers_connect(fheb_tally_peers* peers, const uint8_t* handles) {
+    FHEB_TRY(ensure_ready());
+    FHEB_REQUIRE(peers != nullptr && handles != nullptr, "peers and handles must not be null");
+    TallyPeers* tp = reinterpret_cast<TallyPeers*>(peers);
+    for (uint32_t p = 0; p < tp->world; ++p) {
+        if (p == tp->rank || tp->peer[p]) continue;
+        cudaIpcMemHandle_t h;
+        std::memcpy(&h, handles + (size_t)p * FHEB_PEER_HANDLE_BYTES, sizeof(h));
+        const cudaError_t e = cudaIpcOpenMemHandle(&tp->peer[p], h, cudaIpcMemLazyEnablePeerAccess);
+        if (e != cudaSuccess) {
+            cudaGetLastError();
+            tp->peer[p] = nullptr;
+            return set_error(FHEB_ERR_NATIVE, "opening the inbox of rank %u failed: %s", p, cudaGetErrorString(e));
+        }
+    }
+    tp->connected = true;
+    return FHEB_OK;
+}
+
+int fheb_tally_peers_run(fheb_tally_peers* peers, const uint64_t* cts, size_t count, uint64_t* out, void* stream) {
+    FHEB_TRY(ensure_ready());
+    FHEB_REQUIRE(peers != nullptr, "peers must not be null");
+    TallyPeers* tp = reinterpret_cast<TallyPeers*>(peers);
+    FHEB_REQUIRE(tp->connected, "fheb_tally_peers_connect has not succeeded on this handle");
+    FHEB_REQUIRE(out != nullptr && (count == 0 || cts != nullptr), "ciphertext pointers must not be null");
+    FHEB_REQUIRE((count == 0 || is_device_pointer(cts)) && is_device_pointer(out), "the fused sharded tally takes device buffers");
+    return tally_peers_run_device(tp, cts, count, out, (cudaStream_t)stream);
+}
+
+int fheb_tally_peers_status(const fheb_tally_peers* peers, int* timed_out) {
+    FHEB_REQUIRE(peers != nullptr && timed_out != nullptr, "peers and timed_out must not be null");
+    const TallyPeers* tp = reinterpret_cast<const TallyPeers*>(peers);
+    unsigned v = 0;
+    FHEB_CUDA(cudaMemcpy(&v, static_cast<const char*>(tp->local) + tp->status_offset(), 4, cudaMemcpyDeviceToHost));
+    *timed_out = (int)v;
+    return FHEB_OK;
+}
+
+int fheb_tally_peers_destroy(fheb_tally_peers* peers) {
+    if (!peers) return FHEB_OK;
+    TallyPeers* tp = reinterpret_cast<TallyPeers*>(peers);
+    cudaDeviceSynchronize();
+    for (uint32_t p = 0; p < tp->world; ++p)
+        if (p != tp->rank && tp->peer[p]) cudaIpcCloseMemHandle(tp->peer[p]);
+    if (tp->local) cudaFree(tp->local);
+    delete tp;
+    return FHEB_OK;
 }
 
 // ---- streaming accumulator ------------------------------------------------------------------

@@ -10,6 +10,11 @@ reference's EncryptionEngine::batch_add / tally_votes (cpp/src/encryption.cpp:10
 
 The exchange is the only data-path collective of the hot path; NTT / polymul / bootstrap
 batches shard with no communication (see shard_range).
+
+On NCCL groups whose ranks can map each other's memory (the GPUs of one NVSwitch box) the exchange and
+the combine are FUSED into the tally kernel (fheb_tally_peers_*: NVLink stores into every peer's inbox,
+a flag per column chunk, one launch per rank instead of three); the all-gather + combine-kernel form
+stays as the general path and is what the first call is checked against.
 """
 from __future__ import annotations
 
@@ -35,7 +40,7 @@ class ShardedTally:
     """
 
     def __init__(self, degree: int, modulus: int, group=None,
-                 local_fn: Optional[Callable] = None, combine_fn: Optional[Callable] = None):
+                 local_fn: Optional[Callable] = None, combine_fn: Optional[Callable] = None, fused: Optional[bool] = None):
         import torch.distributed as dist
 
         self.dist = dist
@@ -46,10 +51,86 @@ class ShardedTally:
         self.local_fn = local_fn or (lambda cts: api.tally_votes(cts, degree, modulus))
         self.combine_fn = combine_fn or (lambda parts: api.tally_combine(parts, degree, modulus))
         self._gathered = None
+        self._peers = None            # fused peer-memory path (set up lazily on the first CUDA call)
+        self._peers_tried = local_fn is not None or combine_fn is not None or fused is False
+        self._peers_checked = False
+
+    def _setup_peers(self, device):
+        """Exchange the IPC handles of the per-rank inboxes with one all-gather; every rank must agree on success."""
+        import ctypes as C
+
+        import numpy as np
+        import torch
+
+        self._peers_tried = True
+        ok = 1
+        handle = np.zeros(64, np.uint8)
+        h = C.c_void_p()
+        try:
+            api.check(api.lib().fheb_tally_peers_create(self.degree, self.modulus, self.world, self.rank, C.byref(h),
+                                                        handle.ctypes.data_as(C.c_void_p)))
+        except api.FheError:
+            ok = 0
+        mine = torch.from_numpy(handle).to(device)
+        everyone = torch.empty(self.world * 64, dtype=torch.uint8, device=device)
+        self.dist.all_gather_into_tensor(everyone, mine, group=self.group)
+        flag = torch.tensor([ok], dtype=torch.int32, device=device)
+        if ok:
+            table = np.ascontiguousarray(everyone.cpu().numpy())
+            if api.lib().fheb_tally_peers_connect(h, table.ctypes.data_as(C.c_void_p)) != 0:
+                flag[0] = 0
+        self.dist.all_reduce(flag, op=self.dist.ReduceOp.MIN, group=self.group)
+        if int(flag.item()) == 1:
+            self._peers = h
+        elif h:
+            api.lib().fheb_tally_peers_destroy(h)
+
+    def _fused(self, local_cts):
+        import ctypes as C
+
+        import torch
+
+        cts = api.as_words(local_cts)
+        out = torch.empty((2, self.degree), dtype=cts.dtype, device=cts.device)
+        count = cts.numel() // (2 * self.degree)
+        api.check(api.lib().fheb_tally_peers_run(self._peers, C.c_void_p(cts.data_ptr()), count, C.c_void_p(out.data_ptr()),
+                                                 C.c_void_p(torch.cuda.current_stream(cts.device).cuda_stream)))
+        return out
+
+    def __del__(self):
+        h, self._peers = getattr(self, "_peers", None), None
+        if h:
+            try:
+                api.lib().fheb_tally_peers_destroy(h)
+            except Exception:
+                pass
 
     def tally(self, local_cts, local_count: Optional[int] = None):
         """local_cts: this rank's ballots [count_r][2][N] (torch tensor on this rank's device).
         Every rank must hold at least one ballot.  Returns the global tally [2][N] on every rank."""
+        import torch
+
+        if self.world > 1 and not self._peers_tried and getattr(local_cts, "is_cuda", False) \
+                and self.dist.get_backend(self.group) == "nccl":
+            self._setup_peers(local_cts.device)
+        if self._peers is not None and getattr(local_cts, "is_cuda", False):
+            res = self._fused(local_cts)
+            if not self._peers_checked:  # first call: the general path must give the same words on every rank
+                self._peers_checked = True
+                ref = self._general(local_cts)
+                same = torch.tensor([int(torch.equal(res.view(-1), ref.view(-1)))], dtype=torch.int32, device=res.device)
+                self.dist.all_reduce(same, op=self.dist.ReduceOp.MIN, group=self.group)
+                if int(same.item()) != 1:  # never expected; keep the general GPU path and say so
+                    import sys
+
+                    print("fheb200: fused sharded tally disagrees with the all-gather path; using the general path", file=sys.stderr)
+                    api.lib().fheb_tally_peers_destroy(self._peers)
+                    self._peers = None
+                    return ref
+            return res
+        return self._general(local_cts)
+
+    def _general(self, local_cts):
         import torch
 
         partial = self.local_fn(local_cts)

@@ -41,5 +41,21 @@ loc = sum(e[0].elapsed_time(e[1]) for e in ev) / iters
 gat = sum(e[1].elapsed_time(e[2]) for e in ev) / iters
 com = sum(e[2].elapsed_time(e[3]) for e in ev) / iters
 whole = ev[0][0].elapsed_time(ev[-1][3]) / iters
+if world > 1:  # the fused path (one launch per rank: local fold + peer-memory exchange + combine)
+    fz = fheb200.ShardedTally(n, q)
+    for _ in range(5):
+        fz.tally(cts)
+    torch.cuda.synchronize()
+    dist.barrier()
+    f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    f0.record()
+    for _ in range(iters):
+        r2 = fz.tally(cts)
+    f1.record()
+    torch.cuda.synchronize()
+    fused_us = f0.elapsed_time(f1) / iters * 1e3
+    same = torch.equal(r2.view(-1), res.view(-1))
+    print(f"rank {rank}/{world}: fused path {'ON' if fz._peers is not None else 'OFF'}: iteration {fused_us:.1f} us -> "
+          f"{total / fused_us:.1f} M ballots/s, same words as the general path: {same}")
 print(f"rank {rank}/{world}: {per} ballots/rank  local {loc * 1e3:.1f} us  all-gather {gat * 1e3:.1f} us  combine {com * 1e3:.1f} us  "
       f"iteration {whole * 1e3:.1f} us -> {total / whole / 1e3:.1f} M ballots/s")
