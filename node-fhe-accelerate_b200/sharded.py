@@ -64,13 +64,15 @@ class ShardedTally:
 
         self._peers_tried = True
         ok = 1
+        why = ""
         handle = np.zeros(64, np.uint8)
         h = C.c_void_p()
         try:
             api.check(api.lib().fheb_tally_peers_create(self.degree, self.modulus, self.world, self.rank, C.byref(h),
                                                         handle.ctypes.data_as(C.c_void_p)))
-        except api.FheError:
+        except api.FheError as exc:
             ok = 0
+            why = str(exc)
         mine = torch.from_numpy(handle).to(device)
         everyone = torch.empty(self.world * 64, dtype=torch.uint8, device=device)
         self.dist.all_gather_into_tensor(everyone, mine, group=self.group)
@@ -79,11 +81,17 @@ class ShardedTally:
             table = np.ascontiguousarray(everyone.cpu().numpy())
             if api.lib().fheb_tally_peers_connect(h, table.ctypes.data_as(C.c_void_p)) != 0:
                 flag[0] = 0
+                why = api.lib().fheb_last_error().decode()
         self.dist.all_reduce(flag, op=self.dist.ReduceOp.MIN, group=self.group)
         if int(flag.item()) == 1:
             self._peers = h
-        elif h:
-            api.lib().fheb_tally_peers_destroy(h)
+        else:
+            import sys
+
+            print(f"fheb200: rank {self.rank}: fused sharded tally unavailable ({why or 'a peer could not set it up'}); "
+                  "using all-gather + combine", file=sys.stderr)
+            if h:
+                api.lib().fheb_tally_peers_destroy(h)
 
     def _fused(self, local_cts):
         import ctypes as C

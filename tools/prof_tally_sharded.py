@@ -11,9 +11,14 @@ import fheb200  # noqa: E402
 
 rank, world = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
 torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", 0)))
+eager = "--eager" in sys.argv  # bench.py's form: communicator created eagerly on the rank's device
 if world > 1:
-    dist.init_process_group("nccl")
-total = int(sys.argv[1]) if len(sys.argv) > 1 else 1 << 20
+    if eager:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", int(os.environ.get("LOCAL_RANK", 0))))
+    else:
+        dist.init_process_group("nccl")
+args = [a for a in sys.argv[1:] if not a.startswith("--")]
+total = int(args[0]) if args else 1 << 20
 n, q = 1024, 1099511678977
 per = total // world
 cts = torch.empty((per, 2, n), dtype=torch.int64, device="cuda")
