@@ -125,7 +125,8 @@ def run(fhe, torch, dist, world, rank, dev, barrier, max_over_ranks, peak):
                           "exchange": ("none (one rank)" if world == 1 else
                                        "fused into the tally kernel over peer memory" if getattr(st, "_peers", None) is not None else
                                        "NCCL all-gather + combine kernel"),
-                          "roofline": _hbm(peak, 16384.0 * per_rank, ms),
+                          "roofline": dict(_hbm(peak, 16384.0 * per_rank, ms),
+                                           note="peak = the measured COPY bandwidth (read + write); a read-only stream can exceed it"),
                           "checksum": int(res[0].view(-1)[:4].sum().item() & 0xFFFFFFFF)}
     del cts
 
