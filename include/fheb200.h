@@ -262,7 +262,7 @@ FHEB_API int fheb_tally_combine(const uint64_t* partials, size_t parts, uint32_t
  * flag, waits for the peers' flags and sums the rows.  Set-up: every rank creates its handle (which exports a
  * 64-byte IPC handle), the ranks exchange those bytes by any means (the Python mirror uses one torch.distributed
  * all-gather), then connect.  run() must be called by all ranks the same number of times (each call is one
- * epoch); a rank that never arrives makes its peers give up after ~3 s and sets the status flag. */
+ * epoch); a rank that never arrives makes its peers give up after ~17 s and sets the status flag. */
 typedef struct fheb_tally_peers fheb_tally_peers;
 #define FHEB_PEER_HANDLE_BYTES 64
 FHEB_API int fheb_tally_peers_create(uint32_t degree, uint64_t modulus, uint32_t world, uint32_t rank, fheb_tally_peers** out,

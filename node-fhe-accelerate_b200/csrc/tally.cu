@@ -154,7 +154,7 @@ __global__ void __launch_bounds__(TALLY_THREADS) tally_kernel(const uint64_t* __
         const unsigned* mine = pa.flags[pa.rank] + (size_t)threadIdx.x * chunks + blockIdx.x;
         const long long t0 = clock64();
         while (ld_acquire_sys(mine) != pa.epoch) {
-            if (clock64() - t0 > (5ll << 30)) {  // ~2.7 s at 2 GHz: a peer never arrived
+            if (clock64() - t0 > (1ll << 35)) {  // ~17 s at 2 GHz: a peer never arrived
                 *pa.status = 1;
                 break;
             }
