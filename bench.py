@@ -304,6 +304,18 @@ def run_ours(args):
                "sample": f"{BATCH} polynomials forward+inverse ({dt:.2f} s, best of 3), N={N_DEG}, same prime",
                "single_core_value": v1, "single_core_sample": f"32 polynomials forward+inverse on one thread ({dt1:.2f} s)"}
 
+    if rank == 0 and world == 1 and isinstance(secondary, dict) and "error" not in secondary:
+        try:  # the reference's CPU path beside every secondary workload (bounded samples, a few seconds)
+            import bench_secondary
+
+            for name, base in bench_secondary.cpu_reference(os.cpu_count() or 1).items():
+                if name in secondary:
+                    secondary[name]["cpu_baseline"] = base
+                else:
+                    secondary.setdefault("cpu_baseline_notes", {})[name] = base
+        except Exception as exc:
+            secondary["cpu_baseline_error"] = repr(exc)
+
     if rank == 0:
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,

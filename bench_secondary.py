@@ -210,3 +210,62 @@ def run_bootstrap(fhe, torch, dist, world, rank, dev, barrier, max_over_ranks, b
             # DFMA/clk/SM (tools/microbench/pipes.cu) x 148 SMs x 1.965 GHz
             "roofline": {"bound": "fp64-pipe", "achieved": n * 197e3 * batch / (ms * 1e-3) / 1e12, "peak": 148 * 64 * 1.965e9 / 1e12,
                          "unit": "T DP-op/s", "frac": n * 197e3 * batch / (ms * 1e-3) / (148 * 64 * 1.965e9)}}
+
+
+def cpu_reference(cores: int):
+    """The reference's own CPU code (oracle/_ref, compiled from its sources) timed on bounded samples of the secondary
+    workloads - SURVEY 8(d): PolynomialRing::multiply, MultiLimbModularArithmetic::montgomery_mul,
+    BootstrapEngine::blind_rotate, batch_add - one engine call per unit spread over `cores` host threads.  Test
+    infrastructure used as the reported baseline only; rank 0 at N=1."""
+    import os
+    import sys
+    import time
+
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "tests"))
+    from oracle_bindings import RefOracle, ref_available
+
+    if not ref_available():
+        return {"unavailable": "oracle/_ref/libref_oracle.so not built"}
+    r = RefOracle()
+    rng = np.random.default_rng(5)
+    out = {}
+
+    def entry(units, dt, unit, sample):
+        return {"value": units / dt, "unit": unit, "cores": cores, "kind": "reference", "sample": f"{sample} ({dt:.2f} s)"}
+
+    n = 16384
+    ring = r.ring_create(n, Q62)
+    a = rng.integers(0, Q62, size=(4 * cores, n), dtype=np.uint64)
+    b = rng.integers(0, Q62, size=(4 * cores, n), dtype=np.uint64)
+    t0 = time.perf_counter()
+    r.ring_op(ring, "multiply", a, b, threads=cores)
+    out["polymul_n16384_b1024"] = entry(a.shape[0], time.perf_counter() - t0, "polymul/s", f"{a.shape[0]} products, N={n}")
+    r.ring_destroy(ring)
+
+    q2 = np.array([0xFFFFFFFFFFFFFF43, 1], np.uint64)
+    ml = r.mlimb_create(q2)
+    x = rng.integers(0, 2**62, size=(1 << 20, 2), dtype=np.uint64)
+    x[:, 1] &= np.uint64(1)
+    t0 = time.perf_counter()
+    r.mlimb_op(ml, "montmul", x, x[::-1].copy(), threads=cores)
+    out["mlimb2_montmul_n16777216"] = entry(x.shape[0], time.perf_counter() - t0, "montmul/s", f"{x.shape[0]} two-limb products")
+    r.mlimb_destroy(ml)
+
+    N, nl = 1024, 742
+    h = r.boot_create(N, QT, nl, 1, 23, 1, 4)
+    r.boot_import_bsk(h, rng.integers(0, QT, size=(nl, 2, 2, N), dtype=np.uint64))
+    lwe = rng.integers(0, QT, size=(cores, nl + 1), dtype=np.uint64)
+    tp = r.boot_default_test_poly(h)
+    t0 = time.perf_counter()
+    r.boot_blind_rotate(h, lwe, tp, threads=cores)
+    out["bootstrap_tfhe128fast_shape"] = entry(cores, time.perf_counter() - t0, "bootstraps/s",
+                                               f"{cores} blind rotations, one per thread, tfhe-128-fast shape")
+    r.boot_destroy(h)
+
+    ring = r.ring_create(1024, QT)
+    cts = rng.integers(0, QT, size=(8192, 2, 1024), dtype=np.uint64)
+    t0 = time.perf_counter()
+    r.tally(ring, cts)
+    out["tally_n1024"] = dict(entry(cts.shape[0], time.perf_counter() - t0, "ballots/s", f"{cts.shape[0]} ballots, batch_add"), cores=1)
+    r.ring_destroy(ring)
+    return out
