@@ -15,6 +15,7 @@
 #include <cstdint>
 #include <stdexcept>
 #include <string>
+#include <memory>
 #include <vector>
 
 #include "fheb200.h"
@@ -138,6 +139,35 @@ class PolynomialRing {
 
    private:
     NTTProcessor ntt_;
+};
+
+// PolynomialRing(degree, moduli) (polynomial_ring.cpp:224-237) with every limb live: data limb-major
+// [limbs][batch][N], limb l computed over moduli[l] by its own plan.  (The reference's multi-modulus ring only ever
+// computes with moduli[0]; limb 0 here is exactly that.)
+class RnsPolynomialRing {
+   public:
+    RnsPolynomialRing(uint32_t degree, const std::vector<uint64_t>& moduli) : degree_(degree) {
+        if (moduli.empty()) throw std::invalid_argument("At least one modulus required");  // polynomial_ring.cpp:228-230
+        for (uint64_t q : moduli) rings_.emplace_back(new PolynomialRing(degree, q));
+    }
+    size_t limbs() const { return rings_.size(); }
+    const PolynomialRing& limb(size_t l) const { return *rings_[l]; }
+    void to_ntt(const uint64_t* a, uint64_t* r, size_t batch, void* s = nullptr) const {
+        for (size_t l = 0; l < limbs(); ++l) rings_[l]->to_ntt(a + l * batch * degree_, r + l * batch * degree_, batch, s);
+    }
+    void from_ntt(const uint64_t* a, uint64_t* r, size_t batch, void* s = nullptr) const {
+        for (size_t l = 0; l < limbs(); ++l) rings_[l]->from_ntt(a + l * batch * degree_, r + l * batch * degree_, batch, s);
+    }
+    void add(const uint64_t* a, const uint64_t* b, uint64_t* r, size_t batch, void* s = nullptr) const {
+        for (size_t l = 0; l < limbs(); ++l) rings_[l]->add(a + l * batch * degree_, b + l * batch * degree_, r + l * batch * degree_, batch, s);
+    }
+    void multiply(const uint64_t* a, const uint64_t* b, uint64_t* c, size_t batch, void* s = nullptr) const {
+        for (size_t l = 0; l < limbs(); ++l) rings_[l]->multiply(a + l * batch * degree_, b + l * batch * degree_, c + l * batch * degree_, batch, s);
+    }
+
+   private:
+    uint32_t degree_;
+    std::vector<std::unique_ptr<PolynomialRing>> rings_;
 };
 
 // EvaluationKey.relin_key on the device (cpp/include/key_manager.h:92-111), pre-transformed once.

@@ -290,6 +290,53 @@ class PolynomialRing:
         return out
 
 
+class RnsPolynomialRing:
+    """PolynomialRing(degree, moduli) (cpp/src/polynomial_ring.cpp:224-237) with a real residue-number-system meaning.
+
+    The reference builds one NTTProcessor per modulus but every method then computes with moduli[0] only
+    (polynomial_ring.cpp:245-539), so its modulus chains (bfv-128-simd, ckks-128-ml: parameter_set.cpp:193-259) are
+    inert.  Here every limb is live: data are limb-major `[limbs][batch][N]`, limb l is an ordinary batch over
+    moduli[l] run by that modulus's plan (same kernels, one launch per limb and method).  Limb 0 of every method is
+    exactly the reference's result; the other limbs are the same reference method over their own modulus."""
+
+    def __init__(self, degree: int, moduli: Sequence[int]):
+        if len(moduli) == 0:
+            raise FheError(_cabi.INVALID_PARAMETERS, "At least one modulus required")  # polynomial_ring.cpp:228-230
+        self.degree, self.moduli = degree, [int(m) for m in moduli]
+        self.rings = [PolynomialRing(degree, m) for m in self.moduli]
+
+    def _each(self, name, *operands, out=None):
+        ops = [as_words(o) for o in operands]
+        limbs = len(self.rings)
+        if any(o.shape[0] != limbs or o.shape[-1] != self.degree for o in ops):
+            raise FheError(_cabi.INVALID_PARAMETERS, "operands must be [limbs][batch][N] with one limb per modulus")
+        out = _like(ops[0]) if out is None else out
+        for l, ring in enumerate(self.rings):
+            getattr(ring, name)(*[o[l] for o in ops], out=out[l])
+        return out
+
+    def add(self, a, b, out=None):
+        return self._each("add", a, b, out=out)
+
+    def subtract(self, a, b, out=None):
+        return self._each("subtract", a, b, out=out)
+
+    def negate(self, a, out=None):
+        return self._each("negate", a, out=out)
+
+    def pointwise_multiply(self, a, b, out=None):
+        return self._each("pointwise_multiply", a, b, out=out)
+
+    def to_ntt(self, a, out=None):
+        return self._each("to_ntt", a, out=out)
+
+    def from_ntt(self, a, out=None):
+        return self._each("from_ntt", a, out=out)
+
+    def multiply(self, a, b, out=None):
+        return self._each("multiply", a, b, out=out)
+
+
 class RelinearizationKey:
     """EvaluationKey.relin_key (cpp/include/key_manager.h:92-111) resident on the device, both polynomials of every
     level pre-transformed.  keys = [key_count][2][N]: (a, b) of every pair in generation order."""

@@ -279,6 +279,31 @@ def test_golden_tally(fhe, torch, name):
     eq(ring.tensor_multiply(cts[0:1], cts[2:3])[0], g["tensor"])
 
 
+def test_rns_ring_every_limb_matches_the_oracle(fhe, torch, oracle):
+    """PolynomialRing(degree, moduli): limb 0 is the reference's result (it only ever uses moduli[0]); here every limb
+    of the chain is live and equals the reference method over its own modulus."""
+    n, batch = 4096, 6
+    moduli = [1152921504606584833, Q62, Q50, Q27]  # Q_60_1, the harness prime, Q_50_1 and an FP64-mode prime
+    ring = fhe.RnsPolynomialRing(n, moduli)
+    rng = np.random.default_rng(77)
+    a = np.stack([rng.integers(0, q, size=(batch, n), dtype=np.uint64) for q in moduli])
+    b = np.stack([rng.integers(0, q, size=(batch, n), dtype=np.uint64) for q in moduli])
+    ad, bd = dev(torch, a), dev(torch, b)
+    prod, fwd_, back, summ = host(ring.multiply(ad, bd)), host(ring.to_ntt(ad)), None, host(ring.add(ad, bd))
+    back = host(ring.from_ntt(dev(torch, fwd_)))
+    eq(back, a)
+    for l, q in enumerate(moduli):
+        fwd, inv, _, _, inv_n = oracle.twiddles(n, q)
+        eq(prod[l], oracle.multiply(a[l], b[l], q, fwd, inv, inv_n))
+        eq(fwd_[l], oracle.forward(a[l], q, fwd))
+        eq(summ[l], oracle.add(a[l], b[l], q))
+    with pytest.raises(fhe.FheError) as e:
+        fhe.RnsPolynomialRing(n, [])
+    assert "At least one modulus required" in str(e.value)
+    with pytest.raises(fhe.FheError):
+        fhe.RnsPolynomialRing(n, [Q62, 1099511627777])  # 2^40 + 1 (the tfhe-128-fast preset's modulus) is not NTT friendly
+
+
 # ----------------------------------------------------------------------- relinearisation --
 @pytest.mark.parametrize("name", ["relin_n64.npz", "relin_n1024.npz", "relin_n4096.npz"])
 def test_golden_relinearize(fhe, torch, name):
