@@ -119,6 +119,21 @@ def test_cabi_host_side_wire_functions(oracle, wire):
     assert "Failed to read header" in str(e.value)
 
 
+def test_empty_ballot_is_written_but_never_read_back(oracle, ref):
+    """A ballot without choices serialises to 61 bytes - below sizeof(SerializationHeader) = 64, so the reference's own
+    deserialize_ballot rejects what its serialize_ballot wrote ("Input too small").  Same bytes, same verdict here."""
+    import fheb200
+    from oracle_bindings import RefError
+
+    none = np.zeros((0, 2, 8), np.uint64)
+    rec = ref.serialize_ballot(none, 97, 5)
+    assert len(rec) == 61 and fheb200.serialize_ballot(none, 97, 5) == rec
+    assert oracle.ballot_parse(rec, 0, 8, 97)[0] == 1
+    with pytest.raises(RefError) as e:
+        ref.deserialize_ballot(rec, 8, 97)
+    assert "Input too small" in str(e.value)
+
+
 # ------------------------------------------------------------------------------- GPU --
 @pytest.fixture(scope="module")
 def fhe():
