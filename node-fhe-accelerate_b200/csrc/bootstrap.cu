@@ -4,6 +4,8 @@
 // C-ABI entry points here (include/fheb200.h): fheb_boot_key_create, fheb_boot_key_set_ksk,
 // fheb_boot_key_destroy, fheb_external_product_batch, fheb_cmux_batch, fheb_blind_rotate_batch,
 // fheb_sample_extract_batch, fheb_key_switch_batch, fheb_bootstrap_batch, fheb_make_test_poly.
+#include <type_traits>
+
 #include "boot_kernel.cuh"
 #include "elementwise.hpp"
 #include "ntt_plan.hpp"
@@ -68,7 +70,7 @@ __global__ void __launch_bounds__(256) sample_extract_kernel(const uint64_t* __r
 }
 
 // ---- key switching (cpp/src/bootstrap_engine.cpp:626-669) -------------------------------------
-// out[j] = (0 - sum_idx t(idx, j)) mod q with t = ((digit_idx * ksk[idx][j]) mod 2^64) % q and
+// out[j] = (0 - sum_idx t(idx, j)) mod q with t = ((digit_idx * ksk[idx][j]) mod 2^64) % q (summed unreduced, see below) and
 // digit_idx the low-bit digit of input coefficient idx / levels; the reference's running
 // `(res + q - t) % q` is this sum in any order.  The b word starts from the input's b instead of 0.
 // Block: KS_COLS output columns x KS_CTS ciphertexts; digits of the block's ciphertexts are staged
@@ -77,19 +79,25 @@ constexpr int KS_COLS = 128;
 constexpr int KS_CTS = 8;
 constexpr int KS_CHUNK = 512;
 
+// SMALL: digits below 2^32 (base_log <= 32) are kept as 32-bit words: the product is one wide and one narrow multiply
+template <bool SMALL>
 __global__ void __launch_bounds__(KS_COLS) key_switch_kernel(const uint64_t* __restrict__ lwe, const uint64_t* __restrict__ ksk,
                                                              uint64_t* __restrict__ out, size_t batch, uint32_t dim_in,
                                                              uint32_t n_out, uint32_t base_log, uint32_t levels, const ModQ m) {
-    __shared__ uint64_t digits[KS_CTS][KS_CHUNK];
+    using Dig = typename std::conditional<SMALL, uint32_t, uint64_t>::type;
+    __shared__ Dig digits[KS_CTS][KS_CHUNK];
     const uint32_t col = blockIdx.x * KS_COLS + threadIdx.x;
     const size_t ct0 = (size_t)blockIdx.y * KS_CTS;
     const uint32_t ncts = (uint32_t)((batch - ct0) < (size_t)KS_CTS ? (batch - ct0) : (size_t)KS_CTS);
     const size_t in_w = (size_t)dim_in + 1, out_w = (size_t)n_out + 1;
     const uint64_t mask = (base_log >= 64) ? ~0ull : ((1ull << base_log) - 1);
     const size_t entries = (size_t)dim_in * levels;
-    uint64_t acc[KS_CTS];
+    // sum_e (x_e % q) == (sum_e x_e) % q for the wrapped 64-bit products x_e = digit * ksk mod 2^64: the raw products are
+    // summed in a 128-bit counter per ciphertext and reduced once (one multiply per term instead of a Barrett
+    // reduction per term; exact for any number of terms)
+    uint64_t lo[KS_CTS], hi[KS_CTS];
 #pragma unroll
-    for (int c = 0; c < KS_CTS; ++c) acc[c] = 0;
+    for (int c = 0; c < KS_CTS; ++c) lo[c] = hi[c] = 0;
     for (size_t e0 = 0; e0 < entries; e0 += KS_CHUNK) {
         const uint32_t chunk = (uint32_t)((entries - e0) < (size_t)KS_CHUNK ? (entries - e0) : (size_t)KS_CHUNK);
         __syncthreads();
@@ -101,7 +109,7 @@ __global__ void __launch_bounds__(KS_COLS) key_switch_kernel(const uint64_t* __r
                 const uint32_t i = (uint32_t)(idx / levels), l = (uint32_t)(idx % levels);
                 d = (lwe[(ct0 + c) * in_w + i] >> ((levels - 1 - l) * base_log)) & mask;
             }
-            digits[c][e] = d;
+            digits[c][e] = (Dig)d;
         }
         __syncthreads();
         if (col < out_w) {
@@ -111,9 +119,7 @@ __global__ void __launch_bounds__(KS_COLS) key_switch_kernel(const uint64_t* __r
                 const uint64_t kv = __ldg(kp + (size_t)e * out_w);
 #pragma unroll
                 for (int c = 0; c < KS_CTS; ++c) {
-                    const uint64_t d = digits[c][e];  // zero digits contribute nothing (:654-657)
-                    const uint64_t t = reduce64(d * kv, m);
-                    acc[c] = csub(acc[c] + t, m.q);
+                    acc128(lo[c], hi[c], (uint64_t)digits[c][e] * kv);  // zero digits contribute nothing (:654-657)
                 }
             }
         }
@@ -122,7 +128,7 @@ __global__ void __launch_bounds__(KS_COLS) key_switch_kernel(const uint64_t* __r
         for (uint32_t c = 0; c < ncts; ++c) {
             uint64_t start = 0;
             if (col == n_out) start = canon_any(lwe[(ct0 + c) * in_w + dim_in], m);
-            out[(ct0 + c) * out_w + col] = submod_canon(start, acc[c], m.q);
+            out[(ct0 + c) * out_w + col] = submod_canon(start, fold128(hi[c], lo[c], m), m.q);
         }
     }
 }
@@ -193,8 +199,12 @@ static int sample_extract_device(const BootKey* key, const uint64_t* glwe, uint6
 static int key_switch_device(const BootKey* key, const uint64_t* lwe, uint64_t* out, size_t batch, cudaStream_t s) {
     const uint32_t dim_in = key->k * key->plan->degree;
     const dim3 grid((key->ksk_n_out + 1 + KS_COLS - 1) / KS_COLS, (unsigned)((batch + KS_CTS - 1) / KS_CTS));
-    key_switch_kernel<<<grid, KS_COLS, 0, s>>>(lwe, key->d_ksk, out, batch, dim_in, key->ksk_n_out, key->ksk_base_log,
-                                               key->ksk_levels, key->plan->mod);
+    if (key->ksk_base_log <= 32)
+        key_switch_kernel<true><<<grid, KS_COLS, 0, s>>>(lwe, key->d_ksk, out, batch, dim_in, key->ksk_n_out, key->ksk_base_log,
+                                                         key->ksk_levels, key->plan->mod);
+    else
+        key_switch_kernel<false><<<grid, KS_COLS, 0, s>>>(lwe, key->d_ksk, out, batch, dim_in, key->ksk_n_out, key->ksk_base_log,
+                                                          key->ksk_levels, key->plan->mod);
     FHEB_CHECK_LAUNCH();
     count_launch();
     return FHEB_OK;
