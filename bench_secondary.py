@@ -197,12 +197,27 @@ def run_bootstrap(fhe, torch, dist, world, rank, dev, barrier, max_over_ranks, b
     e1.record()
     barrier()
     ms = max_over_ranks(e0.elapsed_time(e1)) / iters
+    # the full chain of BootstrapEngine::bootstrap with a key switching key (synthetic, the preset's gadget: one level)
+    ksk = torch.randint(0, q, (k * N * level, n + 1), dtype=torch.int64, device=dev, generator=gen)
+    eng.set_key_switch_key(ksk, n, base_log, level)
+    out_ks = torch.empty((batch, n + 1), dtype=torch.int64, device=dev)
+    eng.bootstrap(lwe[:256], tp, out=out_ks[:256])
+    barrier()
+    k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    k0.record()
+    for _ in range(iters):
+        eng.bootstrap(lwe, tp, out=out_ks)
+    k1.record()
+    barrier()
+    ms_ks = max_over_ranks(k0.elapsed_time(k1)) / iters
     # integer work actually executed per bootstrap: n steps x ((k+1)L forward + (k+1) inverse transforms of
     # (N/2) log2 N butterflies + (k+1)^2 L N multiply-accumulates)
     bfly = n * ((k + 1) * level + (k + 1)) * (N // 2) * 10
     macs = n * (k + 1) * (k + 1) * level * N
     return {"value": world * batch / (ms * 1e-3), "unit": "bootstraps/s", "ms": ms, "batch_per_gpu": batch, "n_gpus": world,
             "shape": f"N={N} k={k} n={n} base_log={base_log} L={level} q={q}",
+            "with_key_switch": {"value": world * batch / (ms_ks * 1e-3), "unit": "bootstraps/s", "ms": ms_ks,
+                                "note": "blind rotation + sample extraction + key switching (one level)"},
             "modmul_per_bootstrap": bfly + macs,
             "gmodmul_per_s_per_gpu": (bfly + macs) * batch / (ms * 1e-3) / 1e9,
             # FP64-pipe roofline: 8 DP operations per butterfly, 7 per multiply-accumulate, ~9 per coefficient
