@@ -10,6 +10,7 @@
 // C-ABI entry points here (include/fheb200.h): fheb_tally, fheb_tally_combine,
 // fheb_tensor_multiply_batch, fheb_synth_ballots.
 #include <cstdlib>
+#include <map>
 
 #include "elementwise.hpp"
 #include "modarith.cuh"
@@ -211,18 +212,23 @@ __global__ void __launch_bounds__(256) synth_ballots_kernel(uint64_t* out, size_
 // on different streams at once.
 constexpr unsigned TALLY_SLOTS = 64, TALLY_MAX_CHUNKS = 256;
 static unsigned* tally_counters() {
-    static unsigned* pool = nullptr;
+    static std::map<int, unsigned*> pools;  // one pool per device the library has been pointed at
     static std::atomic<unsigned> next{0};
     static std::mutex mu;
+    unsigned* pool = nullptr;
     {
         std::lock_guard<std::mutex> lock(mu);
-        if (!pool) {
-            if (cudaMalloc(&pool, (size_t)TALLY_SLOTS * TALLY_MAX_CHUNKS * sizeof(unsigned)) != cudaSuccess ||
-                cudaMemset(pool, 0, (size_t)TALLY_SLOTS * TALLY_MAX_CHUNKS * sizeof(unsigned)) != cudaSuccess) {
+        const int dev = ctx().device;
+        auto it = pools.find(dev);
+        if (it == pools.end()) {
+            const size_t bytes = (size_t)TALLY_SLOTS * TALLY_MAX_CHUNKS * sizeof(unsigned);
+            if (cudaMalloc(&pool, bytes) != cudaSuccess || cudaMemset(pool, 0, bytes) != cudaSuccess) {
                 cudaGetLastError();
-                pool = nullptr;
                 return nullptr;  // falls back to the two-launch form
             }
+            pools[dev] = pool;
+        } else {
+            pool = it->second;
         }
     }
     return pool + (size_t)(next.fetch_add(1) % TALLY_SLOTS) * TALLY_MAX_CHUNKS;
