@@ -141,6 +141,32 @@ class PolynomialRing {
     NTTProcessor ntt_;
 };
 
+// Sharded tally over the GPUs of one box with the exchange fused into the tally kernel (one process per GPU):
+// create on every rank, exchange handle() bytes by any transport, connect(), then run() per batch gives the global
+// tally on every rank in one launch.  See fheb_tally_peers_* in fheb200.h.
+class ShardedTallyPeers {
+   public:
+    ShardedTallyPeers(uint32_t degree, uint64_t modulus, uint32_t world, uint32_t rank) {
+        check(fheb_tally_peers_create(degree, modulus, world, rank, &peers_, handle_));
+    }
+    ~ShardedTallyPeers() { fheb_tally_peers_destroy(peers_); }
+    ShardedTallyPeers(const ShardedTallyPeers&) = delete;
+    ShardedTallyPeers& operator=(const ShardedTallyPeers&) = delete;
+    const uint8_t* handle() const { return handle_; }  // FHEB_PEER_HANDLE_BYTES bytes to send to every peer
+    void connect(const uint8_t* all_handles /* [world][FHEB_PEER_HANDLE_BYTES], rank order */) { check(fheb_tally_peers_connect(peers_, all_handles)); }
+    // local_cts = this rank's ballots [count][2][N] (device); out = [2][N] (device): the global tally
+    void run(const uint64_t* local_cts, size_t count, uint64_t* out, void* s = nullptr) { check(fheb_tally_peers_run(peers_, local_cts, count, out, s)); }
+    bool timed_out() const {
+        int v = 0;
+        check(fheb_tally_peers_status(peers_, &v));
+        return v != 0;
+    }
+
+   private:
+    fheb_tally_peers* peers_ = nullptr;
+    uint8_t handle_[FHEB_PEER_HANDLE_BYTES] = {};
+};
+
 // PolynomialRing(degree, moduli) (polynomial_ring.cpp:224-237) with every limb live: data limb-major
 // [limbs][batch][N], limb l computed over moduli[l] by its own plan.  (The reference's multi-modulus ring only ever
 // computes with moduli[0]; limb 0 here is exactly that.)
