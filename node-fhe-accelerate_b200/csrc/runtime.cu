@@ -174,27 +174,7 @@ int run_host_pipeline(size_t items, std::vector<PipeArg> args, const PipeFn& fn,
     size_t chunk = chunk_items ? chunk_items : chunk_bytes / max_stride;
     if (chunk < 1) chunk = 1;
     if (chunk > items) chunk = items;
-    // Chunk schedule: full-size chunks in the middle, geometrically smaller ones at both ends, so that the time before
-    // the first kernel can start (one copy-in) and after the last one ends (one copy-out) is that of a small chunk.
-    std::vector<size_t> sizes;
-    {
-        const bool ramp = chunk_items == 0 && chunk >= 16 && items > 2 * chunk;
-        std::vector<size_t> head;
-        size_t used = 0;
-        if (ramp)
-            for (size_t c = chunk / 8; c < chunk && used + 2 * c + chunk <= items; c *= 2) {
-                head.push_back(c);
-                used += 2 * c;  // mirrored at the tail
-            }
-        sizes = head;
-        size_t left = items - used;
-        while (left > 0) {
-            const size_t c = left < chunk ? left : chunk;
-            sizes.push_back(c);
-            left -= c;
-        }
-        for (size_t i = head.size(); i-- > 0;) sizes.push_back(head[i]);
-    }
+    const std::vector<size_t> sizes = pipeline_chunk_sizes(items, chunk, chunk_items == 0);
     const size_t nchunks = sizes.size();
     const int slots = (int)(nchunks < (size_t)SLOTS ? nchunks : (size_t)SLOTS);
 

@@ -103,6 +103,33 @@ struct PipeArg {
     bool in, out;       // copied to the device before / back to the host after the chunk's kernels
 };
 using PipeFn = std::function<int(void* const* dev, size_t first_item, size_t n_items, cudaStream_t s)>;
+// Chunk schedule of the pipeline (pure host logic, unit-tested on the CPU): full-size chunks in the middle,
+// geometrically smaller ones (chunk/8, chunk/4, chunk/2) mirrored at both ends when `ramp` is set and there is room,
+// so that the time before the first kernel can start (one copy-in) and after the last one ends (one copy-out) is
+// that of a small chunk.  The sizes are positive, none exceeds `chunk`, and they sum to `items`.
+inline std::vector<size_t> pipeline_chunk_sizes(size_t items, size_t chunk, bool ramp) {
+    std::vector<size_t> sizes;
+    if (items == 0) return sizes;
+    if (chunk < 1) chunk = 1;
+    if (chunk > items) chunk = items;
+    std::vector<size_t> head;
+    size_t used = 0;
+    if (ramp && chunk >= 16 && items > 2 * chunk)
+        for (size_t c = chunk / 8; c < chunk && used + 2 * c + chunk <= items; c *= 2) {
+            head.push_back(c);
+            used += 2 * c;  // mirrored at the tail
+        }
+    sizes = head;
+    size_t left = items - used;
+    while (left > 0) {
+        const size_t c = left < chunk ? left : chunk;
+        sizes.push_back(c);
+        left -= c;
+    }
+    for (size_t i = head.size(); i-- > 0;) sizes.push_back(head[i]);
+    return sizes;
+}
+
 bool all_host(std::initializer_list<const void*> ptrs);  // true when no non-null pointer is device memory
 int run_host_pipeline(size_t items, std::vector<PipeArg> args, const PipeFn& fn, size_t chunk_items = 0 /* 0: ~16 MB per buffer */);
 
