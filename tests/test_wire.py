@@ -134,6 +134,59 @@ def test_empty_ballot_is_written_but_never_read_back(oracle, ref):
     assert "Input too small" in str(e.value)
 
 
+def test_speculative_checksum_schedule_is_exact():
+    """The warp-parallel schedule of ballot_validate_kernel (csrc/wire.cu) restated lane by lane: 32 slices, start
+    states guessed from `warmup` bytes run from state 0, neighbour checks, repair rounds until every check holds.
+    Whatever the guesses are worth, the end state must be the serial checksum's (the table is not linear, so this is
+    a property of the schedule, not of the CRC)."""
+    table = [0] * 256
+    for i in range(60):
+        c = i
+        for _ in range(8):
+            c = (0xEDB88320 ^ (c >> 1)) if c & 1 else c >> 1
+        table[i] = c
+
+    def run(state, data):
+        for b in data:
+            state = table[(state ^ b) & 0xFF] ^ (state >> 8)
+        return state
+
+    rng = np.random.default_rng(2024)
+    total_rounds = 0
+    for trial in range(120):
+        n = int(rng.integers(4096, 9000))
+        kind = trial % 3
+        if kind == 0:
+            data = rng.integers(0, 256, size=n, dtype=np.uint8)
+        elif kind == 1:   # 62-bit residues: the slowest to forget the start state
+            data = rng.integers(0, 4611686018326724609, size=n // 8 + 1, dtype=np.uint64).view(np.uint8)[:n]
+        else:             # low bytes only: long stretches of table entries below 60
+            data = rng.integers(0, 60, size=n, dtype=np.uint8)
+        data = [int(x) for x in data]
+        warmup = (0, 8, 128)[trial % 3 if trial >= 60 else 2]
+        chunk = (n + 31) // 32
+        lo = [min(k * chunk, n) for k in range(32)]
+        hi = [min(l + chunk, n) for l in lo]
+        warm = [0 if l < warmup else l - warmup for l in lo]
+        a = [run(0xFFFFFFFF if warm[k] == 0 else 0, data[warm[k]:lo[k]]) for k in range(32)]
+        e = [run(a[k], data[lo[k]:hi[k]]) for k in range(32)]
+        rounds = 0
+        while True:
+            ok = [k == 0 or (warm[k] == 0 and warmup != 0) or e[k - 1] == a[k] for k in range(32)]
+            if all(ok):
+                break
+            prev = list(e)
+            for k in range(32):
+                if not ok[k]:
+                    a[k] = prev[k - 1]
+                    e[k] = run(a[k], data[lo[k]:hi[k]])
+            rounds += 1
+            assert rounds <= 32
+        total_rounds += rounds
+        assert e[31] == run(0xFFFFFFFF, data), (trial, warmup)
+    assert total_rounds > 0  # the forced-miss trials (warmup 0 and 8) did exercise the repair rounds
+
+
 # ------------------------------------------------------------------------------- GPU --
 @pytest.fixture(scope="module")
 def fhe():
