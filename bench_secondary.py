@@ -33,6 +33,54 @@ def _hbm(peak, algo_bytes, ms):
     return {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak}
 
 
+def _hash64(t):
+    """FNV-1a over ALL result words (as 64-bit units), so that equal hashes across N mean equal tallies."""
+    h = 0xCBF29CE484222325
+    for w in t.detach().cpu().numpy().view(np.uint64).reshape(-1).tolist():
+        h = ((h ^ w) * 0x100000001B3) & 0xFFFFFFFFFFFFFFFF
+    return h
+
+
+def _tally_parity(fhe, torch, dist, world, rank, dev, n, q, per_rank=65536):
+    """Parity of the SHARDED tally where the driver runs it: every rank tallies a 65 536-ballot slice of synthetic
+    ballots through the same ShardedTally path as the timed loop (fused peer exchange when world > 1) and the result
+    is compared, all 2N words, with the CPU oracle's tally of per-chunk oracle tallies (each rank folds its own slice
+    with the oracle, the per-rank oracle tallies are gathered and folded by the oracle again).  The oracle is the
+    checker here, outside every timed region."""
+    import os
+    import sys
+
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "tests"))
+    try:
+        from oracle_bindings import Oracle
+
+        orc = Oracle()
+    except Exception as exc:  # the oracle is test infrastructure: say so rather than fail the bench
+        return {"parity_vs_oracle": None, "parity_note": f"oracle unavailable: {exc}"}
+    cts = torch.empty((per_rank, 2, n), dtype=torch.int64, device=dev)
+    fhe.synth_ballots(cts, (1 << 30) + rank * per_rank, per_rank, n, q, 0x0B200)
+    st = fhe.ShardedTally(n, q)
+    got = None
+    for _ in range(2):  # both inbox parities
+        got = st.tally(cts)
+    torch.cuda.synchronize()
+    host = cts.cpu().numpy().view(np.uint64)
+    mine = np.stack([orc.tally(host[i:i + 8192], q) for i in range(0, per_rank, 8192)])
+    mine = orc.tally(mine, q)
+    if world > 1:
+        parts = [torch.empty((2, n), dtype=torch.int64, device=dev) for _ in range(world)]
+        dist.all_gather(parts, torch.from_numpy(mine.view(np.int64)).to(dev))
+        exp = orc.tally(np.stack([p.cpu().numpy().view(np.uint64) for p in parts]), q)
+    else:
+        exp = mine
+    ok = bool(np.array_equal(got.cpu().numpy().view(np.uint64), exp))
+    flag = torch.tensor([int(ok)], dtype=torch.int32, device=dev)
+    if world > 1:
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+    return {"parity_vs_oracle": bool(flag.item() == 1),
+            "parity_note": f"{per_rank} ballots per rank through the timed path, all {2 * n} words vs the CPU oracle on every rank"}
+
+
 def run(fhe, torch, dist, world, rank, dev, barrier, max_over_ranks, peak):
     out = {}
     gen = torch.Generator(device=dev).manual_seed(99 + rank)
@@ -127,7 +175,10 @@ def run(fhe, torch, dist, world, rank, dev, barrier, max_over_ranks, peak):
                                        "NCCL all-gather + combine kernel"),
                           "roofline": dict(_hbm(peak, 16384.0 * per_rank, ms),
                                            note="peak = the measured COPY bandwidth (read + write); a read-only stream can exceed it"),
-                          "checksum": int(res[0].view(-1)[:4].sum().item() & 0xFFFFFFFF)}
+                          "hash64": _hash64(res[0])}
+    out["tally_n1024"].update(_tally_parity(fhe, torch, dist, world, rank, dev, n, QT))
+    if hasattr(st, "check"):
+        st.check()  # raises when an exchange of the timed loop timed out
     del cts
 
     # ---- N4: multiply -> relinearize chain (tensor product + relinearisation with a pre-transformed key)

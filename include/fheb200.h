@@ -63,6 +63,15 @@ typedef struct fheb_relin_key fheb_relin_key; /* replaces EvaluationKey.relin_ke
 /* replaces initialize(): src/native/lib.rs:23-30.  device < 0 selects the current device. */
 FHEB_API int fheb_init(int device);
 FHEB_API int fheb_shutdown(void);
+/* One process, several GPUs (the reference's addon is a single Node process: src/native/lib.rs:23-133).  After
+ * fheb_set_devices every entry point whose batch lives in HOST memory (transforms, products, blind rotation,
+ * bootstrap, tally) splits the batch into contiguous shares, one per device, each copied and computed on its own
+ * GPU over its own PCIe link by its own host thread; plans and keys are replicated on a device on first use.
+ * Calls on DEVICE buffers run where the buffers live (make that device current first).  count < 0 selects every
+ * visible device; devices == NULL selects 0..count-1; count == 0 or 1 turns spreading off.
+ * fheb_get_devices returns the number configured (and fills out[0..capacity)). */
+FHEB_API int fheb_set_devices(const int* devices, int count);
+FHEB_API int fheb_get_devices(int* out, int capacity);
 /* replaces version(): src/native/lib.rs:129-133 */
 FHEB_API const char* fheb_version(void);
 FHEB_API const char* fheb_last_error(void);
@@ -262,7 +271,9 @@ FHEB_API int fheb_tally_combine(const uint64_t* partials, size_t parts, uint32_t
  * flag, waits for the peers' flags and sums the rows.  Set-up: every rank creates its handle (which exports a
  * 64-byte IPC handle), the ranks exchange those bytes by any means (the Python mirror uses one torch.distributed
  * all-gather), then connect.  run() must be called by all ranks the same number of times (each call is one
- * epoch); a rank that never arrives makes its peers give up after ~17 s and sets the status flag. */
+ * epoch; the epoch advances only when the launch succeeded).  A rank that never arrives makes its peers give up
+ * after the timeout (~17 s unless set): the result words of that call become all-ones (never a residue), the
+ * host-mapped status word records the failing epoch, and every later run() on the handle fails until reset. */
 typedef struct fheb_tally_peers fheb_tally_peers;
 #define FHEB_PEER_HANDLE_BYTES 64
 FHEB_API int fheb_tally_peers_create(uint32_t degree, uint64_t modulus, uint32_t world, uint32_t rank, fheb_tally_peers** out,
@@ -270,8 +281,26 @@ FHEB_API int fheb_tally_peers_create(uint32_t degree, uint64_t modulus, uint32_t
 FHEB_API int fheb_tally_peers_connect(fheb_tally_peers* peers, const uint8_t* handles /* [world][FHEB_PEER_HANDLE_BYTES], rank order */);
 /* cts = this rank's ballots [count][2][N] (device), out = [2][N] (device): the GLOBAL tally, on every rank */
 FHEB_API int fheb_tally_peers_run(fheb_tally_peers* peers, const uint64_t* cts, size_t count, uint64_t* out, void* stream);
-FHEB_API int fheb_tally_peers_status(const fheb_tally_peers* peers, int* timed_out); /* synchronises */
+/* timed_out = epoch of the first exchange that timed out, 0 if none.  Reads a host-mapped word: no copy and no
+ * synchronisation; call it after synchronising the stream to learn about the calls issued so far. */
+FHEB_API int fheb_tally_peers_status(const fheb_tally_peers* peers, int* timed_out);
+FHEB_API uint32_t fheb_tally_peers_epoch(const fheb_tally_peers* peers); /* calls launched so far */
+/* After a failure: all ranks synchronise, agree on an unused epoch (e.g. max over ranks of _epoch() + 2), reset. */
+FHEB_API int fheb_tally_peers_reset(fheb_tally_peers* peers, uint32_t epoch);
+FHEB_API int fheb_tally_peers_set_timeout(fheb_tally_peers* peers, double seconds);
 FHEB_API int fheb_tally_peers_destroy(fheb_tally_peers* peers);
+
+/* The same sharded tally driven from ONE process that owns several GPUs (the reference's addon is a single Node
+ * process: src/native/lib.rs:23-133).  The group enables peer access between its devices; fheb_tally_sharded
+ * launches the fused kernel on every device from the calling thread and returns when the global tally is in `out`.
+ * replaces EncryptionEngine::tally_votes over sharded ballots: cpp/src/encryption.cpp:1061-1067,1327-1458.
+ * devices = NULL selects devices 0..ndev-1.  cts[i] = counts[i] ballots [count][2][N] in the memory of device i of
+ * the group (counts may be zero for some, not all, devices); out = [2][N], host memory or any device's memory. */
+typedef struct fheb_tally_group fheb_tally_group;
+FHEB_API int fheb_tally_group_create(uint32_t degree, uint64_t modulus, const int* devices, uint32_t ndev, fheb_tally_group** out);
+FHEB_API int fheb_tally_sharded(fheb_tally_group* group, const uint64_t* const* cts, const size_t* counts, uint64_t* out);
+FHEB_API uint32_t fheb_tally_group_size(const fheb_tally_group* group);
+FHEB_API int fheb_tally_group_destroy(fheb_tally_group* group);
 
 /* Streaming tally: replaces the running accumulator of
  * CiphertextStreamProcessor::stream_add (cpp/src/streaming_processor.cpp:460-526) and the accumulate path

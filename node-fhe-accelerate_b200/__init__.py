@@ -10,4 +10,4 @@ from .api import (  # noqa: F401
     launch_count, modadd_batch, modmul_batch, modmul_scalar_batch, modneg_batch, modsub_batch, synchronize,
     ingest_ballots, serialize_ballot, synth_ballots, tally_combine, tally_noise_budget, tally_votes, tally_wire, version, wire_crc32, wire_header,
 )
-from .sharded import ShardedTally, shard_range  # noqa: F401
+from .sharded import ShardedTally, TallyGroup, shard_range  # noqa: F401

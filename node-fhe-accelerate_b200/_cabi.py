@@ -55,6 +55,8 @@ u32, u64, sz, p, i = C.c_uint32, C.c_uint64, C.c_size_t, C.c_void_p, C.c_int
 SIGNATURES = {
     "fheb_init": ([i], i),
     "fheb_shutdown": ([], i),
+    "fheb_set_devices": ([p, i], i),
+    "fheb_get_devices": ([p, i], i),
     "fheb_version": ([], C.c_char_p),
     "fheb_last_error": ([], C.c_char_p),
     "fheb_device_info_get": ([p], i),
@@ -107,7 +109,14 @@ SIGNATURES = {
     "fheb_tally_peers_connect": ([p, p], i),
     "fheb_tally_peers_run": ([p, p, sz, p, p], i),
     "fheb_tally_peers_status": ([p, p], i),
+    "fheb_tally_peers_epoch": ([p], u32),
+    "fheb_tally_peers_reset": ([p, u32], i),
+    "fheb_tally_peers_set_timeout": ([p, C.c_double], i),
     "fheb_tally_peers_destroy": ([p], i),
+    "fheb_tally_group_create": ([u32, u64, p, u32, p], i),
+    "fheb_tally_sharded": ([p, p, p, p], i),
+    "fheb_tally_group_size": ([p], u32),
+    "fheb_tally_group_destroy": ([p], i),
     "fheb_tally_stream_create": ([u32, u64, p], i),
     "fheb_tally_stream_add": ([p, p, sz, p], i),
     "fheb_tally_stream_total": ([p, p, p], i),

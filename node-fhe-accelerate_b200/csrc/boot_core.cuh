@@ -289,11 +289,24 @@ FHEB_HD void boot_phase(uint32_t tid, uint32_t nthreads, const BootStep& s, cons
 
 // Rotation amounts of blind_rotate (cpp/src/bootstrap_engine.cpp:558,564): wrapping u64 product,
 // truncation to int32, sign applied before the normalisation of rotate_polynomial.
-FHEB_HD uint32_t lwe_rotation(uint64_t word, bool negate, uint32_t N, uint64_t q) {
+FHEB_HD int32_t lwe_rotation_raw(uint64_t word, bool negate, uint32_t N, uint64_t q) {
     const uint64_t scaled = (word * 2ull * (uint64_t)N + q / 2) / q;
     int32_t r = (int32_t)(uint32_t)scaled;
     if (negate) r = (int32_t)(0u - (uint32_t)r);
-    return normalise_rotation(r, N);
+    return r;
+}
+FHEB_HD uint32_t lwe_rotation(uint64_t word, bool negate, uint32_t N, uint64_t q) {
+    return normalise_rotation(lwe_rotation_raw(word, negate, N, q), N);
+}
+// The reference skips a step on the RAW int32 rotation being zero (:564-566), before rotate_polynomial normalises it.
+// A raw rotation that is a non-zero multiple of 2N (a_i >= q - q/4N rounds up to 2N) therefore still executes a CMux
+// with ct1 = X^0 * acc: diff = 0, product = 0, and `product + ct0` leaves the accumulator CANONICALISED (:533-537).
+// Encoded for the kernel as the value 2N (step code masks it to rotation 0): such a step must run while the
+// accumulator may still hold unreduced caller words and is the identity afterwards.
+FHEB_HD uint32_t lwe_step_rotation(uint64_t word, uint32_t N, uint64_t q) {
+    const int32_t raw = lwe_rotation_raw(word, false, N, q);
+    const uint32_t rot = normalise_rotation(raw, N);
+    return (rot == 0 && raw != 0) ? 2u * N : rot;
 }
 
 // sample_extract (cpp/src/bootstrap_engine.cpp:594-624): word idx of the LWE [k*N + 1] extracted from glwe

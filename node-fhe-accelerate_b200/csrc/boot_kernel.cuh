@@ -115,7 +115,7 @@ __global__ void __launch_bounds__(BootGeometry<L>::LB_THREADS, BootGeometry<L>::
         if (a.mode == BOOT_BLIND) {
             if (valid) {
                 const uint64_t* lwe = a.in0 + ct * ((size_t)a.n + 1);
-                for (uint32_t i = tid; i < a.n; i += TPC) rots[i] = lwe_rotation(lwe[i], false, N, a.m.q);
+                for (uint32_t i = tid; i < a.n; i += TPC) rots[i] = lwe_step_rotation(lwe[i], N, a.m.q);
                 // acc = X^(-round(b * 2N / q)) * (0, .., 0, test_poly): multiply_glwe_by_monomial, :558-559
                 const uint32_t rb = lwe_rotation(lwe[a.n], true, N, a.m.q);
                 for (uint32_t i = tid; i < GW; i += TPC) {
@@ -152,8 +152,11 @@ __global__ void __launch_bounds__(BootGeometry<L>::LB_THREADS, BootGeometry<L>::
             bool active = valid;
             if (a.mode == BOOT_BLIND) {
                 const uint32_t rot = valid ? rots[i] : 0u;
-                active = rot != 0;  // :566 - a zero rotation skips the CMux (uniform per ciphertext)
-                s.rot = rot;
+                // :564-566 - a zero RAW rotation skips the CMux (uniform per ciphertext).  rot == 2N marks a raw rotation
+                // that is a non-zero multiple of 2N: the reference runs a CMux with diff = 0, whose only effect is to
+                // canonicalise the accumulator - the identity once every word is canonical (maybe_raw == 0)
+                active = (rot & (2u * N - 1u)) != 0 || (rot != 0 && s.maybe_raw != 0);
+                s.rot = rot & (2u * N - 1u);
                 s.ggsw = reinterpret_cast<const Tw*>(reinterpret_cast<const char*>(a.bsk) + (size_t)i * ggsw_words * (DP ? 8 : 16));
             }
             boot_run_step<L, DP, KP1, RAWOK>(active, tid, TPC, s, a);

@@ -127,8 +127,34 @@ __global__ void __launch_bounds__(KS_COLS) key_switch_kernel(const uint64_t* __r
     if (col < out_w) {
         for (uint32_t c = 0; c < ncts; ++c) {
             uint64_t start = 0;
-            if (col == n_out) start = canon_any(lwe[(ct0 + c) * in_w + dim_in], m);
-            out[(ct0 + c) * out_w + col] = submod_canon(start, fold128(hi[c], lo[c], m), m.q);
+            const uint64_t total = fold128(hi[c], lo[c], m);
+            if (col == n_out) {
+                const uint64_t* in = lwe + (ct0 + c) * in_w;
+                const uint64_t b = in[dim_in];
+                start = b;
+                if (b >= m.q) {
+                    // Unreduced b (:640,665): the reference keeps lwe.b RAW until the first non-zero digit, whose update
+                    // `(b + q - t1) % q` is computed in wrapping u64 arithmetic; with no non-zero digit b is returned as
+                    // it came.  Rare path: one thread re-scans the digits for t1.
+                    bool found = false;
+                    uint64_t t1 = 0;
+                    for (size_t idx = 0; idx < entries && !found; ++idx) {
+                        const uint32_t i = (uint32_t)(idx / levels), l = (uint32_t)(idx % levels);
+                        const uint64_t d = (in[i] >> ((levels - 1 - l) * base_log)) & mask;
+                        if (d != 0) {
+                            found = true;
+                            t1 = reduce64(d * ksk[idx * out_w + n_out], m);
+                        }
+                    }
+                    if (!found) {
+                        out[(ct0 + c) * out_w + col] = b;
+                        continue;
+                    }
+                    const uint64_t r1 = reduce64(b + (m.q - t1), m);  // wraps modulo 2^64 as the reference's sum does
+                    start = addmod_canon(r1, t1, m.q);               // `total` below includes t1 again
+                }
+            }
+            out[(ct0 + c) * out_w + col] = submod_canon(start, total, m.q);
         }
     }
 }

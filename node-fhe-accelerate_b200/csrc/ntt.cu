@@ -81,6 +81,7 @@ static int upload_heap(const std::vector<T>& heap, Tw** out) {
 
 static int plan_finish(NttPlan* p) {
     const uint64_t q = p->modulus;
+    p->device = ctx().device;
     p->logn = log2_exact(p->degree);
     p->mod = make_modq(q);
     p->ninv = p->mod.dp ? Tw{double_to_bits((double)(p->inv_n % q)), 0} : Tw{p->inv_n % q, shoup_companion(p->inv_n % q, q)};
@@ -115,6 +116,37 @@ static int plan_finish(NttPlan* p) {
         FHEB_TRY(upload_heap(build_heap_table(p->inv_table.data(), p->logn, q), &p->d_inv));
     }
     return FHEB_OK;
+}
+
+static void plan_free(NttPlan* p) {
+    if (!p) return;
+    for (auto& kv : p->replicas) plan_free(kv.second);
+    if (p->d_fwd) cudaFree(p->d_fwd);
+    if (p->d_inv) cudaFree(p->d_inv);
+    if (p->d_top_fwd) cudaFree(p->d_top_fwd);
+    if (p->d_top_inv) cudaFree(p->d_top_inv);
+    delete p;
+}
+
+const NttPlan* plan_on_device(const NttPlan* p, int device) {
+    if (p->device == device) return p;
+    std::lock_guard<std::mutex> lock(p->replica_mutex);
+    auto it = p->replicas.find(device);
+    if (it != p->replicas.end()) return it->second;
+    NttPlan* r = new NttPlan();  // same host-side tables, device tables rebuilt on the current device
+    r->degree = p->degree;
+    r->modulus = p->modulus;
+    r->psi = p->psi;
+    r->psi_inv = p->psi_inv;
+    r->inv_n = p->inv_n;
+    r->fwd_table = p->fwd_table;
+    r->inv_table = p->inv_table;
+    if (plan_finish(r) != FHEB_OK || r->device != device) {
+        plan_free(r);
+        return nullptr;  // the error text is set
+    }
+    p->replicas[device] = r;
+    return r;
 }
 
 // ---- kernel dispatch --------------------------------------------------------------------
@@ -313,6 +345,17 @@ static int transform_entry(const fheb_ntt_plan* plan, int dir, const uint64_t* i
     const size_t bytes = batch * (size_t)p->degree * 8;
     if (all_host({in, out})) {  // host buffers: chunked copy-in / transform / copy-out pipeline
         const size_t row = (size_t)p->degree * 8;
+        if (spread_over_devices(batch, bytes))  // one share, one host thread and one pipeline per configured GPU
+            return run_on_devices(batch, [&](int device, size_t first, size_t n) {
+                const NttPlan* pd = plan_on_device(p, device);
+                if (!pd) return (int)FHEB_ERR_NATIVE;
+                const uint64_t* in_d = in + first * p->degree;
+                uint64_t* out_d = out + first * p->degree;
+                return run_host_pipeline(n, {{in_d, row, 0, true, false}, {out_d, row, 0, false, true}},
+                                         [&](void* const* d, size_t, size_t m, cudaStream_t ps) {
+                                             return dispatch_transform(pd, dir, static_cast<const uint64_t*>(d[0]), static_cast<uint64_t*>(d[1]), m, ps);
+                                         });
+            });
         return run_host_pipeline(batch, {{in, row, 0, true, false}, {out, row, 0, false, true}},
                                  [&](void* const* d, size_t, size_t n, cudaStream_t ps) {
                                      return dispatch_transform(p, dir, static_cast<const uint64_t*>(d[0]), static_cast<uint64_t*>(d[1]), n, ps);
@@ -389,13 +432,7 @@ int fheb_ntt_plan_create_with_tables(uint32_t degree, uint64_t modulus, const ui
 }
 
 int fheb_ntt_plan_destroy(fheb_ntt_plan* plan) {
-    NttPlan* p = reinterpret_cast<NttPlan*>(plan);
-    if (!p) return FHEB_OK;
-    if (p->d_fwd) cudaFree(p->d_fwd);
-    if (p->d_inv) cudaFree(p->d_inv);
-    if (p->d_top_fwd) cudaFree(p->d_top_fwd);
-    if (p->d_top_inv) cudaFree(p->d_top_inv);
-    delete p;
+    plan_free(reinterpret_cast<NttPlan*>(plan));
     return FHEB_OK;
 }
 
@@ -435,6 +472,17 @@ int fheb_polymul_batch(const fheb_ntt_plan* plan, const uint64_t* a, const uint6
     const size_t bytes = batch * (size_t)p->degree * 8;
     if (all_host({a, b, c})) {
         const size_t row = (size_t)p->degree * 8;
+        if (spread_over_devices(batch, bytes))
+            return run_on_devices(batch, [&](int device, size_t first, size_t n) {
+                const NttPlan* pd = plan_on_device(p, device);
+                if (!pd) return (int)FHEB_ERR_NATIVE;
+                const size_t off = first * p->degree;
+                return run_host_pipeline(n, {{a + off, row, 0, true, false}, {b + off, row, 0, true, false}, {c + off, row, 0, false, true}},
+                                         [&](void* const* d, size_t, size_t m, cudaStream_t ps) {
+                                             return dispatch_polymul(pd, static_cast<const uint64_t*>(d[0]), static_cast<const uint64_t*>(d[1]),
+                                                                     static_cast<uint64_t*>(d[2]), m, ps);
+                                         });
+            });
         return run_host_pipeline(batch, {{a, row, 0, true, false}, {b, row, 0, true, false}, {c, row, 0, false, true}},
                                  [&](void* const* d, size_t, size_t n, cudaStream_t ps) {
                                      return dispatch_polymul(p, static_cast<const uint64_t*>(d[0]), static_cast<const uint64_t*>(d[1]),

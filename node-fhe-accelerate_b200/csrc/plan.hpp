@@ -4,6 +4,8 @@
 #include <cuda_runtime.h>
 
 #include <cstdint>
+#include <map>
+#include <mutex>
 #include <vector>
 
 #include "modarith.cuh"
@@ -27,7 +29,15 @@ struct NttPlan {
     Tw* d_top_fwd = nullptr;
     Tw* d_top_inv = nullptr;
     Tw one{};
+    // the device whose memory holds the tables above, and copies of the plan on other devices (made on first use when
+    // a host batch is spread over several GPUs; owned by this plan)
+    int device = 0;
+    mutable std::map<int, NttPlan*> replicas;
+    mutable std::mutex replica_mutex;
 };
+
+// the plan's tables on `device` (the calling thread's current device): the plan itself or a replica built on demand
+const NttPlan* plan_on_device(const NttPlan* p, int device);
 
 // device-pointer entry points shared between translation units
 int ntt_forward_device(const NttPlan* p, const uint64_t* in, uint64_t* out, size_t batch, cudaStream_t s);

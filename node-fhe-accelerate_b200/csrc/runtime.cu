@@ -4,14 +4,30 @@
 // fheb_synchronize, fheb_launch_count (declared in include/fheb200.h).
 #include "runtime.hpp"
 
+#include <thread>
+
 namespace fheb {
 
 static thread_local std::string t_error;
+// One context per device (a process may drive several GPUs, from one thread that switches devices or from one thread
+// per device): looked up by the calling thread's CURRENT device, created on first use, never re-targeted.
+constexpr int MAX_DEVICES = 64;
 static std::mutex g_ctx_mutex;
-static Context g_ctx;
+static Context g_ctx[MAX_DEVICES];
+static std::atomic<bool> g_ctx_ready[MAX_DEVICES];
 std::atomic<uint64_t> g_launches{0};
 
-Context& ctx() { return g_ctx; }
+static int current_device() {
+    int d = 0;
+    if (cudaGetDevice(&d) != cudaSuccess) {
+        cudaGetLastError();
+        d = 0;
+    }
+    return (d >= 0 && d < MAX_DEVICES) ? d : 0;
+}
+
+Context& ctx() { return g_ctx[current_device()]; }
+Context& ctx_of(int device) { return g_ctx[(device >= 0 && device < MAX_DEVICES) ? device : 0]; }
 
 int set_error(int code, const char* fmt, ...) {
     char buf[512];
@@ -23,6 +39,7 @@ int set_error(int code, const char* fmt, ...) {
     return code;
 }
 
+// makes `device` (or, when negative, the current device) current and creates its context if it has none
 static int init_locked(int device) {
     int count = 0;
     cudaError_t e = cudaGetDeviceCount(&count);
@@ -35,8 +52,11 @@ static int init_locked(int device) {
     if (device < 0) {
         if (cudaGetDevice(&device) != cudaSuccess) device = 0;
     }
-    if (device >= count) return set_error(FHEB_ERR_INVALID_PARAMETERS, "device %d out of range (%d devices)", device, count);
+    if (device >= count || device >= MAX_DEVICES)
+        return set_error(FHEB_ERR_INVALID_PARAMETERS, "device %d out of range (%d devices)", device, count);
     FHEB_CUDA(cudaSetDevice(device));
+    Context& c = g_ctx[device];
+    if (c.ready) return FHEB_OK;
     cudaDeviceProp prop;
     FHEB_CUDA(cudaGetDeviceProperties(&prop, device));
     if (prop.major != 10) {
@@ -44,43 +64,30 @@ static int init_locked(int device) {
                          "device %d (%s) is sm_%d%d; this library ships sm_100a code only", device, prop.name,
                          prop.major, prop.minor);
     }
-    if (g_ctx.ready && g_ctx.device != device) {
-        // re-target: drop the old staging streams
-        cudaStreamDestroy(g_ctx.copy_in);
-        cudaStreamDestroy(g_ctx.copy_out);
-        cudaStreamDestroy(g_ctx.work);
-        for (auto& ps : g_ctx.pipe) cudaStreamDestroy(ps);
-        g_ctx.ready = false;
-    }
-    if (!g_ctx.ready) {
-        g_ctx.device = device;
-        g_ctx.prop = prop;
-        g_ctx.sm_count = prop.multiProcessorCount;
-        FHEB_CUDA(cudaStreamCreateWithFlags(&g_ctx.copy_in, cudaStreamNonBlocking));
-        FHEB_CUDA(cudaStreamCreateWithFlags(&g_ctx.copy_out, cudaStreamNonBlocking));
-        FHEB_CUDA(cudaStreamCreateWithFlags(&g_ctx.work, cudaStreamNonBlocking));
-        for (auto& ps : g_ctx.pipe) FHEB_CUDA(cudaStreamCreateWithFlags(&ps, cudaStreamNonBlocking));
-        {   // staging buffers come from the stream-ordered allocator on every call: keep its memory cached
-            // across synchronisations instead of returning it to the driver each time
-            cudaMemPool_t pool = nullptr;
-            if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
-                unsigned long long keep = ~0ull;
-                cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
-            }
+    c.device = device;
+    c.prop = prop;
+    c.sm_count = prop.multiProcessorCount;
+    FHEB_CUDA(cudaStreamCreateWithFlags(&c.copy_in, cudaStreamNonBlocking));
+    FHEB_CUDA(cudaStreamCreateWithFlags(&c.copy_out, cudaStreamNonBlocking));
+    FHEB_CUDA(cudaStreamCreateWithFlags(&c.work, cudaStreamNonBlocking));
+    for (auto& ps : c.pipe) FHEB_CUDA(cudaStreamCreateWithFlags(&ps, cudaStreamNonBlocking));
+    {   // staging buffers come from the stream-ordered allocator on every call: keep its memory cached
+        // across synchronisations instead of returning it to the driver each time
+        cudaMemPool_t pool = nullptr;
+        if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+            unsigned long long keep = ~0ull;
+            cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
         }
-        g_ctx.ready = true;
     }
+    c.ready = true;
+    g_ctx_ready[device].store(true, std::memory_order_release);
     return FHEB_OK;
 }
 
 int ensure_ready() {
+    const int d = current_device();
+    if (g_ctx_ready[d].load(std::memory_order_acquire)) return FHEB_OK;  // kernels run on the calling thread's current device
     std::lock_guard<std::mutex> lock(g_ctx_mutex);
-    if (g_ctx.ready) {
-        // Kernels must run on the device the context was made for.
-        int cur = -1;
-        if (cudaGetDevice(&cur) == cudaSuccess && cur != g_ctx.device) return init_locked(cur);
-        return FHEB_OK;
-    }
     return init_locked(-1);
 }
 
@@ -139,6 +146,51 @@ int sync_if_staged(cudaStream_t stream, std::initializer_list<const Staged*> buf
     bool any = false;
     for (const Staged* b : bufs) any = any || b->staged();
     if (any) FHEB_CUDA(cudaStreamSynchronize(stream));
+    return FHEB_OK;
+}
+
+static std::mutex g_devices_mutex;
+static std::vector<int> g_devices;
+
+std::vector<int> device_list() {
+    std::lock_guard<std::mutex> lock(g_devices_mutex);
+    return g_devices;
+}
+
+bool spread_over_devices(size_t items, size_t bytes) {
+    size_t n;
+    {
+        std::lock_guard<std::mutex> lock(g_devices_mutex);
+        n = g_devices.size();
+    }
+    return n > 1 && items >= 2 * n && bytes >= ((size_t)4 << 20) * n;  // a few MB per device at least: below that one GPU wins
+}
+
+int run_on_devices(size_t items, const DeviceFn& fn) {
+    const std::vector<int> devs = device_list();
+    const size_t nd = devs.empty() ? 1 : devs.size();
+    std::vector<int> rcs(nd, FHEB_OK);
+    std::vector<std::string> msgs(nd);
+    std::vector<std::thread> threads;
+    const size_t base = items / nd, rem = items % nd;
+    size_t first = 0;
+    for (size_t d = 0; d < nd; ++d) {
+        const size_t n = base + (d < rem ? 1 : 0);
+        const size_t f = first;
+        first += n;
+        if (n == 0) continue;
+        threads.emplace_back([&, d, f, n] {
+            int rc = FHEB_OK;
+            if (!devs.empty() && cudaSetDevice(devs[d]) != cudaSuccess) rc = set_error(FHEB_ERR_NATIVE, "cudaSetDevice(%d) failed", devs[d]);
+            if (rc == FHEB_OK) rc = ensure_ready();
+            if (rc == FHEB_OK) rc = fn(devs.empty() ? ctx().device : devs[d], f, n);
+            rcs[d] = rc;
+            if (rc != FHEB_OK) msgs[d] = t_error;  // error text is thread-local: hand it to the caller's thread
+        });
+    }
+    for (auto& t : threads) t.join();
+    for (size_t d = 0; d < nd; ++d)
+        if (rcs[d] != FHEB_OK) return set_error(rcs[d], "device %d: %s", devs.empty() ? -1 : devs[d], msgs[d].c_str());
     return FHEB_OK;
 }
 
@@ -257,17 +309,64 @@ int fheb_init(int device) {
 
 int fheb_shutdown(void) {
     std::lock_guard<std::mutex> lock(g_ctx_mutex);
-    if (g_ctx.ready) {
-        cudaStreamDestroy(g_ctx.copy_in);
-        cudaStreamDestroy(g_ctx.copy_out);
-        cudaStreamDestroy(g_ctx.work);
-        for (auto& ps : g_ctx.pipe) cudaStreamDestroy(ps);
-        g_ctx = Context{};
+    int cur = -1;
+    cudaGetDevice(&cur);
+    for (int d = 0; d < MAX_DEVICES; ++d) {
+        Context& c = g_ctx[d];
+        if (!c.ready) continue;
+        g_ctx_ready[d].store(false, std::memory_order_release);
+        cudaSetDevice(d);
+        cudaStreamDestroy(c.copy_in);
+        cudaStreamDestroy(c.copy_out);
+        cudaStreamDestroy(c.work);
+        for (auto& ps : c.pipe) cudaStreamDestroy(ps);
+        c = Context{};
     }
+    if (cur >= 0) cudaSetDevice(cur);
+    cudaGetLastError();
     return FHEB_OK;
 }
 
-const char* fheb_version(void) { return "0.1.0-b200"; }
+int fheb_set_devices(const int* devices, int count) {
+    int visible = 0;
+    if (cudaGetDeviceCount(&visible) != cudaSuccess || visible == 0) {
+        cudaGetLastError();
+        return set_error(FHEB_ERR_HARDWARE_UNAVAILABLE, "no CUDA device available; this backend has no CPU fallback");
+    }
+    std::vector<int> list;
+    if (count < 0) count = visible;  // all visible devices
+    for (int k = 0; k < count; ++k) {
+        const int d = devices ? devices[k] : k;
+        FHEB_REQUIRE(d >= 0 && d < visible && d < MAX_DEVICES, "device %d out of range (%d devices)", d, visible);
+        for (int seen : list) FHEB_REQUIRE(seen != d, "device %d listed twice", d);
+        list.push_back(d);
+    }
+    int cur = -1;
+    cudaGetDevice(&cur);
+    {
+        std::lock_guard<std::mutex> lock(g_ctx_mutex);
+        for (int d : list) {
+            const int rc = init_locked(d);  // every device must be an sm_100 part; creates its context
+            if (rc != FHEB_OK) {
+                if (cur >= 0) cudaSetDevice(cur);
+                return rc;
+            }
+        }
+    }
+    if (cur >= 0) cudaSetDevice(cur);
+    std::lock_guard<std::mutex> lock(g_devices_mutex);
+    g_devices = list;
+    return FHEB_OK;
+}
+
+int fheb_get_devices(int* out, int capacity) {
+    const std::vector<int> list = device_list();
+    for (int k = 0; k < (int)list.size() && k < capacity; ++k)
+        if (out) out[k] = list[k];
+    return (int)list.size();
+}
+
+const char* fheb_version(void) { return "0.2.0-b200"; }
 
 const char* fheb_last_error(void) { return t_error.c_str(); }
 

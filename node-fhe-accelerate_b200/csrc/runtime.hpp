@@ -30,9 +30,10 @@ struct Context {
     cudaStream_t pipe[PIPE_SLOTS] = {nullptr, nullptr, nullptr};  // host-buffer pipeline: copy-in / kernels / copy-out per chunk
 };
 
-Context& ctx();
+Context& ctx();            // context of the calling thread's current device (valid after ensure_ready())
+Context& ctx_of(int device);
 int set_error(int code, const char* fmt, ...);
-int ensure_ready();  // lazily initialises the context; FHEB_ERR_HARDWARE_UNAVAILABLE if no sm_100 GPU
+int ensure_ready();  // lazily initialises the current device's context; FHEB_ERR_HARDWARE_UNAVAILABLE if no sm_100 GPU
 extern std::atomic<uint64_t> g_launches;
 
 inline void count_launch(uint64_t n = 1) { g_launches.fetch_add(n, std::memory_order_relaxed); }
@@ -129,6 +130,16 @@ inline std::vector<size_t> pipeline_chunk_sizes(size_t items, size_t chunk, bool
     for (size_t i = head.size(); i-- > 0;) sizes.push_back(head[i]);
     return sizes;
 }
+
+// ---- several GPUs driven by one process -------------------------------------------------------
+// fheb_set_devices() names the GPUs that HOST-buffer batches are spread over (the reference's addon is one process,
+// src/native/lib.rs:23-133; every unit of the path is independent).  Each device gets a contiguous share
+// and its own host thread running the chunked copy/compute/copy pipeline on its own PCIe link; plans and keys are
+// replicated on a device the first time it is used.  Device buffers always run where they live, on the current device.
+std::vector<int> device_list();                        // empty or one entry: no spreading
+bool spread_over_devices(size_t items, size_t bytes);  // more than one device configured and the batch is worth splitting
+using DeviceFn = std::function<int(int device, size_t first, size_t n)>;
+int run_on_devices(size_t items, const DeviceFn& fn);  // fn runs with `device` current and its context ready; first error wins
 
 bool all_host(std::initializer_list<const void*> ptrs);  // true when no non-null pointer is device memory
 int run_host_pipeline(size_t items, std::vector<PipeArg> args, const PipeFn& fn, size_t chunk_items = 0 /* 0: ~16 MB per buffer */);

@@ -103,13 +103,20 @@ class ShardedTally:
         count = cts.numel() // (2 * self.degree)
         api.check(api.lib().fheb_tally_peers_run(self._peers, C.c_void_p(cts.data_ptr()), count, C.c_void_p(out.data_ptr()),
                                                  C.c_void_p(torch.cuda.current_stream(cts.device).cuda_stream)))
-        self._fused_calls = getattr(self, "_fused_calls", 0) + 1
-        if self._fused_calls % 1024 == 0:  # a peer that never arrived leaves a status word behind: look now and then
+        # (fheb_tally_peers_run itself refuses to launch once an earlier exchange of this handle has timed out: the
+        # status word is host-mapped, reading it costs nothing.  A timed-out call also leaves all-ones words in `out`.)
+        return out
+
+    def check(self):
+        """After synchronising: raises if any exchange issued so far has timed out (a peer rank never arrived)."""
+        import ctypes as C
+
+        if self._peers is not None:
             timed_out = C.c_int(0)
             api.check(api.lib().fheb_tally_peers_status(self._peers, C.byref(timed_out)))
             if timed_out.value:
-                raise api.FheError(4, "fused sharded tally: a peer rank did not take part in an exchange (results since are invalid)")
-        return out
+                raise api.FheError(4, f"fused sharded tally: a peer rank did not take part in exchange {timed_out.value} "
+                                      "(its result and all later ones are invalid)")
 
     def __del__(self):
         h, self._peers = getattr(self, "_peers", None), None
@@ -154,3 +161,54 @@ class ShardedTally:
             self._gathered = torch.empty(self.world * 2 * self.degree, dtype=partial.dtype, device=partial.device)
         self.dist.all_gather_into_tensor(self._gathered, partial.contiguous().view(-1), group=self.group)
         return self.combine_fn(self._gathered.view(self.world, 2, self.degree))
+
+
+class TallyGroup:
+    """The sharded tally driven from ONE process that owns several GPUs (fheb_tally_group_*): the shape the
+    reference's single-process addon needs (src/native/lib.rs:23-133).  shards[i] lives on devices[i]."""
+
+    def __init__(self, degree: int, modulus: int, devices=None, ndev: Optional[int] = None):
+        import ctypes as C
+
+        self.degree, self.modulus = degree, modulus
+        self.devices = list(devices) if devices is not None else list(range(int(ndev)))
+        arr = (C.c_int * len(self.devices))(*self.devices)
+        self._h = C.c_void_p()
+        api.check(api.lib().fheb_tally_group_create(degree, modulus, arr, len(self.devices), C.byref(self._h)))
+
+    def tally(self, shards, out=None):
+        """shards: one tensor [count_i][2][N] per device of the group (None / empty = no ballots there).
+        Returns the global tally [2][N] as a numpy array (or fills `out`, host array or CUDA tensor)."""
+        import ctypes as C
+
+        import numpy as np
+
+        n = len(self.devices)
+        assert len(shards) == n
+        ptrs = (C.c_void_p * n)()
+        counts = (C.c_size_t * n)()
+        keep = []
+        for k, sh in enumerate(shards):
+            if sh is None or sh.numel() == 0:
+                ptrs[k], counts[k] = None, 0
+                continue
+            w = api.as_words(sh)
+            assert w.is_cuda and w.device.index == self.devices[k], "shard k must live on device k of the group"
+            keep.append(w)
+            ptrs[k], counts[k] = w.data_ptr(), w.numel() // (2 * self.degree)
+        if out is None:
+            out = np.empty((2, self.degree), dtype=np.uint64)
+        import torch
+
+        for d in self.devices:  # the shards were produced on torch's streams
+            torch.cuda.synchronize(d)
+        api.check(api.lib().fheb_tally_sharded(self._h, ptrs, counts, C.c_void_p(api._ptr(out))))
+        return out
+
+    def __del__(self):
+        h, self._h = getattr(self, "_h", None), None
+        if h:
+            try:
+                api.lib().fheb_tally_group_destroy(h)
+            except Exception:
+                pass

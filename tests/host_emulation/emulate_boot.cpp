@@ -111,11 +111,13 @@ static int check(uint32_t threads, uint32_t levels, uint32_t base_log, uint32_t 
     if (out != ref) { std::printf("L=%d dp=%d kp1=%d levels=%u: CMUX mismatch\n", L, DP, KP1, levels); ++bad; }
 
     // --- blind rotation
-    for (int trial = 0; trial < 2; ++trial) {
+    for (int trial = 0; trial < 3; ++trial) {
         std::vector<uint64_t> lwe(n + 1), test(N);
         for (auto& v : lwe) v = rng() % q;
         if (trial == 1) { lwe[0] = 0; lwe[n] = 0; if (n > 2) lwe[2] = q - 1; }  // zero rotations are skipped
-        for (auto& v : test) v = (raw_inputs && trial == 0) ? rng() : rng() % q;
+        // raw rotation 2N (a_i = q - 1): the reference runs a CMux with diff = 0 that canonicalises an unreduced accumulator
+        if (trial == 2) { lwe[0] = q - 1; for (uint32_t i = 1; i < n; ++i) lwe[i] = (i == 1 && n > 3) ? q / 3 : 0; }
+        for (auto& v : test) v = (raw_inputs && trial != 1) ? rng() : rng() % q;
         std::fill(ref.begin(), ref.end(), 0);
         std::memcpy(ref.data() + (size_t)k * N, test.data(), N * 8);
         orc_blind_rotate(&p, ref.data(), lwe.data(), bsk.data());
@@ -126,9 +128,9 @@ static int check(uint32_t threads, uint32_t levels, uint32_t base_log, uint32_t 
         s.gout = nullptr;
         s.maybe_raw = 1;
         for (uint32_t i = 0; i < n; ++i) {
-            const uint32_t rot = lwe_rotation(lwe[i], false, N, q);
-            if (rot == 0) continue;
-            s.rot = rot;
+            const uint32_t rot = lwe_step_rotation(lwe[i], N, q);  // same decision as boot_kernel
+            if (!((rot & (2u * N - 1u)) != 0 || (rot != 0 && s.maybe_raw != 0))) continue;
+            s.rot = rot & (2u * N - 1u);
             s.ggsw = reinterpret_cast<const Tw*>(g.data() + (size_t)i * ggsw_w * GE);
             run_step<L, DP, KP1>(threads, s, hf, hi, ninv, m);
             s.maybe_raw = 0;

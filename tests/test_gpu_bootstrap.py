@@ -149,6 +149,14 @@ def test_key_switch_ragged_shapes(fhe, torch, oracle):
         lwe = rng.integers(0, q, size=(batch, k * N + 1), dtype=np.uint64)
         lwe[0, :k * N] = 0  # all digits zero: result is (0, .., 0, b)
         eq(host(eng.key_switch(dev(torch, lwe))), oracle.key_switch(lwe, q, ksk, n_out, base_log, level))
+        # unreduced b (bootstrap_engine.cpp:640,665): kept raw when every digit is zero, and `(b + q - t) % q` of the
+        # first non-zero digit wraps modulo 2^64 - the kernel mirrors both
+        raw = lwe.copy()
+        raw[:, k * N] = rng.integers(2**64 - q, 2**64, size=batch, dtype=np.uint64)
+        raw[batch // 2, k * N] = np.uint64(q)
+        raw[-1, k * N] = np.uint64(2**64 - 1)
+        raw[-1, :k * N - 1] = 0  # only the last coefficient has digits
+        eq(host(eng.key_switch(dev(torch, raw))), oracle.key_switch(raw, q, ksk, n_out, base_log, level))
 
 
 def test_bootstrap_errors(fhe):
@@ -195,9 +203,20 @@ def test_blind_rotation_with_unreduced_test_polynomial(fhe, torch, oracle, N, q,
     p = oracle.boot_params(N, q, n, 1, base_log, level, 4, fwd, inv, inv_n)
     bsk = rng.integers(0, q, size=(n, 2 * level, 2, N), dtype=np.uint64)
     eng = fhe.BootstrapEngine(N, q, n, 1, base_log, level, bsk)
-    lwe = rng.integers(0, q, size=(5, n + 1), dtype=np.uint64)
+    lwe = rng.integers(0, q, size=(8, n + 1), dtype=np.uint64)
     lwe[0, :] = 0     # no step executes: the raw words pass through the initial rotation only
     lwe[1, :2] = 0    # the first executed step comes late
+    # a_i >= q - q/4N rounds to the RAW rotation 2N: the reference tests the int32 before rotate_polynomial normalises
+    # it (bootstrap_engine.cpp:564-566), so it still runs a CMux with diff = 0, which canonicalises an unreduced
+    # accumulator.  (q-1, q/3, 0, ..; b = 0) and (0, q/3, 0, ..) differ under the reference once the test polynomial
+    # holds unreduced words; so do "only step is a 2N one" and "2N step after a real one" (the identity by then).
+    lwe[5, :] = 0
+    lwe[5, 0], lwe[5, 1] = q - 1, q // 3
+    lwe[6, :] = 0
+    lwe[6, 1] = q // 3
+    lwe[7, :] = 0
+    lwe[7, n - 1] = q - 1
+    lwe[4, 0], lwe[4, 1] = q // 5, q - 2
     clean = oracle.default_test_poly(p)
     raw = clean.copy()
     raw[::7] += np.uint64(q)                          # same residues, unreduced

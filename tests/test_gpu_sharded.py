@@ -35,7 +35,44 @@ for total in (world * 700 + 3, world, 5000):          # ragged split, one ballot
         assert fused._peers is not None, "peer path was not set up"
         assert np.array_equal(a.cpu().numpy().view(np.uint64), exp), (rank, total, "fused")
         assert np.array_equal(b.cpu().numpy().view(np.uint64), exp), (rank, total, "general")
+    fused.check()
     del fused, general
+# many back-to-back epochs on a tiny count: a peer may run one call ahead and overwrite its flag with epoch k+1
+# before this rank has looked at epoch k - the wait is "reached", not "equals" (no timeout, same words every time)
+cts = np.random.default_rng(7).integers(0, q, size=(world * 2, 2, n), dtype=np.uint64)
+exp = orc.tally(cts, q)
+mine = torch.from_numpy(cts[rank * 2:rank * 2 + 2].view(np.int64)).cuda()
+fused = fheb200.ShardedTally(n, q)
+outs = [fused.tally(mine) for _ in range(400)]
+torch.cuda.synchronize()
+fused.check()
+for o in outs[::37] + outs[-3:]:
+    assert np.array_equal(o.cpu().numpy().view(np.uint64), exp), (rank, "back-to-back epochs")
+del fused, outs
+# a peer that never arrives: the waiting rank's words become all-ones, its status names the call, later calls fail
+dist.barrier()
+lone = fheb200.ShardedTally(n, q)
+first = lone.tally(mine)            # sets the peers up (collective) and checks the first call
+torch.cuda.synchronize()
+import ctypes as C
+fheb200.lib().fheb_tally_peers_set_timeout(lone._peers, C.c_double(0.2))
+dist.barrier()
+if rank == 0:
+    bad = lone.tally(mine)          # nobody else takes part in this exchange
+    torch.cuda.synchronize()
+    assert bool((bad.cpu().numpy().view(np.uint64) == np.uint64(2**64 - 1)).all()), "timed-out exchange must poison its result"
+    try:
+        lone.check()
+        raise SystemExit("status did not report the timed-out exchange")
+    except fheb200.FheError:
+        pass
+    try:
+        lone.tally(mine)
+        raise SystemExit("a later call on the failed handle must be refused")
+    except fheb200.FheError:
+        pass
+dist.barrier()
+del lone
 torch.cuda.synchronize()
 dist.barrier()
 dist.destroy_process_group()
@@ -55,3 +92,45 @@ def test_fused_and_general_sharded_tally_match_the_oracle(tmp_path):
                         "--master-addr", "127.0.0.1", "--master-port", "29577", str(script)],
                        capture_output=True, text=True, timeout=600)
     assert r.returncode == 0 and r.stdout.count("sharded tally ok") == world, r.stdout[-2000:] + r.stderr[-4000:]
+
+
+def _group_case(fhe, torch, oracle, ndev, total, n=1024, q=1099511678977):
+    import numpy as np
+
+    rng = np.random.default_rng(total + ndev)
+    cts = rng.integers(0, q, size=(total, 2, n), dtype=np.uint64)
+    cts[0, 1, :3] = [q, q + 5, 2**64 - 1]  # unreduced words
+    shards = []
+    for r in range(ndev):
+        lo, hi = fhe.shard_range(total, r, ndev)
+        shards.append(torch.from_numpy(cts[lo:hi].view(np.int64)).to(f"cuda:{r}") if hi > lo else None)
+    return cts, shards
+
+
+@pytest.mark.parametrize("total", [1, 3, 700, 5000])
+def test_single_process_group_on_the_visible_gpus(total):
+    """fheb_tally_group_* / fheb_tally_sharded: ONE process drives every visible GPU (peer access, no IPC, no torch
+    collectives).  On a 1-GPU box the group has one member and the kernel still runs its exchange stage (inbox, flag,
+    epoch parity) against itself - the fused path is covered wherever the suite runs."""
+    import numpy as np
+    import torch
+
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import fheb200
+    from oracle_bindings import Oracle
+
+    ndev = min(torch.cuda.device_count(), 8)
+    n, q = 1024, 1099511678977
+    grp = fheb200.TallyGroup(n, q, ndev=ndev)
+    cts, shards = _group_case(fheb200, torch, Oracle(), ndev, total)
+    exp = Oracle().tally(cts, q) if total > 1 else None
+    for _ in range(3):  # both inbox parities
+        got = grp.tally(shards)
+        if total == 1:   # the group sums canonical partials: a lone ballot comes back reduced (batch_add would return it raw)
+            assert np.array_equal(got, cts[0] % np.uint64(q))
+        else:
+            assert np.array_equal(got, exp)
+    out_dev = torch.empty((2, n), dtype=torch.int64, device="cuda:0")
+    grp.tally(shards, out=out_dev)
+    assert np.array_equal(out_dev.cpu().numpy().view(np.uint64), exp if total > 1 else cts[0] % np.uint64(q))

@@ -2,6 +2,8 @@
 // between the integer and the FP64 formulation of the modular butterfly.
 #include <cstdio>
 #include <cstdint>
+#include <cstdlib>
+#include <string>
 #include <cuda_runtime.h>
 
 template <int MODE>
@@ -27,6 +29,9 @@ __global__ void __launch_bounds__(512) k(uint64_t* out, int iters, double da, ui
     out[blockIdx.x * blockDim.x + threadIdx.x] = acc;
 }
 
+static bool g_json = false;
+static double g_tops[8];
+
 template <int MODE>
 void run(const char* name, int ops_per_iter) {
     uint64_t* out;
@@ -42,15 +47,32 @@ void run(const char* name, int ops_per_iter) {
     float ms; cudaEventElapsedTime(&ms, a, b);
     double ops = (double)148 * 4 * 512 * iters * ops_per_iter;
     int clk; cudaDeviceGetAttribute(&clk, cudaDevAttrClockRate, 0);
-    printf("%-28s %8.3f ms  %7.2f Tops/s  %6.1f ops/clk/SM (at %d MHz nominal)\n", name, ms, ops / ms / 1e9, ops / (ms * 1e-3) / 148 / (clk * 1e3), clk / 1000);
+    g_tops[MODE] = ops / ms / 1e9;
+    if (!g_json)
+        printf("%-28s %8.3f ms  %7.2f Tops/s  %6.1f ops/clk/SM (at %d MHz nominal)\n", name, ms, ops / ms / 1e9, ops / (ms * 1e-3) / 148 / (clk * 1e3), clk / 1000);
     cudaFree(out);
 }
 
-int main() {
+// usage: pipes [--json] [device]   (--json: one line of thread-operations per second, for bench.py's roofline)
+int main(int argc, char** argv) {
+    int dev = 0;
+    for (int i = 1; i < argc; ++i) {
+        if (std::string(argv[i]) == "--json") g_json = true;
+        else dev = atoi(argv[i]);
+    }
+    if (cudaSetDevice(dev) != cudaSuccess) { fprintf(stderr, "no device %d\n", dev); return 1; }
     run<0>("DFMA", 8);
     run<1>("IMAD.WIDE.U32", 8);
     run<2>("IMAD (32-bit)", 8);
     run<3>("umul64hi", 8);
     run<4>("DFMA + IMAD.WIDE together", 16);
+    if (g_json) {
+        int clk = 0, sms = 0;
+        cudaDeviceGetAttribute(&clk, cudaDevAttrClockRate, dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        printf("{\"dfma_tops\": %.4f, \"imad_wide_tops\": %.4f, \"imad_tops\": %.4f, \"umul64hi_tops\": %.4f, "
+               "\"dfma_plus_imad_wide_tops\": %.4f, \"sm_count\": %d, \"nominal_mhz\": %d}\n",
+               g_tops[0], g_tops[1], g_tops[2], g_tops[3], g_tops[4], sms, clk / 1000);
+    }
     return 0;
 }
