@@ -70,6 +70,7 @@ FHEB_API int fheb_shutdown(void);
  * Calls on DEVICE buffers run where the buffers live (make that device current first).  count < 0 selects every
  * visible device; devices == NULL selects 0..count-1; count == 0 or 1 turns spreading off.
  * fheb_get_devices returns the number configured (and fills out[0..capacity)). */
+FHEB_API int fheb_device_count(void); /* visible sm_100 devices (0 when there is none) */
 FHEB_API int fheb_set_devices(const int* devices, int count);
 FHEB_API int fheb_get_devices(int* out, int capacity);
 /* replaces version(): src/native/lib.rs:129-133 */
@@ -261,6 +262,11 @@ FHEB_API int fheb_make_test_poly(const fheb_ntt_plan* plan, int kind, uint64_t a
  * the ballot's words untouched, as the reference does (:1332-1334). */
 FHEB_API int fheb_tally(const uint64_t* cts, size_t count, uint32_t degree, uint64_t modulus, uint64_t* out,
                         void* stream);
+/* noise_budget metadata of the tally variants (host arithmetic; the words above do not depend on the variant):
+ * replaces the budget bookkeeping of EncryptionEngine::batch_add (variant 0: min - log2(count),
+ * cpp/src/encryption.cpp:1337-1360), batch_add_tree / tally_votes (variant 1: min(pair) - 1 per level, odd element
+ * carried, :1390-1456) and a left fold with add (variant 2: :613). */
+FHEB_API int fheb_tally_noise_budget(const double* budgets, size_t count, int variant, double* out);
 /* Second step of the sharded tally: folds `parts` partial tallies ([parts][2][N], canonical,
  * e.g. the result of an NCCL all-gather of per-GPU fheb_tally outputs) into out = [2][N]. */
 FHEB_API int fheb_tally_combine(const uint64_t* partials, size_t parts, uint32_t degree, uint64_t modulus,

@@ -30,6 +30,11 @@ inline void check(int rc) {
 }
 
 inline void initialize(int device = -1) { check(fheb_init(device)); }
+// One process, several GPUs: host-buffer batches of every class below are split over these devices (empty = all visible).
+inline int set_devices(const std::vector<int>& devices = {}) {
+    check(devices.empty() ? fheb_set_devices(nullptr, -1) : fheb_set_devices(devices.data(), (int)devices.size()));
+    return fheb_get_devices(nullptr, 0);
+}
 
 struct TwiddleFactors {  // cpp/include/ntt_processor.h:29-41
     std::vector<uint64_t> forward, inverse;
@@ -132,6 +137,28 @@ class PolynomialRing {
     void multiply(const uint64_t* a, const uint64_t* b, uint64_t* c, size_t batch = 1, void* s = nullptr) const {
         check(fheb_polymul_batch(ntt_.handle(), a, b, c, batch, s));
     }
+    // The same with the reference's Polynomial::is_ntt flags on flat buffers (polynomial_ring.cpp:421-447): when BOTH
+    // operands are already in transform form the product is the pointwise one and stays in transform form (:425-427);
+    // otherwise operands not yet transformed are transformed, and the result comes back in coefficient form.
+    // Returns the result's is_ntt flag.
+    bool multiply(const uint64_t* a, bool a_is_ntt, const uint64_t* b, bool b_is_ntt, uint64_t* c, size_t batch = 1, void* s = nullptr) const {
+        if (a_is_ntt && b_is_ntt) {
+            pointwise_multiply(a, b, c, batch, s);
+            return true;
+        }
+        if (!a_is_ntt && !b_is_ntt) {
+            multiply(a, b, c, batch, s);
+            return false;
+        }
+        // mixed: transform the coefficient-form operand into c, multiply pointwise, transform back (:433-444)
+        const uint64_t* coeff = a_is_ntt ? b : a;
+        const uint64_t* ntt = a_is_ntt ? a : b;
+        if (c == ntt) throw std::invalid_argument("out must not alias the transform-form operand of a mixed product");
+        to_ntt(coeff, c, batch, s);
+        pointwise_multiply(c, ntt, c, batch, s);
+        from_ntt(c, c, batch, s);
+        return false;
+    }
     // EncryptionEngine::multiply tensor product: [batch][2][N] x [batch][2][N] -> [batch][3][N]
     void tensor_multiply(const uint64_t* ct1, const uint64_t* ct2, uint64_t* out, size_t batch = 1, void* s = nullptr) const {
         check(fheb_tensor_multiply_batch(ntt_.handle(), ct1, ct2, out, batch, s));
@@ -156,15 +183,40 @@ class ShardedTallyPeers {
     void connect(const uint8_t* all_handles /* [world][FHEB_PEER_HANDLE_BYTES], rank order */) { check(fheb_tally_peers_connect(peers_, all_handles)); }
     // local_cts = this rank's ballots [count][2][N] (device); out = [2][N] (device): the global tally
     void run(const uint64_t* local_cts, size_t count, uint64_t* out, void* s = nullptr) { check(fheb_tally_peers_run(peers_, local_cts, count, out, s)); }
-    bool timed_out() const {
+    bool timed_out() const {  // after synchronising the stream: has any exchange issued so far timed out?
         int v = 0;
         check(fheb_tally_peers_status(peers_, &v));
         return v != 0;
     }
+    uint32_t epoch() const { return fheb_tally_peers_epoch(peers_); }
+    void reset(uint32_t epoch) { check(fheb_tally_peers_reset(peers_, epoch)); }
+    void set_timeout(double seconds) { check(fheb_tally_peers_set_timeout(peers_, seconds)); }
 
    private:
     fheb_tally_peers* peers_ = nullptr;
     uint8_t handle_[FHEB_PEER_HANDLE_BYTES] = {};
+};
+
+// The same sharded tally driven by ONE process that owns several GPUs (the shape of the reference's single-process
+// addon): shards[i] = counts[i] ballots in the memory of device i of the group.  See fheb_tally_group_*.
+class ShardedTallyGroup {
+   public:
+    ShardedTallyGroup(uint32_t degree, uint64_t modulus, const std::vector<int>& devices) {
+        check(fheb_tally_group_create(degree, modulus, devices.data(), (uint32_t)devices.size(), &group_));
+    }
+    ShardedTallyGroup(uint32_t degree, uint64_t modulus, uint32_t ndev) { check(fheb_tally_group_create(degree, modulus, nullptr, ndev, &group_)); }
+    ~ShardedTallyGroup() { fheb_tally_group_destroy(group_); }
+    ShardedTallyGroup(const ShardedTallyGroup&) = delete;
+    ShardedTallyGroup& operator=(const ShardedTallyGroup&) = delete;
+    uint32_t size() const { return fheb_tally_group_size(group_); }
+    // EncryptionEngine::tally_votes over the shards; out = [2][N] in host memory or in any device's memory
+    void tally_votes(const std::vector<const uint64_t*>& shards, const std::vector<size_t>& counts, uint64_t* out) {
+        if (shards.size() != size() || counts.size() != size()) throw std::invalid_argument("one shard and one count per device of the group");
+        check(fheb_tally_sharded(group_, shards.data(), counts.data(), out));
+    }
+
+   private:
+    fheb_tally_group* group_ = nullptr;
 };
 
 // PolynomialRing(degree, moduli) (polynomial_ring.cpp:224-237) with every limb live: data limb-major
@@ -296,6 +348,33 @@ class BootstrapEngine {
 // EncryptionEngine::batch_add / tally_votes words: cts = [count][2][N] -> out = [2][N]
 inline void tally_votes(const uint64_t* cts, size_t count, uint32_t degree, uint64_t modulus, uint64_t* out, void* s = nullptr) {
     check(fheb_tally(cts, count, degree, modulus, out, s));
+}
+
+// Ciphertext::noise_budget of the result (encryption.h:40-89): the words do not depend on the tally variant, this does.
+enum class TallyVariant { BatchAdd = 0, BatchAddTree = 1, AddFold = 2 };  // encryption.cpp:1359-1360 / :1413,1437 / :613
+inline double tally_noise_budget(const std::vector<double>& budgets, TallyVariant variant = TallyVariant::BatchAddTree) {
+    double out = 0.0;
+    check(fheb_tally_noise_budget(budgets.data(), budgets.size(), (int)variant, &out));
+    return out;
+}
+// the reference's Ciphertext, as far as the tally touches it: words [2][N] + metadata
+struct TallyResult {
+    std::vector<uint64_t> words;  // c0 then c1
+    double noise_budget = 0.0;
+    uint64_t key_id = 0;
+};
+// EncryptionEngine::tally_votes (= batch_add_tree, encryption.cpp:1061-1067) with the metadata checks of :1345-1347
+inline TallyResult tally_votes(const uint64_t* cts, size_t count, uint32_t degree, uint64_t modulus, const std::vector<double>& budgets,
+                               const std::vector<uint64_t>& key_ids, TallyVariant variant = TallyVariant::BatchAddTree) {
+    if (budgets.size() != count || key_ids.size() != count) throw std::invalid_argument("one noise budget and one key id per ballot");
+    for (size_t i = 1; i < count; ++i)
+        if (key_ids[i] != key_ids[0]) throw std::invalid_argument("All ciphertexts must be encrypted with the same key");
+    TallyResult r;
+    r.words.resize((size_t)2 * degree);
+    tally_votes(cts, count, degree, modulus, r.words.data());
+    r.noise_budget = tally_noise_budget(budgets, variant);
+    r.key_id = count ? key_ids[0] : 0;
+    return r;
 }
 
 }  // namespace fheb200

@@ -55,6 +55,7 @@ u32, u64, sz, p, i = C.c_uint32, C.c_uint64, C.c_size_t, C.c_void_p, C.c_int
 SIGNATURES = {
     "fheb_init": ([i], i),
     "fheb_shutdown": ([], i),
+    "fheb_device_count": ([], i),
     "fheb_set_devices": ([p, i], i),
     "fheb_get_devices": ([p, i], i),
     "fheb_version": ([], C.c_char_p),
@@ -105,6 +106,7 @@ SIGNATURES = {
     "fheb_make_test_poly": ([p, i, u64, u64, p], i),
     "fheb_tally": ([p, sz, u32, u64, p, p], i),
     "fheb_tally_combine": ([p, sz, u32, u64, p, p], i),
+    "fheb_tally_noise_budget": ([p, sz, i, p], i),
     "fheb_tally_peers_create": ([u32, u64, u32, u32, p, p], i),
     "fheb_tally_peers_connect": ([p, p], i),
     "fheb_tally_peers_run": ([p, p, sz, p, p], i),

@@ -671,15 +671,24 @@ class CiphertextStreamAccumulator:
 
 
 def tally_noise_budget(budgets: Sequence[float], variant: str = "linear") -> float:
-    """noise_budget metadata of the reference's tally variants (host-side):
-    linear = min - log2(count) (encryption.cpp:1359-1360); tree = min - 1 per level (:1413,1437)."""
-    import math
-    lo, count = min(budgets), len(budgets)
-    if count == 1:
-        return lo
-    if variant == "linear":
-        return lo - math.log2(count)
-    return lo - math.ceil(math.log2(count))
+    """noise_budget metadata of the reference's tally variants (host-side) through fheb_tally_noise_budget:
+    "linear" = batch_add: min - log2(count) (encryption.cpp:1359-1360); "tree" = batch_add_tree / tally_votes: min(pair) - 1
+    per level with the odd element carried (:1413,1437); "add" = a left fold with EncryptionEngine::add (:613)."""
+    b = np.ascontiguousarray(budgets, dtype=np.float64)
+    out = C.c_double(0.0)
+    check(lib().fheb_tally_noise_budget(b.ctypes.data_as(C.c_void_p), int(b.size), {"linear": 0, "tree": 1, "add": 2}[variant], C.byref(out)))
+    return float(out.value)
+
+
+def set_devices(devices=None) -> int:
+    """One process, several GPUs: host-buffer batches are split over `devices` (None = every visible GPU, [] = off).
+    Returns the number of devices configured."""
+    if devices is None:
+        check(lib().fheb_set_devices(None, -1))
+    else:
+        arr = (C.c_int * max(len(devices), 1))(*devices)
+        check(lib().fheb_set_devices(arr, len(devices)))
+    return int(lib().fheb_get_devices(None, 0))
 
 
 def tally_wire(wire, count: int, num_choices: int, degree: int, modulus: int, offsets=None, out=None, device=None):

@@ -4,6 +4,8 @@
 // C-ABI entry points here (include/fheb200.h): fheb_boot_key_create, fheb_boot_key_set_ksk,
 // fheb_boot_key_destroy, fheb_external_product_batch, fheb_cmux_batch, fheb_blind_rotate_batch,
 // fheb_sample_extract_batch, fheb_key_switch_batch, fheb_bootstrap_batch, fheb_make_test_poly.
+#include <map>
+#include <mutex>
 #include <type_traits>
 
 #include "boot_kernel.cuh"
@@ -21,7 +23,65 @@ struct BootKey {
     size_t ksk_entries = 0;
     uint32_t ksk_n_out = 0, ksk_base_log = 0, ksk_levels = 0;
     int* d_raw_flag = nullptr;      // "the test polynomial of the running blind rotation has words >= q" (lean / general kernel choice)
+    // device that holds the buffers above, and copies of the key on other devices (made on first use when a host batch
+    // is spread over several GPUs; owned by this key, dropped when the key switching key changes)
+    int device = 0;
+    mutable std::map<int, BootKey*> replicas;
+    mutable std::mutex replica_mutex;
 };
+
+static size_t glwe_words(const BootKey* key);
+static size_t ggsw_words(const BootKey* key);
+
+static void boot_key_free(BootKey* key) {
+    if (!key) return;
+    for (auto& kv : key->replicas) boot_key_free(kv.second);
+    if (key->d_bsk) cudaFree(key->d_bsk);
+    if (key->d_ksk) cudaFree(key->d_ksk);
+    if (key->d_raw_flag) cudaFree(key->d_raw_flag);
+    delete key;
+}
+
+// the key on `device` (the calling thread's current device): the transformed key is copied device to device, the plan
+// is replicated the same way
+static const BootKey* boot_key_on_device(const BootKey* key, int device) {
+    if (key->device == device) return key;
+    std::lock_guard<std::mutex> lock(key->replica_mutex);
+    auto it = key->replicas.find(device);
+    if (it != key->replicas.end()) return it->second;
+    const NttPlan* pd = plan_on_device(key->plan, device);
+    if (!pd) return nullptr;
+    BootKey* r = new BootKey();
+    r->plan = pd;
+    r->n = key->n;
+    r->k = key->k;
+    r->base_log = key->base_log;
+    r->levels = key->levels;
+    r->device = device;
+    r->ksk_entries = key->ksk_entries;
+    r->ksk_n_out = key->ksk_n_out;
+    r->ksk_base_log = key->ksk_base_log;
+    r->ksk_levels = key->ksk_levels;
+    const size_t bsk_bytes = (size_t)key->n * ggsw_words(key) * (pd->mod.dp ? 8 : sizeof(Tw));
+    const size_t ksk_bytes = key->d_ksk ? key->ksk_entries * ((size_t)key->ksk_n_out + 1) * 8 : 0;
+    cudaError_t e = cudaMalloc(&r->d_bsk, bsk_bytes);
+    if (e == cudaSuccess) e = cudaMemcpy(r->d_bsk, key->d_bsk, bsk_bytes, cudaMemcpyDefault);
+    if (e == cudaSuccess && ksk_bytes) e = cudaMalloc(&r->d_ksk, ksk_bytes);
+    if (e == cudaSuccess && ksk_bytes) e = cudaMemcpy(r->d_ksk, key->d_ksk, ksk_bytes, cudaMemcpyDefault);
+    if (e == cudaSuccess && cudaMalloc(&r->d_raw_flag, sizeof(int)) != cudaSuccess) {
+        cudaGetLastError();
+        r->d_raw_flag = nullptr;
+    }
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        set_error(e == cudaErrorMemoryAllocation ? FHEB_ERR_OUT_OF_MEMORY : FHEB_ERR_NATIVE, "replicating the bootstrapping key on device %d failed: %s",
+                  device, cudaGetErrorString(e));
+        boot_key_free(r);
+        return nullptr;
+    }
+    key->replicas[device] = r;
+    return r;
+}
 
 // ---- key preparation --------------------------------------------------------------------
 // in: transforms y = [ggsw][row][j][N] in the reference's output order (index p of the permuted array).
@@ -259,6 +319,7 @@ static int bootstrap_chain_device(const BootKey* key, const uint64_t* lwe, const
 // The chain is compute bound (tens of microseconds per ciphertext, a few KB each way): host batches are
 // cut only into very large chunks so that every launch still fills the GPU for many waves.
 constexpr size_t BOOT_HOST_CHUNK = 16384;
+constexpr size_t BOOT_SPREAD_MIN = 128;  // ciphertexts per device below which spreading a host batch over several GPUs is not worth a thread
 
 static int check_key(const fheb_boot_key* key) {
     FHEB_TRY(ensure_ready());
@@ -292,6 +353,7 @@ int fheb_boot_key_create(const fheb_ntt_plan* plan, const fheb_boot_params* para
     key->k = params->glwe_dimension;
     key->base_log = params->decomp_base_log;
     key->levels = params->decomp_level;
+    key->device = ctx().device;
     if (cudaMalloc(&key->d_raw_flag, sizeof(int)) != cudaSuccess) {  // without it only the general kernel runs
         cudaGetLastError();
         key->d_raw_flag = nullptr;
@@ -335,6 +397,11 @@ int fheb_boot_key_set_ksk(fheb_boot_key* key_, const uint64_t* ksk, size_t entri
     FHEB_REQUIRE(entries == (size_t)key->k * key->plan->degree * level,
                  "key switching key must hold k * N * level entries (got %zu)", entries);
     FHEB_REQUIRE(n_out >= 1, "output dimension must be positive");
+    {   // replicas carry the old key switching key: drop them, they are rebuilt on demand
+        std::lock_guard<std::mutex> lock(key->replica_mutex);
+        for (auto& kv : key->replicas) boot_key_free(kv.second);
+        key->replicas.clear();
+    }
     if (key->d_ksk) cudaFree(key->d_ksk);
     key->d_ksk = nullptr;
     const size_t bytes = entries * ((size_t)n_out + 1) * 8;
@@ -348,12 +415,7 @@ int fheb_boot_key_set_ksk(fheb_boot_key* key_, const uint64_t* ksk, size_t entri
 }
 
 int fheb_boot_key_destroy(fheb_boot_key* key_) {
-    BootKey* key = reinterpret_cast<BootKey*>(key_);
-    if (!key) return FHEB_OK;
-    if (key->d_bsk) cudaFree(key->d_bsk);
-    if (key->d_ksk) cudaFree(key->d_ksk);
-    if (key->d_raw_flag) cudaFree(key->d_raw_flag);
-    delete key;
+    boot_key_free(reinterpret_cast<BootKey*>(key_));
     return FHEB_OK;
 }
 
@@ -402,6 +464,19 @@ int fheb_blind_rotate_batch(const fheb_boot_key* key_, const uint64_t* lwe, cons
     FHEB_REQUIRE(lwe != nullptr && test_poly != nullptr && out != nullptr, "ciphertext pointers must not be null");
     cudaStream_t s = (cudaStream_t)stream;
     if (all_host({lwe, test_poly, out})) {
+        if (device_list().size() > 1 && batch >= 2 * BOOT_SPREAD_MIN)
+            return run_on_devices(batch, [&](int device, size_t first, size_t n) {
+                const BootKey* kd = boot_key_on_device(key, device);
+                if (!kd) return (int)FHEB_ERR_NATIVE;
+                return run_host_pipeline(n, {{lwe + first * ((size_t)key->n + 1), ((size_t)key->n + 1) * 8, 0, true, false},
+                                             {test_poly, 0, (size_t)key->plan->degree * 8, true, false},
+                                             {out + first * glwe_words(key), glwe_words(key) * 8, 0, false, true}},
+                                         [&](void* const* d, size_t, size_t m, cudaStream_t ps) {
+                                             return blind_rotate_device(kd, static_cast<const uint64_t*>(d[0]), static_cast<const uint64_t*>(d[1]),
+                                                                        static_cast<uint64_t*>(d[2]), m, ps);
+                                         },
+                                         BOOT_HOST_CHUNK);
+            });
         return run_host_pipeline(batch, {{lwe, ((size_t)key->n + 1) * 8, 0, true, false}, {test_poly, 0, (size_t)key->plan->degree * 8, true, false},
                                          {out, glwe_words(key) * 8, 0, false, true}},
                                  [&](void* const* d, size_t, size_t n, cudaStream_t ps) {
@@ -458,6 +533,19 @@ int fheb_bootstrap_batch(const fheb_boot_key* key_, const uint64_t* lwe, const u
     const size_t ext_w = (size_t)key->k * key->plan->degree + 1;
     const size_t out_w = key->d_ksk ? (size_t)key->ksk_n_out + 1 : ext_w;
     if (all_host({lwe, test_poly, out})) {
+        if (device_list().size() > 1 && batch >= 2 * BOOT_SPREAD_MIN)  // compute bound: worth spreading from a few hundred ciphertexts
+            return run_on_devices(batch, [&](int device, size_t first, size_t n) {
+                const BootKey* kd = boot_key_on_device(key, device);
+                if (!kd) return (int)FHEB_ERR_NATIVE;
+                return run_host_pipeline(n, {{lwe + first * ((size_t)key->n + 1), ((size_t)key->n + 1) * 8, 0, true, false},
+                                             {test_poly, 0, (size_t)key->plan->degree * 8, true, false},
+                                             {out + first * out_w, out_w * 8, 0, false, true}},
+                                         [&](void* const* d, size_t, size_t m, cudaStream_t ps) {
+                                             return bootstrap_chain_device(kd, static_cast<const uint64_t*>(d[0]), static_cast<const uint64_t*>(d[1]),
+                                                                           static_cast<uint64_t*>(d[2]), m, ps);
+                                         },
+                                         BOOT_HOST_CHUNK);
+            });
         return run_host_pipeline(batch, {{lwe, ((size_t)key->n + 1) * 8, 0, true, false}, {test_poly, 0, (size_t)key->plan->degree * 8, true, false},
                                          {out, out_w * 8, 0, false, true}},
                                  [&](void* const* d, size_t, size_t n, cudaStream_t ps) {

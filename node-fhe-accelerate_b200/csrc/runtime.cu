@@ -327,6 +327,21 @@ int fheb_shutdown(void) {
     return FHEB_OK;
 }
 
+int fheb_device_count(void) {
+    int visible = 0;
+    if (cudaGetDeviceCount(&visible) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    int usable = 0;
+    for (int d = 0; d < visible; ++d) {
+        int major = 0;
+        if (cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, d) == cudaSuccess && major == 10) ++usable;
+    }
+    cudaGetLastError();
+    return usable;
+}
+
 int fheb_set_devices(const int* devices, int count) {
     int visible = 0;
     if (cudaGetDeviceCount(&visible) != cudaSuccess || visible == 0) {

@@ -9,6 +9,8 @@
 //
 // C-ABI entry points here (include/fheb200.h): fheb_tally, fheb_tally_combine,
 // fheb_tensor_multiply_batch, fheb_synth_ballots.
+#include <algorithm>
+#include <cmath>
 #include <cstdlib>
 #include <map>
 
@@ -461,6 +463,8 @@ static int tally_peers_run_device(TallyPeers* tp, const uint64_t* cts, size_t co
     return FHEB_OK;
 }
 
+static int tally_entry_single(const uint64_t* cts, size_t count, uint32_t degree, uint64_t q, uint64_t* out, void* stream, bool single_raw = false);
+
 static int tally_entry(const uint64_t* cts, size_t count, uint32_t degree, uint64_t q, uint64_t* out, bool single_raw,
                        void* stream) {
     FHEB_TRY(ensure_ready());
@@ -471,27 +475,58 @@ static int tally_entry(const uint64_t* cts, size_t count, uint32_t degree, uint6
     FHEB_REQUIRE(cts != nullptr && out != nullptr, "ciphertext pointers must not be null");
     cudaStream_t s = (cudaStream_t)stream;
     const uint32_t width = 2 * degree;
-    if (count > 1 && all_host({cts, out}) && count * (size_t)width * 8 >= (16u << 20)) {
-        // host ballots: each chunk is copied in and folded to one partial tally while the next chunk is in
-        // flight; the partials are folded at the end (any grouping gives the same words)
+    if (count > 1 && all_host({cts, out}) && spread_over_devices(count, count * (size_t)width * 8)) {
+        // host ballots, several GPUs: every device folds a contiguous share (own thread, own PCIe link) into one row of
+        // `parts`; the rows are canonical partial tallies and are folded on the current device
+        const std::vector<int> devs = device_list();
+        std::vector<uint64_t> parts(devs.size() * (size_t)width, 0);
+        std::vector<char> used(devs.size(), 0);
+        FHEB_TRY(run_on_devices(count, [&](int device, size_t first, size_t n) {
+            size_t slot = 0;
+            while (slot < devs.size() && devs[slot] != device) ++slot;
+            used[slot] = 1;
+            // single_raw = false: a share of one ballot must come back reduced, it is an operand of the final fold;
+            // the caller's stream belongs to the caller's device: every worker uses its own device's default stream
+            return tally_entry_single(cts + first * width, n, degree, q, parts.data() + slot * (size_t)width, nullptr, false);
+        }));
+        std::vector<uint64_t> rows;
+        for (size_t d = 0; d < devs.size(); ++d)
+            if (used[d]) rows.insert(rows.end(), parts.begin() + d * width, parts.begin() + (d + 1) * width);
+        const size_t nrows = rows.size() / width;
+        Staged sin, sout;
+        FHEB_TRY(sin.bind(rows.data(), rows.size() * 8, true, false, s));
+        FHEB_TRY(sout.bind(out, (size_t)width * 8, false, true, s));
+        FHEB_TRY(tally_device(sin.ptr<const uint64_t>(), nrows, width, q, sout.ptr<uint64_t>(), false, s));
+        FHEB_TRY(sout.finish());
+        return sync_if_staged(s, {&sin, &sout});
+    }
+    return tally_entry_single(cts, count, degree, q, out, stream, single_raw);
+}
+
+static int tally_entry_single(const uint64_t* cts, size_t count, uint32_t degree, uint64_t q, uint64_t* out, void* stream, bool single_raw) {
+    cudaStream_t s = (cudaStream_t)stream;
+    const uint32_t width = 2 * degree;
+    if (count > 1 && all_host({cts}) && count * (size_t)width * 8 >= (16u << 20)) {
+        // host ballots (the result may live on either side: the streaming accumulator passes a device row): each
+        // chunk is copied in and folded to one partial tally while the next chunk is in flight; the partials are
+        // folded at the end (any grouping gives the same words)
         const size_t row = (size_t)width * 8;
         size_t chunk = (8u << 20) / row;
         if (chunk < 1) chunk = 1;
         const size_t nchunks = (count + chunk - 1) / chunk;
+        const bool out_dev = is_device_pointer(out);
         uint64_t* partial = nullptr;
-        FHEB_CUDA(cudaMalloc(&partial, nchunks * row));
+        FHEB_CUDA(cudaMalloc(&partial, (nchunks + 1) * row));
+        uint64_t* dout = out_dev ? out : partial + nchunks * (size_t)width;
         int rc = run_host_pipeline(count, {{cts, row, 0, true, false}},
                                    [&](void* const* d, size_t first, size_t n, cudaStream_t ps) {
                                        return tally_device(static_cast<const uint64_t*>(d[0]), n, width, q, partial + (first / chunk) * width, false, ps);
                                    },
                                    chunk);
-        uint64_t* dout = nullptr;
-        if (rc == FHEB_OK && cudaMalloc(&dout, row) != cudaSuccess) rc = set_error(FHEB_ERR_OUT_OF_MEMORY, "cudaMalloc failed");
         if (rc == FHEB_OK) rc = tally_device(partial, nchunks, width, q, dout, false, s);
-        if (rc == FHEB_OK && cudaMemcpyAsync(out, dout, row, cudaMemcpyDeviceToHost, s) != cudaSuccess) rc = set_error(FHEB_ERR_NATIVE, "copy of the tally failed");
+        if (rc == FHEB_OK && !out_dev && cudaMemcpyAsync(out, dout, row, cudaMemcpyDeviceToHost, s) != cudaSuccess) rc = set_error(FHEB_ERR_NATIVE, "copy of the tally failed");
         if (rc == FHEB_OK && cudaStreamSynchronize(s) != cudaSuccess) rc = set_error(FHEB_ERR_NATIVE, "tally failed");
         cudaFree(partial);
-        if (dout) cudaFree(dout);
         return rc;
     }
     Staged sin, sout;
@@ -802,7 +837,7 @@ int fheb_tally_stream_add(fheb_tally_stream* ts, const uint64_t* cts, size_t cou
     const bool raw_single = (t->count == 0 && count == 1);
     if (is_device_pointer(cts)) {
         FHEB_TRY(tally_device(cts, count, width, t->modulus, dst, raw_single, s));
-    } else {  // host chunk: reuse the one-shot entry point's staging / pipelining into a device result
+    } else {  // host chunk: the one-shot entry point pipelines it (chunked copies overlapped with the folds) into the device row
         FHEB_TRY(tally_entry(cts, count, t->degree, t->modulus, dst, raw_single, stream));
     }
     if (t->count != 0) FHEB_TRY(elementwise_device(0 /* add: reduces both inputs first */, t->d_total, t->d_part, 0, t->d_total, width, t->modulus, s));
@@ -865,6 +900,43 @@ int fheb_tensor_multiply_batch(const fheb_ntt_plan* plan, const uint64_t* ct1, c
     FHEB_TRY(rc);
     FHEB_TRY(so.finish());
     return sync_if_staged(s, {&s1, &s2, &so});
+}
+
+int fheb_tally_noise_budget(const double* budgets, size_t count, int variant, double* out) {
+    // The noise_budget metadata of the reference's tally variants (the polynomial words do not depend on the variant;
+    // this number does - SURVEY B11).  Host arithmetic on doubles, same operations in the same order:
+    //   0 batch_add        min over all - log2(count)                       cpp/src/encryption.cpp:1337-1360
+    //   1 batch_add_tree   min(pair) - 1 per level, odd element carried      cpp/src/encryption.cpp:1390-1456 (:1413,:1437)
+    //   2 add, left fold   min(running, next) - 1 per ciphertext             cpp/src/encryption.cpp:613 (stream_add's accumulate)
+    // A single ciphertext keeps its budget in every variant (:1332-1334, :1374-1376).
+    FHEB_REQUIRE(budgets != nullptr && out != nullptr, "budgets and out must not be null");
+    FHEB_REQUIRE(count != 0, "Cannot add empty vector of ciphertexts");
+    FHEB_REQUIRE(variant >= 0 && variant <= 2, "unknown tally variant %d", variant);
+    if (count == 1) {
+        *out = budgets[0];
+        return FHEB_OK;
+    }
+    if (variant == 0) {
+        double lo = budgets[0];
+        for (size_t i = 1; i < count; ++i) lo = std::min(lo, budgets[i]);
+        *out = lo - std::log2(static_cast<double>(count));
+        return FHEB_OK;
+    }
+    if (variant == 2) {
+        double acc = budgets[0];
+        for (size_t i = 1; i < count; ++i) acc = std::min(acc, budgets[i]) - 1.0;
+        *out = acc;
+        return FHEB_OK;
+    }
+    std::vector<double> level(budgets, budgets + count), next;
+    while (level.size() > 1) {
+        next.clear();
+        for (size_t i = 0; i + 1 < level.size(); i += 2) next.push_back(std::min(level[i], level[i + 1]) - 1.0);
+        if (level.size() % 2 == 1) next.push_back(level.back());
+        level.swap(next);
+    }
+    *out = level[0];
+    return FHEB_OK;
 }
 
 int fheb_synth_ballots(uint64_t* cts_device, size_t first_ballot, size_t count, uint32_t degree, uint64_t modulus,

@@ -504,7 +504,11 @@ int fheb_ballots_ingest(const void* wire, size_t wire_bytes, const uint64_t* off
         d_wire = const_cast<uint8_t*>(w);
     } else {
         FHEB_CUDA(cudaMallocAsync(&d_wire, wire_bytes, s));
-        FHEB_CUDA(cudaMemcpyAsync(d_wire, w, wire_bytes, cudaMemcpyHostToDevice, s));
+        const cudaError_t e = cudaMemcpyAsync(d_wire, w, wire_bytes, cudaMemcpyHostToDevice, s);
+        if (e != cudaSuccess) {  // do not leave the staging copy of the wire behind
+            cudaFreeAsync(d_wire, s);
+            return set_error(FHEB_ERR_NATIVE, "copy of the wire bytes failed: %s", cudaGetErrorString(e));
+        }
     }
     uint64_t* d_off = nullptr;
     uint8_t* d_status = nullptr;

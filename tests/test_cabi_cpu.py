@@ -103,6 +103,23 @@ def test_noise_budget_metadata(fhe):
     assert fhe.tally_noise_budget([30.0] * 20000, "linear") == pytest.approx(30.0 - np.log2(20000))
     assert fhe.tally_noise_budget([30.0] * 20000, "tree") == 15.0
     assert fhe.tally_noise_budget([12.5], "tree") == 12.5
+    # heterogeneous budgets: the tree subtracts 1 per level along each path and carries the odd element
+    # (cpp/src/encryption.cpp:1413,1437,1449-1451); restated here level by level
+    bud = [30.0, 28.5, 31.0, 29.25, 27.0, 33.0, 30.5]
+    lvl = list(bud)
+    while len(lvl) > 1:
+        nxt = [min(lvl[i], lvl[i + 1]) - 1.0 for i in range(0, len(lvl) - 1, 2)]
+        if len(lvl) % 2:
+            nxt.append(lvl[-1])
+        lvl = nxt
+    assert fhe.tally_noise_budget(bud, "tree") == lvl[0]
+    acc = bud[0]
+    for b in bud[1:]:
+        acc = min(acc, b) - 1.0   # EncryptionEngine::add, :613
+    assert fhe.tally_noise_budget(bud, "add") == acc
+    assert fhe.tally_noise_budget(bud, "linear") == min(bud) - np.log2(len(bud))
+    with pytest.raises(fhe.FheError):
+        fhe.tally_noise_budget([], "tree")
 
 
 _WORKER = r"""

@@ -224,3 +224,38 @@ def test_blind_rotation_with_unreduced_test_polynomial(fhe, torch, oracle, N, q,
     for tp in (raw, clean, raw):                      # alternate: the flag is recomputed on every call
         eq(host(eng.blind_rotate(dev(torch, lwe), dev(torch, tp))), oracle.blind_rotate(p, lwe, bsk, tp))
     eq(eng.blind_rotate(lwe, raw), oracle.blind_rotate(p, lwe, bsk, raw))  # host buffers
+
+
+def test_c4_full_shape_with_the_reference_own_keys(fhe, torch):
+    """BASELINE C4 at its full shape (N=1024, k=1, n=742, base_log=23, L=1; substitute prime - SURVEY H6) with keys and
+    inputs made by the reference ITSELF, live: KeyManager-style key generation + BootstrapEngine::encrypt_ggsw x 742
+    (cpp/src/bootstrap_engine.cpp:268-364,391-421) and encrypt_lwe, through oracle/_ref (the reference's own sources
+    compiled where they lie; the built library travels to the GPU box).  The GPU's blind-rotation and sample-extraction
+    words must equal the reference's BootstrapEngine::blind_rotate / sample_extract (:547-577, :594-624) on 16
+    ciphertexts.  A 24 MB key is too large for a committed fixture, hence live generation (about 15 s of host time)."""
+    from oracle_bindings import RefOracle, ref_available
+
+    if not ref_available():
+        pytest.skip("oracle/_ref/libref_oracle.so not built (needs the reference sources at build time)")
+    N, q, n, k, base_log, level, t = 1024, QT, 742, 1, 23, 1, 4
+    r = RefOracle()
+    h = r.boot_create(N, q, n, k, base_log, level, t)
+    try:
+        sk = r.boot_keygen(h)                      # the reference's own secret key and 742 GGSW ciphertexts
+        assert set(np.unique(sk).tolist()) <= {0, 1}
+        bsk = r.boot_export_bsk(h)
+        assert bsk.shape == (n, (k + 1) * level, k + 1, N)
+        msgs = np.arange(16, dtype=np.uint64) % np.uint64(t)
+        lwe = r.boot_encrypt_lwe(h, msgs * np.uint64(q // t), sk)
+        tp = r.boot_default_test_poly(h)
+        cores = min(os.cpu_count() or 1, 16)
+        exp_acc = r.boot_blind_rotate(h, lwe, tp, threads=cores)
+        exp_ext = r.boot_sample_extract(h, exp_acc)
+    finally:
+        r.boot_destroy(h)
+    eng = fhe.BootstrapEngine(N, q, n, k, base_log, level, bsk, plaintext_modulus=t)
+    eq(eng.get_default_test_poly(), tp)
+    acc = host(eng.blind_rotate(dev(torch, lwe), dev(torch, tp)))
+    eq(acc, exp_acc)
+    eq(host(eng.sample_extract(dev(torch, acc))), exp_ext)
+    eq(eng.bootstrap(lwe, tp), exp_ext)            # host buffers, whole chain (no key switching key: stops after extraction)

@@ -134,3 +134,36 @@ def test_single_process_group_on_the_visible_gpus(total):
     out_dev = torch.empty((2, n), dtype=torch.int64, device="cuda:0")
     grp.tally(shards, out=out_dev)
     assert np.array_equal(out_dev.cpu().numpy().view(np.uint64), exp if total > 1 else cts[0] % np.uint64(q))
+
+
+def test_host_batches_spread_over_the_visible_gpus():
+    """fheb_set_devices: one process, every visible GPU; host batches are split into contiguous shares, one host thread and
+    one copy/compute pipeline per device, plans and keys replicated on first use.  Same words as the one-GPU path."""
+    import numpy as np
+    import torch
+
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import fheb200
+    from oracle_bindings import Oracle
+
+    orc = Oracle()
+    n, q = 4096, 4611686018326724609
+    ndev = min(torch.cuda.device_count(), 8)
+    rng = np.random.default_rng(11)
+    batch = 96 * ndev + 5
+    a = rng.integers(0, q, size=(batch, n), dtype=np.uint64)
+    b = rng.integers(0, q, size=(batch, n), dtype=np.uint64)
+    ring = fheb200.PolynomialRing(n, q)
+    single_t, single_p = ring.to_ntt(a), ring.multiply(a, b)
+    assert fheb200.set_devices() == torch.cuda.device_count()
+    try:
+        spread_t, spread_p = ring.to_ntt(a), ring.multiply(a, b)
+        assert np.array_equal(spread_t, single_t) and np.array_equal(spread_p, single_p)
+        fwd, inv, _, _, inv_n = orc.twiddles(n, q)
+        for i in (0, batch // 2, batch - 1):
+            assert np.array_equal(spread_p[i], orc.multiply(a[i:i + 1], b[i:i + 1], q, fwd, inv, inv_n)[0])
+        cts = rng.integers(0, q, size=(batch, 2, n), dtype=np.uint64)
+        assert np.array_equal(fheb200.tally_votes(cts, n, q), orc.tally(cts, q))
+    finally:
+        fheb200.set_devices([])

@@ -1,0 +1,97 @@
+"""Dynamic instruction mix of the launches in an .ncu-rep (read here, no GPU): executed WARP instructions per SASS opcode
+class, from the report's source page, divided by the work units of the launch.
+
+    python tools/ncu_opmix.py <report> <units per launch> [--json key] [kernel-index]
+
+The classes are what the integer / FP64 pipe rooflines of bench.py need:
+  imad_wide   IMAD.WIDE*            (64-bit product of 32-bit words: quarter-rate on the FMA-heavy pipe, tools/microbench/pipes.cu)
+  imad_hi     IMAD.HI*
+  imad        every other IMAD* (IMAD, IMAD.X, IMAD.IADD, IMAD.MOV, IMAD.SHL ...): FMA pipe, 64 lanes/clk/SM
+  fp64        DFMA, DADD, DMUL, DSETP, F2F.F64*, I2F.F64*, F2I*.F64
+  alu         IADD3*, LOP3*, SHF*, SEL, ISETP*, PRMT, LEA*, MOV, IABS, FSEL ... (ALU pipe)
+  lsu         LD*, ST*, ATOM*, RED*
+  other       everything else (BAR, BRA, S2R, ...)
+"""
+import csv
+import io
+import json
+import subprocess
+import sys
+from collections import Counter
+
+
+def classify(op: str) -> str:
+    if op.startswith("IMAD.WIDE"):
+        return "imad_wide"
+    if op.startswith("IMAD.HI"):
+        return "imad_hi"
+    if op.startswith("IMAD"):
+        return "imad"
+    if op[:4] in ("DFMA", "DADD", "DMUL", "DSET", "DMNM") or ".F64" in op:
+        return "fp64"
+    if op.split(".")[0] in ("LDG", "STG", "LDS", "STS", "LD", "ST", "LDL", "STL", "ATOM", "ATOMG", "ATOMS", "RED", "LDGSTS", "LDSM", "UBLKCP", "LDC", "LDCU"):
+        return "lsu"
+    if op.split(".")[0] in ("IADD3", "IADD", "LOP3", "SHF", "SEL", "ISETP", "PRMT", "LEA", "MOV", "IABS", "FSEL", "IMNMX", "VIADD", "VIMNMX", "SGXT", "BMSK", "FLO", "POPC", "PLOP3", "UIADD3", "ULOP3", "USHF", "UMOV", "UISETP", "USEL", "ULEA", "UIMAD", "R2UR", "P2R", "R2P", "CS2R"):
+        return "alu"
+    return "other"
+
+
+def main():
+    rep, units = sys.argv[1], float(sys.argv[2])
+    key = None
+    rest = sys.argv[3:]
+    if rest and rest[0] == "--json":
+        key, rest = rest[1], rest[2:]
+    which = int(rest[0]) if rest else 0
+    raw = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--print-source", "sass", "--print-kernel-base", "function"],
+                         capture_output=True, text=True).stdout
+    # one table per profiled launch, separated by blank lines / kernel headers
+    tables, cur = [], []
+    for line in raw.splitlines():
+        if line.startswith('"Kernel Name"') or line.startswith("Kernel Name"):
+            if cur:
+                tables.append(cur)
+            cur = [line]
+        elif cur:
+            cur.append(line)
+    if cur:
+        tables.append(cur)
+    if not tables:
+        tables = [raw.splitlines()]
+    rows = list(csv.reader(io.StringIO("\n".join(tables[which]))))
+    hi = next(i for i, r in enumerate(rows) if "Source" in r and any(c.startswith("Instructions Executed") for c in r))
+    hdr = rows[hi]
+    ix = {h: i for i, h in enumerate(hdr)}
+    kname = rows[0][1] if len(rows[0]) > 1 else ""
+    mix, byop = Counter(), Counter()
+    tot = 0
+    for r in rows[hi + 1:]:
+        if len(r) <= ix["Source"] or not r[ix["Source"]].strip():
+            continue
+        toks = r[ix["Source"]].split()
+        op = toks[1] if toks[0].startswith("@") and len(toks) > 1 else toks[0]
+        try:
+            n = int(r[ix["Instructions Executed"]])
+        except ValueError:
+            continue
+        mix[classify(op)] += n
+        byop[op] += n
+        tot += n
+    per = {k: v / units for k, v in mix.items()}
+    out = {"kernel": kname, "report": rep, "units_per_launch": units, "warp_instructions": tot, "warp_instructions_per_unit": tot / units,
+           "per_unit": per, "top_opcodes_per_unit": {k: v / units for k, v in byop.most_common(16)}}
+    print(json.dumps(out, indent=1))
+    if key:
+        path = "profiles/r02_opmix.json"
+        try:
+            with open(path) as f:
+                allm = json.load(f)
+        except Exception:
+            allm = {}
+        allm[key] = out
+        with open(path, "w") as f:
+            json.dump(allm, f, indent=1)
+
+
+if __name__ == "__main__":
+    main()

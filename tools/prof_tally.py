@@ -39,6 +39,12 @@ def timed(count, iters=30):
     return e0.elapsed_time(e1) / iters * 1e3
 
 
+if len(sys.argv) > 2 and sys.argv[1] == "--one":  # the shipped shape only (ncu capture): python tools/prof_tally.py --one 131072
+    count = int(sys.argv[2])
+    us = timed(count, 6)
+    print(f"count={count}: {us:.1f} us  {count * 16384 / us / 1e6:.3f} TB/s")
+    sys.exit(0)
+
 for count in (131072, 1 << 20):
     for bpsm in (2, 3, 4, 5, 6, 8):
         for item in (8, 16, 32, 64, 128, 256):
