@@ -40,6 +40,11 @@ QT = 1099511678977  # substitute prime for the tfhe-128-fast shape (preset modul
 METRIC = "ntt_coeffs_per_sec_n16384_batched"
 WORKLOAD = f"forward+inverse transform, N={N_DEG}, batch {BATCH} per GPU, q={Q62}"
 UNIT = "coeff/s"
+NSETS = 4  # rotate input sets: 4 x 134 MB in + 134 MB out never fit the 126 MB L2 together
+# the same dict in both arms (the driver compares them); per-arm remarks go to config_notes
+CONFIG = {"workload": WORKLOAD,
+          "l2": f"{NSETS} rotating input sets of 134 MB + 2 output buffers: larger than the 126 MB L2 (no flush needed)",
+          "sharding": "batch split across ranks, no collective"}
 
 
 _REAL_STDOUT = None
@@ -166,10 +171,11 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "u64", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "note": "reference arm: each step is a bounded sample of the workload (cpu_baseline.sample)"},
+        "config": CONFIG,
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": used, "kind": kind, "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
+        "config_notes": {"reference_arm": "each step is a bounded sample of the workload (cpu_baseline.sample)"},
     }
     emit(line)
 
@@ -203,9 +209,14 @@ def run_ours(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
+    import bench_roofline
+
+    try:  # per-instruction-class issue rates of THIS GPU, measured now (a few tens of milliseconds of kernels)
+        pipes = bench_roofline.pipe_peaks(local)
+    except Exception as exc:
+        pipes = {"error": repr(exc)}
     ntt = fheb200.NTTProcessor(N_DEG, Q62)
     gen = torch.Generator(device=dev).manual_seed(1234 + rank)
-    NSETS = 4  # rotate input sets: 4 x 134 MB in + 134 MB out never fit the 126 MB L2 together
     xs = [torch.randint(0, Q62, (BATCH, N_DEG), dtype=torch.int64, device=dev, generator=gen) for _ in range(NSETS)]
     y = torch.empty_like(xs[0])
     z = torch.empty_like(xs[0])
@@ -248,25 +259,24 @@ def run_ours(args):
     peak, peak_src = measured_peaks()
     algo_bytes = 16.0 * BATCH * N_DEG
     achieved = algo_bytes / (fwd_ms * 1e-3) / 1e9
-    roofline = {"bound": "hbm", "kernel": "ntt_forward_kernel<14>", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                "frac": achieved / peak, "traffic": 212.9e6, "traffic_source": "profiles/r01_ntt_n16384_q62_ncu_summary.txt",
-                "peak_source": peak_src, "algorithmic_bytes_per_launch": algo_bytes, "avg_launch_ms": fwd_ms}
-
-    # The transform is integer-multiply bound before it is HBM bound: a Shoup butterfly is
-    # 6 IMAD.WIDE (4 FMA-heavy-pipe cycles per warp each, measured by tools/microbench/pipes.cu) + ~8.1 narrow
-    # IMAD (2 cycles) = ~40.2 pipe cycles per warp-butterfly, so one SM sustains at most 4 * 32 / 40.2 = 3.18
-    # butterflies per clock.  The live figure below uses the measured launch time and the nominal 1965 MHz.
+    # The transform binds on the integer multiply pipe long before HBM, so the roofline is the pipe
+    # ceiling: instruction-class rates measured by tools/microbench/pipes (pipes, above: before the timed region, same
+    # GPU) x the kernel's dynamic instruction mix per butterfly from its ncu capture (profiles/r02_opmix.json).  Nothing
+    # below is a pasted constant; the HBM fraction is kept beside it as the secondary figure.
     bfly = BATCH * (N_DEG // 2) * 14
-    bfly_per_clk_sm = bfly / (fwd_ms * 1e-3) / (148 * 1.965e9)
-    roofline["integer_pipe"] = {"butterflies_per_clk_per_sm": bfly_per_clk_sm, "ceiling": 3.18, "frac": bfly_per_clk_sm / 3.18,
-                                "ncu_fmaheavy_pct": 62.0, "source": "profiles/README.md"}
+    try:
+        roofline = bench_roofline.pipe_roofline("ntt_forward_n16384_q62", bfly, fwd_ms * 1e-3, pipes, "butterfly")
+    except Exception as exc:
+        roofline = {"bound": "integer-pipe", "achieved": None, "peak": None, "unit": "G butterfly/s", "frac": None, "traffic": None,
+                    "error": repr(exc)}
+    roofline.update({"kernel": "ntt_forward_kernel<14>", "avg_launch_ms": fwd_ms, "butterflies_per_launch": bfly,
+                     "hbm": {"achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "peak_source": peak_src,
+                             "algorithmic_bytes_per_launch": algo_bytes}})
 
     # ---- end to end: pinned host buffers through the C ABI, copies inside the timed region
-    hx = torch.empty((BATCH, N_DEG), dtype=torch.int64).pin_memory()
-    hx.copy_(xs[0])
-    hy = torch.empty_like(hx).pin_memory()
-    hz = torch.empty_like(hx).pin_memory()
-    hxn, hyn, hzn = (t.numpy().view(np.uint64) for t in (hx, hy, hz))
+    # pinned buffers from the library's own allocator (fheb_host_alloc: placed on the NUMA node next to this rank's GPU)
+    hxn, hyn, hzn = (fheb200.pinned_empty((BATCH, N_DEG)) for _ in range(3))
+    hxn[:] = xs[0].cpu().numpy().view(np.uint64)
     e2e_steps = max(2, min(args.steps, 5))
     ntt.forward_ntt(hxn, out=hyn)
     barrier()
@@ -286,7 +296,7 @@ def run_ours(args):
         try:
             import bench_secondary
 
-            secondary = bench_secondary.run(fheb200, torch, dist, world, rank, dev, barrier, max_over_ranks, peak)
+            secondary = bench_secondary.run(fheb200, torch, dist, world, rank, dev, barrier, max_over_ranks, peak, pipes)
         except Exception as exc:  # secondary numbers never take the headline down
             secondary = {"error": repr(exc)}
 
@@ -321,9 +331,7 @@ def run_ours(args):
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64",
             "data": "synthetic",
-            "config": {"workload": WORKLOAD,
-                       "l2": f"{NSETS} rotating input sets of 134 MB + 2 output buffers: larger than the 126 MB L2",
-                       "sharding": "batch split across ranks, no collective"},
+            "config": CONFIG,
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches),
             "clocks": clk.summary(), "secondary": secondary,
         }

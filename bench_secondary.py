@@ -81,8 +81,22 @@ def _tally_parity(fhe, torch, dist, world, rank, dev, n, q, per_rank=65536):
             "parity_note": f"{per_rank} ballots per rank through the timed path, all {2 * n} words vs the CPU oracle on every rank"}
 
 
-def run(fhe, torch, dist, world, rank, dev, barrier, max_over_ranks, peak):
+def _pipe(mix_key, units, ms, pipes, unit_name, hbm=None):
+    """Pipe roofline of a compute-bound line (bench_roofline.pipe_roofline) with the HBM fraction beside it."""
+    import bench_roofline
+
+    try:
+        r = bench_roofline.pipe_roofline(mix_key, units, ms * 1e-3, pipes, unit_name)
+    except Exception as exc:
+        r = {"bound": "pipe", "achieved": None, "peak": None, "unit": None, "frac": None, "error": repr(exc)}
+    if hbm is not None:
+        r["hbm"] = {k: hbm[k] for k in ("achieved", "peak", "unit", "frac")}
+    return r
+
+
+def run(fhe, torch, dist, world, rank, dev, barrier, max_over_ranks, peak, pipes=None):
     out = {}
+    pipes = pipes or {}
     gen = torch.Generator(device=dev).manual_seed(99 + rank)
 
     # ---- the published M4 Max rows use q = 132120577 at every size: same transform, FP64-pipe arithmetic (q < 2^42)
@@ -99,8 +113,11 @@ def run(fhe, torch, dist, world, rank, dev, barrier, max_over_ranks, peak):
             ntt.inverse_ntt(y, out=z)
 
         ms = _time(torch, fwd_inv, 10)
+        logn = n.bit_length() - 1
         out[f"ntt_n{n}_{tag}_b{batch}"] = {"value": 2.0 * batch * n / (ms * 1e-3), "unit": "coeff/s", "ms": ms,
-                                            "roofline": _hbm(peak, 32.0 * n * batch, ms)}
+                                            # forward + inverse: 2 * (N/2) log2 N butterflies per polynomial; the forward kernel's mix
+                                            "roofline": _pipe("ntt_forward_n16384_q27_fp64" if n == 16384 else "ntt_forward_n1024_qt_fp64",
+                                                              2.0 * batch * (n // 2) * logn, ms, pipes, "butterfly", _hbm(peak, 32.0 * n * batch, ms))}
         del xs, y, z
 
     # ---- C1: the reference's own CPU-runnable case (test_ntt_processor): N = 1024, q = 132120577, batch 1 - latency only
@@ -125,8 +142,12 @@ def run(fhe, torch, dist, world, rank, dev, barrier, max_over_ranks, peak):
         b = [torch.randint(0, Q62, (1024, n), dtype=torch.int64, device=dev, generator=gen) for _ in range(sets)]
         c = torch.empty_like(a[0])
         ms = _time(torch, lambda i: ring.multiply(a[i % sets], b[i % sets], out=c), 10)
+        logn = n.bit_length() - 1
         out[f"polymul_n{n}_b1024"] = {"value": 1024 / (ms * 1e-3), "unit": "polymul/s", "ms": ms,
-                                       "roofline": _hbm(peak, 24.0 * n * 1024, ms)}
+                                       # three transforms per product; the pointwise multiplies are inside the per-butterfly mix
+                                       # of the fused kernel's capture (N = 16384; used for N = 4096 as well: same code, 12 stages)
+                                       "roofline": _pipe("polymul_n16384_q62", 3.0 * 1024 * (n // 2) * logn, ms, pipes, "butterfly",
+                                                         _hbm(peak, 24.0 * n * 1024, ms))}
         del a, b, c
 
     # ---- C3: two-limb Montgomery products (n = 65536 is launch-bound; 2^24 shows the bandwidth)
@@ -194,7 +215,10 @@ def run(fhe, torch, dist, world, rank, dev, barrier, max_over_ranks, peak):
     out[f"relinearize_n{n}_L{levels}_b{batch}"] = {"value": batch / (ms * 1e-3), "unit": "ciphertexts/s", "ms": ms,
                                                      "transforms_per_ct": levels + 2,
                                                      "coeff_transforms_per_s": (levels + 2) * n * batch / (ms * 1e-3),
-                                                     "roofline": _hbm(peak, 40.0 * n * batch, ms)}
+                                                     # levels forward + 2 inverse transforms per ciphertext on the transform kernels
+                                                     # (their N = 16384 mix: same code), digits / MAC / finish kernels not counted
+                                                     "roofline": _pipe("ntt_forward_n16384_q62", (levels + 2.0) * batch * (n // 2) * 12, ms, pipes,
+                                                                       "butterfly", _hbm(peak, 40.0 * n * batch, ms))}
     del ct3, o2, keys
 
     # ---- N3: FHEV ballot records -> device ingest (checksum + realign), wire bytes already in HBM
@@ -223,11 +247,11 @@ def run(fhe, torch, dist, world, rank, dev, barrier, max_over_ranks, peak):
                                "note": "checksum validation + tally straight from the wire bytes (no unpacked ciphertexts)",
                                "roofline": _hbm(peak, 2.0 * len(recs[0]) * cnt, ms)}  # the wire is read twice
     del wire, ing, res
-    out["bootstrap_tfhe128fast_shape"] = run_bootstrap(fhe, torch, dist, world, rank, dev, barrier, max_over_ranks)
+    out["bootstrap_tfhe128fast_shape"] = run_bootstrap(fhe, torch, dist, world, rank, dev, barrier, max_over_ranks, pipes=pipes)
     return out
 
 
-def run_bootstrap(fhe, torch, dist, world, rank, dev, barrier, max_over_ranks, batch=4096, n=742, iters=2):
+def run_bootstrap(fhe, torch, dist, world, rank, dev, barrier, max_over_ranks, batch=4096, n=742, iters=2, pipes=None):
     """C4: tfhe-128-fast SHAPE (N=1024, k=1, n=742, base_log=23, L=1) with the substitute prime
     1099511678977 (the preset's 2^40+1 is composite) and a synthetic uniformly random key; each rank
     bootstraps its own `batch` LWE ciphertexts (blind rotation + sample extraction), no collective."""
@@ -271,11 +295,9 @@ def run_bootstrap(fhe, torch, dist, world, rank, dev, barrier, max_over_ranks, b
                                 "note": "blind rotation + sample extraction + key switching (one level)"},
             "modmul_per_bootstrap": bfly + macs,
             "gmodmul_per_s_per_gpu": (bfly + macs) * batch / (ms * 1e-3) / 1e9,
-            # FP64-pipe roofline: 8 DP operations per butterfly, 7 per multiply-accumulate, ~9 per coefficient
-            # for the conversions and reductions of a step (ncu: 197 k DP operations per step); peak = 64
-            # DFMA/clk/SM (tools/microbench/pipes.cu) x 148 SMs x 1.965 GHz
-            "roofline": {"bound": "fp64-pipe", "achieved": n * 197e3 * batch / (ms * 1e-3) / 1e12, "peak": 148 * 64 * 1.965e9 / 1e12,
-                         "unit": "T DP-op/s", "frac": n * 197e3 * batch / (ms * 1e-3) / (148 * 64 * 1.965e9)}}
+            # FP64-pipe roofline per GPU: executed FP64 instructions per ciphertext-step from the kernel's ncu capture
+            # (profiles/r02_opmix.json) against the DFMA rate measured by tools/microbench/pipes in this run
+            "roofline": _pipe("boot_lean_tfhe128_step", float(n) * batch, ms, pipes or {}, "ciphertext-step")}
 
 
 def cpu_reference(cores: int):

@@ -680,6 +680,21 @@ def tally_noise_budget(budgets: Sequence[float], variant: str = "linear") -> flo
     return float(out.value)
 
 
+def pinned_empty(shape) -> np.ndarray:
+    """uint64 host array in page-locked memory from the library's own allocator (fheb_host_alloc): placed on the NUMA node
+    of the current GPU, usable from every device.  Freed when the array (and every view of it) is garbage collected."""
+    import weakref
+
+    shape = tuple(int(x) for x in (shape if isinstance(shape, (tuple, list)) else (shape,)))
+    nbytes = int(np.prod(shape)) * 8
+    ptr = C.c_void_p()
+    check(lib().fheb_host_alloc(C.byref(ptr), max(nbytes, 8)))
+    buf = (C.c_uint64 * (max(nbytes, 8) // 8)).from_address(ptr.value)
+    arr = np.frombuffer(buf, dtype=np.uint64, count=int(np.prod(shape))).reshape(shape)
+    weakref.finalize(buf, lib().fheb_host_free, C.c_void_p(ptr.value))
+    return arr
+
+
 def set_devices(devices=None) -> int:
     """One process, several GPUs: host-buffer batches are split over `devices` (None = every visible GPU, [] = off).
     Returns the number of devices configured."""

@@ -161,13 +161,29 @@ struct Geometry {  // threads per block, polynomials per block
     static constexpr size_t SMEM = (Plan<L>::P > 1) ? (size_t)PPC * (1u << L) * 8 : 0;
 };
 
+// Attribute set-up and occupancy of a kernel are looked up once per (kernel, shared memory, threads, device) and cached:
+// at batch 1 the two driver calls cost more than the transform itself.
 template <class K>
 static int configure(K kernel, size_t smem, int threads, int* blocks_per_sm) {
+    struct Entry {
+        const void* fn;
+        size_t smem;
+        int threads, device, bps;
+    };
     static std::mutex mu;
+    static std::vector<Entry> cache;
+    const int device = ctx().device;
+    const void* fn = reinterpret_cast<const void*>(kernel);
     std::lock_guard<std::mutex> lock(mu);
+    for (const Entry& e : cache)
+        if (e.fn == fn && e.smem == smem && e.threads == threads && e.device == device) {
+            *blocks_per_sm = e.bps;
+            return FHEB_OK;
+        }
     if (smem > 48 * 1024) FHEB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     FHEB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, kernel, threads, smem));
     if (*blocks_per_sm < 1) return set_error(FHEB_ERR_NATIVE, "kernel does not fit on an SM (smem %zu)", smem);
+    cache.push_back({fn, smem, threads, device, *blocks_per_sm});
     return FHEB_OK;
 }
 

@@ -4,6 +4,9 @@
 // fheb_synchronize, fheb_launch_count (declared in include/fheb200.h).
 #include "runtime.hpp"
 
+#include <sched.h>
+
+#include <cctype>
 #include <thread>
 
 namespace fheb {
@@ -149,6 +152,59 @@ int sync_if_staged(cudaStream_t stream, std::initializer_list<const Staged*> buf
     return FHEB_OK;
 }
 
+// ---- host placement: the CPUs and memory next to a GPU ----------------------------------------
+// A pinned buffer that lives on the other socket crosses the inter-socket link on every copy.  The CPUs local to a GPU
+// come from sysfs (/sys/bus/pci/devices/<bdf>/local_cpulist); binding the calling thread to them while cudaHostAlloc
+// faults the pages in places the buffer on the GPU's NUMA node (first touch).  No-op where sysfs has no answer.
+static bool device_local_cpus(int device, cpu_set_t* set) {
+    char bdf[32] = {0};
+    if (cudaDeviceGetPCIBusId(bdf, sizeof(bdf), device) != cudaSuccess) {
+        cudaGetLastError();
+        return false;
+    }
+    for (char* c = bdf; *c; ++c) *c = (char)tolower(*c);
+    const std::string path = std::string("/sys/bus/pci/devices/") + bdf + "/local_cpulist";
+    FILE* f = fopen(path.c_str(), "r");
+    if (!f) return false;
+    char line[4096] = {0};
+    const bool got = fgets(line, sizeof(line), f) != nullptr;
+    fclose(f);
+    if (!got) return false;
+    CPU_ZERO(set);
+    int any = 0;
+    for (char* tok = strtok(line, ",\n"); tok; tok = strtok(nullptr, ",\n")) {
+        int lo = 0, hi = 0;
+        const int k = sscanf(tok, "%d-%d", &lo, &hi);
+        if (k < 1) continue;
+        if (k == 1) hi = lo;
+        for (int c = lo; c <= hi && c < CPU_SETSIZE; ++c) {
+            CPU_SET(c, set);
+            ++any;
+        }
+    }
+    return any > 0;
+}
+
+class LocalCpuScope {  // binds the calling thread to the CPUs next to `device` for its lifetime
+   public:
+    explicit LocalCpuScope(int device) {
+        cpu_set_t want;
+        if (getenv("FHEB_NO_NUMA_BIND") == nullptr && device_local_cpus(device, &want) &&
+            sched_getaffinity(0, sizeof(old_), &old_) == 0) {
+            cpu_set_t both;
+            CPU_AND(&both, &want, &old_);  // never leave the set the process was given (containers, taskset)
+            if (CPU_COUNT(&both) > 0 && sched_setaffinity(0, sizeof(both), &both) == 0) bound_ = true;
+        }
+    }
+    ~LocalCpuScope() {
+        if (bound_) sched_setaffinity(0, sizeof(old_), &old_);
+    }
+
+   private:
+    cpu_set_t old_;
+    bool bound_ = false;
+};
+
 static std::mutex g_devices_mutex;
 static std::vector<int> g_devices;
 
@@ -181,6 +237,7 @@ int run_on_devices(size_t items, const DeviceFn& fn) {
         if (n == 0) continue;
         threads.emplace_back([&, d, f, n] {
             int rc = FHEB_OK;
+            LocalCpuScope near_gpu(devs.empty() ? current_device() : devs[d]);  // the thread that feeds a GPU runs on the CPUs next to it
             if (!devs.empty() && cudaSetDevice(devs[d]) != cudaSuccess) rc = set_error(FHEB_ERR_NATIVE, "cudaSetDevice(%d) failed", devs[d]);
             if (rc == FHEB_OK) rc = ensure_ready();
             if (rc == FHEB_OK) rc = fn(devs.empty() ? ctx().device : devs[d], f, n);
@@ -416,7 +473,8 @@ int fheb_device_free(void* p) {
 int fheb_host_alloc(void** out, size_t bytes) {
     FHEB_REQUIRE(out != nullptr, "out must not be null");
     FHEB_TRY(ensure_ready());
-    FHEB_CUDA(cudaHostAlloc(out, bytes ? bytes : 1, cudaHostAllocDefault));
+    LocalCpuScope near_gpu(current_device());  // pages are faulted in by this thread: place them on the current GPU's NUMA node
+    FHEB_CUDA(cudaHostAlloc(out, bytes ? bytes : 1, cudaHostAllocPortable));
     return FHEB_OK;
 }
 

@@ -8,7 +8,12 @@ from collections import Counter
 
 rep = sys.argv[1]
 bucket = int(sys.argv[2]) if len(sys.argv) > 2 else 64
-raw = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--print-source", "sass"], capture_output=True, text=True).stdout
+if rep.endswith(".gz"):
+    import gzip
+
+    raw = gzip.open(rep, "rt").read()
+else:
+    raw = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--print-source", "sass"], capture_output=True, text=True).stdout
 rows = list(csv.reader(io.StringIO(raw)))
 hdr = rows[1]
 ix = {h: i for i, h in enumerate(hdr)}

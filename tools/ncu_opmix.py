@@ -1,7 +1,9 @@
 """Dynamic instruction mix of the launches in an .ncu-rep (read here, no GPU): executed WARP instructions per SASS opcode
 class, from the report's source page, divided by the work units of the launch.
 
-    python tools/ncu_opmix.py <report> <units per launch> [--json key] [kernel-index]
+    python tools/ncu_opmix.py <report | source.csv.gz> <units per launch> [--json key] [--raw raw.csv] [kernel-index]
+
+--raw adds the launch's DRAM traffic, duration and pipe utilisation from the raw page (exported CSV) to the entry.
 
 The classes are what the integer / FP64 pipe rooflines of bench.py need:
   imad_wide   IMAD.WIDE*            (64-bit product of 32-bit words: quarter-rate on the FMA-heavy pipe, tools/microbench/pipes.cu)
@@ -42,9 +44,16 @@ def main():
     rest = sys.argv[3:]
     if rest and rest[0] == "--json":
         key, rest = rest[1], rest[2:]
+    rawcsv = None
+    if rest and rest[0] == "--raw":
+        rawcsv, rest = rest[1], rest[2:]
     which = int(rest[0]) if rest else 0
-    raw = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--print-source", "sass", "--print-kernel-base", "function"],
-                         capture_output=True, text=True).stdout
+    if rep.endswith(".gz"):  # source page already exported on the GPU box (tools/ncu_round2.sh)
+        import gzip
+
+        raw = gzip.open(rep, "rt").read()
+    else:
+        raw = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--print-source", "sass"], capture_output=True, text=True).stdout
     # one table per profiled launch, separated by blank lines / kernel headers
     tables, cur = [], []
     for line in raw.splitlines():
@@ -80,6 +89,22 @@ def main():
     per = {k: v / units for k, v in mix.items()}
     out = {"kernel": kname, "report": rep, "units_per_launch": units, "warp_instructions": tot, "warp_instructions_per_unit": tot / units,
            "per_unit": per, "top_opcodes_per_unit": {k: v / units for k, v in byop.most_common(16)}}
+    if rawcsv:
+        rr = list(csv.reader(open(rawcsv)))
+        h, row = rr[0], rr[2 + which]
+        g = lambda name: float(row[h.index(name)].replace(",", "")) if name in h and row[h.index(name)] not in ("", "n/a") else None
+        u = lambda name: rr[1][h.index(name)] if name in h else ""
+        scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+        rd = g("dram__bytes_read.sum") * scale.get(u("dram__bytes_read.sum"), 1.0)
+        wr = g("dram__bytes_write.sum") * scale.get(u("dram__bytes_write.sum"), 1.0)
+        dur = g("gpu__time_duration.sum") * {"us": 1.0, "ms": 1e3, "ns": 1e-3, "s": 1e6}.get(u("gpu__time_duration.sum"), 1.0)
+        out.update({"dram_bytes": rd + wr, "dram_bytes_read": rd, "dram_bytes_write": wr, "duration_us_under_ncu": dur,
+                    "pipe_busy_pct": {"fmaheavy_cycles_active": g("sm__pipe_fmaheavy_cycles_active.avg.pct_of_peak_sustained_elapsed"),
+                                      "fp64_cycles_active": g("sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active"),
+                                      "alu_inst": g("sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active"),
+                                      "issue_active": g("smsp__issue_active.avg.pct_of_peak_sustained_active"),
+                                      "dram_throughput": g("gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed")},
+                    "raw_source": rawcsv})
     print(json.dumps(out, indent=1))
     if key:
         path = "profiles/r02_opmix.json"
