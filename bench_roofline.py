@@ -58,7 +58,8 @@ def pipe_roofline(mix_key: str, units: float, seconds: float, peaks: dict, unit_
     fp64, alu = per.get("fp64", 0.0), per.get("alu", 0.0)
     r_wide, r_imad, r_dfma = peaks["imad_wide_tops"] * 1e12, peaks["imad_tops"] * 1e12, peaks["dfma_tops"] * 1e12
     r_alu = peaks.get("alu_tops", peaks["imad_tops"]) * 1e12
-    r_hi = peaks["umul64hi_tops"] * 1e12 * 6.0  # __umul64hi is 6 wide multiplies; IMAD.HI alone is rare in these kernels
+    # IMAD.HI.U32 (the 32-bit kernels' Shoup quotient): measured directly when the microbenchmark has the mode
+    r_hi = peaks.get("imad_hi_tops", peaks["umul64hi_tops"] * 6.0) * 1e12
     t = {
         # DFMA and IMAD.WIDE do not overlap (measured: together they take the sum of their times), so the FP64 work
         # is charged to the same issue path as the wide multiplies
@@ -75,5 +76,5 @@ def pipe_roofline(mix_key: str, units: float, seconds: float, peaks: dict, unit_
             "mix_per_unit": {k: per.get(k, 0.0) for k in ("imad_wide", "imad_hi", "imad", "fp64", "alu", "lsu", "other")},
             "mix_source": f"profiles/r02_opmix.json[{mix_key}] (kernel {m.get('kernel', '?')[:60]}, ncu source page)",
             "ncu_pipe_busy_pct": m.get("pipe_busy_pct"),
-            "pipe_rates_tops": {k: peaks[k] for k in ("imad_wide_tops", "imad_tops", "dfma_tops", "alu_tops") if k in peaks},
+            "pipe_rates_tops": {k: peaks[k] for k in ("imad_wide_tops", "imad_hi_tops", "imad_tops", "dfma_tops", "alu_tops") if k in peaks},
             "pipe_rates_source": peaks.get("source")}

@@ -99,8 +99,15 @@ def run(fhe, torch, dist, world, rank, dev, barrier, max_over_ranks, peak, pipes
     pipes = pipes or {}
     gen = torch.Generator(device=dev).manual_seed(99 + rank)
 
-    # ---- the published M4 Max rows use q = 132120577 at every size: same transform, FP64-pipe arithmetic (q < 2^42)
-    for n, q, tag in ((16384, Q27, "q132120577"), (1024, QT, "q1099511678977")):
+    # ---- the published M4 Max rows use q = 132120577 at every size: same transform; 27-bit primes run the 32-bit kernels
+    # (MODE_U32), the same prime with those switched off and the 41-bit tfhe prime run on the FP64 pipe (q < 2^42)
+    import os
+
+    for n, q, tag, mix, no_u32 in ((16384, Q27, "q132120577", "ntt_forward_n16384_q27_u32", False),
+                                   (16384, Q27, "q132120577_fp64mode", "ntt_forward_n16384_q27_fp64", True),
+                                   (1024, QT, "q1099511678977", "ntt_forward_n1024_qt_fp64", False)):
+        if no_u32:
+            os.environ["FHEB_NO_U32"] = "1"  # read by the library on every call
         ntt = fhe.NTTProcessor(n, q)
         batch = 1024 if n == 16384 else 16384
         sets = 4
@@ -113,11 +120,11 @@ def run(fhe, torch, dist, world, rank, dev, barrier, max_over_ranks, peak, pipes
             ntt.inverse_ntt(y, out=z)
 
         ms = _time(torch, fwd_inv, 10)
+        os.environ.pop("FHEB_NO_U32", None)
         logn = n.bit_length() - 1
         out[f"ntt_n{n}_{tag}_b{batch}"] = {"value": 2.0 * batch * n / (ms * 1e-3), "unit": "coeff/s", "ms": ms,
                                             # forward + inverse: 2 * (N/2) log2 N butterflies per polynomial; the forward kernel's mix
-                                            "roofline": _pipe("ntt_forward_n16384_q27_fp64" if n == 16384 else "ntt_forward_n1024_qt_fp64",
-                                                              2.0 * batch * (n // 2) * logn, ms, pipes, "butterfly", _hbm(peak, 32.0 * n * batch, ms))}
+                                            "roofline": _pipe(mix, 2.0 * batch * (n // 2) * logn, ms, pipes, "butterfly", _hbm(peak, 32.0 * n * batch, ms))}
         del xs, y, z
 
     # ---- C1: the reference's own CPU-runnable case (test_ntt_processor): N = 1024, q = 132120577, batch 1 - latency only

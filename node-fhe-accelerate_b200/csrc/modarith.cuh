@@ -39,6 +39,8 @@ struct ModQ {
     uint64_t v;      // Moeller-Granlund reciprocal of dn: floor((2^128 - 1) / dn) - 2^64
     uint32_t sh;     // clz(q)
     uint32_t dp;     // 1 when q < 2^42: transforms run on the FP64 pipe (exact integer arithmetic in doubles)
+    uint32_t mu32;   // floor(2^32 / q) when q < 2^31 (32-bit mode of the plain transforms, q < 2^27), else 0
+    uint32_t pad_;
     double qd;       // (double)q
     double qinv;     // 1.0 / q, rounded to nearest
 };
@@ -238,6 +240,8 @@ inline ModQ make_modq(uint64_t q) {
     m.dn = q << m.sh;
     m.v = (uint64_t)((~(u128)0) / m.dn - (((u128)1) << 64));
     m.dp = (q < (1ULL << DP_QBITS)) ? 1u : 0u;
+    m.mu32 = (q < (1ULL << 31)) ? (uint32_t)((1ULL << 32) / q) : 0u;
+    m.pad_ = 0;
     m.qd = (double)q;
     m.qinv = 1.0 / (double)q;
     return m;

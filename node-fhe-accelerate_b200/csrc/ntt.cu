@@ -108,6 +108,12 @@ static int plan_finish(NttPlan* p) {
         }
         return FHEB_OK;
     }
+    if (q < (1ULL << U32_QBITS)) {  // 32-bit mode of the plain transforms and the fused product (ntt_core.cuh MODE_U32)
+        FHEB_TRY(upload_heap(build_heap_table_u32(p->fwd_table.data(), p->logn, q), &p->d_fwd32));
+        FHEB_TRY(upload_heap(build_heap_table_u32(p->inv_table.data(), p->logn, q), &p->d_inv32));
+        const uint64_t ni = p->inv_n % q;
+        p->ninv32 = Tw{ni, (ni << 32) / q};
+    }
     if (p->mod.dp) {  // FP64 mode: one double per twiddle
         FHEB_TRY(upload_heap(build_heap_table_dp(p->fwd_table.data(), p->logn, q), &p->d_fwd));
         FHEB_TRY(upload_heap(build_heap_table_dp(p->inv_table.data(), p->logn, q), &p->d_inv));
@@ -125,6 +131,8 @@ static void plan_free(NttPlan* p) {
     if (p->d_inv) cudaFree(p->d_inv);
     if (p->d_top_fwd) cudaFree(p->d_top_fwd);
     if (p->d_top_inv) cudaFree(p->d_top_inv);
+    if (p->d_fwd32) cudaFree(p->d_fwd32);
+    if (p->d_inv32) cudaFree(p->d_inv32);
     delete p;
 }
 
@@ -150,7 +158,7 @@ const NttPlan* plan_on_device(const NttPlan* p, int device) {
 }
 
 // ---- kernel dispatch --------------------------------------------------------------------
-template <int L, bool DP>
+template <int L, int DP>
 struct Geometry {  // threads per block, polynomials per block
     static constexpr int PPC = (L <= 9) ? (1024 >> L) : (L == 10 ? 2 : 1);
 #if defined(FHEB_EXP_R3)
@@ -200,30 +208,33 @@ static unsigned persistent_grid(size_t work_groups, int blocks_per_sm) {
 
 enum { DIR_FWD = 0, DIR_INV = 1, DIR_INV_FWDNET = 2 };
 
-template <int L, bool DP>
+template <int L, int DP>
 static int launch_transform(const NttPlan* p, int dir, const uint64_t* in, uint64_t* out, size_t batch, cudaStream_t s) {
     using G = Geometry<L, DP>;
+    const Tw* d_fwd = (DP == MODE_U32) ? p->d_fwd32 : p->d_fwd;
+    const Tw* d_inv = (DP == MODE_U32) ? p->d_inv32 : p->d_inv;
+    const Tw ninv = (DP == MODE_U32) ? p->ninv32 : p->ninv;
     const size_t groups = (batch + G::PPC - 1) / G::PPC;
     int bps = 0;
     if (dir == DIR_INV) {
         auto k = ntt_inverse_kernel<L, DP, G::THREADS, G::PPC>;
         FHEB_TRY(configure(k, G::SMEM, G::THREADS, &bps));
-        k<<<persistent_grid(groups, bps), G::THREADS, G::SMEM, s>>>(in, out, batch, p->d_inv, p->ninv, p->mod);
+        k<<<persistent_grid(groups, bps), G::THREADS, G::SMEM, s>>>(in, out, batch, d_inv, ninv, p->mod);
     } else if (dir == DIR_FWD) {
         auto k = ntt_forward_kernel<L, DP, G::THREADS, G::PPC, false>;
         FHEB_TRY(configure(k, G::SMEM, G::THREADS, &bps));
-        k<<<persistent_grid(groups, bps), G::THREADS, G::SMEM, s>>>(in, out, batch, p->d_fwd, p->ninv, p->mod);
+        k<<<persistent_grid(groups, bps), G::THREADS, G::SMEM, s>>>(in, out, batch, d_fwd, ninv, p->mod);
     } else {
         auto k = ntt_forward_kernel<L, DP, G::THREADS, G::PPC, true>;
         FHEB_TRY(configure(k, G::SMEM, G::THREADS, &bps));
-        k<<<persistent_grid(groups, bps), G::THREADS, G::SMEM, s>>>(in, out, batch, p->d_inv, p->ninv, p->mod);
+        k<<<persistent_grid(groups, bps), G::THREADS, G::SMEM, s>>>(in, out, batch, d_inv, ninv, p->mod);
     }
     FHEB_CHECK_LAUNCH();
     count_launch();
     return FHEB_OK;
 }
 
-template <int L, bool DP>
+template <int L, int DP>
 static int launch_polymul(const NttPlan* p, const uint64_t* a, const uint64_t* b, uint64_t* c, size_t batch,
                           cudaStream_t s) {
     using G = Geometry<L, DP>;
@@ -239,7 +250,8 @@ static int launch_polymul(const NttPlan* p, const uint64_t* a, const uint64_t* b
         // per-block scratch for T(a); small enough to stay L2 resident (grid x 128 KB)
         FHEB_CUDA(cudaMallocAsync(&stash, (size_t)grid * G::PPC * (1u << L) * 8, s));
     }
-    k<<<grid, G::THREADS, SMEM, s>>>(a, b, c, batch, p->d_fwd, p->d_inv, p->ninv, p->mod, stash);
+    if (DP == MODE_U32) k<<<grid, G::THREADS, SMEM, s>>>(a, b, c, batch, p->d_fwd32, p->d_inv32, p->ninv32, p->mod, stash);
+    else k<<<grid, G::THREADS, SMEM, s>>>(a, b, c, batch, p->d_fwd, p->d_inv, p->ninv, p->mod, stash);
     FHEB_CHECK_LAUNCH();
     count_launch();
     if (stash) FHEB_CUDA(cudaFreeAsync(stash, s));
@@ -247,7 +259,7 @@ static int launch_polymul(const NttPlan* p, const uint64_t* a, const uint64_t* b
 }
 
 // Degrees 2^15 and 2^16: top stages + 2^D sub-transforms of 2^14 (two launches, one scratch pass).
-template <bool DP>
+template <int DP>
 static int launch_transform_big(const NttPlan* p, int dir, const uint64_t* in, uint64_t* out, size_t batch, cudaStream_t s) {
     constexpr int LS = 14;
     using G = Geometry<LS, DP>;
@@ -281,7 +293,7 @@ static int launch_transform_big(const NttPlan* p, int dir, const uint64_t* in, u
 }
 
 // Product for degrees above 2^14: T(a), T(b), pointwise, T^-1 as separate launches.
-template <bool DP>
+template <int DP>
 static int launch_polymul_big(const NttPlan* p, const uint64_t* a, const uint64_t* b, uint64_t* c, size_t batch, cudaStream_t s) {
     const size_t words = batch << p->logn;
     uint64_t* ta = nullptr;
@@ -297,10 +309,14 @@ static int launch_polymul_big(const NttPlan* p, const uint64_t* a, const uint64_
 
 #define FHEB_DISPATCH_L(FN, L_, ...)                                         \
     case L_:                                                                 \
-        return dp ? FN<L_, true>(__VA_ARGS__) : FN<L_, false>(__VA_ARGS__);
+        return u32 ? FN<L_, MODE_U32>(__VA_ARGS__) : dp ? FN<L_, MODE_DP>(__VA_ARGS__) : FN<L_, MODE_INT>(__VA_ARGS__);
+
+// FHEB_NO_U32=1 (read per call: the parity tests run both ways) keeps moduli below 2^27 on the FP64-pipe kernels
+static bool use_u32(const NttPlan* p) { return p->d_fwd32 != nullptr && p->logn <= 14 && getenv("FHEB_NO_U32") == nullptr; }
 
 static int dispatch_transform(const NttPlan* p, int dir, const uint64_t* in, uint64_t* out, size_t batch, cudaStream_t s) {
     const bool dp = p->mod.dp != 0;
+    const bool u32 = use_u32(p);
     switch (p->logn) {
         FHEB_DISPATCH_L(launch_transform, 2, p, dir, in, out, batch, s)
         FHEB_DISPATCH_L(launch_transform, 3, p, dir, in, out, batch, s)
@@ -316,13 +332,14 @@ static int dispatch_transform(const NttPlan* p, int dir, const uint64_t* in, uin
         FHEB_DISPATCH_L(launch_transform, 13, p, dir, in, out, batch, s)
         FHEB_DISPATCH_L(launch_transform, 14, p, dir, in, out, batch, s)
         case 15:
-        case 16: return dp ? launch_transform_big<true>(p, dir, in, out, batch, s) : launch_transform_big<false>(p, dir, in, out, batch, s);
+        case 16: return dp ? launch_transform_big<MODE_DP>(p, dir, in, out, batch, s) : launch_transform_big<MODE_INT>(p, dir, in, out, batch, s);
     }
     return set_error(FHEB_ERR_INVALID_PARAMETERS, "unsupported degree 2^%u", p->logn);
 }
 
 static int dispatch_polymul(const NttPlan* p, const uint64_t* a, const uint64_t* b, uint64_t* c, size_t batch, cudaStream_t s) {
     const bool dp = p->mod.dp != 0;
+    const bool u32 = use_u32(p);
     switch (p->logn) {
         FHEB_DISPATCH_L(launch_polymul, 2, p, a, b, c, batch, s)
         FHEB_DISPATCH_L(launch_polymul, 3, p, a, b, c, batch, s)
@@ -338,7 +355,7 @@ static int dispatch_polymul(const NttPlan* p, const uint64_t* a, const uint64_t*
         FHEB_DISPATCH_L(launch_polymul, 13, p, a, b, c, batch, s)
         FHEB_DISPATCH_L(launch_polymul, 14, p, a, b, c, batch, s)
         case 15:
-        case 16: return dp ? launch_polymul_big<true>(p, a, b, c, batch, s) : launch_polymul_big<false>(p, a, b, c, batch, s);
+        case 16: return dp ? launch_polymul_big<MODE_DP>(p, a, b, c, batch, s) : launch_polymul_big<MODE_INT>(p, a, b, c, batch, s);
     }
     return set_error(FHEB_ERR_INVALID_PARAMETERS, "unsupported degree 2^%u", p->logn);
 }

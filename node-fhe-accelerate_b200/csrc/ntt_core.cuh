@@ -62,35 +62,61 @@ FHEB_HD uint32_t bitrev_rt(uint32_t x, int bits) {
 #endif
 }
 
+// Arithmetic mode of a kernel instantiation (the template parameter called DP for historical reasons):
+//   MODE_INT (0)  q < 2^62: 64-bit words, Shoup products from IMAD.WIDE chains, values in [0, 4q)
+//   MODE_DP  (1)  q < 2^42: integers held in doubles, products on the FP64 pipe, |v| < 128 q
+//   MODE_U32 (2)  q < 2^27: 32-bit words (kept zero-extended in the 64-bit register/shared-memory slots), Shoup products
+//                 from ONE IMAD.HI + two IMAD, values in [0, 32q) - 14 lazy stages need no conditional subtraction.
+//                 132120577, the modulus of every published reference row, is such a prime.
+constexpr int MODE_INT = 0, MODE_DP = 1, MODE_U32 = 2;
 constexpr int CAP_STRICT = 4;   // q < 2^62: 4q fits a word
 constexpr int CAP_DP = 128;     // q < 2^42: |v| < 128 q <= 2^49 keeps every FP64 step exact with margin
-
-template <bool DP>
-constexpr int cap_of() { return DP ? CAP_DP : CAP_STRICT; }
+constexpr int CAP_U32 = 32;     // q < 2^27: 32q fits 32 bits
+constexpr int U32_UNIT_CAP = 8; // unit-twiddle butterflies double the bound: they reduce first once it would pass 8q
 
 // ---- compile-time range tracking -----------------------------------------------------
-constexpr int fwd_next_k(int K, bool has_unit, bool has_nonunit, bool dp) {
-    if (dp) {  // |A +- t| <= K + 1 (|t| < q), |A +- B| <= 2K; never reduced (static_assert at the use)
+constexpr int fwd_next_k(int K, bool has_unit, bool has_nonunit, int mode) {
+    if (mode == MODE_DP) {  // |A +- t| <= K + 1 (|t| < q), |A +- B| <= 2K; never reduced (static_assert at the use)
         int kn = has_nonunit ? K + 1 : 0;
         int ku = has_unit ? 2 * K : 0;
+        return kn > ku ? kn : ku;
+    }
+    if (mode == MODE_U32) {  // t in [0, 2q): A +- t < (K + 2) q; unit: A +- B < 2K q, both reduced to [0, 2q) first when 2K > 8
+        int kn = has_nonunit ? (((K + 2 > CAP_U32) ? 2 : K) + 2) : 0;
+        int ku = has_unit ? ((2 * K > U32_UNIT_CAP) ? 4 : 2 * K) : 0;
         return kn > ku ? kn : ku;
     }
     int kn = has_nonunit ? (((K + 2 > CAP_STRICT) ? 2 : K) + 2) : 0;
     int ku = has_unit ? ((2 * K > CAP_STRICT) ? 4 : 2 * K) : 0;
     return kn > ku ? kn : ku;
 }
-constexpr int fwd_pass_k(int K, int R, bool unit_first, bool dp) {
-    for (int a = 0; a < R; ++a) K = fwd_next_k(K, unit_first, !(unit_first && a == 0), dp);
+constexpr int fwd_pass_k(int K, int R, bool unit_first, int mode) {
+    for (int a = 0; a < R; ++a) K = fwd_next_k(K, unit_first, !(unit_first && a == 0), mode);
     return K;
 }
-constexpr int inv_next_k(int K, bool dp) {
-    if (dp) return (2 * K > CAP_DP) ? 1 : 2 * K;
+constexpr int inv_next_k(int K, int mode) {
+    if (mode == MODE_DP) return (2 * K > CAP_DP) ? 1 : 2 * K;
+    if (mode == MODE_U32) return (2 * K > CAP_U32 / 2) ? 2 : 2 * K;  // sums kept below 16q so that the next sum fits 32 bits
     return (2 * K > CAP_STRICT / 2) ? 2 : 2 * K;
 }
-constexpr int inv_pass_k(int K, int R, bool dp) {
-    for (int a = 0; a < R; ++a) K = inv_next_k(K, dp);
+constexpr int inv_pass_k(int K, int R, int mode) {
+    for (int a = 0; a < R; ++a) K = inv_next_k(K, mode);
     return K;
 }
+
+// ---- 32-bit arithmetic of MODE_U32 (q < 2^27) --------------------------------------------------
+FHEB_HD uint32_t mulhi32(uint32_t a, uint32_t b) {
+#if defined(__CUDA_ARCH__)
+    return __umulhi(a, b);
+#else
+    return (uint32_t)(((uint64_t)a * b) >> 32);
+#endif
+}
+// x * w mod q, lazily: [0, 2q) for ANY 32-bit x, given w < q and wp = floor(w * 2^32 / q)
+FHEB_HD uint32_t shoup32(uint32_t x, uint32_t w, uint32_t wp, uint32_t q) { return x * w - mulhi32(x, wp) * q; }
+// any 32-bit x -> [0, 2q)  (one-word Barrett with mu32 = floor(2^32 / q))
+FHEB_HD uint32_t lazy32(uint32_t x, const ModQ& m) { return x - mulhi32(x, m.mu32) * (uint32_t)m.q; }
+FHEB_HD uint32_t csub32(uint32_t x, uint32_t q) { return x >= q ? x - q : x; }
 
 template <int K>
 FHEB_HD uint64_t kq(const ModQ& m) {
@@ -100,14 +126,34 @@ FHEB_HD uint64_t kq(const ModQ& m) {
 }
 
 // Forward butterfly on values bounded by K*q; leaves values bounded by fwd_next_k(K)*q.
-template <int K, bool DP, bool UNIT>
+template <int K, int DP, bool UNIT>
 FHEB_HD void fwd_bfly(uint64_t& A, uint64_t& B, const Tw& w, const ModQ& m) {
-    if constexpr (DP) {
+    if constexpr (DP == MODE_DP) {
         static_assert(fwd_next_k(K, UNIT, !UNIT, true) <= CAP_DP, "FP64 range exceeded in a forward stage");
         const double a = bits_to_double(A);
         const double t = UNIT ? bits_to_double(B) : dp_mulmod(bits_to_double(B), bits_to_double(w.w), m);
         A = double_to_bits(dp_add(a, t));
         B = double_to_bits(dp_add(a, -t));
+    } else if constexpr (DP == MODE_U32) {
+        const uint32_t q = (uint32_t)m.q;
+        uint32_t a = (uint32_t)A, b = (uint32_t)B;
+        if constexpr (UNIT) {
+            constexpr bool red = (2 * K > U32_UNIT_CAP);
+            if constexpr (red) {
+                a = lazy32(a, m);
+                b = lazy32(b, m);
+            }
+            constexpr int KT = red ? 2 : K;
+            static_assert(2 * KT <= CAP_U32, "32-bit range exceeded in a unit forward stage");
+            A = a + b;
+            B = a - b + (uint32_t)KT * q;
+        } else {
+            constexpr bool red = (K + 2 > CAP_U32);
+            if constexpr (red) a = lazy32(a, m);
+            const uint32_t t = shoup32(b, (uint32_t)w.w, (uint32_t)w.wp, q);  // [0, 2q) for any b
+            A = a + t;
+            B = a - t + 2u * q;
+        }
     } else if constexpr (UNIT) {  // twiddle == 1: no multiplication
         constexpr bool red = (2 * K > CAP_STRICT);
         static_assert(!red || K <= 4, "conditional subtraction only halves [0,4q)");
@@ -131,9 +177,9 @@ FHEB_HD void fwd_bfly(uint64_t& A, uint64_t& B, const Tw& w, const ModQ& m) {
 }
 
 // Inverse (Gentleman-Sande) butterfly on values bounded by K*q; leaves values bounded by inv_next_k(K)*q.
-template <int K, bool DP, bool UNIT>
+template <int K, int DP, bool UNIT>
 FHEB_HD void inv_bfly(uint64_t& A, uint64_t& B, const Tw& w, const ModQ& m) {
-    if constexpr (DP) {
+    if constexpr (DP == MODE_DP) {
         static_assert(2 * K <= 2 * CAP_DP, "FP64 range exceeded in an inverse stage");
         constexpr bool red = (2 * K > CAP_DP);
         const double a = bits_to_double(A), b = bits_to_double(B);
@@ -147,6 +193,21 @@ FHEB_HD void inv_bfly(uint64_t& A, uint64_t& B, const Tw& w, const ModQ& m) {
         }
         A = double_to_bits(s);
         B = double_to_bits(d);
+    } else if constexpr (DP == MODE_U32) {
+        static_assert(2 * K <= CAP_U32, "sum would overflow 32 bits");
+        constexpr bool red = (2 * K > CAP_U32 / 2);
+        const uint32_t q = (uint32_t)m.q;
+        const uint32_t a = (uint32_t)A, b = (uint32_t)B;
+        uint32_t s = a + b;
+        uint32_t d = a - b + (uint32_t)K * q;
+        if constexpr (red) s = lazy32(s, m);
+        A = s;
+        if constexpr (UNIT) {
+            if constexpr (red) d = lazy32(d, m);
+            B = d;
+        } else {
+            B = shoup32(d, (uint32_t)w.w, (uint32_t)w.wp, q);
+        }
     } else {
         static_assert(2 * K <= CAP_STRICT, "sum would overflow the word");
         constexpr bool red = (2 * K > CAP_STRICT / 2);
@@ -189,11 +250,12 @@ FHEB_HD void stream_store(uint64_t* p, uint64_t v) {
 #endif
 }
 
-// Twiddle tables: integer mode = (value, Shoup companion) pairs, 16 bytes; DP mode = one double, 8 bytes.
-template <bool DP>
+// Twiddle tables: integer mode = (value, Shoup companion) pairs, 16 bytes; DP mode = one double, 8 bytes;
+// U32 mode = (value, 32-bit Shoup companion) packed into 8 bytes.
+template <int DP>
 FHEB_HD Tw load_tw(const Tw* __restrict__ tw, uint32_t idx) {
     Tw t;
-    if constexpr (DP) {
+    if constexpr (DP == MODE_DP) {
         const uint64_t* p = reinterpret_cast<const uint64_t*>(tw);
 #if defined(__CUDA_ARCH__)
         t.w = __ldg(p + idx);
@@ -201,6 +263,15 @@ FHEB_HD Tw load_tw(const Tw* __restrict__ tw, uint32_t idx) {
         t.w = p[idx];
 #endif
         t.wp = 0;
+    } else if constexpr (DP == MODE_U32) {  // (w, w') as two 32-bit halves of one 8-byte entry
+        const uint64_t* p = reinterpret_cast<const uint64_t*>(tw);
+#if defined(__CUDA_ARCH__)
+        const uint64_t v = __ldg(p + idx);
+#else
+        const uint64_t v = p[idx];
+#endif
+        t.w = v & 0xFFFFFFFFull;
+        t.wp = v >> 32;
     } else {
 #if defined(__CUDA_ARCH__)
         const ulonglong2 v = __ldg(reinterpret_cast<const ulonglong2*>(tw) + idx);
@@ -217,7 +288,7 @@ FHEB_HD Tw load_tw(const Tw* __restrict__ tw, uint32_t idx) {
 // position bit of the pass.  The pass starts at stage S0; TB = table offset of the pass + the index
 // of this item's block among the 2^S0 blocks of stage S0 (see tw_index below).
 // REGTW: `tw` points at this item's twiddles already held in registers, entry ((1 << a) - 1) + g.
-template <int R, int S0, int K, bool DP, bool UNITFIRST, int A = 0, bool REGTW = false>
+template <int R, int S0, int K, int DP, bool UNITFIRST, int A = 0, bool REGTW = false>
 FHEB_HD void fwd_stages(uint64_t (&x)[1 << R], const Tw* __restrict__ tw, uint32_t TB, const ModQ& m) {
     if constexpr (A < R) {
         constexpr int half = 1 << (R - 1 - A);
@@ -238,7 +309,7 @@ FHEB_HD void fwd_stages(uint64_t (&x)[1 << R], const Tw* __restrict__ tw, uint32
 }
 
 // R inverse stages, highest stage of the pass first (element bit 0 first).
-template <int R, int S0, int K, bool DP, bool UNITFIRST, int A = R - 1, bool REGTW = false>
+template <int R, int S0, int K, int DP, bool UNITFIRST, int A = R - 1, bool REGTW = false>
 FHEB_HD void inv_stages(uint64_t (&x)[1 << R], const Tw* __restrict__ tw, uint32_t TB, const ModQ& m) {
     if constexpr (A >= 0) {
         constexpr int half = 1 << (R - 1 - A);
@@ -259,7 +330,7 @@ FHEB_HD void inv_stages(uint64_t (&x)[1 << R], const Tw* __restrict__ tw, uint32
 }
 
 // all (2^R - 1) twiddles of one item into registers, entry ((1 << a) - 1) + g
-template <int R, int S0, bool DP>
+template <int R, int S0, int DP>
 FHEB_HD void load_item_tw(const Tw* __restrict__ tw, uint32_t TB, Tw (&w)[(1 << R) - 1]) {
 #pragma unroll
     for (int a = 0; a < R; ++a)
@@ -268,12 +339,17 @@ FHEB_HD void load_item_tw(const Tw* __restrict__ tw, uint32_t TB, Tw (&w)[(1 << 
 }
 
 // value bounded by K*q  ->  canonical word
-template <int K, bool DP = false>
+template <int K, int DP = false>
 FHEB_HD uint64_t canon_k(uint64_t x, const ModQ& m) {
-    if constexpr (DP) {
+    if constexpr (DP == MODE_DP) {
         double r = bits_to_double(x);
         if constexpr (K > 1) r = dp_reduce(r, m);
         return dp_canon_word(r, m);
+    } else if constexpr (DP == MODE_U32) {
+        uint32_t v = (uint32_t)x;
+        if constexpr (K > 2) v = lazy32(v, m);
+        if constexpr (K > 1) v = csub32(v, (uint32_t)m.q);
+        return v;
     } else if constexpr (K <= 1) return x;
     else if constexpr (K == 2) return csub(x, m.q);
     else if constexpr (K <= 4) return csub(csub(x, m.q2), m.q);
@@ -281,14 +357,14 @@ FHEB_HD uint64_t canon_k(uint64_t x, const ModQ& m) {
 }
 
 // caller word (any 64-bit value) -> the mode's register representation of its residue
-template <bool DP>
+template <int DP>
 FHEB_HD uint64_t load_word(uint64_t v, const ModQ& m) {
     const uint64_t c = canon_any(v, m);
-    if constexpr (DP) return double_to_bits(dp_from_uint(c));
+    if constexpr (DP == MODE_DP) return double_to_bits(dp_from_uint(c));
     else return c;
 }
 // the same for a whole item: unreduced words are rare, so one test covers the item's 2^R words
-template <bool DP, int E>
+template <int DP, int E>
 FHEB_HD void load_words(uint64_t (&x)[E], const ModQ& m) {
     bool raw = false;
 #pragma unroll
@@ -297,23 +373,24 @@ FHEB_HD void load_words(uint64_t (&x)[E], const ModQ& m) {
 #pragma unroll
         for (int c = 0; c < E; ++c) x[c] = canon_any(x[c], m);
     }
-    if constexpr (DP) {
+    if constexpr (DP == MODE_DP) {
 #pragma unroll
         for (int c = 0; c < E; ++c) x[c] = double_to_bits(dp_from_uint(x[c]));
     }
 }
 
 // finished transform parked for the fused product: canonical word (integer) / reduced double (DP)
-template <int K, bool DP>
+template <int K, int DP>
 FHEB_HD uint64_t park_word(uint64_t x, const ModQ& m) {
-    if constexpr (DP) return (K > 1) ? double_to_bits(dp_reduce(bits_to_double(x), m)) : x;
-    else return canon_k<K>(x, m);
+    if constexpr (DP == MODE_DP) return (K > 1) ? double_to_bits(dp_reduce(bits_to_double(x), m)) : x;
+    else return canon_k<K, DP>(x, m);
 }
 
 // x * N^-1 -> canonical word (x bounded by K*q, K within the mode's cap)
-template <bool DP>
+template <int DP>
 FHEB_HD uint64_t scale_word(uint64_t x, const Tw& ninv, const ModQ& m) {
-    if constexpr (DP) return dp_canon_word(dp_mulmod(bits_to_double(x), bits_to_double(ninv.w), m), m);
+    if constexpr (DP == MODE_DP) return dp_canon_word(dp_mulmod(bits_to_double(x), bits_to_double(ninv.w), m), m);
+    else if constexpr (DP == MODE_U32) return csub32(shoup32((uint32_t)x, (uint32_t)ninv.w, (uint32_t)ninv.wp, (uint32_t)m.q), (uint32_t)m.q);
     else return csub(shoup_lazy(x, ninv.w, ninv.wp, m.q), m.q);
 }
 
@@ -379,7 +456,7 @@ inline void plan_runtime(int L, int& P, int (&R)[5]) {
 
 // SUB: the L stages are the tail of a larger transform (degrees above 2^14, see ntt_device.cuh): the first
 // pass has no unit twiddles then.
-template <int L, bool DP, int PASS, bool SUB = false>
+template <int L, int DP, int PASS, bool SUB = false>
 constexpr int plan_fwd_kin() {  // bound on values entering forward pass PASS (inputs canonical)
     int K = 1;
     for (int p = 0; p < PASS; ++p) K = fwd_pass_k(K, Plan<L>::R[p], p == 0 && !SUB, DP);
@@ -391,7 +468,7 @@ constexpr int plan_fwd_kin() {  // bound on values entering forward pass PASS (i
 struct GlobalMap {
     uint32_t shift, low;
 };
-template <int L, bool DP, int PASS, int KSTART = 1>
+template <int L, int DP, int PASS, int KSTART = 1>
 constexpr int plan_inv_kin() {  // bound entering inverse pass PASS (run order P-1 .. 0), first executed pass fed values < KSTART*q
     int K = KSTART;
     for (int p = Plan<L>::P - 1; p > PASS; --p) K = inv_pass_k(K, Plan<L>::R[p], DP);
@@ -417,7 +494,7 @@ enum {
 //   SCALE      : multiply the outputs by `ninv` (fast_ntt_inverse semantics)
 // OUT == IO_STASH_*: the finished transform is parked (position order, no bit reversal) in
 // `gout` for the fused polynomial product; canonical words in integer mode, lazy doubles (|v| < KOUT*q) in DP mode.
-template <int L, bool DP, int PASS, int IN, int OUT, bool BITREV_OUT = true, bool SCALE = false, int IPT = 0, bool SUB = false, bool PIPE = false>
+template <int L, int DP, int PASS, int IN, int OUT, bool BITREV_OUT = true, bool SCALE = false, int IPT = 0, bool SUB = false, bool PIPE = false>
 FHEB_HD void fwd_pass(uint32_t tid, uint32_t nthreads, uint32_t polys, const uint64_t* gin, uint64_t* gout,
                       uint64_t* smem, const Tw* __restrict__ tw, const ModQ& m, const Tw ninv = Tw{0, 0},
                       const GlobalMap map = GlobalMap{0, 0}) {
@@ -543,7 +620,7 @@ FHEB_HD void fwd_pass(uint32_t tid, uint32_t nthreads, uint32_t polys, const uin
 //   IN    : IO_GLOBAL when the plan has a single pass (b read from caller memory), else IO_SMEM
 //   OUT   : IO_GLOBAL when the plan has a single pass (scaled, canonical), else IO_SMEM
 //   STASH : IO_STASH_SMEM or IO_STASH_GLOBAL (where fwd_pass parked T(a))
-template <int L, bool DP, int IN, int OUT, int STASH>
+template <int L, int DP, int IN, int OUT, int STASH>
 FHEB_HD void polymul_mid_pass(uint32_t tid, uint32_t nthreads, uint32_t polys, const uint64_t* gin, uint64_t* gout,
                               uint64_t* smem, const uint64_t* stash, const Tw* __restrict__ twf,
                               const Tw* __restrict__ twi, const Tw ninv, const ModQ& m) {
@@ -558,7 +635,7 @@ FHEB_HD void polymul_mid_pass(uint32_t tid, uint32_t nthreads, uint32_t polys, c
     constexpr uint32_t ITEMS = N >> R;
     static_assert(EB == 0, "the last forward pass covers the lowest position bits");
     // DP: the parked operand is reduced (|a| <= q/2 + 1), this one stays lazy: |a*b| <= KOUT q^2 / 2
-    static_assert(!DP || KOUT <= 2 * CAP_DP, "FP64 product bound");
+    static_assert(DP != MODE_DP || KOUT <= 2 * CAP_DP, "FP64 product bound");
 
     for (uint32_t U = tid; U < polys * ITEMS; U += nthreads) {
         const uint32_t poly = U >> (L - R);
@@ -582,8 +659,8 @@ FHEB_HD void polymul_mid_pass(uint32_t tid, uint32_t nthreads, uint32_t polys, c
 #pragma unroll
         for (int c = 0; c < E; ++c) {
             const uint64_t av = (STASH == IO_STASH_GLOBAL) ? sa[base | (uint32_t)c] : sa[pb ^ swz((uint32_t)c)];
-            if constexpr (DP) x[c] = double_to_bits(dp_mulmod(bits_to_double(av), bits_to_double(x[c]), m));
-            else x[c] = mulmod(av, canon_k<KOUT>(x[c], m), m);
+            if constexpr (DP == MODE_DP) x[c] = double_to_bits(dp_mulmod(bits_to_double(av), bits_to_double(x[c]), m));
+            else x[c] = mulmod(av, canon_k<KOUT, DP>(x[c], m), m);  // canonical x canonical (U32 mode: generic 64-bit reduction, once per coefficient)
         }
         inv_stages<R, S0, 1, DP, PASS == 0>(x, twi, TB, m);
         if (OUT == IO_GLOBAL) {
@@ -602,7 +679,7 @@ FHEB_HD void polymul_mid_pass(uint32_t tid, uint32_t nthreads, uint32_t polys, c
 // may read the reference's input order (bit-reversed positions) from global memory; the
 // last one executed (PASS == 0) multiplies by N^-1 (`ninv`, Shoup pair) and stores canonical
 // values in natural order.
-template <int L, bool DP, int PASS, int IN, int OUT, bool BITREV_IN = true, int IPT = 0, int KSTART = 1, bool SUB = false, bool PIPE = false>
+template <int L, int DP, int PASS, int IN, int OUT, bool BITREV_IN = true, int IPT = 0, int KSTART = 1, bool SUB = false, bool PIPE = false>
 FHEB_HD void inv_pass(uint32_t tid, uint32_t nthreads, uint32_t polys, const uint64_t* gin, uint64_t* gout,
                       uint64_t* smem, const Tw* __restrict__ tw, const Tw ninv, const ModQ& m,
                       const GlobalMap map = GlobalMap{0, 0}) {

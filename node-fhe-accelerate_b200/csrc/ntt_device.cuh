@@ -14,7 +14,7 @@ __device__ __forceinline__ void prefetch_l2_bulk(const void* p, uint32_t bytes) 
         asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
 }
 
-template <int L, bool DP, int PASS, bool SUB = false>
+template <int L, int DP, int PASS, bool SUB = false>
 __device__ __forceinline__ void fwd_middle(uint32_t tid, uint32_t nthreads, uint32_t polys, uint64_t* smem,
                                            const Tw* __restrict__ tw, const ModQ& m) {
     if constexpr (PASS < Plan<L>::P - 1) {
@@ -24,7 +24,7 @@ __device__ __forceinline__ void fwd_middle(uint32_t tid, uint32_t nthreads, uint
     }
 }
 
-template <int L, bool DP, int PASS, bool SUB = false>
+template <int L, int DP, int PASS, bool SUB = false>
 __device__ __forceinline__ void inv_middle(uint32_t tid, uint32_t nthreads, uint32_t polys, uint64_t* smem,
                                            const Tw* __restrict__ tw, const Tw ninv, const ModQ& m) {
     if constexpr (PASS > 0) {
@@ -36,7 +36,7 @@ __device__ __forceinline__ void inv_middle(uint32_t tid, uint32_t nthreads, uint
 
 // Forward transform of `batch` polynomials, [batch][N] -> [batch][N] (in may equal out).
 // SCALE = true gives fast_ntt_inverse semantics when `tw` is the inverse table.
-template <int L, bool DP, int THREADS, int PPC, bool SCALE>
+template <int L, int DP, int THREADS, int PPC, bool SCALE>
 __global__ void __launch_bounds__(THREADS) ntt_forward_kernel(const uint64_t* in, uint64_t* out, size_t batch,
                                                               const Tw* __restrict__ tw, const Tw ninv, const ModQ m) {
     extern __shared__ __align__(16) uint64_t smem[];
@@ -68,7 +68,7 @@ __global__ void __launch_bounds__(THREADS) ntt_forward_kernel(const uint64_t* in
 
 // Inverse transform (Gentleman-Sande network, bit-reversal folded into the loads, N^-1 folded
 // into the last pass).
-template <int L, bool DP, int THREADS, int PPC>
+template <int L, int DP, int THREADS, int PPC>
 __global__ void __launch_bounds__(THREADS) ntt_inverse_kernel(const uint64_t* in, uint64_t* out, size_t batch,
                                                               const Tw* __restrict__ tw, const Tw ninv, const ModQ m) {
     extern __shared__ __align__(16) uint64_t smem[];
@@ -105,7 +105,7 @@ __global__ void __launch_bounds__(THREADS) ntt_inverse_kernel(const uint64_t* in
 // twiddle table (the tail of the big network: no unit twiddles; 2 * 2^14 entries each, see ntt_plan.hpp) and scatters the results into the
 // reference's output order, index (r << D) | bitrev_D(h) for word r of sub-block h.  The inverse runs
 // the same two kernels backwards.
-template <int D, bool DP, bool INVERSE>
+template <int D, int DP, bool INVERSE>
 __global__ void __launch_bounds__(256) ntt_top_kernel(const uint64_t* in, uint64_t* out, size_t batch, uint32_t L,
                                                       const Tw* __restrict__ tw, const Tw ninv, const ModQ m) {
     constexpr int E = 1 << D;
@@ -135,7 +135,7 @@ __global__ void __launch_bounds__(256) ntt_top_kernel(const uint64_t* in, uint64
 
 // 14-stage tail of a larger forward transform: sub-block g of `tmp` (natural positions, canonical)
 // -> caller memory in the reference's order.  tables = 2^D consecutive twiddle tables.
-template <int L, bool DP, int THREADS, bool SCALE>
+template <int L, int DP, int THREADS, bool SCALE>
 __global__ void __launch_bounds__(THREADS) ntt_forward_sub_kernel(const uint64_t* tmp, uint64_t* out, size_t subs, uint32_t D,
                                                                   const Tw* __restrict__ tables, const Tw ninv, const ModQ m) {
     extern __shared__ __align__(16) uint64_t smem[];
@@ -157,7 +157,7 @@ __global__ void __launch_bounds__(THREADS) ntt_forward_sub_kernel(const uint64_t
 
 // 14-stage head of a larger inverse transform: caller memory (reference order) -> `tmp` (natural
 // positions, canonical, unscaled); the top D stages and the scaling follow in ntt_top_kernel.
-template <int L, bool DP, int THREADS>
+template <int L, int DP, int THREADS>
 __global__ void __launch_bounds__(THREADS) ntt_inverse_sub_kernel(const uint64_t* in, uint64_t* tmp, size_t subs, uint32_t D,
                                                                   const Tw* __restrict__ tables, const Tw one, const ModQ m) {
     extern __shared__ __align__(16) uint64_t smem[];
@@ -180,7 +180,7 @@ __global__ void __launch_bounds__(THREADS) ntt_inverse_sub_kernel(const uint64_t
 // c = T^-1(T(a) . T(b)) in one launch (PolynomialRing::multiply, polynomial_ring.cpp:421-447).
 // T(a) is parked either in a second shared-memory buffer or, when two operands do not fit
 // (N = 16384), in a per-block global scratch that stays L2 resident.
-template <int L, bool DP, int THREADS, int PPC, bool STASH_GLOBAL>
+template <int L, int DP, int THREADS, int PPC, bool STASH_GLOBAL>
 __global__ void __launch_bounds__(THREADS) polymul_kernel(const uint64_t* a, const uint64_t* b, uint64_t* c, size_t batch,
                                                           const Tw* __restrict__ twf, const Tw* __restrict__ twi,
                                                           const Tw ninv, const ModQ m, uint64_t* scratch) {

@@ -104,6 +104,18 @@ inline std::vector<uint64_t> build_heap_table_dp(const uint64_t* table, uint32_t
     return out;
 }
 
+// U32 mode (q < 2^27): value and floor(w * 2^32 / q) packed into one 8-byte entry (low half: w)
+constexpr int U32_QBITS = 27;
+inline std::vector<uint64_t> build_heap_table_u32(const uint64_t* table, uint32_t L, uint64_t q) {
+    std::vector<uint64_t> out((size_t)1 << L, 0);
+    for_each_twiddle(L, [&](uint32_t at, uint32_t e) {
+        const uint64_t w = table[e] % q;
+        out[at] = w | (((w << 32) / q) << 32);
+    });
+    append_bitrev_last_pass(out, L);
+    return out;
+}
+
 // ---- degrees above 2^14: tables of the 2^D sub-blocks and of the top D stages (ntt_device.cuh) -------
 // Sub-block h runs stages D..L-1 of the big network; its stage s' = s - D has blocks b' whose big-network
 // block is b = (h << s') + b', i.e. twiddle table[bitrev_s(b) << (L-1-s)].  Same entry order as above.

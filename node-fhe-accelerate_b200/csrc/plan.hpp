@@ -29,6 +29,11 @@ struct NttPlan {
     Tw* d_top_fwd = nullptr;
     Tw* d_top_inv = nullptr;
     Tw one{};
+    // moduli below 2^27 (e.g. 132120577): a second table set for the 32-bit kernels of the plain transforms and the fused
+    // product (8 bytes per entry: value and 32-bit Shoup companion); everything else keeps using the tables above
+    Tw* d_fwd32 = nullptr;
+    Tw* d_inv32 = nullptr;
+    Tw ninv32{};
     // the device whose memory holds the tables above, and copies of the plan on other devices (made on first use when
     // a host batch is spread over several GPUs; owned by this plan)
     int device = 0;

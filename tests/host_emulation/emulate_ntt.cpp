@@ -22,7 +22,7 @@
 
 using namespace fheb;
 
-template <int L, bool DP, int PASS>
+template <int L, int DP, int PASS>
 static void run_fwd(uint32_t threads, uint32_t polys, const uint64_t* gin, uint64_t* gout, uint64_t* smem,
                     const Tw* tw, const ModQ& m) {
     constexpr int P = Plan<L>::P;
@@ -37,7 +37,7 @@ static void run_fwd(uint32_t threads, uint32_t polys, const uint64_t* gin, uint6
     }
 }
 
-template <int L, bool DP, int PASS>
+template <int L, int DP, int PASS>
 static void run_inv(uint32_t threads, uint32_t polys, const uint64_t* gin, uint64_t* gout, uint64_t* smem,
                     const Tw* tw, const Tw& ninv, const ModQ& m) {
     constexpr int P = Plan<L>::P;
@@ -53,25 +53,28 @@ static void run_inv(uint32_t threads, uint32_t polys, const uint64_t* gin, uint6
 }
 
 // the device twiddle heap as raw words: (w, w') pairs, or one double per entry in DP mode
-static std::vector<uint64_t> heap_words(const uint64_t* table, uint32_t L, uint64_t q, bool dp) {
-    if (dp) return build_heap_table_dp(table, L, q);
+static std::vector<uint64_t> heap_words(const uint64_t* table, uint32_t L, uint64_t q, int mode) {
+    if (mode == MODE_U32) return build_heap_table_u32(table, L, q);
+    if (mode == MODE_DP) return build_heap_table_dp(table, L, q);
     const std::vector<Tw> h = build_heap_table(table, L, q);
     std::vector<uint64_t> w(h.size() * 2);
     std::memcpy(w.data(), h.data(), w.size() * 8);
     return w;
 }
 
-static uint64_t pick_prime(int L, bool lazy) {
+static uint64_t pick_prime(int L, int mode) {
     // q == 1 (mod 2N), coprime to 2^64-1 where possible
+    if (mode == MODE_U32) return (L <= 5) ? 97ULL + 0 * L : 132120577ULL;  // 2N | q - 1: 97 up to N = 16 ... see check()
+    const bool lazy = mode == MODE_DP;
     if (lazy) return (L <= 10) ? 1099511678977ULL /* 41 bit */ : 132120577ULL /* 27 bit, 2N | q-1 up to 2^20 */;
     return 4611686018326724609ULL;  // 62 bit
 }
 
-template <int L, bool DP>
-static int check(uint32_t threads, uint32_t polys) {
+template <int L, int DP>
+static int check(uint32_t threads, uint32_t polys, uint64_t q_override = 0) {
     const uint32_t N = 1u << L;
-    uint64_t q = pick_prime(L, DP);
-    if (L <= 3 && !DP) q = 4611686018326724609ULL;
+    uint64_t q = q_override ? q_override : pick_prime(L, DP);
+    if (L <= 3 && DP == MODE_INT) q = 4611686018326724609ULL;
     std::vector<uint64_t> fwd(N), inv(N);
     uint64_t sc[3];
     if (orc_precompute_twiddles(N, q, fwd.data(), inv.data(), sc) != 0) {
@@ -79,14 +82,19 @@ static int check(uint32_t threads, uint32_t polys) {
         return 1;
     }
     ModQ m = make_modq(q);
-    if ((m.dp != 0) != DP) {
+    if (DP != MODE_U32 && (int)(m.dp != 0) != DP) {
         std::printf("L=%d: mode mismatch\n", L);
+        return 1;
+    }
+    if (DP == MODE_U32 && (q >= (1ULL << U32_QBITS) || m.mu32 == 0)) {
+        std::printf("L=%d: prime %llu too large for the 32-bit mode\n", L, (unsigned long long)q);
         return 1;
     }
     const std::vector<uint64_t> hfw = heap_words(fwd.data(), L, q, DP), hiw = heap_words(inv.data(), L, q, DP);
     const Tw* hf = reinterpret_cast<const Tw*>(hfw.data());
     const Tw* hi = reinterpret_cast<const Tw*>(hiw.data());
-    const Tw ninv = DP ? Tw{double_to_bits((double)sc[2]), 0} : Tw{sc[2], shoup_companion(sc[2], q)};
+    const Tw ninv = DP == MODE_U32 ? Tw{sc[2], (sc[2] << 32) / q}
+                    : DP == MODE_DP ? Tw{double_to_bits((double)sc[2]), 0} : Tw{sc[2], shoup_companion(sc[2], q)};
     std::mt19937_64 rng(1234 + L);
     std::vector<uint64_t> x((size_t)polys * N), ref, got((size_t)polys * N), smem((size_t)polys * N);
     int bad = 0;
@@ -114,10 +122,15 @@ static int check(uint32_t threads, uint32_t polys) {
 template <int L>
 static int check_all() {
     int bad = 0;
-    bad += check<L, false>(64, 1);
-    bad += check<L, true>(64, 1);
-    bad += check<L, false>(96, 3);  // thread count not dividing the work, several polynomials per block
-    bad += check<L, true>(32, 2);
+    bad += check<L, MODE_INT>(64, 1);
+    bad += check<L, MODE_DP>(64, 1);
+    bad += check<L, MODE_INT>(96, 3);  // thread count not dividing the work, several polynomials per block
+    bad += check<L, MODE_DP>(32, 2);
+    // 32-bit mode (q < 2^27): the published rows' prime, the largest 27-bit prime with 2^15 | q - 1 (range bookkeeping at
+    // the top of the 32 q window), and tiny primes where they are NTT-friendly
+    bad += check<L, MODE_U32>(64, 1, 132120577ULL);
+    bad += check<L, MODE_U32>(96, 3, 133857281ULL);  // the largest prime below 2^27 with 2^15 | q - 1
+    if constexpr (L <= 4) bad += check<L, MODE_U32>(32, 2, 97ULL);
     if constexpr (L < 14) bad += check_all<L + 1>();
     return bad;
 }
@@ -144,6 +157,18 @@ static int check_arith() {
             uint64_t ac = a % q, bc = b % q;
             if (addmod_canon(ac, bc, q) != (uint64_t)(((u128)ac + bc) % q)) { ++bad; break; }
             if (submod_canon(ac, bc, q) != (uint64_t)(((u128)ac + q - bc) % q)) { ++bad; break; }
+        }
+    }
+    for (uint64_t q : {17ULL, 97ULL, 132120577ULL, 133857281ULL, (1ULL << 27) - 39}) {  // 32-bit primitives of MODE_U32
+        ModQ m = make_modq(q);
+        for (int i = 0; i < 200000; ++i) {
+            uint32_t x = (uint32_t)rng();
+            if (i < 4) x = (i & 1) ? 0xFFFFFFFFu : (uint32_t)(32 * q - 1);
+            const uint32_t w = (uint32_t)(rng() % q), wp = (uint32_t)(((uint64_t)w << 32) / q);
+            const uint32_t r = shoup32(x, w, wp, (uint32_t)q);
+            if (r >= 2 * q || r % q != (uint64_t)x * w % q) { ++bad; break; }
+            const uint32_t l = lazy32(x, m);
+            if (l >= 2 * q || l % q != x % q) { ++bad; break; }
         }
     }
     if (bad) std::printf("arithmetic primitive mismatch (%d moduli)\n", bad);

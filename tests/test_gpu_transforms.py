@@ -95,17 +95,26 @@ def test_golden_transforms(fhe, torch, path):
     eq(host(ring.multiply(dev(torch, x[:h]), dev(torch, x[h:2 * h]))), g["product"])
 
 
-def _prime_for(logn, lazy):
+def _prime_for(logn, mode):
+    """q62: 64-bit integer kernels; q<2^42: FP64-pipe kernels (41-bit prime up to N = 1024, then the 27-bit prime of the
+    published rows with the 32-bit kernels switched off); q<2^27: the 32-bit kernels (132120577 and, at the top of the
+    32 q window, the largest prime below 2^27 with 2^15 | q - 1)."""
     n = 1 << logn
-    if not lazy:
+    if mode == "q62":
         return Q62
-    return QT if n <= 1024 else Q27
+    if mode == "q<2^42":
+        return QT if n <= 1024 else Q27
+    return Q27 if logn % 2 == 0 else 133857281
 
 
-@pytest.mark.parametrize("lazy", [False, True], ids=["q62", "q<2^46"])
+@pytest.mark.parametrize("lazy", ["q62", "q<2^42", "q<2^27"])
 @pytest.mark.parametrize("logn", range(2, 15))
-def test_transforms_match_oracle_all_degrees(fhe, torch, oracle, logn, lazy):
+def test_transforms_match_oracle_all_degrees(fhe, torch, oracle, logn, lazy, monkeypatch):
     n, q = 1 << logn, _prime_for(logn, lazy)
+    if lazy == "q<2^42":
+        monkeypatch.setenv("FHEB_NO_U32", "1")  # read per call by the library: keeps 27-bit primes on the FP64-pipe kernels
+    else:
+        monkeypatch.delenv("FHEB_NO_U32", raising=False)
     ntt = fhe.NTTProcessor(n, q)
     fwd, inv, psi, psi_inv, inv_n = oracle.twiddles(n, q)
     gf, gi, gpsi, gpsi_inv, ginv_n = ntt.get_twiddles()

@@ -21,6 +21,7 @@ __global__ void __launch_bounds__(512) k(uint64_t* out, int iters, double da, ui
             if (MODE == 2) v[i] = v[i] * (uint32_t)ua + v[(i + 1) & 7];                        // IMAD
             if (MODE == 3) u[i] = __umul64hi(u[i], ua) + u[(i + 1) & 7];
             if (MODE == 5) v[i] = __funnelshift_l(v[i], v[(i + 1) & 7], 3) ^ (uint32_t)ua;       // SHF + LOP3 (ALU pipe)
+            if (MODE == 6) v[i] = __umulhi(v[i], (uint32_t)ua) + v[(i + 1) & 7];                   // IMAD.HI.U32
             if (MODE == 4) { d[i] = fma(d[i], da, d[(i + 1) & 7]); u[i] = (uint64_t)(uint32_t)u[i] * (uint32_t)ua + u[(i + 1) & 7]; }
         }
     }
@@ -68,13 +69,14 @@ int main(int argc, char** argv) {
     run<3>("umul64hi", 8);
     run<4>("DFMA + IMAD.WIDE together", 16);
     run<5>("SHF + LOP3 (ALU pipe)", 16);
+    run<6>("IMAD.HI.U32", 8);
     if (g_json) {
         int clk = 0, sms = 0;
         cudaDeviceGetAttribute(&clk, cudaDevAttrClockRate, dev);
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
         printf("{\"dfma_tops\": %.4f, \"imad_wide_tops\": %.4f, \"imad_tops\": %.4f, \"umul64hi_tops\": %.4f, "
-               "\"dfma_plus_imad_wide_tops\": %.4f, \"alu_tops\": %.4f, \"sm_count\": %d, \"nominal_mhz\": %d}\n",
-               g_tops[0], g_tops[1], g_tops[2], g_tops[3], g_tops[4], g_tops[5], sms, clk / 1000);
+               "\"dfma_plus_imad_wide_tops\": %.4f, \"alu_tops\": %.4f, \"imad_hi_tops\": %.4f, \"sm_count\": %d, \"nominal_mhz\": %d}\n",
+               g_tops[0], g_tops[1], g_tops[2], g_tops[3], g_tops[4], g_tops[5], g_tops[6], sms, clk / 1000);
     }
     return 0;
 }
