@@ -426,6 +426,33 @@ napi_value MultiplyRelinearize(napi_env env, napi_callback_info info) {
     return res;
 }
 
+// ---- modAddBatch / modSubBatch(a, b, modulus: bigint) -> new BigUint64Array: PolynomialRing::add / subtract over a batch -------
+template <int (*FN)(const uint64_t*, const uint64_t*, uint64_t*, size_t, uint64_t, void*)>
+napi_value ElementwiseBinary(napi_env env, napi_callback_info info) {
+    Args a;
+    if (!get_args(env, info, &a, 3)) return nullptr;
+    uint64_t *x = nullptr, *y = nullptr, *z = nullptr;
+    size_t cx = 0, cy = 0;
+    uint64_t modulus = 0;
+    if (!get_words(env, a.argv[0], &x, &cx) || !get_words(env, a.argv[1], &y, &cy) || !get_u64(env, a.argv[2], &modulus)) return nullptr;
+    if (cx != cy) {
+        napi_throw_error(env, "INVALID_PARAMETERS", "Polynomial degree mismatch");  // polynomial_ring.cpp:241-257
+        return nullptr;
+    }
+    napi_value out = new_words(env, cx, &z);
+    if (!out) return nullptr;
+    FHEB_OK_OR_THROW(FN(x, y, z, cx, modulus, nullptr));
+    return out;
+}
+
+// ---- setDevices(): one Node process, every visible GPU (fheb_set_devices); returns the number of devices in use ----------
+napi_value SetDevices(napi_env env, napi_callback_info) {
+    FHEB_OK_OR_THROW(fheb_set_devices(nullptr, -1));
+    napi_value v;
+    NAPI_OK(napi_create_uint32(env, (uint32_t)fheb_get_devices(nullptr, 0), &v));
+    return v;
+}
+
 #define METHOD(name, fn) {name, nullptr, fn, nullptr, nullptr, nullptr, napi_default, nullptr}
 
 }  // namespace
@@ -438,6 +465,9 @@ NAPI_MODULE_INIT() {
         METHOD("tallyVotes", TallyVotes),
         METHOD("ingestBallots", IngestBallots),
         METHOD("multiplyRelinearize", MultiplyRelinearize),
+        METHOD("modAddBatch", ElementwiseBinary<fheb_modadd_batch>),
+        METHOD("modSubBatch", ElementwiseBinary<fheb_modsub_batch>),
+        METHOD("setDevices", SetDevices),
     };
     NAPI_OK(napi_define_properties(env, exports, sizeof(functions) / sizeof(functions[0]), functions));
 

@@ -38,6 +38,11 @@ declare namespace fheb {
                 bsk: BigUint64Array)
     bootstrapBatch(lwe: BigUint64Array, testPoly: BigUint64Array): BigUint64Array   // [batch][n+1] -> [batch][k*degree+1]
   }
+  // PolynomialRing::add / subtract over whole ciphertexts or batches (element-wise, any length)
+  function modAddBatch(a: BigUint64Array, b: BigUint64Array, modulus: bigint): BigUint64Array
+  function modSubBatch(a: BigUint64Array, b: BigUint64Array, modulus: bigint): BigUint64Array
+  // one Node process, every visible GPU: host batches of every bulk call below are spread over them; returns the count
+  function setDevices(): number
   // ballots: [count][2][degree] -> [2][degree]
   function tallyVotes(ballots: BigUint64Array, degree: number, modulus: bigint): BigUint64Array
   // FHEV records back to back; status[i]: 0 ok, 1 too small, 2 bad magic, 3 checksum, 4 shape

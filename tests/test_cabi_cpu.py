@@ -205,3 +205,28 @@ def test_node_addon_source_type_checks_and_links(fhe, tmp_path):
     assert all(re.search(rf"\b{s}\(", stub) for s in napi)
     defined = subprocess.run(["nm", "-D", "--defined-only", out], capture_output=True, text=True).stdout
     assert "napi_register_module_v1" in defined     # the entry point node looks up
+
+
+def _build_addon_and_host(fhe, out_dir):
+    """The addon as the shared object node-gyp would produce (addon/binding.gyp), and the mock Node-API host that loads it."""
+    node = os.path.join(out_dir, "fheb_addon.node")
+    host = os.path.join(out_dir, "mock_napi")
+    lib_dir = os.path.dirname(fhe.LIB_PATH)
+    subprocess.check_call(["g++", "-std=c++17", "-O2", "-shared", "-fPIC", "-I", os.path.join(ROOT, "addon", "stub"),
+                           "-I", os.path.join(ROOT, "include"), "-o", node, os.path.join(ROOT, "addon", "fheb_addon.cc"),
+                           "-L" + lib_dir, "-lfheb200", "-Wl,-rpath," + lib_dir])
+    subprocess.check_call(["g++", "-std=c++17", "-O2", "-I", os.path.join(ROOT, "addon", "stub"), "-o", host,
+                           os.path.join(ROOT, "tests", "napi_host", "mock_napi.cpp"), os.path.join(ROOT, "oracle", "fhe_oracle.c"),
+                           "-ldl", "-rdynamic"])
+    return host, node
+
+
+def test_node_addon_runs_under_a_mock_node_api_host(fhe, tmp_path):
+    """SURVEY 8f N1, as far as this image allows: the addon is built into the .node shared object, loaded with dlopen +
+    napi_register_module_v1 exactly as Node loads it, and its exports are driven by tests/napi_host/mock_napi.cpp (a small
+    Node-API host: values, typed arrays, classes, exceptions).  Without a GPU the scalar ModularArithmetic surface of
+    index.d.ts:14-44 runs end to end and initialize() must fail with HARDWARE_UNAVAILABLE (no CPU fallback); the bulk
+    entry points run in the GPU suite (tests/test_gpu_cpp.py)."""
+    host, node = _build_addon_and_host(fhe, str(tmp_path))
+    r = subprocess.run([host, node, "cpu"], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0 and "NAPI HOST CPU OK" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]

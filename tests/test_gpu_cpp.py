@@ -18,3 +18,20 @@ def test_cpp_classes_over_cabi():
                            os.path.join(ROOT, "oracle", "fhe_oracle.c"), "-L" + lib_dir, "-lfheb200", "-Wl,-rpath," + lib_dir])
     r = subprocess.run([exe], capture_output=True, text=True, timeout=600)
     assert r.returncode == 0 and "CPP CABI TESTS OK" in r.stdout, r.stdout[-3000:] + r.stderr[-2000:]
+
+
+def test_node_addon_bulk_entry_points_under_the_mock_host():
+    """The Node-API addon (addon/fheb_addon.cc) built as a .node shared object and driven through a mock Node-API host on
+    the GPU: initialize, detectHardware, setDevices, NttProcessor, tallyVotes, modAddBatch against the oracle."""
+    import sys
+
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import fheb200
+    from test_cabi_cpu import _build_addon_and_host
+
+    out = os.path.join(ROOT, "build")
+    os.makedirs(out, exist_ok=True)
+    host, node = _build_addon_and_host(fheb200, out)
+    r = subprocess.run([host, node, "gpu"], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and "NAPI HOST GPU OK" in r.stdout, r.stdout[-3000:] + r.stderr[-2000:]
