@@ -208,6 +208,18 @@ static unsigned persistent_grid(size_t work_groups, int blocks_per_sm) {
 
 enum { DIR_FWD = 0, DIR_INV = 1, DIR_INV_FWDNET = 2 };
 
+// Where the bulk-async (TMA) landing buffer is the default: exactly the (degree, mode, direction) cells that measured
+// faster in BOTH runs of tools/prof_tma.py (profiles/r02_tma_vs_plain.txt: +4..7 % forward at N <= 1024, +13 % inverse at
+// N = 4096 in 32-bit mode; it LOSES 7..12 % for the inverse at N = 256 and 3..4 % at N = 2048, which stay on plain loads).
+template <int L, int DP>
+constexpr bool TMA_DEFAULT(bool inverse) {
+    if (L == 6) return true;
+    if (L == 8) return !inverse;
+    if (L == 10) return !inverse || DP != MODE_INT;
+    if (L == 12) return inverse ? true : DP == MODE_INT;
+    return false;
+}
+
 template <int L, int DP>
 static int launch_transform(const NttPlan* p, int dir, const uint64_t* in, uint64_t* out, size_t batch, cudaStream_t s) {
     using G = Geometry<L, DP>;
@@ -216,6 +228,28 @@ static int launch_transform(const NttPlan* p, int dir, const uint64_t* in, uint6
     const Tw ninv = (DP == MODE_U32) ? p->ninv32 : p->ninv;
     const size_t groups = (batch + G::PPC - 1) / G::PPC;
     int bps = 0;
+    // Bulk-async (TMA) landing buffer for the next group's words: multi-pass plans up to N = 4096 (two buffers fit several
+    // blocks per SM), 16-byte aligned input, and only where it measured faster (FHEB_TMA=0/1 overrides: experiments).
+    if constexpr (Plan<L>::P > 1 && L <= 12) {
+        const char* tma_s = getenv("FHEB_TMA");  // read per call: the parity suite forces both settings
+        const int tma_env = tma_s ? atoi(tma_s) : -1;
+        const bool tma = (tma_env < 0 ? TMA_DEFAULT<L, DP>(dir == DIR_INV) : tma_env != 0) && (reinterpret_cast<uintptr_t>(in) & 15u) == 0 && dir != DIR_INV_FWDNET;
+        if (tma) {
+            constexpr size_t SMEM_TMA = 2 * G::SMEM + 16;
+            if (dir == DIR_INV) {
+                auto k = ntt_inverse_kernel<L, DP, G::THREADS, G::PPC, true>;
+                FHEB_TRY(configure(k, SMEM_TMA, G::THREADS, &bps));
+                k<<<persistent_grid(groups, bps), G::THREADS, SMEM_TMA, s>>>(in, out, batch, d_inv, ninv, p->mod);
+            } else {
+                auto k = ntt_forward_kernel<L, DP, G::THREADS, G::PPC, false, true>;
+                FHEB_TRY(configure(k, SMEM_TMA, G::THREADS, &bps));
+                k<<<persistent_grid(groups, bps), G::THREADS, SMEM_TMA, s>>>(in, out, batch, d_fwd, ninv, p->mod);
+            }
+            FHEB_CHECK_LAUNCH();
+            count_launch();
+            return FHEB_OK;
+        }
+    }
     if (dir == DIR_INV) {
         auto k = ntt_inverse_kernel<L, DP, G::THREADS, G::PPC>;
         FHEB_TRY(configure(k, G::SMEM, G::THREADS, &bps));

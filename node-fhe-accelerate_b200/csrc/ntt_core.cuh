@@ -486,8 +486,15 @@ enum {
     IO_SMEM = 0,          // the block's work buffer in shared memory (swizzled)
     IO_GLOBAL = 1,        // caller memory
     IO_STASH_SMEM = 2,    // second shared-memory buffer holding a finished transform (swizzled)
-    IO_STASH_GLOBAL = 3   // per-block global scratch holding a finished transform (natural index)
+    IO_STASH_GLOBAL = 3,  // per-block global scratch holding a finished transform (natural index)
+    IO_LANDING = 4        // caller words already copied into shared memory by a bulk-async (TMA) load: natural index, raw words
 };
+// first-pass input word: streaming global load, or a plain load from the landing buffer
+template <int IN>
+FHEB_HD uint64_t input_word(const uint64_t* p) {
+    if constexpr (IN == IO_LANDING) return *p;
+    else return stream_load(p);
+}
 
 // Forward pass PASS of an L-stage transform.  `gin`/`gout` point at the block's first
 // polynomial.  The last pass stores in the reference's (bit-reversed) output order.
@@ -512,7 +519,7 @@ FHEB_HD void fwd_pass(uint32_t tid, uint32_t nthreads, uint32_t polys, const uin
     // block index bit-reversed: ntt_plan.hpp) is indexed by t, so consecutive lanes read consecutive twiddles
     constexpr bool BRTW = LAST && OUT == IO_GLOBAL && BITREV_OUT && S0 > 0;
     static_assert(!BRTW || (EB == 0 && S0 == L - R), "the last pass covers the lowest position bits");
-    static_assert(IN == IO_SMEM || PASS == 0, "only the first pass reads global memory");
+    static_assert(IN == IO_SMEM || PASS == 0, "only the first pass reads caller words");
     static_assert(OUT == IO_SMEM || LAST, "only the last pass writes outside the work buffer");
 
     // IPT > 0: the thread's item count is known (IPT items, stride nthreads) and all their twiddles are
@@ -537,7 +544,7 @@ FHEB_HD void fwd_pass(uint32_t tid, uint32_t nthreads, uint32_t polys, const uin
     // PIPE (chosen by the kernel): software-pipelined global loads of a multi-pass plan's first pass, for the
     // degrees where a thread has several items.  +1 % (integer) / +5 % (FP64 mode) in the plain transform at
     // N = 16384; the fused product kernel loses 7 % with it (register pressure) and does not ask for it.
-    constexpr bool PIPE_IN = PIPE && IN == IO_GLOBAL && OUT == IO_SMEM && IPT == 0;
+    constexpr bool PIPE_IN = PIPE && IN == IO_GLOBAL && OUT == IO_SMEM && IPT == 0;  // (never with IO_LANDING: nothing to hide)
     uint64_t xnext[PIPE_IN ? E : 1];
     bool have_next = false;
     for (uint32_t U0 = tid; U0 < (IPT > 0 ? tid + 1 : polys * ITEMS); U0 += nthreads) {
@@ -553,7 +560,7 @@ FHEB_HD void fwd_pass(uint32_t tid, uint32_t nthreads, uint32_t polys, const uin
         if (OUT == IO_GLOBAL && BITREV_OUT) u = bitrev_rt(t, L - R);
         const uint32_t base = ((u >> EB) << (EB + R)) | (u & ((1u << EB) - 1u));
         uint64_t x[E];
-        if (IN == IO_GLOBAL) {
+        if (IN == IO_GLOBAL || IN == IO_LANDING) {
             if constexpr (PIPE_IN) {
                 // the words of this item were requested one trip ago; request the next item's now, so that the
                 // global-memory latency of the first pass is paid once per polynomial instead of once per item
@@ -577,7 +584,7 @@ FHEB_HD void fwd_pass(uint32_t tid, uint32_t nthreads, uint32_t polys, const uin
             } else {
                 const uint64_t* src = gin + (size_t)poly * N;
 #pragma unroll
-                for (int c = 0; c < E; ++c) x[c] = stream_load(src + (base | ((uint32_t)c << EB)));
+                for (int c = 0; c < E; ++c) x[c] = input_word<IN>(src + (base | ((uint32_t)c << EB)));
             }
             load_words<DP, E>(x, m);
         } else {
@@ -691,9 +698,10 @@ FHEB_HD void inv_pass(uint32_t tid, uint32_t nthreads, uint32_t polys, const uin
     constexpr bool FIRST = (PASS == Plan<L>::P - 1);
     constexpr uint32_t N = 1u << L;
     constexpr uint32_t ITEMS = N >> R;
-    constexpr bool BRTW = FIRST && IN == IO_GLOBAL && BITREV_IN && S0 > 0;  // see fwd_pass
+    constexpr bool EXT_IN = (IN == IO_GLOBAL || IN == IO_LANDING);  // caller words: from global memory or from the landing buffer
+    constexpr bool BRTW = FIRST && EXT_IN && BITREV_IN && S0 > 0;  // see fwd_pass
     static_assert(!BRTW || (EB == 0 && S0 == L - R), "the last pass covers the lowest position bits");
-    static_assert(IN == IO_SMEM || FIRST, "only the first executed pass reads global memory");
+    static_assert(IN == IO_SMEM || FIRST, "only the first executed pass reads caller words");
     static_assert(OUT == IO_SMEM || PASS == 0, "only the last executed pass writes global memory");
 
     constexpr int NW = E - 1;  // IPT > 0: all twiddles of the thread's IPT items requested up front (see fwd_pass)
@@ -706,7 +714,7 @@ FHEB_HD void inv_pass(uint32_t tid, uint32_t nthreads, uint32_t polys, const uin
             if (U < polys * ITEMS) {
                 const uint32_t t0 = U & (ITEMS - 1);
                 uint32_t u = t0;
-                if (FIRST && IN == IO_GLOBAL && BITREV_IN) u = bitrev_rt(u, L - R);
+                if (FIRST && EXT_IN && BITREV_IN) u = bitrev_rt(u, L - R);
                 const uint32_t base = ((u >> EB) << (EB + R)) | (u & ((1u << EB) - 1u));
                 load_item_tw<R, S0, DP>(tw, BRTW ? (N + t0) : plan_tw_offset<L, PASS>() + (S0 ? (base >> (L - S0)) : 0u), wall[k]);
             }
@@ -723,7 +731,7 @@ FHEB_HD void inv_pass(uint32_t tid, uint32_t nthreads, uint32_t polys, const uin
         const uint32_t poly = U >> (L - R);
         uint32_t u = U & (ITEMS - 1);
         const uint32_t t = u;
-        if (FIRST && IN == IO_GLOBAL && BITREV_IN) u = bitrev_rt(t, L - R);
+        if (FIRST && EXT_IN && BITREV_IN) u = bitrev_rt(t, L - R);
         const uint32_t base = ((u >> EB) << (EB + R)) | (u & ((1u << EB) - 1u));
         uint64_t x[E];
         if constexpr (PIPE_IN) {  // plain transform, reference-order input: this item's words were requested one trip ago
@@ -744,17 +752,17 @@ FHEB_HD void inv_pass(uint32_t tid, uint32_t nthreads, uint32_t polys, const uin
                 for (int c = 0; c < E; ++c) xnext[c] = stream_load(srcn + ((bitrev_c((uint32_t)c, R) << (L - R)) | tn));
             }
             load_words<DP, E>(x, m);
-        } else if (IN == IO_GLOBAL) {
+        } else if (EXT_IN) {
             const uint64_t* src = gin + (size_t)poly * N;
             if (SUB && BITREV_IN) {
 #pragma unroll
-                for (int c = 0; c < E; ++c) x[c] = stream_load(src + ((((bitrev_c((uint32_t)c, R) << (L - R)) | t) << map.shift) | map.low));
+                for (int c = 0; c < E; ++c) x[c] = input_word<IN>(src + ((((bitrev_c((uint32_t)c, R) << (L - R)) | t) << map.shift) | map.low));
             } else if (BITREV_IN) {
 #pragma unroll
-                for (int c = 0; c < E; ++c) x[c] = stream_load(src + ((bitrev_c((uint32_t)c, R) << (L - R)) | t));
+                for (int c = 0; c < E; ++c) x[c] = input_word<IN>(src + ((bitrev_c((uint32_t)c, R) << (L - R)) | t));
             } else {
 #pragma unroll
-                for (int c = 0; c < E; ++c) x[c] = stream_load(src + (base | ((uint32_t)c << EB)));
+                for (int c = 0; c < E; ++c) x[c] = input_word<IN>(src + (base | ((uint32_t)c << EB)));
             }
             load_words<DP, E>(x, m);
         } else {

@@ -14,6 +14,33 @@ __device__ __forceinline__ void prefetch_l2_bulk(const void* p, uint32_t bytes) 
         asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
 }
 
+// ---- bulk-async (TMA) loads of the next polynomials into a landing buffer ------------------------------------
+// One thread asks the copy engine for the whole PPC x N x 8 bytes of the block's NEXT group (cp.async.bulk, 1-D: the rows
+// of a batch are contiguous, no tensor map needed) while the block transforms the current one; completion is counted on an
+// mbarrier in shared memory.  The first pass then reads its words from shared memory instead of waiting on global loads.
+__device__ __forceinline__ uint32_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_addr(bar)), "r"(count) : "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // make the initialised barrier visible to the copy engine
+}
+__device__ __forceinline__ void tma_load_1d(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_addr(bar)), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_addr(dst)), "l"(src),
+                 "r"(bytes), "r"(smem_addr(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE_%=;\n\t"
+        "bra WAIT_%=;\n\t"
+        "DONE_%=:\n\t}" ::"r"(smem_addr(bar)),
+        "r"(parity)
+        : "memory");
+}
+
 template <int L, int DP, int PASS, bool SUB = false>
 __device__ __forceinline__ void fwd_middle(uint32_t tid, uint32_t nthreads, uint32_t polys, uint64_t* smem,
                                            const Tw* __restrict__ tw, const ModQ& m) {
@@ -36,7 +63,9 @@ __device__ __forceinline__ void inv_middle(uint32_t tid, uint32_t nthreads, uint
 
 // Forward transform of `batch` polynomials, [batch][N] -> [batch][N] (in may equal out).
 // SCALE = true gives fast_ntt_inverse semantics when `tw` is the inverse table.
-template <int L, int DP, int THREADS, int PPC, bool SCALE>
+// TMA = true (multi-pass plans, degrees up to 4096): shared memory = work buffer | landing buffer | mbarrier; the
+// next group's words are bulk-copied into the landing buffer while this group's later passes run.
+template <int L, int DP, int THREADS, int PPC, bool SCALE, bool TMA = false>
 __global__ void __launch_bounds__(THREADS) ntt_forward_kernel(const uint64_t* in, uint64_t* out, size_t batch,
                                                               const Tw* __restrict__ tw, const Tw ninv, const ModQ m) {
     extern __shared__ __align__(16) uint64_t smem[];
@@ -44,6 +73,34 @@ __global__ void __launch_bounds__(THREADS) ntt_forward_kernel(const uint64_t* in
     constexpr size_t N = (size_t)1 << L;
     const uint32_t tid = threadIdx.x;
     const size_t groups = (batch + PPC - 1) / PPC;
+    if constexpr (TMA && P > 1) {
+        uint64_t* landing = smem + (size_t)PPC * N;
+        uint64_t* bar = landing + (size_t)PPC * N;
+        auto group_bytes = [&](size_t g) {
+            const size_t q0 = g * PPC;
+            return (uint32_t)(((batch - q0) < (size_t)PPC ? (batch - q0) : (size_t)PPC) * N * 8);
+        };
+        if (tid == 0) {
+            mbar_init(bar, 1);
+            if ((size_t)blockIdx.x < groups) tma_load_1d(landing, in + (size_t)blockIdx.x * PPC * N, group_bytes(blockIdx.x), bar);
+        }
+        __syncthreads();
+        uint32_t parity = 0;
+        for (size_t g = blockIdx.x; g < groups; g += gridDim.x) {
+            const size_t p0 = g * PPC;
+            const uint32_t polys = (uint32_t)((batch - p0) < (size_t)PPC ? (batch - p0) : (size_t)PPC);
+            uint64_t* gout = out + p0 * N;
+            mbar_wait(bar, parity);  // this group's words have landed
+            parity ^= 1u;
+            fwd_pass<L, DP, 0, IO_LANDING, IO_SMEM>(tid, THREADS, polys, landing, gout, smem, tw, m);
+            __syncthreads();  // every thread is done with the landing buffer: the next group may land
+            if (tid == 0 && g + gridDim.x < groups) tma_load_1d(landing, in + (g + gridDim.x) * PPC * N, group_bytes(g + gridDim.x), bar);
+            fwd_middle<L, DP, 1>(tid, THREADS, polys, smem, tw, m);
+            fwd_pass<L, DP, P - 1, IO_SMEM, IO_GLOBAL, true, SCALE>(tid, THREADS, polys, nullptr, gout, smem, tw, m, ninv);
+            __syncthreads();
+        }
+        return;
+    }
     for (size_t g = blockIdx.x; g < groups; g += gridDim.x) {
         const size_t p0 = g * PPC;
         const uint32_t polys = (uint32_t)((batch - p0) < (size_t)PPC ? (batch - p0) : (size_t)PPC);
@@ -68,7 +125,7 @@ __global__ void __launch_bounds__(THREADS) ntt_forward_kernel(const uint64_t* in
 
 // Inverse transform (Gentleman-Sande network, bit-reversal folded into the loads, N^-1 folded
 // into the last pass).
-template <int L, int DP, int THREADS, int PPC>
+template <int L, int DP, int THREADS, int PPC, bool TMA = false>
 __global__ void __launch_bounds__(THREADS) ntt_inverse_kernel(const uint64_t* in, uint64_t* out, size_t batch,
                                                               const Tw* __restrict__ tw, const Tw ninv, const ModQ m) {
     extern __shared__ __align__(16) uint64_t smem[];
@@ -76,6 +133,34 @@ __global__ void __launch_bounds__(THREADS) ntt_inverse_kernel(const uint64_t* in
     constexpr size_t N = (size_t)1 << L;
     const uint32_t tid = threadIdx.x;
     const size_t groups = (batch + PPC - 1) / PPC;
+    if constexpr (TMA && P > 1) {  // see ntt_forward_kernel
+        uint64_t* landing = smem + (size_t)PPC * N;
+        uint64_t* bar = landing + (size_t)PPC * N;
+        auto group_bytes = [&](size_t g) {
+            const size_t q0 = g * PPC;
+            return (uint32_t)(((batch - q0) < (size_t)PPC ? (batch - q0) : (size_t)PPC) * N * 8);
+        };
+        if (tid == 0) {
+            mbar_init(bar, 1);
+            if ((size_t)blockIdx.x < groups) tma_load_1d(landing, in + (size_t)blockIdx.x * PPC * N, group_bytes(blockIdx.x), bar);
+        }
+        __syncthreads();
+        uint32_t parity = 0;
+        for (size_t g = blockIdx.x; g < groups; g += gridDim.x) {
+            const size_t p0 = g * PPC;
+            const uint32_t polys = (uint32_t)((batch - p0) < (size_t)PPC ? (batch - p0) : (size_t)PPC);
+            uint64_t* gout = out + p0 * N;
+            mbar_wait(bar, parity);
+            parity ^= 1u;
+            inv_pass<L, DP, P - 1, IO_LANDING, IO_SMEM>(tid, THREADS, polys, landing, gout, smem, tw, ninv, m);
+            __syncthreads();
+            if (tid == 0 && g + gridDim.x < groups) tma_load_1d(landing, in + (g + gridDim.x) * PPC * N, group_bytes(g + gridDim.x), bar);
+            inv_middle<L, DP, P - 2>(tid, THREADS, polys, smem, tw, ninv, m);
+            inv_pass<L, DP, 0, IO_SMEM, IO_GLOBAL>(tid, THREADS, polys, nullptr, gout, smem, tw, ninv, m);
+            __syncthreads();
+        }
+        return;
+    }
     for (size_t g = blockIdx.x; g < groups; g += gridDim.x) {
         const size_t p0 = g * PPC;
         const uint32_t polys = (uint32_t)((batch - p0) < (size_t)PPC ? (batch - p0) : (size_t)PPC);

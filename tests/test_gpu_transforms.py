@@ -140,6 +140,37 @@ def test_transforms_match_oracle_all_degrees(fhe, torch, oracle, logn, lazy, mon
     eq(ring.multiply(a[:2], a[:2]), oracle.multiply(a[:2], a[:2], q, fwd, inv, inv_n))  # aliased operands
 
 
+@pytest.mark.parametrize("tma", ["1", "0"], ids=["tma-landing-buffer", "plain-loads"])
+@pytest.mark.parametrize("logn", range(5, 13))
+def test_first_pass_input_paths_match_oracle(fhe, torch, oracle, logn, tma, monkeypatch):
+    """The first pass reads its words either with streaming global loads or from a shared-memory landing buffer filled by
+    bulk-async (TMA) copies of the block's next group (cp.async.bulk + mbarrier, ntt_device.cuh).  The library picks per
+    degree / mode / direction from measurements; FHEB_TMA forces either path.  Both, in all three arithmetic modes, against
+    the oracle - ragged batches (last group partly filled), more groups than resident blocks, in-place operation."""
+    monkeypatch.setenv("FHEB_TMA", tma)
+    n = 1 << logn
+    for q in (Q62, QT if n <= 1024 else 1099511592961 if (1099511592961 - 1) % (2 * n) == 0 else None, Q27):
+        if q is None or (q - 1) % (2 * n) != 0:
+            continue
+        ntt = fhe.NTTProcessor(n, q)
+        fwd, inv, _, _, inv_n = oracle.twiddles(n, q)
+        rng = np.random.default_rng(logn * 7 + 1)
+        per_block = max(1, 1024 >> logn) if logn <= 9 else (2 if logn == 10 else 1)
+        batch = 148 * 8 * per_block // (1 << max(0, logn - 7)) + 3  # several groups per block, ragged tail
+        batch = min(batch, 1500)
+        x = rng.integers(0, q, size=(batch, n), dtype=np.uint64)
+        x[1, :7] = rng.integers(q, 2**64, size=7, dtype=np.uint64)  # unreduced words are reduced on load
+        check = sorted(set([0, 1, batch // 2, batch - 2, batch - 1]))
+        xd = dev(torch, x)
+        f = host(ntt.forward_ntt(xd))
+        eq(f[check], oracle.forward(x[check], q, fwd))
+        i = host(ntt.inverse_ntt(xd))
+        eq(i[check], oracle.inverse(x[check], q, inv, inv_n))
+        y = dev(torch, x)
+        ntt.forward_ntt(y, out=y)   # in place
+        eq(host(y), f)
+
+
 def test_reference_test_ntt_processor_configs(fhe, oracle):
     """cpp/tests/test_ntt_processor.cpp:198-235,276-300: seeds 42/123, (8,17), (16,97), (1024,132120577)."""
     for n, q, iters in [(8, 17, 100), (16, 97, 100), (1024, Q27, 20)]:
