@@ -158,15 +158,23 @@ const NttPlan* plan_on_device(const NttPlan* p, int device) {
 }
 
 // ---- kernel dispatch --------------------------------------------------------------------
+#if !defined(FHEB_U32_BIG_THREADS)
+#define FHEB_U32_BIG_THREADS 256
+#endif
 template <int L, int DP>
 struct Geometry {  // threads per block, polynomials per block
-    static constexpr int PPC = (L <= 9) ? (1024 >> L) : (L == 10 ? 2 : 1);
+    static constexpr int UNITS = (L <= 9) ? (1024 >> L) : (L == 10 ? 2 : 1);  // work-buffer units (N slots each) per block
+    static constexpr int PPC = (DP == MODE_U32P) ? 2 * UNITS : UNITS;          // pair mode: two polynomials per unit
 #if defined(FHEB_EXP_R3)
     static constexpr int THREADS = (L <= 11) ? 128 : (L == 12 ? 256 : 1024);
 #else
-    static constexpr int THREADS = (L <= 11) ? 128 : (L == 12 ? 256 : 512);
+    // MODE_U32 at N >= 8192: 4-byte slots halve the footprint (64 KB at N = 16384), and 256-thread blocks let TWO blocks
+    // share an SM's registers and shared memory, so one block's global loads and stores overlap the other's butterflies
+    // (with one 512-thread block per SM the memory phases and the compute phases of a polynomial simply add up)
+    static constexpr int THREADS = (L <= 11) ? 128 : (L == 12 ? 256 : (DP == MODE_U32 ? FHEB_U32_BIG_THREADS : 512));
 #endif
-    static constexpr size_t SMEM = (Plan<L>::P > 1) ? (size_t)PPC * (1u << L) * 8 : 0;
+    static constexpr size_t SLOT = smem_slot_bytes<DP>();
+    static constexpr size_t SMEM = (Plan<L>::P > 1) ? (size_t)UNITS * (1u << L) * SLOT : 0;
 };
 
 // Attribute set-up and occupancy of a kernel are looked up once per (kernel, shared memory, threads, device) and cached:
@@ -223,19 +231,19 @@ constexpr bool TMA_DEFAULT(bool inverse) {
 template <int L, int DP>
 static int launch_transform(const NttPlan* p, int dir, const uint64_t* in, uint64_t* out, size_t batch, cudaStream_t s) {
     using G = Geometry<L, DP>;
-    const Tw* d_fwd = (DP == MODE_U32) ? p->d_fwd32 : p->d_fwd;
-    const Tw* d_inv = (DP == MODE_U32) ? p->d_inv32 : p->d_inv;
-    const Tw ninv = (DP == MODE_U32) ? p->ninv32 : p->ninv;
+    const Tw* d_fwd = is_u32(DP) ? p->d_fwd32 : p->d_fwd;
+    const Tw* d_inv = is_u32(DP) ? p->d_inv32 : p->d_inv;
+    const Tw ninv = is_u32(DP) ? p->ninv32 : p->ninv;
     const size_t groups = (batch + G::PPC - 1) / G::PPC;
     int bps = 0;
     // Bulk-async (TMA) landing buffer for the next group's words: multi-pass plans up to N = 4096 (two buffers fit several
     // blocks per SM), 16-byte aligned input, and only where it measured faster (FHEB_TMA=0/1 overrides: experiments).
-    if constexpr (Plan<L>::P > 1 && L <= 12) {
+    if constexpr (Plan<L>::P > 1 && L <= 12 && DP != MODE_U32P) {
         const char* tma_s = getenv("FHEB_TMA");  // read per call: the parity suite forces both settings
         const int tma_env = tma_s ? atoi(tma_s) : -1;
         const bool tma = (tma_env < 0 ? TMA_DEFAULT<L, DP>(dir == DIR_INV) : tma_env != 0) && (reinterpret_cast<uintptr_t>(in) & 15u) == 0 && dir != DIR_INV_FWDNET;
         if (tma) {
-            constexpr size_t SMEM_TMA = 2 * G::SMEM + 16;
+            constexpr size_t SMEM_TMA = G::SMEM + (size_t)G::PPC * (1u << L) * 8 + 16;  // work | landing (raw 8-byte words) | mbarrier
             if (dir == DIR_INV) {
                 auto k = ntt_inverse_kernel<L, DP, G::THREADS, G::PPC, true>;
                 FHEB_TRY(configure(k, SMEM_TMA, G::THREADS, &bps));
@@ -273,7 +281,7 @@ static int launch_polymul(const NttPlan* p, const uint64_t* a, const uint64_t* b
                           cudaStream_t s) {
     using G = Geometry<L, DP>;
     constexpr bool STASH_GLOBAL = (L >= 14);  // two 128 KB operands do not fit in shared memory
-    constexpr size_t SMEM = STASH_GLOBAL ? G::SMEM : 2 * (size_t)G::PPC * (1u << L) * 8;
+    constexpr size_t SMEM = STASH_GLOBAL ? G::SMEM : 2 * (size_t)G::UNITS * (1u << L) * G::SLOT;  // work buffer | stash (also for single-pass plans)
     const size_t groups = (batch + G::PPC - 1) / G::PPC;
     int bps = 0;
     auto k = polymul_kernel<L, DP, G::THREADS, G::PPC, STASH_GLOBAL>;
@@ -282,9 +290,9 @@ static int launch_polymul(const NttPlan* p, const uint64_t* a, const uint64_t* b
     uint64_t* stash = nullptr;
     if (STASH_GLOBAL) {
         // per-block scratch for T(a); small enough to stay L2 resident (grid x 128 KB)
-        FHEB_CUDA(cudaMallocAsync(&stash, (size_t)grid * G::PPC * (1u << L) * 8, s));
+        FHEB_CUDA(cudaMallocAsync(&stash, (size_t)grid * G::UNITS * (1u << L) * 8, s));
     }
-    if (DP == MODE_U32) k<<<grid, G::THREADS, SMEM, s>>>(a, b, c, batch, p->d_fwd32, p->d_inv32, p->ninv32, p->mod, stash);
+    if (is_u32(DP)) k<<<grid, G::THREADS, SMEM, s>>>(a, b, c, batch, p->d_fwd32, p->d_inv32, p->ninv32, p->mod, stash);
     else k<<<grid, G::THREADS, SMEM, s>>>(a, b, c, batch, p->d_fwd, p->d_inv, p->ninv, p->mod, stash);
     FHEB_CHECK_LAUNCH();
     count_launch();
@@ -341,16 +349,30 @@ static int launch_polymul_big(const NttPlan* p, const uint64_t* a, const uint64_
     return rc;
 }
 
-#define FHEB_DISPATCH_L(FN, L_, ...)                                         \
-    case L_:                                                                 \
+// 32-bit kernels: two polynomials per work-buffer slot (MODE_U32P) for multi-pass plans whenever the batch has a pair
+#define FHEB_DISPATCH_L(FN, L_, ...)                                                                                   \
+    case L_:                                                                                                           \
+        if (u32 && pair && Plan<L_>::P > 1) return FN<L_, (Plan<L_>::P > 1 ? MODE_U32P : MODE_U32)>(__VA_ARGS__);     \
         return u32 ? FN<L_, MODE_U32>(__VA_ARGS__) : dp ? FN<L_, MODE_DP>(__VA_ARGS__) : FN<L_, MODE_INT>(__VA_ARGS__);
 
 // FHEB_NO_U32=1 (read per call: the parity tests run both ways) keeps moduli below 2^27 on the FP64-pipe kernels
 static bool use_u32(const NttPlan* p) { return p->d_fwd32 != nullptr && p->logn <= 14 && getenv("FHEB_NO_U32") == nullptr; }
 
+// FHEB_U32_PAIR=0/1 (read per call: parity tests, experiments) overrides where the 32-bit kernels pack two polynomials
+// per 8-byte slot (MODE_U32P) instead of one per 4-byte slot (MODE_U32); defaults from profiles/r02_u32_modes.txt
+// (tools/prof_u32_modes.sh): the plain transforms are faster one polynomial per 4-byte slot at every degree but the
+// forward at N = 16384 (92.5 vs 88.9 us, while the inverse is 91.3 vs 97.3 us); the fused product gains 2..6 % from the pair
+// layout at N >= 8192 (its two operands then fit shared memory as ONE buffer each) and loses below.
+static bool u32_pair_wanted(bool product, uint32_t logn) {
+    const char* e = getenv("FHEB_U32_PAIR");
+    if (e) return atoi(e) != 0;
+    return product && logn >= 13;
+}
+
 static int dispatch_transform(const NttPlan* p, int dir, const uint64_t* in, uint64_t* out, size_t batch, cudaStream_t s) {
     const bool dp = p->mod.dp != 0;
     const bool u32 = use_u32(p);
+    const bool pair = batch >= 2 && u32_pair_wanted(false, p->logn);
     switch (p->logn) {
         FHEB_DISPATCH_L(launch_transform, 2, p, dir, in, out, batch, s)
         FHEB_DISPATCH_L(launch_transform, 3, p, dir, in, out, batch, s)
@@ -374,6 +396,7 @@ static int dispatch_transform(const NttPlan* p, int dir, const uint64_t* in, uin
 static int dispatch_polymul(const NttPlan* p, const uint64_t* a, const uint64_t* b, uint64_t* c, size_t batch, cudaStream_t s) {
     const bool dp = p->mod.dp != 0;
     const bool u32 = use_u32(p);
+    const bool pair = batch >= 2 && u32_pair_wanted(true, p->logn);
     switch (p->logn) {
         FHEB_DISPATCH_L(launch_polymul, 2, p, a, b, c, batch, s)
         FHEB_DISPATCH_L(launch_polymul, 3, p, a, b, c, batch, s)

@@ -48,6 +48,16 @@ FHEB_HD uint32_t swz(uint32_t i) {
     return i ^ (parity32(h & 0xF59u) | (parity32(h & 0x1EBu) << 1) | (parity32(h & 0x3D6u) << 2) | (parity32(h & 0x7ACu) << 3));
 }
 
+// The same construction for 4-byte words (MODE_U32 keeps one 32-bit word per shared-memory slot): a warp-wide 4-byte
+// access is ONE wavefront of 32 lanes over 32 banks, so the five index bits that vary across the lanes must map to
+// independent vectors of GF(2)^5: index bit j -> beta^j, beta a primitive element of GF(32) (x^5 + x^3 + 1; the other
+// primitive polynomials leave conflicts in some pass geometry - tools/check_swizzle.py checks all plans exhaustively).
+FHEB_HD uint32_t swz32(uint32_t i) {
+    const uint32_t h = i >> 5;
+    return i ^ (parity32(h & 0x375u) | (parity32(h & 0x6EAu) << 1) | (parity32(h & 0x5D4u) << 2) | (parity32(h & 0x0DDu) << 3) |
+                (parity32(h & 0x1BAu) << 4));
+}
+
 FHEB_HD constexpr uint32_t bitrev_c(uint32_t x, int bits) {
     uint32_t r = 0;
     for (int i = 0; i < bits; ++i) r |= ((x >> i) & 1u) << (bits - 1 - i);
@@ -68,7 +78,35 @@ FHEB_HD uint32_t bitrev_rt(uint32_t x, int bits) {
 //   MODE_U32 (2)  q < 2^27: 32-bit words (kept zero-extended in the 64-bit register/shared-memory slots), Shoup products
 //                 from ONE IMAD.HI + two IMAD, values in [0, 32q) - 14 lazy stages need no conditional subtraction.
 //                 132120577, the modulus of every published reference row, is such a prime.
-constexpr int MODE_INT = 0, MODE_DP = 1, MODE_U32 = 2;
+//   MODE_U32P (3) the same arithmetic on TWO polynomials at once: slot i of the work buffer holds word i of polynomial A
+//                 in its low half and word i of polynomial B in its high half.  Index math, swizzle, bank behaviour and
+//                 the twiddles are shared, so shared-memory instructions, twiddle loads, address arithmetic and block
+//                 barriers per polynomial are halved; a 64-bit register pair simply carries both words.
+constexpr int MODE_INT = 0, MODE_DP = 1, MODE_U32 = 2, MODE_U32P = 3;
+constexpr bool is_u32(int mode) { return mode == MODE_U32 || mode == MODE_U32P; }
+// work-buffer units (slots arrays) for `polys` polynomials: pairs in MODE_U32P
+template <int DP>
+FHEB_HD constexpr uint32_t units_of(uint32_t polys) { return DP == MODE_U32P ? (polys + 1) / 2 : polys; }
+FHEB_HD uint32_t lo32(uint64_t x) { return (uint32_t)x; }
+FHEB_HD uint32_t hi32(uint64_t x) { return (uint32_t)(x >> 32); }
+FHEB_HD uint64_t pack32(uint32_t lo, uint32_t hi) { return (uint64_t)lo | ((uint64_t)hi << 32); }
+
+// Shared-memory work buffer: N slots per unit.  A slot is 8 bytes (a 64-bit word, a double, or a pair of 32-bit words)
+// except in MODE_U32, where it is one 4-byte word: half the footprint, so two blocks of N = 16384 share an SM.
+template <int DP>
+constexpr uint32_t smem_slot_bytes() { return DP == MODE_U32 ? 4u : 8u; }
+template <int DP>
+FHEB_HD uint32_t swzm(uint32_t i) { return DP == MODE_U32 ? swz32(i) : swz(i); }
+template <int DP>
+FHEB_HD uint64_t sm_load(const uint64_t* buf, size_t unit, uint32_t N, uint32_t slot) {
+    if constexpr (DP == MODE_U32) return reinterpret_cast<const uint32_t*>(buf)[unit * N + slot];
+    else return buf[unit * N + slot];
+}
+template <int DP>
+FHEB_HD void sm_store(uint64_t* buf, size_t unit, uint32_t N, uint32_t slot, uint64_t v) {
+    if constexpr (DP == MODE_U32) reinterpret_cast<uint32_t*>(buf)[unit * N + slot] = (uint32_t)v;
+    else buf[unit * N + slot] = v;
+}
 constexpr int CAP_STRICT = 4;   // q < 2^62: 4q fits a word
 constexpr int CAP_DP = 128;     // q < 2^42: |v| < 128 q <= 2^49 keeps every FP64 step exact with margin
 constexpr int CAP_U32 = 32;     // q < 2^27: 32q fits 32 bits
@@ -81,7 +119,7 @@ constexpr int fwd_next_k(int K, bool has_unit, bool has_nonunit, int mode) {
         int ku = has_unit ? 2 * K : 0;
         return kn > ku ? kn : ku;
     }
-    if (mode == MODE_U32) {  // t in [0, 2q): A +- t < (K + 2) q; unit: A +- B < 2K q, both reduced to [0, 2q) first when 2K > 8
+    if (is_u32(mode)) {  // t in [0, 2q): A +- t < (K + 2) q; unit: A +- B < 2K q, both reduced to [0, 2q) first when 2K > 8
         int kn = has_nonunit ? (((K + 2 > CAP_U32) ? 2 : K) + 2) : 0;
         int ku = has_unit ? ((2 * K > U32_UNIT_CAP) ? 4 : 2 * K) : 0;
         return kn > ku ? kn : ku;
@@ -96,7 +134,7 @@ constexpr int fwd_pass_k(int K, int R, bool unit_first, int mode) {
 }
 constexpr int inv_next_k(int K, int mode) {
     if (mode == MODE_DP) return (2 * K > CAP_DP) ? 1 : 2 * K;
-    if (mode == MODE_U32) return (2 * K > CAP_U32 / 2) ? 2 : 2 * K;  // sums kept below 16q so that the next sum fits 32 bits
+    if (is_u32(mode)) return (2 * K > CAP_U32 / 2) ? 2 : 2 * K;  // sums kept below 16q so that the next sum fits 32 bits
     return (2 * K > CAP_STRICT / 2) ? 2 : 2 * K;
 }
 constexpr int inv_pass_k(int K, int R, int mode) {
@@ -118,6 +156,46 @@ FHEB_HD uint32_t shoup32(uint32_t x, uint32_t w, uint32_t wp, uint32_t q) { retu
 FHEB_HD uint32_t lazy32(uint32_t x, const ModQ& m) { return x - mulhi32(x, m.mu32) * (uint32_t)m.q; }
 FHEB_HD uint32_t csub32(uint32_t x, uint32_t q) { return x >= q ? x - q : x; }
 
+// the 32-bit butterflies on one (a, b) pair of words; bounds as in fwd_next_k / inv_next_k
+template <int K, bool UNIT>
+FHEB_HD void fwd_bfly32(uint32_t& a, uint32_t& b, uint32_t w, uint32_t wp, const ModQ& m) {
+    const uint32_t q = (uint32_t)m.q;
+    if constexpr (UNIT) {
+        constexpr bool red = (2 * K > U32_UNIT_CAP);
+        if constexpr (red) {
+            a = lazy32(a, m);
+            b = lazy32(b, m);
+        }
+        constexpr int KT = red ? 2 : K;
+        static_assert(2 * KT <= CAP_U32, "32-bit range exceeded in a unit forward stage");
+        const uint32_t s = a + b;
+        b = a - b + (uint32_t)KT * q;
+        a = s;
+    } else {
+        constexpr bool red = (K + 2 > CAP_U32);
+        if constexpr (red) a = lazy32(a, m);
+        const uint32_t t = shoup32(b, w, wp, q);  // [0, 2q) for any b
+        b = a - t + 2u * q;
+        a = a + t;
+    }
+}
+template <int K, bool UNIT>
+FHEB_HD void inv_bfly32(uint32_t& a, uint32_t& b, uint32_t w, uint32_t wp, const ModQ& m) {
+    static_assert(2 * K <= CAP_U32, "sum would overflow 32 bits");
+    constexpr bool red = (2 * K > CAP_U32 / 2);
+    const uint32_t q = (uint32_t)m.q;
+    uint32_t s = a + b;
+    uint32_t d = a - b + (uint32_t)K * q;
+    if constexpr (red) s = lazy32(s, m);
+    a = s;
+    if constexpr (UNIT) {
+        if constexpr (red) d = lazy32(d, m);
+        b = d;
+    } else {
+        b = shoup32(d, w, wp, q);
+    }
+}
+
 template <int K>
 FHEB_HD uint64_t kq(const ModQ& m) {
     if constexpr (K == 1) return m.q;
@@ -135,25 +213,16 @@ FHEB_HD void fwd_bfly(uint64_t& A, uint64_t& B, const Tw& w, const ModQ& m) {
         A = double_to_bits(dp_add(a, t));
         B = double_to_bits(dp_add(a, -t));
     } else if constexpr (DP == MODE_U32) {
-        const uint32_t q = (uint32_t)m.q;
         uint32_t a = (uint32_t)A, b = (uint32_t)B;
-        if constexpr (UNIT) {
-            constexpr bool red = (2 * K > U32_UNIT_CAP);
-            if constexpr (red) {
-                a = lazy32(a, m);
-                b = lazy32(b, m);
-            }
-            constexpr int KT = red ? 2 : K;
-            static_assert(2 * KT <= CAP_U32, "32-bit range exceeded in a unit forward stage");
-            A = a + b;
-            B = a - b + (uint32_t)KT * q;
-        } else {
-            constexpr bool red = (K + 2 > CAP_U32);
-            if constexpr (red) a = lazy32(a, m);
-            const uint32_t t = shoup32(b, (uint32_t)w.w, (uint32_t)w.wp, q);  // [0, 2q) for any b
-            A = a + t;
-            B = a - t + 2u * q;
-        }
+        fwd_bfly32<K, UNIT>(a, b, (uint32_t)w.w, (uint32_t)w.wp, m);
+        A = a;
+        B = b;
+    } else if constexpr (DP == MODE_U32P) {  // two polynomials per slot, the same twiddle
+        uint32_t a0 = lo32(A), b0 = lo32(B), a1 = hi32(A), b1 = hi32(B);
+        fwd_bfly32<K, UNIT>(a0, b0, (uint32_t)w.w, (uint32_t)w.wp, m);
+        fwd_bfly32<K, UNIT>(a1, b1, (uint32_t)w.w, (uint32_t)w.wp, m);
+        A = pack32(a0, a1);
+        B = pack32(b0, b1);
     } else if constexpr (UNIT) {  // twiddle == 1: no multiplication
         constexpr bool red = (2 * K > CAP_STRICT);
         static_assert(!red || K <= 4, "conditional subtraction only halves [0,4q)");
@@ -194,20 +263,16 @@ FHEB_HD void inv_bfly(uint64_t& A, uint64_t& B, const Tw& w, const ModQ& m) {
         A = double_to_bits(s);
         B = double_to_bits(d);
     } else if constexpr (DP == MODE_U32) {
-        static_assert(2 * K <= CAP_U32, "sum would overflow 32 bits");
-        constexpr bool red = (2 * K > CAP_U32 / 2);
-        const uint32_t q = (uint32_t)m.q;
-        const uint32_t a = (uint32_t)A, b = (uint32_t)B;
-        uint32_t s = a + b;
-        uint32_t d = a - b + (uint32_t)K * q;
-        if constexpr (red) s = lazy32(s, m);
-        A = s;
-        if constexpr (UNIT) {
-            if constexpr (red) d = lazy32(d, m);
-            B = d;
-        } else {
-            B = shoup32(d, (uint32_t)w.w, (uint32_t)w.wp, q);
-        }
+        uint32_t a = (uint32_t)A, b = (uint32_t)B;
+        inv_bfly32<K, UNIT>(a, b, (uint32_t)w.w, (uint32_t)w.wp, m);
+        A = a;
+        B = b;
+    } else if constexpr (DP == MODE_U32P) {
+        uint32_t a0 = lo32(A), b0 = lo32(B), a1 = hi32(A), b1 = hi32(B);
+        inv_bfly32<K, UNIT>(a0, b0, (uint32_t)w.w, (uint32_t)w.wp, m);
+        inv_bfly32<K, UNIT>(a1, b1, (uint32_t)w.w, (uint32_t)w.wp, m);
+        A = pack32(a0, a1);
+        B = pack32(b0, b1);
     } else {
         static_assert(2 * K <= CAP_STRICT, "sum would overflow the word");
         constexpr bool red = (2 * K > CAP_STRICT / 2);
@@ -263,7 +328,7 @@ FHEB_HD Tw load_tw(const Tw* __restrict__ tw, uint32_t idx) {
         t.w = p[idx];
 #endif
         t.wp = 0;
-    } else if constexpr (DP == MODE_U32) {  // (w, w') as two 32-bit halves of one 8-byte entry
+    } else if constexpr (is_u32(DP)) {  // (w, w') as two 32-bit halves of one 8-byte entry
         const uint64_t* p = reinterpret_cast<const uint64_t*>(tw);
 #if defined(__CUDA_ARCH__)
         const uint64_t v = __ldg(p + idx);
@@ -350,6 +415,8 @@ FHEB_HD uint64_t canon_k(uint64_t x, const ModQ& m) {
         if constexpr (K > 2) v = lazy32(v, m);
         if constexpr (K > 1) v = csub32(v, (uint32_t)m.q);
         return v;
+    } else if constexpr (DP == MODE_U32P) {  // both halves
+        return pack32((uint32_t)canon_k<K, MODE_U32>(lo32(x), m), (uint32_t)canon_k<K, MODE_U32>(hi32(x), m));
     } else if constexpr (K <= 1) return x;
     else if constexpr (K == 2) return csub(x, m.q);
     else if constexpr (K <= 4) return csub(csub(x, m.q2), m.q);
@@ -379,6 +446,65 @@ FHEB_HD void load_words(uint64_t (&x)[E], const ModQ& m) {
     }
 }
 
+enum {
+    IO_SMEM = 0,          // the block's work buffer in shared memory (swizzled)
+    IO_GLOBAL = 1,        // caller memory
+    IO_STASH_SMEM = 2,    // second shared-memory buffer holding a finished transform (swizzled)
+    IO_STASH_GLOBAL = 3,  // per-block global scratch holding a finished transform (natural index)
+    IO_LANDING = 4        // caller words already copied into shared memory by a bulk-async (TMA) load: natural index, raw words
+};
+// first-pass input word: streaming global load, or a plain load from the landing buffer
+template <int IN>
+FHEB_HD uint64_t input_word(const uint64_t* p) {
+    if constexpr (IN == IO_LANDING) return *p;
+    else return stream_load(p);
+}
+
+// The E caller words of work unit `unit` (a polynomial; in MODE_U32P the pair 2*unit, 2*unit+1 of the block's `polys`
+// polynomials, the missing partner of an odd tail reads as zero) at word indices idx(c), in the mode's representation.
+// `src` = first polynomial of the block (global memory, or the landing buffer).
+template <int DP, int IN, int E, class Idx>
+FHEB_HD void load_unit(uint64_t (&x)[E], const uint64_t* src, uint32_t unit, uint32_t polys, uint32_t N, Idx idx, const ModQ& m) {
+    if constexpr (DP == MODE_U32P) {
+        const uint64_t* s0 = src + (size_t)(2 * unit) * N;
+        const bool has1 = 2 * unit + 1 < polys;
+        const uint64_t* s1 = has1 ? s0 + N : s0;
+        uint64_t y[E];
+        bool raw = false;
+#pragma unroll
+        for (int c = 0; c < E; ++c) {
+            x[c] = input_word<IN>(s0 + idx(c));
+            y[c] = input_word<IN>(s1 + idx(c));
+            raw = raw || x[c] >= m.q || y[c] >= m.q;
+        }
+        if (raw) {  // unreduced words are rare: one test per item
+#pragma unroll
+            for (int c = 0; c < E; ++c) {
+                x[c] = canon_any(x[c], m);
+                y[c] = canon_any(y[c], m);
+            }
+        }
+#pragma unroll
+        for (int c = 0; c < E; ++c) x[c] = pack32((uint32_t)x[c], has1 ? (uint32_t)y[c] : 0u);
+    } else {
+        const uint64_t* s0 = src + (size_t)unit * N;
+#pragma unroll
+        for (int c = 0; c < E; ++c) x[c] = input_word<IN>(s0 + idx(c));
+        load_words<DP, E>(x, m);
+    }
+}
+// one finished word (canonical, or both canonical halves) of work unit `unit` to word index idx of its polynomial(s)
+template <int DP>
+FHEB_HD void store_unit_word(uint64_t* dst, uint32_t unit, uint32_t polys, uint32_t N, size_t idx, uint64_t v) {
+    if constexpr (DP == MODE_U32P) {
+        uint64_t* d0 = dst + (size_t)(2 * unit) * N;
+        stream_store(d0 + idx, (uint64_t)lo32(v));
+        if (2 * unit + 1 < polys) stream_store(d0 + N + idx, (uint64_t)hi32(v));
+    } else {
+        stream_store(dst + (size_t)unit * N + idx, v);
+    }
+}
+
 // finished transform parked for the fused product: canonical word (integer) / reduced double (DP)
 template <int K, int DP>
 FHEB_HD uint64_t park_word(uint64_t x, const ModQ& m) {
@@ -391,6 +517,7 @@ template <int DP>
 FHEB_HD uint64_t scale_word(uint64_t x, const Tw& ninv, const ModQ& m) {
     if constexpr (DP == MODE_DP) return dp_canon_word(dp_mulmod(bits_to_double(x), bits_to_double(ninv.w), m), m);
     else if constexpr (DP == MODE_U32) return csub32(shoup32((uint32_t)x, (uint32_t)ninv.w, (uint32_t)ninv.wp, (uint32_t)m.q), (uint32_t)m.q);
+    else if constexpr (DP == MODE_U32P) return pack32((uint32_t)scale_word<MODE_U32>(lo32(x), ninv, m), (uint32_t)scale_word<MODE_U32>(hi32(x), ninv, m));
     else return csub(shoup_lazy(x, ninv.w, ninv.wp, m.q), m.q);
 }
 
@@ -482,19 +609,7 @@ constexpr int plan_inv_kin() {  // bound entering inverse pass PASS (run order P
 //   OUT_GLOBAL : values go to global memory (last pass)         else to shared memory
 // Shared memory holds `polys` polynomials of N words each, word index swizzled by swz().
 
-enum {
-    IO_SMEM = 0,          // the block's work buffer in shared memory (swizzled)
-    IO_GLOBAL = 1,        // caller memory
-    IO_STASH_SMEM = 2,    // second shared-memory buffer holding a finished transform (swizzled)
-    IO_STASH_GLOBAL = 3,  // per-block global scratch holding a finished transform (natural index)
-    IO_LANDING = 4        // caller words already copied into shared memory by a bulk-async (TMA) load: natural index, raw words
-};
-// first-pass input word: streaming global load, or a plain load from the landing buffer
-template <int IN>
-FHEB_HD uint64_t input_word(const uint64_t* p) {
-    if constexpr (IN == IO_LANDING) return *p;
-    else return stream_load(p);
-}
+
 
 // Forward pass PASS of an L-stage transform.  `gin`/`gout` point at the block's first
 // polynomial.  The last pass stores in the reference's (bit-reversed) output order.
@@ -515,6 +630,7 @@ FHEB_HD void fwd_pass(uint32_t tid, uint32_t nthreads, uint32_t polys, const uin
     constexpr bool LAST = (PASS == Plan<L>::P - 1);
     constexpr uint32_t N = 1u << L;
     constexpr uint32_t ITEMS = N >> R;  // per polynomial
+    const uint32_t units = units_of<DP>(polys);  // work-buffer units: polynomials, or pairs of them (MODE_U32P)
     // BRTW: items are walked in bit-reversed order (u = bitrev(t)); the table's second copy of this pass (offset N,
     // block index bit-reversed: ntt_plan.hpp) is indexed by t, so consecutive lanes read consecutive twiddles
     constexpr bool BRTW = LAST && OUT == IO_GLOBAL && BITREV_OUT && S0 > 0;
@@ -532,7 +648,7 @@ FHEB_HD void fwd_pass(uint32_t tid, uint32_t nthreads, uint32_t polys, const uin
 #pragma unroll
         for (int k = 0; k < IPT; ++k) {
             const uint32_t U = tid + (uint32_t)k * nthreads;
-            if (U < polys * ITEMS) {
+            if (U < units * ITEMS) {
                 const uint32_t t0 = U & (ITEMS - 1);
                 uint32_t u = t0;
                 if (OUT == IO_GLOBAL && BITREV_OUT) u = bitrev_rt(u, L - R);
@@ -544,14 +660,14 @@ FHEB_HD void fwd_pass(uint32_t tid, uint32_t nthreads, uint32_t polys, const uin
     // PIPE (chosen by the kernel): software-pipelined global loads of a multi-pass plan's first pass, for the
     // degrees where a thread has several items.  +1 % (integer) / +5 % (FP64 mode) in the plain transform at
     // N = 16384; the fused product kernel loses 7 % with it (register pressure) and does not ask for it.
-    constexpr bool PIPE_IN = PIPE && IN == IO_GLOBAL && OUT == IO_SMEM && IPT == 0;  // (never with IO_LANDING: nothing to hide)
+    constexpr bool PIPE_IN = PIPE && IN == IO_GLOBAL && OUT == IO_SMEM && IPT == 0 && DP != MODE_U32P;  // (never with IO_LANDING: nothing to hide)
     uint64_t xnext[PIPE_IN ? E : 1];
     bool have_next = false;
-    for (uint32_t U0 = tid; U0 < (IPT > 0 ? tid + 1 : polys * ITEMS); U0 += nthreads) {
+    for (uint32_t U0 = tid; U0 < (IPT > 0 ? tid + 1 : units * ITEMS); U0 += nthreads) {
 #pragma unroll
       for (int k = 0; k < TRIPS; ++k) {
         const uint32_t U = U0 + (uint32_t)k * nthreads;
-        if (IPT > 0 && U >= polys * ITEMS) break;
+        if (IPT > 0 && U >= units * ITEMS) break;
         const uint32_t poly = U >> (L - R);
         uint32_t u = U & (ITEMS - 1);
         // In the last pass consecutive threads take bit-reversed item indices so that the
@@ -573,7 +689,7 @@ FHEB_HD void fwd_pass(uint32_t tid, uint32_t nthreads, uint32_t polys, const uin
                     for (int c = 0; c < E; ++c) x[c] = stream_load(src + (base | ((uint32_t)c << EB)));
                 }
                 const uint32_t Un = U + nthreads;
-                have_next = Un < polys * ITEMS;
+                have_next = Un < units * ITEMS;
                 if (have_next) {
                     const uint32_t un = Un & (ITEMS - 1);
                     const uint32_t basen = ((un >> EB) << (EB + R)) | (un & ((1u << EB) - 1u));
@@ -581,40 +697,36 @@ FHEB_HD void fwd_pass(uint32_t tid, uint32_t nthreads, uint32_t polys, const uin
 #pragma unroll
                     for (int c = 0; c < E; ++c) xnext[c] = stream_load(srcn + (basen | ((uint32_t)c << EB)));
                 }
+                load_words<DP, E>(x, m);
             } else {
-                const uint64_t* src = gin + (size_t)poly * N;
-#pragma unroll
-                for (int c = 0; c < E; ++c) x[c] = input_word<IN>(src + (base | ((uint32_t)c << EB)));
+                load_unit<DP, IN, E>(x, gin, poly, polys, N, [&](int c) { return base | ((uint32_t)c << EB); }, m);
             }
-            load_words<DP, E>(x, m);
         } else {
-            const uint64_t* src = smem + (size_t)poly * N;
-            const uint32_t pb = swz(base);
+            const uint32_t pb = swzm<DP>(base);
 #pragma unroll
-            for (int c = 0; c < E; ++c) x[c] = src[pb ^ swz((uint32_t)c << EB)];
+            for (int c = 0; c < E; ++c) x[c] = sm_load<DP>(smem, poly, N, pb ^ swzm<DP>((uint32_t)c << EB));
         }
         const uint32_t TB = BRTW ? (N + t) : plan_tw_offset<L, PASS>() + (S0 ? (base >> (L - S0)) : 0u);
         if constexpr (IPT > 0) fwd_stages<R, S0, KIN, DP, UNIT, 0, true>(x, wall[k], 0u, m);
         else fwd_stages<R, S0, KIN, DP, UNIT>(x, tw, TB, m);
         if (OUT == IO_GLOBAL) {
-            uint64_t* dst = gout + (size_t)poly * N;
 #pragma unroll
             for (int c = 0; c < E; ++c) {
                 const uint64_t v = SCALE ? scale_word<DP>(x[c], ninv, m) : canon_k<KOUT, DP>(x[c], m);
-                if (SUB) stream_store(dst + ((((bitrev_c((uint32_t)c, R) << (L - R)) | t) << map.shift) | map.low), v);
-                else if (BITREV_OUT) stream_store(dst + ((bitrev_c((uint32_t)c, R) << (L - R)) | t), v);
-                else stream_store(dst + (base | ((uint32_t)c << EB)), v);
+                if (SUB) store_unit_word<DP>(gout, poly, polys, N, (((bitrev_c((uint32_t)c, R) << (L - R)) | t) << map.shift) | map.low, v);
+                else if (BITREV_OUT) store_unit_word<DP>(gout, poly, polys, N, (bitrev_c((uint32_t)c, R) << (L - R)) | t, v);
+                else store_unit_word<DP>(gout, poly, polys, N, base | ((uint32_t)c << EB), v);
             }
         } else if (OUT == IO_STASH_GLOBAL) {
             uint64_t* dst = gout + (size_t)poly * N;
 #pragma unroll
             for (int c = 0; c < E; ++c) dst[base | ((uint32_t)c << EB)] = park_word<KOUT, DP>(x[c], m);
         } else {
-            uint64_t* dst = (OUT == IO_STASH_SMEM ? gout : smem) + (size_t)poly * N;
-            const uint32_t pb = swz(base);
+            uint64_t* dst = (OUT == IO_STASH_SMEM ? gout : smem);
+            const uint32_t pb = swzm<DP>(base);
 #pragma unroll
             for (int c = 0; c < E; ++c)
-                dst[pb ^ swz((uint32_t)c << EB)] = (OUT == IO_STASH_SMEM) ? park_word<KOUT, DP>(x[c], m) : x[c];
+                sm_store<DP>(dst, poly, N, pb ^ swzm<DP>((uint32_t)c << EB), (OUT == IO_STASH_SMEM) ? park_word<KOUT, DP>(x[c], m) : x[c]);
         }
       }
     }
@@ -641,14 +753,16 @@ FHEB_HD void polymul_mid_pass(uint32_t tid, uint32_t nthreads, uint32_t polys, c
     constexpr uint32_t N = 1u << L;
     constexpr uint32_t ITEMS = N >> R;
     static_assert(EB == 0, "the last forward pass covers the lowest position bits");
+    static_assert(DP != MODE_U32P || (IN == IO_SMEM && OUT == IO_SMEM), "pair mode is used with multi-pass plans only");
+    const uint32_t units = units_of<DP>(polys);
     // DP: the parked operand is reduced (|a| <= q/2 + 1), this one stays lazy: |a*b| <= KOUT q^2 / 2
     static_assert(DP != MODE_DP || KOUT <= 2 * CAP_DP, "FP64 product bound");
 
-    for (uint32_t U = tid; U < polys * ITEMS; U += nthreads) {
+    for (uint32_t U = tid; U < units * ITEMS; U += nthreads) {
         const uint32_t poly = U >> (L - R);
         const uint32_t u = U & (ITEMS - 1);
         const uint32_t base = u << R;
-        const uint32_t pb = swz(base);
+        const uint32_t pb = swzm<DP>(base);
         uint64_t x[E];
         if (IN == IO_GLOBAL) {
             const uint64_t* src = gin + (size_t)poly * N;
@@ -656,17 +770,20 @@ FHEB_HD void polymul_mid_pass(uint32_t tid, uint32_t nthreads, uint32_t polys, c
             for (int c = 0; c < E; ++c) x[c] = stream_load(src + (base | (uint32_t)c));
             load_words<DP, E>(x, m);
         } else {
-            const uint64_t* src = smem + (size_t)poly * N;
 #pragma unroll
-            for (int c = 0; c < E; ++c) x[c] = src[pb ^ swz((uint32_t)c)];
+            for (int c = 0; c < E; ++c) x[c] = sm_load<DP>(smem, poly, N, pb ^ swzm<DP>((uint32_t)c));
         }
         const uint32_t TB = plan_tw_offset<L, PASS>() + (S0 ? (base >> (L - S0)) : 0u);
         fwd_stages<R, S0, KIN, DP, PASS == 0>(x, twf, TB, m);
         const uint64_t* sa = stash + (size_t)poly * N;
 #pragma unroll
         for (int c = 0; c < E; ++c) {
-            const uint64_t av = (STASH == IO_STASH_GLOBAL) ? sa[base | (uint32_t)c] : sa[pb ^ swz((uint32_t)c)];
+            const uint64_t av = (STASH == IO_STASH_GLOBAL) ? sa[base | (uint32_t)c] : sm_load<DP>(stash, poly, N, pb ^ swzm<DP>((uint32_t)c));
             if constexpr (DP == MODE_DP) x[c] = double_to_bits(dp_mulmod(bits_to_double(av), bits_to_double(x[c]), m));
+            else if constexpr (DP == MODE_U32P) {
+                const uint64_t xc = canon_k<KOUT, DP>(x[c], m);
+                x[c] = pack32((uint32_t)mulmod(lo32(av), lo32(xc), m), (uint32_t)mulmod(hi32(av), hi32(xc), m));
+            }
             else x[c] = mulmod(av, canon_k<KOUT, DP>(x[c], m), m);  // canonical x canonical (U32 mode: generic 64-bit reduction, once per coefficient)
         }
         inv_stages<R, S0, 1, DP, PASS == 0>(x, twi, TB, m);
@@ -675,9 +792,8 @@ FHEB_HD void polymul_mid_pass(uint32_t tid, uint32_t nthreads, uint32_t polys, c
 #pragma unroll
             for (int c = 0; c < E; ++c) stream_store(dst + (base | (uint32_t)c), scale_word<DP>(x[c], ninv, m));
         } else {
-            uint64_t* dst = smem + (size_t)poly * N;
 #pragma unroll
-            for (int c = 0; c < E; ++c) dst[pb ^ swz((uint32_t)c)] = x[c];
+            for (int c = 0; c < E; ++c) sm_store<DP>(smem, poly, N, pb ^ swzm<DP>((uint32_t)c), x[c]);
         }
     }
 }
@@ -698,6 +814,7 @@ FHEB_HD void inv_pass(uint32_t tid, uint32_t nthreads, uint32_t polys, const uin
     constexpr bool FIRST = (PASS == Plan<L>::P - 1);
     constexpr uint32_t N = 1u << L;
     constexpr uint32_t ITEMS = N >> R;
+    const uint32_t units = units_of<DP>(polys);
     constexpr bool EXT_IN = (IN == IO_GLOBAL || IN == IO_LANDING);  // caller words: from global memory or from the landing buffer
     constexpr bool BRTW = FIRST && EXT_IN && BITREV_IN && S0 > 0;  // see fwd_pass
     static_assert(!BRTW || (EB == 0 && S0 == L - R), "the last pass covers the lowest position bits");
@@ -711,7 +828,7 @@ FHEB_HD void inv_pass(uint32_t tid, uint32_t nthreads, uint32_t polys, const uin
 #pragma unroll
         for (int k = 0; k < IPT; ++k) {
             const uint32_t U = tid + (uint32_t)k * nthreads;
-            if (U < polys * ITEMS) {
+            if (U < units * ITEMS) {
                 const uint32_t t0 = U & (ITEMS - 1);
                 uint32_t u = t0;
                 if (FIRST && EXT_IN && BITREV_IN) u = bitrev_rt(u, L - R);
@@ -720,14 +837,14 @@ FHEB_HD void inv_pass(uint32_t tid, uint32_t nthreads, uint32_t polys, const uin
             }
         }
     }
-    constexpr bool PIPE_IN = PIPE && FIRST && IN == IO_GLOBAL && BITREV_IN && !SUB && IPT == 0;  // see fwd_pass
+    constexpr bool PIPE_IN = PIPE && FIRST && IN == IO_GLOBAL && BITREV_IN && !SUB && IPT == 0 && DP != MODE_U32P;  // see fwd_pass
     uint64_t xnext[PIPE_IN ? E : 1];
     bool have_next = false;
-    for (uint32_t U0 = tid; U0 < (IPT > 0 ? tid + 1 : polys * ITEMS); U0 += nthreads) {
+    for (uint32_t U0 = tid; U0 < (IPT > 0 ? tid + 1 : units * ITEMS); U0 += nthreads) {
 #pragma unroll
       for (int k = 0; k < TRIPS; ++k) {
         const uint32_t U = U0 + (uint32_t)k * nthreads;
-        if (IPT > 0 && U >= polys * ITEMS) break;
+        if (IPT > 0 && U >= units * ITEMS) break;
         const uint32_t poly = U >> (L - R);
         uint32_t u = U & (ITEMS - 1);
         const uint32_t t = u;
@@ -744,7 +861,7 @@ FHEB_HD void inv_pass(uint32_t tid, uint32_t nthreads, uint32_t polys, const uin
                 for (int c = 0; c < E; ++c) x[c] = stream_load(src + ((bitrev_c((uint32_t)c, R) << (L - R)) | t));
             }
             const uint32_t Un = U + nthreads;
-            have_next = Un < polys * ITEMS;
+            have_next = Un < units * ITEMS;
             if (have_next) {
                 const uint64_t* srcn = gin + (size_t)(Un >> (L - R)) * N;
                 const uint32_t tn = Un & (ITEMS - 1);
@@ -753,37 +870,24 @@ FHEB_HD void inv_pass(uint32_t tid, uint32_t nthreads, uint32_t polys, const uin
             }
             load_words<DP, E>(x, m);
         } else if (EXT_IN) {
-            const uint64_t* src = gin + (size_t)poly * N;
-            if (SUB && BITREV_IN) {
-#pragma unroll
-                for (int c = 0; c < E; ++c) x[c] = input_word<IN>(src + ((((bitrev_c((uint32_t)c, R) << (L - R)) | t) << map.shift) | map.low));
-            } else if (BITREV_IN) {
-#pragma unroll
-                for (int c = 0; c < E; ++c) x[c] = input_word<IN>(src + ((bitrev_c((uint32_t)c, R) << (L - R)) | t));
-            } else {
-#pragma unroll
-                for (int c = 0; c < E; ++c) x[c] = input_word<IN>(src + (base | ((uint32_t)c << EB)));
-            }
-            load_words<DP, E>(x, m);
+            if (SUB && BITREV_IN) load_unit<DP, IN, E>(x, gin, poly, polys, N, [&](int c) { return (((bitrev_c((uint32_t)c, R) << (L - R)) | t) << map.shift) | map.low; }, m);
+            else if (BITREV_IN) load_unit<DP, IN, E>(x, gin, poly, polys, N, [&](int c) { return (bitrev_c((uint32_t)c, R) << (L - R)) | t; }, m);
+            else load_unit<DP, IN, E>(x, gin, poly, polys, N, [&](int c) { return base | ((uint32_t)c << EB); }, m);
         } else {
-            const uint64_t* src = smem + (size_t)poly * N;
-            const uint32_t pb = swz(base);
+            const uint32_t pb = swzm<DP>(base);
 #pragma unroll
-            for (int c = 0; c < E; ++c) x[c] = src[pb ^ swz((uint32_t)c << EB)];
+            for (int c = 0; c < E; ++c) x[c] = sm_load<DP>(smem, poly, N, pb ^ swzm<DP>((uint32_t)c << EB));
         }
         const uint32_t TB = BRTW ? (N + t) : plan_tw_offset<L, PASS>() + (S0 ? (base >> (L - S0)) : 0u);
         if constexpr (IPT > 0) inv_stages<R, S0, KIN, DP, (PASS == 0 && !SUB), R - 1, true>(x, wall[k], 0u, m);
         else inv_stages<R, S0, KIN, DP, (PASS == 0 && !SUB)>(x, tw, TB, m);
         if (OUT == IO_GLOBAL) {
-            uint64_t* dst = gout + (size_t)poly * N;
 #pragma unroll
-            for (int c = 0; c < E; ++c)
-                stream_store(dst + (base | ((uint32_t)c << EB)), scale_word<DP>(x[c], ninv, m));
+            for (int c = 0; c < E; ++c) store_unit_word<DP>(gout, poly, polys, N, base | ((uint32_t)c << EB), scale_word<DP>(x[c], ninv, m));
         } else {
-            uint64_t* dst = smem + (size_t)poly * N;
-            const uint32_t pb = swz(base);
+            const uint32_t pb = swzm<DP>(base);
 #pragma unroll
-            for (int c = 0; c < E; ++c) dst[pb ^ swz((uint32_t)c << EB)] = x[c];
+            for (int c = 0; c < E; ++c) sm_store<DP>(smem, poly, N, pb ^ swzm<DP>((uint32_t)c << EB), x[c]);
         }
       }
     }

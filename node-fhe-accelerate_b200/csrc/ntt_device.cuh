@@ -74,7 +74,8 @@ __global__ void __launch_bounds__(THREADS) ntt_forward_kernel(const uint64_t* in
     const uint32_t tid = threadIdx.x;
     const size_t groups = (batch + PPC - 1) / PPC;
     if constexpr (TMA && P > 1) {
-        uint64_t* landing = smem + (size_t)PPC * N;
+        // work buffer (PPC x N slots of the mode's width) | landing buffer (PPC x N raw 8-byte words) | mbarrier
+        uint64_t* landing = reinterpret_cast<uint64_t*>(reinterpret_cast<char*>(smem) + (size_t)PPC * N * smem_slot_bytes<DP>());
         uint64_t* bar = landing + (size_t)PPC * N;
         auto group_bytes = [&](size_t g) {
             const size_t q0 = g * PPC;
@@ -134,7 +135,8 @@ __global__ void __launch_bounds__(THREADS) ntt_inverse_kernel(const uint64_t* in
     const uint32_t tid = threadIdx.x;
     const size_t groups = (batch + PPC - 1) / PPC;
     if constexpr (TMA && P > 1) {  // see ntt_forward_kernel
-        uint64_t* landing = smem + (size_t)PPC * N;
+        // work buffer (PPC x N slots of the mode's width) | landing buffer (PPC x N raw 8-byte words) | mbarrier
+        uint64_t* landing = reinterpret_cast<uint64_t*>(reinterpret_cast<char*>(smem) + (size_t)PPC * N * smem_slot_bytes<DP>());
         uint64_t* bar = landing + (size_t)PPC * N;
         auto group_bytes = [&](size_t g) {
             const size_t q0 = g * PPC;
@@ -273,7 +275,9 @@ __global__ void __launch_bounds__(THREADS) polymul_kernel(const uint64_t* a, con
     constexpr int P = Plan<L>::P;
     constexpr size_t N = (size_t)1 << L;
     constexpr int STASH = STASH_GLOBAL ? IO_STASH_GLOBAL : IO_STASH_SMEM;
-    uint64_t* stash = STASH_GLOBAL ? scratch + (size_t)blockIdx.x * PPC * N : smem + (size_t)PPC * N;
+    constexpr int UPB = (DP == MODE_U32P) ? PPC / 2 : PPC;  // work-buffer units per block (pairs of polynomials in pair mode)
+    uint64_t* stash = STASH_GLOBAL ? scratch + (size_t)blockIdx.x * UPB * N
+                                   : reinterpret_cast<uint64_t*>(reinterpret_cast<char*>(smem) + (size_t)UPB * N * smem_slot_bytes<DP>());
     const uint32_t tid = threadIdx.x;
     const size_t groups = (batch + PPC - 1) / PPC;
     for (size_t g = blockIdx.x; g < groups; g += gridDim.x) {

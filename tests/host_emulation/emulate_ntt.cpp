@@ -54,7 +54,7 @@ static void run_inv(uint32_t threads, uint32_t polys, const uint64_t* gin, uint6
 
 // the device twiddle heap as raw words: (w, w') pairs, or one double per entry in DP mode
 static std::vector<uint64_t> heap_words(const uint64_t* table, uint32_t L, uint64_t q, int mode) {
-    if (mode == MODE_U32) return build_heap_table_u32(table, L, q);
+    if (is_u32(mode)) return build_heap_table_u32(table, L, q);
     if (mode == MODE_DP) return build_heap_table_dp(table, L, q);
     const std::vector<Tw> h = build_heap_table(table, L, q);
     std::vector<uint64_t> w(h.size() * 2);
@@ -82,18 +82,18 @@ static int check(uint32_t threads, uint32_t polys, uint64_t q_override = 0) {
         return 1;
     }
     ModQ m = make_modq(q);
-    if (DP != MODE_U32 && (int)(m.dp != 0) != DP) {
+    if (!is_u32(DP) && (int)(m.dp != 0) != DP) {
         std::printf("L=%d: mode mismatch\n", L);
         return 1;
     }
-    if (DP == MODE_U32 && (q >= (1ULL << U32_QBITS) || m.mu32 == 0)) {
+    if (is_u32(DP) && (q >= (1ULL << U32_QBITS) || m.mu32 == 0)) {
         std::printf("L=%d: prime %llu too large for the 32-bit mode\n", L, (unsigned long long)q);
         return 1;
     }
     const std::vector<uint64_t> hfw = heap_words(fwd.data(), L, q, DP), hiw = heap_words(inv.data(), L, q, DP);
     const Tw* hf = reinterpret_cast<const Tw*>(hfw.data());
     const Tw* hi = reinterpret_cast<const Tw*>(hiw.data());
-    const Tw ninv = DP == MODE_U32 ? Tw{sc[2], (sc[2] << 32) / q}
+    const Tw ninv = is_u32(DP) ? Tw{sc[2], (sc[2] << 32) / q}
                     : DP == MODE_DP ? Tw{double_to_bits((double)sc[2]), 0} : Tw{sc[2], shoup_companion(sc[2], q)};
     std::mt19937_64 rng(1234 + L);
     std::vector<uint64_t> x((size_t)polys * N), ref, got((size_t)polys * N), smem((size_t)polys * N);
@@ -131,6 +131,11 @@ static int check_all() {
     bad += check<L, MODE_U32>(64, 1, 132120577ULL);
     bad += check<L, MODE_U32>(96, 3, 133857281ULL);  // the largest prime below 2^27 with 2^15 | q - 1
     if constexpr (L <= 4) bad += check<L, MODE_U32>(32, 2, 97ULL);
+    if constexpr (Plan<L>::P > 1) {  // pair mode (two polynomials per work-buffer slot): even, odd and single batches
+        bad += check<L, MODE_U32P>(64, 4, 132120577ULL);
+        bad += check<L, MODE_U32P>(96, 3, 133857281ULL);
+        bad += check<L, MODE_U32P>(32, 1, 132120577ULL);
+    }
     if constexpr (L < 14) bad += check_all<L + 1>();
     return bad;
 }

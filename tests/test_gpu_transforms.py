@@ -107,14 +107,16 @@ def _prime_for(logn, mode):
     return Q27 if logn % 2 == 0 else 133857281
 
 
-@pytest.mark.parametrize("lazy", ["q62", "q<2^42", "q<2^27"])
+@pytest.mark.parametrize("lazy", ["q62", "q<2^42", "q<2^27", "q<2^27-paired"])
 @pytest.mark.parametrize("logn", range(2, 15))
 def test_transforms_match_oracle_all_degrees(fhe, torch, oracle, logn, lazy, monkeypatch):
     n, q = 1 << logn, _prime_for(logn, lazy)
+    monkeypatch.delenv("FHEB_NO_U32", raising=False)
+    monkeypatch.setenv("FHEB_U32_PAIR", "0")   # 32-bit kernels, one polynomial per 4-byte shared-memory slot
     if lazy == "q<2^42":
         monkeypatch.setenv("FHEB_NO_U32", "1")  # read per call by the library: keeps 27-bit primes on the FP64-pipe kernels
-    else:
-        monkeypatch.delenv("FHEB_NO_U32", raising=False)
+    if lazy == "q<2^27-paired":
+        monkeypatch.setenv("FHEB_U32_PAIR", "1")   # 32-bit kernels, two polynomials per 8-byte slot
     ntt = fhe.NTTProcessor(n, q)
     fwd, inv, psi, psi_inv, inv_n = oracle.twiddles(n, q)
     gf, gi, gpsi, gpsi_inv, ginv_n = ntt.get_twiddles()
