@@ -225,6 +225,7 @@ constexpr bool TMA_DEFAULT(bool inverse) {
     if (L == 8) return !inverse;
     if (L == 10) return !inverse || DP != MODE_INT;
     if (L == 12) return inverse ? true : DP == MODE_INT;
+    if (L == 13) return DP == MODE_INT || (!inverse && DP == MODE_U32);  // 32-bit forward +15 %, 64-bit integer +3.5 / +4.4 % (profiles/r02_u32_tma_big.txt); 32-bit N = 16384: no difference
     return false;
 }
 
@@ -238,20 +239,23 @@ static int launch_transform(const NttPlan* p, int dir, const uint64_t* in, uint6
     int bps = 0;
     // Bulk-async (TMA) landing buffer for the next group's words: multi-pass plans up to N = 4096 (two buffers fit several
     // blocks per SM), 16-byte aligned input, and only where it measured faster (FHEB_TMA=0/1 overrides: experiments).
-    if constexpr (Plan<L>::P > 1 && L <= 12 && DP != MODE_U32P) {
+    if constexpr (Plan<L>::P > 1 && DP != MODE_U32P && (L <= 13 || DP == MODE_U32)) {
+        // (N = 8192 / 16384 in the 32-bit mode: the 4-byte work buffer leaves room for a landing buffer of raw 8-byte
+        // words, 96 / 192 KB in all; one 512-thread block per SM then, against two 256-thread blocks without it)
         const char* tma_s = getenv("FHEB_TMA");  // read per call: the parity suite forces both settings
         const int tma_env = tma_s ? atoi(tma_s) : -1;
         const bool tma = (tma_env < 0 ? TMA_DEFAULT<L, DP>(dir == DIR_INV) : tma_env != 0) && (reinterpret_cast<uintptr_t>(in) & 15u) == 0 && dir != DIR_INV_FWDNET;
         if (tma) {
+            constexpr int T = (L >= 13) ? 512 : G::THREADS;
             constexpr size_t SMEM_TMA = G::SMEM + (size_t)G::PPC * (1u << L) * 8 + 16;  // work | landing (raw 8-byte words) | mbarrier
             if (dir == DIR_INV) {
-                auto k = ntt_inverse_kernel<L, DP, G::THREADS, G::PPC, true>;
-                FHEB_TRY(configure(k, SMEM_TMA, G::THREADS, &bps));
-                k<<<persistent_grid(groups, bps), G::THREADS, SMEM_TMA, s>>>(in, out, batch, d_inv, ninv, p->mod);
+                auto k = ntt_inverse_kernel<L, DP, T, G::PPC, true>;
+                FHEB_TRY(configure(k, SMEM_TMA, T, &bps));
+                k<<<persistent_grid(groups, bps), T, SMEM_TMA, s>>>(in, out, batch, d_inv, ninv, p->mod);
             } else {
-                auto k = ntt_forward_kernel<L, DP, G::THREADS, G::PPC, false, true>;
-                FHEB_TRY(configure(k, SMEM_TMA, G::THREADS, &bps));
-                k<<<persistent_grid(groups, bps), G::THREADS, SMEM_TMA, s>>>(in, out, batch, d_fwd, ninv, p->mod);
+                auto k = ntt_forward_kernel<L, DP, T, G::PPC, false, true>;
+                FHEB_TRY(configure(k, SMEM_TMA, T, &bps));
+                k<<<persistent_grid(groups, bps), T, SMEM_TMA, s>>>(in, out, batch, d_fwd, ninv, p->mod);
             }
             FHEB_CHECK_LAUNCH();
             count_launch();
