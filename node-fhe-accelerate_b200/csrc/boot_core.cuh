@@ -141,9 +141,9 @@ FHEB_HD void boot_first_pass(uint32_t tid, uint32_t nthreads, const BootStep& s,
                 x[e] = DP ? double_to_bits(dp_from_uint(g)) : g;
             }
             fwd_stages<R, 0, 1, DP, true>(x, tw, 0u, m);
-            uint64_t* dst = s.work + (size_t)(c * s.levels + l) * N;
+            const SlotRef<MODE_INT> dst = slot_ref<MODE_INT>(s.work, c * s.levels + l, N, pb);
 #pragma unroll
-            for (int e = 0; e < E; ++e) dst[pb ^ swz((uint32_t)e << EB)] = x[e];
+            for (int e = 0; e < E; ++e) slot_store<MODE_INT>(dst, swz((uint32_t)e << EB), x[e]);
         }
     }
 }
@@ -174,10 +174,10 @@ FHEB_HD void boot_mid_pass(uint32_t tid, uint32_t nthreads, const BootStep& s, c
         Tw wf[E - 1];  // this item's forward twiddles: the same for every digit row
         load_item_tw<R, S0, DP>(twf, TB, wf);
         for (uint32_t row = 0; row < rows; ++row) {
-            const uint64_t* src = s.work + (size_t)row * N;
+            const SlotRef<MODE_INT> src = slot_ref<MODE_INT>(s.work, row, N, pb);
             uint64_t x[E];
 #pragma unroll
-            for (int e = 0; e < E; ++e) x[e] = src[pb ^ swz((uint32_t)e)];
+            for (int e = 0; e < E; ++e) x[e] = slot_load<MODE_INT>(src, swz((uint32_t)e));
             fwd_stages<R, S0, KIN, DP, false, 0, true>(x, wf, 0u, m);
             // key element (row, position u*E + e, component j) lives at ((row*E + e)*ITEMS + u)*KP1 + j: lanes
             // (consecutive u) read consecutive entries, and the k+1 components of one position are adjacent
@@ -204,7 +204,7 @@ FHEB_HD void boot_mid_pass(uint32_t tid, uint32_t nthreads, const BootStep& s, c
                         const double t = dp_mulmod(bits_to_double(x[e]), bits_to_double(w[j].w), m);
                         out[j][e] = double_to_bits(dp_add(bits_to_double(out[j][e]), t));
                     } else {  // t in [0, 2q) for any x; keep the running sum in [0, 2q)
-                        out[j][e] = csub(out[j][e] + shoup_lazy(x[e], w[j].w, w[j].wp, m.q), m.q2);
+                        out[j][e] = csub(out[j][e] + shoup_lazy(x[e], w[j].w, w[j].wp, m), m.q2);
                     }
                 }
             }
@@ -218,9 +218,9 @@ FHEB_HD void boot_mid_pass(uint32_t tid, uint32_t nthreads, const BootStep& s, c
                 }
             }
             inv_stages<R, S0, boot_kacc<DP>(), DP, false>(out[j], twi, TB, m);
-            uint64_t* dst = s.work + (size_t)j * N;
+            const SlotRef<MODE_INT> dst = slot_ref<MODE_INT>(s.work, j, N, pb);
 #pragma unroll
-            for (int e = 0; e < E; ++e) dst[pb ^ swz((uint32_t)e)] = out[j][e];
+            for (int e = 0; e < E; ++e) slot_store<MODE_INT>(dst, swz((uint32_t)e), out[j][e]);
         }
     }
 }
@@ -240,10 +240,10 @@ FHEB_HD void boot_final_pass(uint32_t tid, uint32_t nthreads, const BootStep& s,
         const uint32_t c = U >> (L - R);
         const uint32_t u = U & (ITEMS - 1);
         const uint32_t pb = swz(u);
-        const uint64_t* src = s.work + (size_t)c * N;
+        const SlotRef<MODE_INT> src = slot_ref<MODE_INT>(s.work, c, N, pb);
         uint64_t x[E];
 #pragma unroll
-        for (int e = 0; e < E; ++e) x[e] = src[pb ^ swz((uint32_t)e << EB)];
+        for (int e = 0; e < E; ++e) x[e] = slot_load<MODE_INT>(src, swz((uint32_t)e << EB));
         inv_stages<R, 0, KIN, DP, true>(x, twi, 0u, m);
         const uint64_t* a = s.acc + (size_t)c * N;
         uint64_t* dst = (s.gout ? s.gout : s.acc) + (size_t)c * N;

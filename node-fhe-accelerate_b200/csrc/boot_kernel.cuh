@@ -55,8 +55,8 @@ inline size_t boot_smem_bytes(int mode, uint32_t N, uint32_t kp1, uint32_t level
     size_t words = (acc_global ? 0 : (size_t)kp1 * N) + (size_t)kp1 * levels * N;
     if (mode != BOOT_BLIND && !acc_global) words += (size_t)kp1 * N;
     size_t bytes = words * 8;
-    if (mode == BOOT_BLIND) bytes += ((size_t)n * 4 + 15) & ~(size_t)15;
-    return bytes;
+    if (mode == BOOT_BLIND) bytes += (size_t)n * 4;
+    return (bytes + 127) & ~(size_t)127;  // every ciphertext's rows start 128-byte aligned (SlotRef, ntt_core.cuh)
 }
 
 // `active` is uniform per ciphertext group; idle groups still take part in the block barriers
@@ -74,7 +74,7 @@ __device__ __forceinline__ void boot_run_step(bool active, uint32_t tid, uint32_
 // raw_flag; the one the flag does not select returns at once.
 template <int L, bool DP, int KP1, bool RAWOK = true>
 __global__ void __launch_bounds__(BootGeometry<L>::LB_THREADS, BootGeometry<L>::LB_BLOCKS) boot_kernel(const BootLaunch a, const uint32_t ct_bytes) {
-    extern __shared__ __align__(16) uint64_t smem[];
+    extern __shared__ __align__(128) uint64_t smem[];
     if (a.raw_flag != nullptr && (*a.raw_flag != 0) != RAWOK) return;  // block-uniform
     constexpr uint32_t N = 1u << L;
     constexpr uint32_t TPC = BootGeometry<L>::TPC;

@@ -43,6 +43,7 @@ struct ModQ {
     uint32_t pad_;
     double qd;       // (double)q
     double qinv;     // 1.0 / q, rounded to nearest
+    uint64_t nq;     // 2^64 - q: x*w - h*q == lo64(x*w + h*nq), one multiply-add chain (shoup_lazy)
 };
 
 FHEB_HD uint64_t mulhi64(uint64_t a, uint64_t b) {
@@ -65,9 +66,31 @@ FHEB_HD void mul128(uint64_t a, uint64_t b, uint64_t& hi, uint64_t& lo) {
 }
 
 // x * w mod q, lazily: result in [0, 2q) for ANY x < 2^64, given w < q and wp = floor(w*2^64/q).
-FHEB_HD uint64_t shoup_lazy(uint64_t x, uint64_t w, uint64_t wp, uint64_t q) {
-    uint64_t h = mulhi64(x, wp);
-    return x * w - h * q;
+FHEB_HD uint64_t shoup_lazy(uint64_t x, uint64_t w, uint64_t wp, const ModQ& m) {
+    const uint64_t h = mulhi64(x, wp);
+#if defined(__CUDA_ARCH__) && !defined(FHEB_EXP_PLAIN_SHOUP)
+    // x*w - h*q == lo64(x*w + h*(2^64 - q)): with the negated modulus as multiplicand both low products accumulate into
+    // ONE chain of 32-bit limbs - 2 IMAD.WIDE + 4 IMAD, no negation, no subtraction.  From `x * w - h * q` ptxas builds
+    // two separate low products, negates one and patches the high words together with IMAD.IADD / IMAD.X: 1.7 more
+    // multiply-pipe and 1.6 more ALU instructions per product (forward N=16384: 2784 -> 2488 instructions, +5.4 %).
+    const uint32_t x0 = (uint32_t)x, x1 = (uint32_t)(x >> 32), h0 = (uint32_t)h, h1 = (uint32_t)(h >> 32);
+    const uint32_t w0 = (uint32_t)w, w1 = (uint32_t)(w >> 32), n0 = (uint32_t)m.nq, n1 = (uint32_t)(m.nq >> 32);
+    uint64_t r;
+    asm("{\n\t.reg .u64 t;\n\t.reg .u32 tl, th;\n\t"
+        "mul.wide.u32 t, %1, %2;\n\t"
+        "mad.wide.u32 t, %3, %4, t;\n\t"
+        "mov.b64 {tl, th}, t;\n\t"
+        "mad.lo.u32 th, %5, %2, th;\n\t"
+        "mad.lo.u32 th, %1, %6, th;\n\t"
+        "mad.lo.u32 th, %7, %4, th;\n\t"
+        "mad.lo.u32 th, %3, %8, th;\n\t"
+        "mov.b64 %0, {tl, th};\n\t}"
+        : "=l"(r)
+        : "r"(h0), "r"(n0), "r"(x0), "r"(w0), "r"(h1), "r"(n1), "r"(x1), "r"(w1));
+    return r;
+#else
+    return x * w - h * m.q;
+#endif
 }
 
 FHEB_HD uint64_t csub(uint64_t x, uint64_t m) {  // x in [0, 2m) -> [0, m)
@@ -244,6 +267,7 @@ inline ModQ make_modq(uint64_t q) {
     m.pad_ = 0;
     m.qd = (double)q;
     m.qinv = 1.0 / (double)q;
+    m.nq = 0 - q;
     return m;
 }
 

@@ -107,6 +107,64 @@ FHEB_HD void sm_store(uint64_t* buf, size_t unit, uint32_t N, uint32_t slot, uin
     if constexpr (DP == MODE_U32) reinterpret_cast<uint32_t*>(buf)[unit * N + slot] = (uint32_t)v;
     else buf[unit * N + slot] = v;
 }
+
+// The 2^R slots of one work item are  pb ^ swz(c << EB),  pb = swz(base) the item's first slot.  Formed as written, every
+// access costs a LOP3 (the XOR) plus an add of the buffer address (ptxas: IMAD.IADD, on the multiply pipe).  SlotRef hoists
+// the address: swz(k) == k ^ f(k >> 4) with f inside the low nibble (five bits for 4-byte slots), and the bits of c << EB
+// above the nibble are zero in pb, so
+//     address(pb ^ swz(k)) = (A ^ (low(swz(k)) * bytes)) + high(swz(k)) * bytes,     A = address of slot pb,
+// provided the unit's first slot is 128-byte aligned (the XOR then never reaches the bits the base address occupies).
+// After unrolling k is a constant: one LOP3 per access, the rest is the immediate offset of the LDS / STS
+// (-1 instruction per access, ~1 per butterfly).  The buffers are declared __align__(128) and units are N * bytes apart
+// (N >= 32 wherever shared memory is used).
+template <int DP>
+struct SlotRef {
+#if defined(__CUDA_ARCH__)
+    uint32_t a;  // shared-window byte address of slot pb
+#else
+    uint64_t* buf;
+    size_t first;  // unit * N
+    uint32_t pb;
+#endif
+};
+template <int DP>
+FHEB_HD SlotRef<DP> slot_ref(const uint64_t* buf, size_t unit, uint32_t N, uint32_t pb) {
+    SlotRef<DP> r;
+#if defined(__CUDA_ARCH__)
+    r.a = (uint32_t)__cvta_generic_to_shared(reinterpret_cast<const char*>(buf) + (unit * N + pb) * smem_slot_bytes<DP>());
+#else
+    r.buf = const_cast<uint64_t*>(buf);
+    r.first = unit * N;
+    r.pb = pb;
+#endif
+    return r;
+}
+#if defined(__CUDA_ARCH__)
+template <int DP>
+__device__ __forceinline__ void* slot_ptr(const SlotRef<DP>& r, uint32_t k) {
+    constexpr uint32_t LOW = (DP == MODE_U32) ? 31u : 15u, SB = smem_slot_bytes<DP>();
+    return __cvta_shared_to_generic((r.a ^ ((k & LOW) * SB)) + (k & ~LOW) * SB);
+}
+#endif
+// k = swzm<DP>(c << EB)
+template <int DP>
+FHEB_HD uint64_t slot_load(const SlotRef<DP>& r, uint32_t k) {
+#if defined(__CUDA_ARCH__)
+    if constexpr (DP == MODE_U32) return *reinterpret_cast<const uint32_t*>(slot_ptr<DP>(r, k));
+    else return *reinterpret_cast<const uint64_t*>(slot_ptr<DP>(r, k));
+#else
+    return sm_load<DP>(r.buf, 0, 0, (uint32_t)r.first + (r.pb ^ k));
+#endif
+}
+template <int DP>
+FHEB_HD void slot_store(const SlotRef<DP>& r, uint32_t k, uint64_t v) {
+#if defined(__CUDA_ARCH__)
+    if constexpr (DP == MODE_U32) *reinterpret_cast<uint32_t*>(slot_ptr<DP>(r, k)) = (uint32_t)v;
+    else *reinterpret_cast<uint64_t*>(slot_ptr<DP>(r, k)) = v;
+#else
+    sm_store<DP>(r.buf, 0, 0, (uint32_t)r.first + (r.pb ^ k), v);
+#endif
+}
 constexpr int CAP_STRICT = 4;   // q < 2^62: 4q fits a word
 constexpr int CAP_DP = 128;     // q < 2^42: |v| < 128 q <= 2^49 keeps every FP64 step exact with margin
 constexpr int CAP_U32 = 32;     // q < 2^27: 32q fits 32 bits
@@ -239,7 +297,7 @@ FHEB_HD void fwd_bfly(uint64_t& A, uint64_t& B, const Tw& w, const ModQ& m) {
         static_assert(!red || K <= 4, "conditional subtraction only halves [0,4q)");
         uint64_t a = A;
         if constexpr (red) a = csub(a, m.q2);
-        uint64_t t = shoup_lazy(B, w.w, w.wp, m.q);  // [0, 2q) for any B
+        uint64_t t = shoup_lazy(B, w.w, w.wp, m);  // [0, 2q) for any B
         A = a + t;
         B = a - t + m.q2;
     }
@@ -285,7 +343,7 @@ FHEB_HD void inv_bfly(uint64_t& A, uint64_t& B, const Tw& w, const ModQ& m) {
             if constexpr (red) d = csub(d, m.q2);
             B = d;
         } else {
-            B = shoup_lazy(d, w.w, w.wp, m.q);
+            B = shoup_lazy(d, w.w, w.wp, m);
         }
     }
 }
@@ -518,7 +576,7 @@ FHEB_HD uint64_t scale_word(uint64_t x, const Tw& ninv, const ModQ& m) {
     if constexpr (DP == MODE_DP) return dp_canon_word(dp_mulmod(bits_to_double(x), bits_to_double(ninv.w), m), m);
     else if constexpr (DP == MODE_U32) return csub32(shoup32((uint32_t)x, (uint32_t)ninv.w, (uint32_t)ninv.wp, (uint32_t)m.q), (uint32_t)m.q);
     else if constexpr (DP == MODE_U32P) return pack32((uint32_t)scale_word<MODE_U32>(lo32(x), ninv, m), (uint32_t)scale_word<MODE_U32>(hi32(x), ninv, m));
-    else return csub(shoup_lazy(x, ninv.w, ninv.wp, m.q), m.q);
+    else return csub(shoup_lazy(x, ninv.w, ninv.wp, m), m.q);
 }
 
 // ---- pass plans: how the L stages are split into register passes ----------------------
@@ -702,9 +760,9 @@ FHEB_HD void fwd_pass(uint32_t tid, uint32_t nthreads, uint32_t polys, const uin
                 load_unit<DP, IN, E>(x, gin, poly, polys, N, [&](int c) { return base | ((uint32_t)c << EB); }, m);
             }
         } else {
-            const uint32_t pb = swzm<DP>(base);
+            const SlotRef<DP> sr = slot_ref<DP>(smem, poly, N, swzm<DP>(base));
 #pragma unroll
-            for (int c = 0; c < E; ++c) x[c] = sm_load<DP>(smem, poly, N, pb ^ swzm<DP>((uint32_t)c << EB));
+            for (int c = 0; c < E; ++c) x[c] = slot_load<DP>(sr, swzm<DP>((uint32_t)c << EB));
         }
         const uint32_t TB = BRTW ? (N + t) : plan_tw_offset<L, PASS>() + (S0 ? (base >> (L - S0)) : 0u);
         if constexpr (IPT > 0) fwd_stages<R, S0, KIN, DP, UNIT, 0, true>(x, wall[k], 0u, m);
@@ -723,10 +781,10 @@ FHEB_HD void fwd_pass(uint32_t tid, uint32_t nthreads, uint32_t polys, const uin
             for (int c = 0; c < E; ++c) dst[base | ((uint32_t)c << EB)] = park_word<KOUT, DP>(x[c], m);
         } else {
             uint64_t* dst = (OUT == IO_STASH_SMEM ? gout : smem);
-            const uint32_t pb = swzm<DP>(base);
+            const SlotRef<DP> sw = slot_ref<DP>(dst, poly, N, swzm<DP>(base));
 #pragma unroll
             for (int c = 0; c < E; ++c)
-                sm_store<DP>(dst, poly, N, pb ^ swzm<DP>((uint32_t)c << EB), (OUT == IO_STASH_SMEM) ? park_word<KOUT, DP>(x[c], m) : x[c]);
+                slot_store<DP>(sw, swzm<DP>((uint32_t)c << EB), (OUT == IO_STASH_SMEM) ? park_word<KOUT, DP>(x[c], m) : x[c]);
         }
       }
     }
@@ -763,6 +821,7 @@ FHEB_HD void polymul_mid_pass(uint32_t tid, uint32_t nthreads, uint32_t polys, c
         const uint32_t u = U & (ITEMS - 1);
         const uint32_t base = u << R;
         const uint32_t pb = swzm<DP>(base);
+        const SlotRef<DP> sr = slot_ref<DP>(smem, poly, N, pb);
         uint64_t x[E];
         if (IN == IO_GLOBAL) {
             const uint64_t* src = gin + (size_t)poly * N;
@@ -771,14 +830,15 @@ FHEB_HD void polymul_mid_pass(uint32_t tid, uint32_t nthreads, uint32_t polys, c
             load_words<DP, E>(x, m);
         } else {
 #pragma unroll
-            for (int c = 0; c < E; ++c) x[c] = sm_load<DP>(smem, poly, N, pb ^ swzm<DP>((uint32_t)c));
+            for (int c = 0; c < E; ++c) x[c] = slot_load<DP>(sr, swzm<DP>((uint32_t)c));
         }
         const uint32_t TB = plan_tw_offset<L, PASS>() + (S0 ? (base >> (L - S0)) : 0u);
         fwd_stages<R, S0, KIN, DP, PASS == 0>(x, twf, TB, m);
         const uint64_t* sa = stash + (size_t)poly * N;
+        const SlotRef<DP> ss = slot_ref<DP>(STASH == IO_STASH_GLOBAL ? smem : stash, poly, N, pb);
 #pragma unroll
         for (int c = 0; c < E; ++c) {
-            const uint64_t av = (STASH == IO_STASH_GLOBAL) ? sa[base | (uint32_t)c] : sm_load<DP>(stash, poly, N, pb ^ swzm<DP>((uint32_t)c));
+            const uint64_t av = (STASH == IO_STASH_GLOBAL) ? sa[base | (uint32_t)c] : slot_load<DP>(ss, swzm<DP>((uint32_t)c));
             if constexpr (DP == MODE_DP) x[c] = double_to_bits(dp_mulmod(bits_to_double(av), bits_to_double(x[c]), m));
             else if constexpr (DP == MODE_U32P) {
                 const uint64_t xc = canon_k<KOUT, DP>(x[c], m);
@@ -793,7 +853,7 @@ FHEB_HD void polymul_mid_pass(uint32_t tid, uint32_t nthreads, uint32_t polys, c
             for (int c = 0; c < E; ++c) stream_store(dst + (base | (uint32_t)c), scale_word<DP>(x[c], ninv, m));
         } else {
 #pragma unroll
-            for (int c = 0; c < E; ++c) sm_store<DP>(smem, poly, N, pb ^ swzm<DP>((uint32_t)c), x[c]);
+            for (int c = 0; c < E; ++c) slot_store<DP>(sr, swzm<DP>((uint32_t)c), x[c]);
         }
     }
 }
@@ -874,9 +934,9 @@ FHEB_HD void inv_pass(uint32_t tid, uint32_t nthreads, uint32_t polys, const uin
             else if (BITREV_IN) load_unit<DP, IN, E>(x, gin, poly, polys, N, [&](int c) { return (bitrev_c((uint32_t)c, R) << (L - R)) | t; }, m);
             else load_unit<DP, IN, E>(x, gin, poly, polys, N, [&](int c) { return base | ((uint32_t)c << EB); }, m);
         } else {
-            const uint32_t pb = swzm<DP>(base);
+            const SlotRef<DP> sr = slot_ref<DP>(smem, poly, N, swzm<DP>(base));
 #pragma unroll
-            for (int c = 0; c < E; ++c) x[c] = sm_load<DP>(smem, poly, N, pb ^ swzm<DP>((uint32_t)c << EB));
+            for (int c = 0; c < E; ++c) x[c] = slot_load<DP>(sr, swzm<DP>((uint32_t)c << EB));
         }
         const uint32_t TB = BRTW ? (N + t) : plan_tw_offset<L, PASS>() + (S0 ? (base >> (L - S0)) : 0u);
         if constexpr (IPT > 0) inv_stages<R, S0, KIN, DP, (PASS == 0 && !SUB), R - 1, true>(x, wall[k], 0u, m);
@@ -885,9 +945,9 @@ FHEB_HD void inv_pass(uint32_t tid, uint32_t nthreads, uint32_t polys, const uin
 #pragma unroll
             for (int c = 0; c < E; ++c) store_unit_word<DP>(gout, poly, polys, N, base | ((uint32_t)c << EB), scale_word<DP>(x[c], ninv, m));
         } else {
-            const uint32_t pb = swzm<DP>(base);
+            const SlotRef<DP> sw = slot_ref<DP>(smem, poly, N, swzm<DP>(base));
 #pragma unroll
-            for (int c = 0; c < E; ++c) sm_store<DP>(smem, poly, N, pb ^ swzm<DP>((uint32_t)c << EB), x[c]);
+            for (int c = 0; c < E; ++c) slot_store<DP>(sw, swzm<DP>((uint32_t)c << EB), x[c]);
         }
       }
     }

@@ -68,7 +68,7 @@ __device__ __forceinline__ void inv_middle(uint32_t tid, uint32_t nthreads, uint
 template <int L, int DP, int THREADS, int PPC, bool SCALE, bool TMA = false>
 __global__ void __launch_bounds__(THREADS) ntt_forward_kernel(const uint64_t* in, uint64_t* out, size_t batch,
                                                               const Tw* __restrict__ tw, const Tw ninv, const ModQ m) {
-    extern __shared__ __align__(16) uint64_t smem[];
+    extern __shared__ __align__(128) uint64_t smem[];
     constexpr int P = Plan<L>::P;
     constexpr size_t N = (size_t)1 << L;
     const uint32_t tid = threadIdx.x;
@@ -129,7 +129,7 @@ __global__ void __launch_bounds__(THREADS) ntt_forward_kernel(const uint64_t* in
 template <int L, int DP, int THREADS, int PPC, bool TMA = false>
 __global__ void __launch_bounds__(THREADS) ntt_inverse_kernel(const uint64_t* in, uint64_t* out, size_t batch,
                                                               const Tw* __restrict__ tw, const Tw ninv, const ModQ m) {
-    extern __shared__ __align__(16) uint64_t smem[];
+    extern __shared__ __align__(128) uint64_t smem[];
     constexpr int P = Plan<L>::P;
     constexpr size_t N = (size_t)1 << L;
     const uint32_t tid = threadIdx.x;
@@ -225,7 +225,7 @@ __global__ void __launch_bounds__(256) ntt_top_kernel(const uint64_t* in, uint64
 template <int L, int DP, int THREADS, bool SCALE>
 __global__ void __launch_bounds__(THREADS) ntt_forward_sub_kernel(const uint64_t* tmp, uint64_t* out, size_t subs, uint32_t D,
                                                                   const Tw* __restrict__ tables, const Tw ninv, const ModQ m) {
-    extern __shared__ __align__(16) uint64_t smem[];
+    extern __shared__ __align__(128) uint64_t smem[];
     constexpr int P = Plan<L>::P;
     constexpr size_t N = (size_t)1 << L;
     const uint32_t tid = threadIdx.x;
@@ -247,7 +247,7 @@ __global__ void __launch_bounds__(THREADS) ntt_forward_sub_kernel(const uint64_t
 template <int L, int DP, int THREADS>
 __global__ void __launch_bounds__(THREADS) ntt_inverse_sub_kernel(const uint64_t* in, uint64_t* tmp, size_t subs, uint32_t D,
                                                                   const Tw* __restrict__ tables, const Tw one, const ModQ m) {
-    extern __shared__ __align__(16) uint64_t smem[];
+    extern __shared__ __align__(128) uint64_t smem[];
     constexpr int P = Plan<L>::P;
     constexpr size_t N = (size_t)1 << L;
     const uint32_t tid = threadIdx.x;
@@ -271,7 +271,7 @@ template <int L, int DP, int THREADS, int PPC, bool STASH_GLOBAL>
 __global__ void __launch_bounds__(THREADS) polymul_kernel(const uint64_t* a, const uint64_t* b, uint64_t* c, size_t batch,
                                                           const Tw* __restrict__ twf, const Tw* __restrict__ twi,
                                                           const Tw ninv, const ModQ m, uint64_t* scratch) {
-    extern __shared__ __align__(16) uint64_t smem[];
+    extern __shared__ __align__(128) uint64_t smem[];
     constexpr int P = Plan<L>::P;
     constexpr size_t N = (size_t)1 << L;
     constexpr int STASH = STASH_GLOBAL ? IO_STASH_GLOBAL : IO_STASH_SMEM;

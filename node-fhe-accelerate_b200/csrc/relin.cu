@@ -55,8 +55,8 @@ __global__ void __launch_bounds__(256) relin_mac_kernel(const uint64_t* __restri
         for (uint32_t l = 0; l < levels; ++l) {
             const uint64_t x = d[(size_t)l * N];
             const size_t k = ((size_t)l * 2) * N + j;
-            s0 = csub(s0 + shoup_lazy(x, key[k], keyp[k], m.q), m.q2);
-            s1 = csub(s1 + shoup_lazy(x, key[k + N], keyp[k + N], m.q), m.q2);
+            s0 = csub(s0 + shoup_lazy(x, key[k], keyp[k], m), m.q2);
+            s1 = csub(s1 + shoup_lazy(x, key[k + N], keyp[k + N], m), m.q2);
         }
         acc[(ct * 2) * N + j] = csub(s0, m.q);
         acc[(ct * 2 + 1) * N + j] = csub(s1, m.q);

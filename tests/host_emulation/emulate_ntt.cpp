@@ -156,7 +156,7 @@ static int check_arith() {
             if (reduce64(a, m) != a % q) { ++bad; break; }
             if (q < (1ULL << 63)) {
                 uint64_t w = b % q, wp = shoup_companion(w, q);
-                uint64_t r = shoup_lazy(a, w, wp, q);
+                uint64_t r = shoup_lazy(a, w, wp, m);
                 if (r >= 2 * q || r % q != (uint64_t)(((u128)a * w) % q)) { ++bad; break; }
             }
             uint64_t ac = a % q, bc = b % q;
