@@ -28,6 +28,7 @@ struct BootStep {          // block-uniform description of one step
     uint64_t* gout;        // when non-null the final pass stores here ([KP1][N], global) instead of acc
     uint32_t rot;          // normalised rotation in [0, 2N) (used when diff == null)
     uint32_t levels;
+    uint32_t rows;         // digit rows summed by the multiply-accumulate: KP1 * levels (external product), levels (relinearisation)
     uint32_t base_log;
     uint32_t add_acc;      // 1: result = acc + product (cmux); 0: product only (external product)
     uint32_t maybe_raw;    // 1: acc may still hold unreduced caller words (>= q); cleared after the first executed step
@@ -161,7 +162,7 @@ FHEB_HD void boot_mid_pass(uint32_t tid, uint32_t nthreads, const BootStep& s, c
     constexpr uint32_t N = 1u << L;
     constexpr uint32_t ITEMS = N >> R;
     static_assert(L - S0 - R == 0, "the last forward pass covers the lowest position bits");
-    const uint32_t rows = (uint32_t)KP1 * s.levels;
+    const uint32_t rows = s.rows;
     for (uint32_t u = tid; u < ITEMS; u += nthreads) {
         const uint32_t base = u << R;
         const uint32_t pb = swz(base);
@@ -277,7 +278,7 @@ FHEB_HD void boot_phase(uint32_t tid, uint32_t nthreads, const BootStep& s, cons
     if constexpr (PH == 0) {
         boot_first_pass<L, DP, KP1, RAWOK>(tid, nthreads, s, twf, m);
     } else if constexpr (PH < P - 1) {
-        fwd_pass<L, DP, PH, IO_SMEM, IO_SMEM>(tid, nthreads, (uint32_t)KP1 * s.levels, nullptr, nullptr, s.work, twf, m);
+        fwd_pass<L, DP, PH, IO_SMEM, IO_SMEM>(tid, nthreads, s.rows, nullptr, nullptr, s.work, twf, m);
     } else if constexpr (PH == P - 1) {
         boot_mid_pass<L, DP, KP1>(tid, nthreads, s, twf, twi, m);
     } else if constexpr (PH < 2 * P - 2) {

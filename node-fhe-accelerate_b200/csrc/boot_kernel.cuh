@@ -103,6 +103,7 @@ __global__ void __launch_bounds__(BootGeometry<L>::LB_THREADS, BootGeometry<L>::
         s.acc = acc;
         s.work = work;
         s.levels = a.levels;
+        s.rows = rows;
         s.base_log = a.base_log;
         s.rot = 0;
         s.ggsw = a.bsk;

@@ -12,6 +12,7 @@
 #include "elementwise.hpp"
 #include "ntt_plan.hpp"
 #include "plan.hpp"
+#include "relin_fused.hpp"
 
 namespace fheb {
 
@@ -114,6 +115,15 @@ __global__ void __launch_bounds__(256) bsk_pack_kernel(const uint64_t* __restric
             g[i] = t;
         }
     }
+}
+
+int pack_key_rows_device(const NttPlan* p, const uint64_t* y, Tw* g, size_t ggsws, uint32_t kp1, uint32_t rows, cudaStream_t s) {
+    const size_t words = ggsws * rows * kp1 * p->degree;
+    bsk_pack_kernel<<<stream_grid(words, 256, 8), 256, 0, s>>>(y, g, words, p->logn, last_pass_width(p->logn), kp1, rows, p->mod,
+                                                                  p->inv_n % p->modulus, (int)p->mod.dp);
+    if (cudaGetLastError() != cudaSuccess) return set_error(FHEB_ERR_NATIVE, "bsk_pack_kernel launch failed");
+    count_launch();
+    return FHEB_OK;
 }
 
 // ---- sample extraction ---------------------------------------------------------------------
@@ -371,10 +381,7 @@ int fheb_boot_key_create(const fheb_ntt_plan* plan, const fheb_boot_params* para
         // T(row polynomial) once, here, instead of on every external product (bootstrap_engine.cpp:478-487)
         if (rc == FHEB_OK) rc = ntt_forward_device(p, in.ptr<const uint64_t>(), tmp, polys, s);
         if (rc == FHEB_OK) {
-            bsk_pack_kernel<<<stream_grid(words, 256, 8), 256, 0, s>>>(tmp, key->d_bsk, words, p->logn, last_pass_width(p->logn), key->k + 1,
-                                                                          (key->k + 1) * key->levels, p->mod, p->inv_n % p->modulus, (int)p->mod.dp);
-            if (cudaGetLastError() != cudaSuccess) rc = set_error(FHEB_ERR_NATIVE, "bsk_pack_kernel launch failed");
-            count_launch();
+            rc = pack_key_rows_device(p, tmp, key->d_bsk, key->n, key->k + 1, (key->k + 1) * key->levels, s);
         }
         if (rc == FHEB_OK && cudaStreamSynchronize(s) != cudaSuccess) rc = set_error(FHEB_ERR_NATIVE, "bootstrapping key upload failed");
     }

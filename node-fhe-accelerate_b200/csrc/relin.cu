@@ -12,9 +12,12 @@
 // companions; a ciphertext costs `levels` forward and two inverse transforms instead of 3*levels + 2*levels.
 //
 // C-ABI entry points here (include/fheb200.h): fheb_relin_key_create / _destroy / _levels, fheb_relinearize_batch.
+#include <cstdlib>
+
 #include "elementwise.hpp"
 #include "modarith.cuh"
 #include "plan.hpp"
+#include "relin_fused.hpp"
 #include "runtime.hpp"
 
 namespace fheb {
@@ -26,6 +29,7 @@ struct RelinKey {
     uint64_t key_id = 0;
     uint64_t* d_key = nullptr;   // [levels][2 (b -> c0, a -> c1)][N] transformed, canonical
     uint64_t* d_keyp = nullptr;  // Shoup companions, same layout
+    Tw* d_pack = nullptr;        // the same key in the packed position-order layout of the fused kernel (relin_fused.cu), times N^-1
 };
 
 // digits of c2: dig[ct][l][j] = (c2[ct][j] >> (l * base_log)) & mask, c2 = cts[ct][2][:]
@@ -115,6 +119,22 @@ int relinearize_device(const RelinKey* k, const uint64_t* cts, uint64_t* out, si
         count_launch();
         return FHEB_OK;
     }
+    if (k->d_pack && !getenv("FHEB_RELIN_UNFUSED")) {  // one launch (relin_fused.cu); FHEB_RELIN_UNFUSED=1: experiments and the parity suite
+        RelinFusedArgs a{};
+        a.cts = cts;
+        a.out = out;
+        a.batch = batch;
+        a.key = k->d_pack;
+        a.levels = k->levels;
+        a.base_log = k->base_log;
+        a.mask = (k->base_log >= 64) ? ~0ull : ((1ull << k->base_log) - 1);
+        a.twf = p->d_fwd;
+        a.twi = p->d_inv;
+        a.ninv = p->ninv;
+        a.m = p->mod;
+        const int rc = relin_fused_launch(p->logn, p->mod.dp != 0, a, s);
+        if (rc != RELIN_FUSED_UNSUPPORTED) return rc;
+    }
     uint64_t* work = nullptr;  // digits [batch][levels][N] | products [batch][2][N]
     const size_t dig_words = batch * k->levels * N;
     FHEB_CUDA(cudaMallocAsync(&work, (dig_words + batch * 2 * N) * 8, s));
@@ -174,6 +194,7 @@ int fheb_relin_key_create(const fheb_ntt_plan* plan, const uint64_t* keys, uint3
     auto fail = [&](int rc) {
         if (k->d_key) cudaFree(k->d_key);
         if (k->d_keyp) cudaFree(k->d_keyp);
+        if (k->d_pack) cudaFree(k->d_pack);
         delete k;
         *out = nullptr;
         return rc;
@@ -192,6 +213,12 @@ int fheb_relin_key_create(const fheb_ntt_plan* plan, const uint64_t* keys, uint3
     if (rc != FHEB_OK) return fail(rc);
     shoup_companions_kernel<<<stream_grid(words, 256, 8), 256, 0, s>>>(k->d_key, k->d_keyp, words, p->mod);
     count_launch();
+    if (p->logn >= 5 && p->logn <= 13 && p->top == 0) {  // degrees the fused kernel covers
+        if (cudaMalloc(&k->d_pack, words * (p->mod.dp ? 8 : sizeof(Tw))) != cudaSuccess)
+            return fail(set_error(FHEB_ERR_OUT_OF_MEMORY, "cudaMalloc of the packed relinearisation key failed"));
+        rc = pack_key_rows_device(p, k->d_key, k->d_pack, 1, 2, levels, s);
+        if (rc != FHEB_OK) return fail(rc);
+    }
     if (cudaGetLastError() != cudaSuccess || cudaStreamSynchronize(s) != cudaSuccess)
         return fail(set_error(FHEB_ERR_NATIVE, "relinearisation key set-up failed: %s", cudaGetErrorString(cudaGetLastError())));
     return FHEB_OK;
@@ -202,6 +229,7 @@ int fheb_relin_key_destroy(fheb_relin_key* key) {
     RelinKey* k = reinterpret_cast<RelinKey*>(key);
     if (k->d_key) cudaFree(k->d_key);
     if (k->d_keyp) cudaFree(k->d_keyp);
+    if (k->d_pack) cudaFree(k->d_pack);
     delete k;
     return FHEB_OK;
 }

@@ -14,6 +14,7 @@
 #include <cstdlib>
 #include <map>
 
+#include "tensor_fused.hpp"
 #include "elementwise.hpp"
 #include "modarith.cuh"
 #include "plan.hpp"
@@ -883,6 +884,15 @@ int fheb_tensor_multiply_batch(const fheb_ntt_plan* plan, const uint64_t* ct1, c
     FHEB_TRY(s1.bind(ct1, batch * 2 * N * 8, true, false, s));
     FHEB_TRY(s2.bind(ct2, batch * 2 * N * 8, true, false, s));
     FHEB_TRY(so.bind(out, batch * 3 * N * 8, false, true, s));
+    if (!getenv("FHEB_TENSOR_UNFUSED") && s1.ptr<uint64_t>() != so.ptr<uint64_t>() && s2.ptr<uint64_t>() != so.ptr<uint64_t>()) {
+        // one launch (tensor_fused.cu); the output must not alias an operand: a block writes 3 N words per 4 N it reads
+        const int frc = tensor_fused_launch(p, s1.ptr<const uint64_t>(), s2.ptr<const uint64_t>(), so.ptr<uint64_t>(), batch, s);
+        if (frc != TENSOR_FUSED_UNSUPPORTED) {
+            FHEB_TRY(frc);
+            FHEB_TRY(so.finish());
+            return sync_if_staged(s, {&s1, &s2, &so});
+        }
+    }
     uint64_t* work = nullptr;  // T(ct1), T(ct2): [batch][2][N] each
     FHEB_CUDA(cudaMallocAsync(&work, batch * 4 * N * 8, s));
     uint64_t* ta = work;

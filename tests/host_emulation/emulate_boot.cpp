@@ -86,6 +86,7 @@ static int check(uint32_t threads, uint32_t levels, uint32_t base_log, uint32_t 
     s.acc = acc.data();
     s.work = work.data();
     s.levels = levels;
+    s.rows = rows;
     s.base_log = base_log;
 
     // --- external product and cmux with bsk[1 % n]

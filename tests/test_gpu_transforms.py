@@ -386,6 +386,25 @@ def test_relinearize_matches_oracle(fhe, torch, oracle, n, q, key_count, bl, lv,
         eq(got[i], oracle.relinearize(ct3h[i], keys, bl, lv, q, fwd, inv, inv_n))
 
 
+def test_relinearize_fused_and_unfused_paths_agree(fhe, torch, oracle, monkeypatch):
+    """The one-launch kernel (relin_fused.cu) and the five-launch path (relin.cu) give the oracle's words; shapes whose digit
+    rows do not fit an SM (N = 8192 with four levels: 256 KB) fall back to the five-launch path by themselves."""
+    for n, q, levels, bl, batch in [(4096, Q62, 4, 15, 3), (512, QT, 3, 13, 7), (8192, Q62, 4, 15, 2)]:
+        rng = np.random.default_rng(n)
+        fwd, inv, _, _, inv_n = oracle.twiddles(n, q)
+        ring = fhe.PolynomialRing(n, q)
+        ct3 = rng.integers(0, q, size=(batch, 3, n), dtype=np.uint64)
+        ct3[0, :2] = rng.integers(0, 2**64, size=(2, n), dtype=np.uint64)  # unreduced c0 / c1: add_inplace reduces them
+        keys = rng.integers(0, q, size=(levels, 2, n), dtype=np.uint64)
+        key = fhe.RelinearizationKey(ring, dev(torch, keys), bl, levels)
+        exp = np.stack([oracle.relinearize(ct3[i], keys, bl, levels, q, fwd, inv, inv_n) for i in range(batch)])
+        monkeypatch.delenv("FHEB_RELIN_UNFUSED", raising=False)
+        eq(host(key.relinearize(dev(torch, ct3))), exp)
+        monkeypatch.setenv("FHEB_RELIN_UNFUSED", "1")
+        eq(host(key.relinearize(dev(torch, ct3))), exp)
+        monkeypatch.delenv("FHEB_RELIN_UNFUSED", raising=False)
+
+
 @pytest.mark.parametrize("count", [2, 3, 63, 64, 65, 1000, 20000])
 def test_tally_matches_oracle(fhe, torch, oracle, count):
     n, q = 1024, QT

@@ -22,6 +22,8 @@ __global__ void __launch_bounds__(512) k(uint64_t* out, int iters, double da, ui
             if (MODE == 3) u[i] = __umul64hi(u[i], ua) + u[(i + 1) & 7];
             if (MODE == 5) v[i] = __funnelshift_l(v[i], v[(i + 1) & 7], 3) ^ (uint32_t)ua;       // SHF + LOP3 (ALU pipe)
             if (MODE == 6) v[i] = __umulhi(v[i], (uint32_t)ua) + v[(i + 1) & 7];                   // IMAD.HI.U32
+            if (MODE == 7) d[i] = rint(d[i] * da) + d[(i + 1) & 7];                                // DMUL + FRND.F64 + DADD
+            if (MODE == 8) d[i] = rint(d[i]);                                                       // FRND.F64 alone (dependent chain per element)
             if (MODE == 4) { d[i] = fma(d[i], da, d[(i + 1) & 7]); u[i] = (uint64_t)(uint32_t)u[i] * (uint32_t)ua + u[(i + 1) & 7]; }
         }
     }
@@ -32,7 +34,7 @@ __global__ void __launch_bounds__(512) k(uint64_t* out, int iters, double da, ui
 }
 
 static bool g_json = false;
-static double g_tops[8];
+static double g_tops[10];
 
 template <int MODE>
 void run(const char* name, int ops_per_iter) {
@@ -70,6 +72,10 @@ int main(int argc, char** argv) {
     run<4>("DFMA + IMAD.WIDE together", 16);
     run<5>("SHF + LOP3 (ALU pipe)", 16);
     run<6>("IMAD.HI.U32", 8);
+    if (!g_json) {
+        run<7>("DMUL + FRND.F64 + DADD (3 ops)", 24);
+        run<8>("FRND.F64 alone", 8);
+    }
     if (g_json) {
         int clk = 0, sms = 0;
         cudaDeviceGetAttribute(&clk, cudaDevAttrClockRate, dev);

@@ -24,18 +24,19 @@ if [ "${1:-all}" = "all" ]; then
 run r02_ntt14_q62_fwd 'ntt_forward_kernel' 5 1 python tools/prof_ntt.py 14
 run r02_ntt14_q62_inv 'ntt_inverse_kernel' 5 1 python tools/prof_ntt.py 14
 run r02_ntt14_q62_mul 'polymul_kernel' 5 1 python tools/prof_ntt.py 14
-run r02_ntt14_q27_fwd 'ntt_forward_kernel' 5 1 python tools/prof_ntt.py 14 132120577
+run r02_ntt14_q27_fwd 'ntt_forward_kernel' 5 1 env FHEB_NO_U32=1 python tools/prof_ntt.py 14 132120577
 run r02_ntt10_qt_fwd 'ntt_forward_kernel' 5 1 python tools/prof_ntt.py 10 1099511678977 16384
 run r02_boot_lean 'boot_kernel' 3 1 python tools/prof_boot.py 740
-run r02_tally_128k 'tally_kernel' 4 1 python tools/prof_tally.py --one 131072
-run r02_pipes 'k' 1 9 tools/microbench/pipes
-elif [ "$1" = "u32" ]; then
-# second batch: the 32-bit kernels (4-byte slots) and the pair-layout fused product, q = 132120577
+run r02_relin_n4096_l4 'relin_fused_kernel' 5 1 python tools/prof_relin.py
+run r02_tensor_n4096 'tensor_fused_kernel' 5 1 python tools/prof_tensor.py
+# the 32-bit kernels (4-byte slots) and the pair-layout fused product, q = 132120577
 run r02_ntt14_q27_u32_fwd 'ntt_forward_kernel' 5 1 python tools/prof_ntt.py 14 132120577
 run r02_ntt14_q27_u32_inv 'ntt_inverse_kernel' 5 1 python tools/prof_ntt.py 14 132120577
 run r02_ntt14_q27_u32p_mul 'polymul_kernel' 5 1 python tools/prof_ntt.py 14 132120577
 run r02_ntt10_q27_u32_fwd 'ntt_forward_kernel' 5 1 python tools/prof_ntt.py 10 132120577 16384
+elif [ "$1" = "rest" ]; then
 run r02_tally_128k 'tally_kernel' 4 1 python tools/prof_tally.py --one 131072
+run r02_pipes 'k' 1 9 tools/microbench/pipes
 else
     "$@"
 fi
