@@ -23,8 +23,15 @@
         }                                                                      \
     } while (0)
 
+struct Row {
+    const char* key;
+    double issue_us, stream_us, done_us, graph_us;
+};
+static std::vector<Row> g_rows;
+static bool g_json = false;
+
 template <class F>
-static void measure(const char* name, cudaStream_t s, F call, bool graph) {
+static void measure(const char* key, const char* name, cudaStream_t s, F call, bool graph) {
     using clk = std::chrono::steady_clock;
     for (int i = 0; i < 50; ++i) call();
     cudaStreamSynchronize(s);
@@ -48,7 +55,8 @@ static void measure(const char* name, cudaStream_t s, F call, bool graph) {
         cudaStreamSynchronize(s);
         single += std::chrono::duration<double, std::micro>(clk::now() - u0).count();
     }
-    std::printf("%-44s issue %6.2f us/call   stream %6.2f us/call   issue->done %6.2f us", name, issue_us, ms * 1e3 / iters, single / 200);
+    Row row{key, issue_us, ms * 1e3 / iters, single / 200, -1.0};
+    if (!g_json) std::printf("%-44s issue %6.2f us/call   stream %6.2f us/call   issue->done %6.2f us", name, issue_us, ms * 1e3 / iters, single / 200);
     if (graph) {
         cudaGraph_t g;
         cudaGraphExec_t ge;
@@ -62,16 +70,19 @@ static void measure(const char* name, cudaStream_t s, F call, bool graph) {
             cudaEventRecord(b, s);
             cudaEventSynchronize(b);
             cudaEventElapsedTime(&ms, a, b);
-            std::printf("   graph of 100: %6.2f us/call", ms * 1e3 / 2000);
-        } else {
+            row.graph_us = ms * 1e3 / 2000;
+            if (!g_json) std::printf("   graph of 100: %6.2f us/call", ms * 1e3 / 2000);
+        } else if (!g_json) {
             std::printf("   graph capture failed: %s", cudaGetErrorString(cudaGetLastError()));
         }
     }
-    std::printf("\n");
+    if (!g_json) std::printf("\n");
+    g_rows.push_back(row);
 }
 
 int main(int argc, char** argv) {
-    const bool graph = argc > 1 && std::strcmp(argv[1], "--graph") == 0;
+    g_json = argc > 1 && std::strcmp(argv[1], "--json") == 0;  // one JSON line for bench.py (graph figures included)
+    const bool graph = g_json || (argc > 1 && std::strcmp(argv[1], "--graph") == 0);
     CK(fheb_init(0));
     cudaStream_t s;
     cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking);
@@ -82,9 +93,9 @@ int main(int argc, char** argv) {
         cudaMalloc(&x, 1024 * 8);
         cudaMalloc(&y, 1024 * 8);
         cudaMemset(x, 1, 1024 * 8);
-        measure("C1 forward N=1024 q=132120577 batch 1", s, [&] { fheb_ntt_forward_batch(plan, x, y, 1, s); }, graph);
-        measure("C1 inverse N=1024 q=132120577 batch 1", s, [&] { fheb_ntt_inverse_batch(plan, y, x, 1, s); }, graph);
-        measure("C1 forward+inverse pair", s, [&] { fheb_ntt_forward_batch(plan, x, y, 1, s); fheb_ntt_inverse_batch(plan, y, x, 1, s); }, graph);
+        measure("c1_forward", "C1 forward N=1024 q=132120577 batch 1", s, [&] { fheb_ntt_forward_batch(plan, x, y, 1, s); }, graph);
+        measure("c1_inverse", "C1 inverse N=1024 q=132120577 batch 1", s, [&] { fheb_ntt_inverse_batch(plan, y, x, 1, s); }, graph);
+        measure("c1_pair", "C1 forward+inverse pair", s, [&] { fheb_ntt_forward_batch(plan, x, y, 1, s); fheb_ntt_inverse_batch(plan, y, x, 1, s); }, graph);
         fheb_ntt_plan_destroy(plan);
     }
     {
@@ -98,7 +109,14 @@ int main(int argc, char** argv) {
         cudaMalloc(&r, n * 16);
         cudaMemset(a, 0, n * 16);
         cudaMemset(b, 0, n * 16);
-        measure("C3 two-limb montgomery_mul n=65536", s, [&] { fheb_mlimb_montmul_batch(a, b, r, n, 2, q, consts[0], s); }, graph);
+        measure("c3_montmul_n65536", "C3 two-limb montgomery_mul n=65536", s, [&] { fheb_mlimb_montmul_batch(a, b, r, n, 2, q, consts[0], s); }, graph);
+    }
+    if (g_json) {
+        std::printf("{");
+        for (size_t i = 0; i < g_rows.size(); ++i)
+            std::printf("%s\"%s\": {\"issue_us\": %.3f, \"stream_us\": %.3f, \"issue_to_done_us\": %.3f, \"graph_us\": %.3f}", i ? ", " : "", g_rows[i].key,
+                        g_rows[i].issue_us, g_rows[i].stream_us, g_rows[i].done_us, g_rows[i].graph_us);
+        std::printf("}\n");
     }
     return 0;
 }
