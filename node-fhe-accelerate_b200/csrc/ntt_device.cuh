@@ -5,6 +5,18 @@
 
 #include "ntt_core.cuh"
 
+// Software-pipelined first-pass loads (PIPE, ntt_core.cuh) pay for the 8-byte kernels, whose one block per SM has nothing
+// else to hide the load latency behind.  The 32-bit kernel with 4-byte slots is the opposite case: without the pipeline's
+// 32 staging registers it needs 64 registers instead of 100, so THREE 256-thread blocks share an SM (64 KB of work buffer
+// each) and cover each other's loads - forward N = 16384, q = 132120577: 0.0916 -> 0.0815 ms (3.30 TB/s, 0.50 of the HBM peak).
+// The inverse already fits 64 registers with the pipeline (0.0901 ms with it, 0.0894 without: kept).
+#if defined(FHEB_EXP_U32_PIPE)
+#define FHEB_PIPE_MODE(DP) true
+#else
+#define FHEB_PIPE_MODE(DP) ((DP) != MODE_U32)
+#endif
+#define FHEB_PIPE_MODE_INV(DP) true
+
 namespace fheb {
 
 // Hint the next polynomials of this block into L2 while the current ones are processed
@@ -115,7 +127,7 @@ __global__ void __launch_bounds__(THREADS) ntt_forward_kernel(const uint64_t* in
         if constexpr (P == 1) {
             fwd_pass<L, DP, 0, IO_GLOBAL, IO_GLOBAL, true, SCALE>(tid, THREADS, polys, gin, gout, smem, tw, m, ninv);
         } else {
-            fwd_pass<L, DP, 0, IO_GLOBAL, IO_SMEM, true, false, 0, false, (L >= 13)>(tid, THREADS, polys, gin, gout, smem, tw, m);
+            fwd_pass<L, DP, 0, IO_GLOBAL, IO_SMEM, true, false, 0, false, (L >= 13 && FHEB_PIPE_MODE(DP))>(tid, THREADS, polys, gin, gout, smem, tw, m);
             __syncthreads();
             fwd_middle<L, DP, 1>(tid, THREADS, polys, smem, tw, m);
             fwd_pass<L, DP, P - 1, IO_SMEM, IO_GLOBAL, true, SCALE>(tid, THREADS, polys, gin, gout, smem, tw, m, ninv);
@@ -176,7 +188,7 @@ __global__ void __launch_bounds__(THREADS) ntt_inverse_kernel(const uint64_t* in
         if constexpr (P == 1) {
             inv_pass<L, DP, 0, IO_GLOBAL, IO_GLOBAL>(tid, THREADS, polys, gin, gout, smem, tw, ninv, m);
         } else {
-            inv_pass<L, DP, P - 1, IO_GLOBAL, IO_SMEM, true, 0, 1, false, (L >= 14)>(tid, THREADS, polys, gin, gout, smem, tw, ninv, m);
+            inv_pass<L, DP, P - 1, IO_GLOBAL, IO_SMEM, true, 0, 1, false, (L >= 14 && FHEB_PIPE_MODE_INV(DP))>(tid, THREADS, polys, gin, gout, smem, tw, ninv, m);
             __syncthreads();
             inv_middle<L, DP, P - 2>(tid, THREADS, polys, smem, tw, ninv, m);
             inv_pass<L, DP, 0, IO_SMEM, IO_GLOBAL>(tid, THREADS, polys, gin, gout, smem, tw, ninv, m);
