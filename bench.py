@@ -243,6 +243,11 @@ def run_ours(args):
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         fwd_ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
         barrier()
+        # The K steps are queued BEHIND a spin kernel (torch.cuda._sleep, ~20 ms), so the device runs them back to back no
+        # matter how fast this Python process issues them: with eight ranks, eight clock samplers and NCCL's threads on one
+        # host, a late launch otherwise shows up as device idle time inside the event bracket (0.376 vs 0.358 ms per step
+        # at 8 ranks vs 1).  The events still sit on the launch stream, around exactly K steps.
+        torch.cuda._sleep(int(20e-3 * 1.9e9))
         ev0.record()
         for i in range(args.steps):
             fwd_ev[i][0].record()
