@@ -175,7 +175,7 @@ def test_bootstrap_errors(fhe):
 
 def test_full_batch_tfhe_shape_properties(fhe, torch, oracle):
     """BASELINE C4 shape (N=1024, k=1, n=742, base_log=23, L=1, batch 4096) with a synthetic key:
-    spot-check ciphertexts against the oracle and check batch-order independence."""
+    eight ciphertexts against the oracle (about a second of CPU each) and batch-order independence on all 4096."""
     N, q, n, k, base_log, level, batch = 1024, QT, 742, 1, 23, 1, 4096
     rng = np.random.default_rng(742)
     bsk = rng.integers(0, q, size=(n, 2, 2, N), dtype=np.uint64)
@@ -186,7 +186,7 @@ def test_full_batch_tfhe_shape_properties(fhe, torch, oracle):
     lwe = rng.integers(0, q, size=(batch, n + 1), dtype=np.uint64)
     lwe_d = dev(torch, lwe)
     acc = eng.blind_rotate(lwe_d, dev(torch, test_poly))
-    sel = [0, 2047, 4095]
+    sel = [0, 1, 591, 592, 2047, 3333, 4094, 4095]  # first / last of the batch, around a wave boundary (592 resident blocks), interior
     eq(host(acc[sel]), oracle.blind_rotate(p, lwe[sel], bsk, test_poly))
     perm = torch.randperm(batch, device="cuda")
     acc_p = eng.blind_rotate(lwe_d[perm].contiguous(), dev(torch, test_poly))

@@ -214,8 +214,9 @@ def test_plan_errors(fhe):
     assert ntt.forward_ntt(np.zeros((0, 8), np.uint64)).shape == (0, 8)  # empty batch
 
 
-def test_full_size_properties(fhe, torch):
-    """BASELINE C2 sizes (N = 4096 / 16384, batch 1024): round trip, linearity, ring axioms."""
+def test_full_size_properties(fhe, torch, oracle):
+    """BASELINE C2 sizes (N = 4096 / 16384, batch 1024): round trip, linearity, ring axioms on the whole batch, and 32 rows
+    spread over the batch (first, last, one per block of 33) against the CPU oracle for the forward transform and the product."""
     for n in (4096, 16384):
         q = Q62
         ring = fhe.PolynomialRing(n, q)
@@ -224,6 +225,11 @@ def test_full_size_properties(fhe, torch):
         b = torch.randint(0, q, (1024, n), dtype=torch.int64, device="cuda", generator=g)
         fa = ring.to_ntt(a)
         assert torch.equal(ring.from_ntt(fa), a)
+        rows = sorted(set([0, 1023] + list(range(7, 1024, 33))))[:32]
+        fwd, inv, _, _, inv_n = oracle.twiddles(n, q)
+        ah, bh = host(a[rows]), host(b[rows])
+        eq(host(fa[rows]), oracle.forward(ah, q, fwd))
+        eq(host(ring.multiply(a, b)[rows]), oracle.multiply(ah, bh, q, fwd, inv, inv_n))
         # T(a + b) == T(a) + T(b)
         assert torch.equal(ring.to_ntt(ring.add(a, b)), ring.add(fa, ring.to_ntt(b)))
         ab = ring.multiply(a, b)
