@@ -239,7 +239,7 @@ static int launch_transform(const NttPlan* p, int dir, const uint64_t* in, uint6
     int bps = 0;
     // Bulk-async (TMA) landing buffer for the next group's words: multi-pass plans up to N = 4096 (two buffers fit several
     // blocks per SM), 16-byte aligned input, and only where it measured faster (FHEB_TMA=0/1 overrides: experiments).
-    if constexpr (Plan<L>::P > 1 && DP != MODE_U32P && (L <= 13 || DP == MODE_U32)) {
+    if constexpr (Plan<L>::P > 1 && DP != MODE_U32P) {
         // (N = 8192 / 16384 in the 32-bit mode: the 4-byte work buffer leaves room for a landing buffer of raw 8-byte
         // words, 96 / 192 KB in all; one 512-thread block per SM then, against two 256-thread blocks without it)
         const char* tma_s = getenv("FHEB_TMA");  // read per call: the parity suite forces both settings
@@ -247,7 +247,8 @@ static int launch_transform(const NttPlan* p, int dir, const uint64_t* in, uint6
         const bool tma = (tma_env < 0 ? TMA_DEFAULT<L, DP>(dir == DIR_INV) : tma_env != 0) && (reinterpret_cast<uintptr_t>(in) & 15u) == 0 && dir != DIR_INV_FWDNET;
         if (tma) {
             constexpr int T = (L >= 13) ? 512 : G::THREADS;
-            constexpr size_t SMEM_TMA = G::SMEM + (size_t)G::PPC * (1u << L) * 8 + 16;  // work | landing (raw 8-byte words) | mbarrier
+            // work | landing (raw 8-byte words; N = 16384 with 8-byte slots: the first LAND_PART_WORDS only) | mbarrier
+            constexpr size_t SMEM_TMA = G::SMEM + ((L == 14 && G::SLOT == 8) ? (size_t)LAND_PART_WORDS : (size_t)G::PPC * (1u << L)) * 8 + 16;
             if (dir == DIR_INV) {
                 auto k = ntt_inverse_kernel<L, DP, T, G::PPC, true>;
                 FHEB_TRY(configure(k, SMEM_TMA, T, &bps));

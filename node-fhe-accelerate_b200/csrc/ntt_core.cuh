@@ -509,8 +509,14 @@ enum {
     IO_GLOBAL = 1,        // caller memory
     IO_STASH_SMEM = 2,    // second shared-memory buffer holding a finished transform (swizzled)
     IO_STASH_GLOBAL = 3,  // per-block global scratch holding a finished transform (natural index)
-    IO_LANDING = 4        // caller words already copied into shared memory by a bulk-async (TMA) load: natural index, raw words
+    IO_LANDING = 4,       // caller words already copied into shared memory by a bulk-async (TMA) load: natural index, raw words
+    IO_LANDING_PART = 5   // N = 16384 with 8-byte slots: only the first LAND_PART_WORDS words landed (96 KB fit beside the 128 KB work buffer), the rest comes from caller memory
 };
+constexpr uint32_t LAND_PART_WORDS = 12288;
+// word idx of a polynomial: landing buffer or caller memory (idx's row is a compile-time constant at every call site)
+FHEB_HD uint64_t part_word(const uint64_t* landing, const uint64_t* global, uint32_t idx, bool landed) {
+    return landed ? landing[idx] : stream_load(global + idx);
+}
 // first-pass input word: streaming global load, or a plain load from the landing buffer
 template <int IN>
 FHEB_HD uint64_t input_word(const uint64_t* p) {
@@ -677,7 +683,7 @@ constexpr int plan_inv_kin() {  // bound entering inverse pass PASS (run order P
 template <int L, int DP, int PASS, int IN, int OUT, bool BITREV_OUT = true, bool SCALE = false, int IPT = 0, bool SUB = false, bool PIPE = false>
 FHEB_HD void fwd_pass(uint32_t tid, uint32_t nthreads, uint32_t polys, const uint64_t* gin, uint64_t* gout,
                       uint64_t* smem, const Tw* __restrict__ tw, const ModQ& m, const Tw ninv = Tw{0, 0},
-                      const GlobalMap map = GlobalMap{0, 0}) {
+                      const GlobalMap map = GlobalMap{0, 0}, const uint64_t* gin_rest = nullptr) {
     constexpr int R = Plan<L>::R[PASS];
     constexpr int E = 1 << R;
     constexpr int S0 = plan_s0<L, PASS>();
@@ -734,7 +740,12 @@ FHEB_HD void fwd_pass(uint32_t tid, uint32_t nthreads, uint32_t polys, const uin
         if (OUT == IO_GLOBAL && BITREV_OUT) u = bitrev_rt(t, L - R);
         const uint32_t base = ((u >> EB) << (EB + R)) | (u & ((1u << EB) - 1u));
         uint64_t x[E];
-        if (IN == IO_GLOBAL || IN == IO_LANDING) {
+        if constexpr (IN == IO_LANDING_PART) {  // one polynomial per block: rows below LAND_PART_WORDS from the landing buffer (gin), the others from caller memory
+            static_assert(PASS == 0 && (LAND_PART_WORDS & ((1u << EB) - 1u)) == 0, "whole rows of the first pass are landed");
+#pragma unroll
+            for (int c = 0; c < E; ++c) x[c] = part_word(gin, gin_rest, base | ((uint32_t)c << EB), ((uint32_t)c << EB) < LAND_PART_WORDS);
+            load_words<DP, E>(x, m);
+        } else if (IN == IO_GLOBAL || IN == IO_LANDING) {
             if constexpr (PIPE_IN) {
                 // the words of this item were requested one trip ago; request the next item's now, so that the
                 // global-memory latency of the first pass is paid once per polynomial instead of once per item
@@ -865,7 +876,7 @@ FHEB_HD void polymul_mid_pass(uint32_t tid, uint32_t nthreads, uint32_t polys, c
 template <int L, int DP, int PASS, int IN, int OUT, bool BITREV_IN = true, int IPT = 0, int KSTART = 1, bool SUB = false, bool PIPE = false>
 FHEB_HD void inv_pass(uint32_t tid, uint32_t nthreads, uint32_t polys, const uint64_t* gin, uint64_t* gout,
                       uint64_t* smem, const Tw* __restrict__ tw, const Tw ninv, const ModQ& m,
-                      const GlobalMap map = GlobalMap{0, 0}) {
+                      const GlobalMap map = GlobalMap{0, 0}, const uint64_t* gin_rest = nullptr) {
     constexpr int R = Plan<L>::R[PASS];
     constexpr int E = 1 << R;
     constexpr int S0 = plan_s0<L, PASS>();
@@ -875,7 +886,7 @@ FHEB_HD void inv_pass(uint32_t tid, uint32_t nthreads, uint32_t polys, const uin
     constexpr uint32_t N = 1u << L;
     constexpr uint32_t ITEMS = N >> R;
     const uint32_t units = units_of<DP>(polys);
-    constexpr bool EXT_IN = (IN == IO_GLOBAL || IN == IO_LANDING);  // caller words: from global memory or from the landing buffer
+    constexpr bool EXT_IN = (IN == IO_GLOBAL || IN == IO_LANDING || IN == IO_LANDING_PART);  // caller words: from global memory or from the landing buffer
     constexpr bool BRTW = FIRST && EXT_IN && BITREV_IN && S0 > 0;  // see fwd_pass
     static_assert(!BRTW || (EB == 0 && S0 == L - R), "the last pass covers the lowest position bits");
     static_assert(IN == IO_SMEM || FIRST, "only the first executed pass reads caller words");
@@ -928,6 +939,12 @@ FHEB_HD void inv_pass(uint32_t tid, uint32_t nthreads, uint32_t polys, const uin
 #pragma unroll
                 for (int c = 0; c < E; ++c) xnext[c] = stream_load(srcn + ((bitrev_c((uint32_t)c, R) << (L - R)) | tn));
             }
+            load_words<DP, E>(x, m);
+        } else if constexpr (IN == IO_LANDING_PART) {  // see fwd_pass; reference-order input: word (bitrev(c) << (L - R)) | t
+            static_assert(FIRST && BITREV_IN && !SUB && (LAND_PART_WORDS & ((1u << (L - R)) - 1u)) == 0, "whole rows of the first executed pass are landed");
+#pragma unroll
+            for (int c = 0; c < E; ++c)
+                x[c] = part_word(gin, gin_rest, (bitrev_c((uint32_t)c, R) << (L - R)) | t, (bitrev_c((uint32_t)c, R) << (L - R)) < LAND_PART_WORDS);
             load_words<DP, E>(x, m);
         } else if (EXT_IN) {
             if (SUB && BITREV_IN) load_unit<DP, IN, E>(x, gin, poly, polys, N, [&](int c) { return (((bitrev_c((uint32_t)c, R) << (L - R)) | t) << map.shift) | map.low; }, m);

@@ -87,15 +87,26 @@ __global__ void __launch_bounds__(THREADS) ntt_forward_kernel(const uint64_t* in
     const size_t groups = (batch + PPC - 1) / PPC;
     if constexpr (TMA && P > 1) {
         // work buffer (PPC x N slots of the mode's width) | landing buffer (PPC x N raw 8-byte words) | mbarrier
+        // PART (N = 16384, 8-byte slots, one polynomial per block): the 128 KB work buffer leaves 99 KB, so only the first
+        // LAND_PART_WORDS words (12 of the 16 rows the first pass reads) are landed; the last 4 rows are prefetched into L2
+        // and read from caller memory
+        constexpr bool PART = (L == 14) && smem_slot_bytes<DP>() == 8;
+        static_assert(!PART || PPC == 1, "partial landing: one polynomial per block");
+        constexpr size_t LWORDS = PART ? (size_t)LAND_PART_WORDS : (size_t)PPC * N;
+        constexpr int IN0 = PART ? IO_LANDING_PART : IO_LANDING;
         uint64_t* landing = reinterpret_cast<uint64_t*>(reinterpret_cast<char*>(smem) + (size_t)PPC * N * smem_slot_bytes<DP>());
-        uint64_t* bar = landing + (size_t)PPC * N;
+        uint64_t* bar = landing + LWORDS;
         auto group_bytes = [&](size_t g) {
             const size_t q0 = g * PPC;
-            return (uint32_t)(((batch - q0) < (size_t)PPC ? (batch - q0) : (size_t)PPC) * N * 8);
+            return PART ? (uint32_t)(LWORDS * 8) : (uint32_t)(((batch - q0) < (size_t)PPC ? (batch - q0) : (size_t)PPC) * N * 8);
+        };
+        auto request = [&](size_t g) {  // one thread: bulk copy of group g's (first) words, L2 prefetch of the rest
+            tma_load_1d(landing, in + g * PPC * N, group_bytes(g), bar);
+            if constexpr (PART) prefetch_l2_bulk(in + g * N + LWORDS, (uint32_t)((N - LWORDS) * 8));
         };
         if (tid == 0) {
             mbar_init(bar, 1);
-            if ((size_t)blockIdx.x < groups) tma_load_1d(landing, in + (size_t)blockIdx.x * PPC * N, group_bytes(blockIdx.x), bar);
+            if ((size_t)blockIdx.x < groups) request(blockIdx.x);
         }
         __syncthreads();
         uint32_t parity = 0;
@@ -105,9 +116,9 @@ __global__ void __launch_bounds__(THREADS) ntt_forward_kernel(const uint64_t* in
             uint64_t* gout = out + p0 * N;
             mbar_wait(bar, parity);  // this group's words have landed
             parity ^= 1u;
-            fwd_pass<L, DP, 0, IO_LANDING, IO_SMEM>(tid, THREADS, polys, landing, gout, smem, tw, m);
+            fwd_pass<L, DP, 0, IN0, IO_SMEM>(tid, THREADS, polys, landing, gout, smem, tw, m, Tw{0, 0}, GlobalMap{0, 0}, in + p0 * N);
             __syncthreads();  // every thread is done with the landing buffer: the next group may land
-            if (tid == 0 && g + gridDim.x < groups) tma_load_1d(landing, in + (g + gridDim.x) * PPC * N, group_bytes(g + gridDim.x), bar);
+            if (tid == 0 && g + gridDim.x < groups) request(g + gridDim.x);
             fwd_middle<L, DP, 1>(tid, THREADS, polys, smem, tw, m);
             fwd_pass<L, DP, P - 1, IO_SMEM, IO_GLOBAL, true, SCALE>(tid, THREADS, polys, nullptr, gout, smem, tw, m, ninv);
             __syncthreads();
@@ -147,16 +158,23 @@ __global__ void __launch_bounds__(THREADS) ntt_inverse_kernel(const uint64_t* in
     const uint32_t tid = threadIdx.x;
     const size_t groups = (batch + PPC - 1) / PPC;
     if constexpr (TMA && P > 1) {  // see ntt_forward_kernel
-        // work buffer (PPC x N slots of the mode's width) | landing buffer (PPC x N raw 8-byte words) | mbarrier
+        constexpr bool PART = (L == 14) && smem_slot_bytes<DP>() == 8;
+        static_assert(!PART || PPC == 1, "partial landing: one polynomial per block");
+        constexpr size_t LWORDS = PART ? (size_t)LAND_PART_WORDS : (size_t)PPC * N;
+        constexpr int IN0 = PART ? IO_LANDING_PART : IO_LANDING;
         uint64_t* landing = reinterpret_cast<uint64_t*>(reinterpret_cast<char*>(smem) + (size_t)PPC * N * smem_slot_bytes<DP>());
-        uint64_t* bar = landing + (size_t)PPC * N;
+        uint64_t* bar = landing + LWORDS;
         auto group_bytes = [&](size_t g) {
             const size_t q0 = g * PPC;
-            return (uint32_t)(((batch - q0) < (size_t)PPC ? (batch - q0) : (size_t)PPC) * N * 8);
+            return PART ? (uint32_t)(LWORDS * 8) : (uint32_t)(((batch - q0) < (size_t)PPC ? (batch - q0) : (size_t)PPC) * N * 8);
+        };
+        auto request = [&](size_t g) {
+            tma_load_1d(landing, in + g * PPC * N, group_bytes(g), bar);
+            if constexpr (PART) prefetch_l2_bulk(in + g * N + LWORDS, (uint32_t)((N - LWORDS) * 8));
         };
         if (tid == 0) {
             mbar_init(bar, 1);
-            if ((size_t)blockIdx.x < groups) tma_load_1d(landing, in + (size_t)blockIdx.x * PPC * N, group_bytes(blockIdx.x), bar);
+            if ((size_t)blockIdx.x < groups) request(blockIdx.x);
         }
         __syncthreads();
         uint32_t parity = 0;
@@ -166,9 +184,9 @@ __global__ void __launch_bounds__(THREADS) ntt_inverse_kernel(const uint64_t* in
             uint64_t* gout = out + p0 * N;
             mbar_wait(bar, parity);
             parity ^= 1u;
-            inv_pass<L, DP, P - 1, IO_LANDING, IO_SMEM>(tid, THREADS, polys, landing, gout, smem, tw, ninv, m);
+            inv_pass<L, DP, P - 1, IN0, IO_SMEM>(tid, THREADS, polys, landing, gout, smem, tw, ninv, m, GlobalMap{0, 0}, in + p0 * N);
             __syncthreads();
-            if (tid == 0 && g + gridDim.x < groups) tma_load_1d(landing, in + (g + gridDim.x) * PPC * N, group_bytes(g + gridDim.x), bar);
+            if (tid == 0 && g + gridDim.x < groups) request(g + gridDim.x);
             inv_middle<L, DP, P - 2>(tid, THREADS, polys, smem, tw, ninv, m);
             inv_pass<L, DP, 0, IO_SMEM, IO_GLOBAL>(tid, THREADS, polys, nullptr, gout, smem, tw, ninv, m);
             __syncthreads();

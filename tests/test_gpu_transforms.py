@@ -161,9 +161,10 @@ def test_first_pass_input_paths_match_oracle(fhe, torch, oracle, logn, tma, monk
         batch = 148 * 8 * per_block // (1 << max(0, logn - 7)) + 3  # several groups per block, ragged tail
         batch = min(batch, 1500)
         if logn >= 13:
-            batch = 148 * 2 + 3  # (the landing-buffer form exists there for the 32-bit mode only; the others take plain loads)
+            batch = 148 * 2 + 3  # (N = 16384 with 8-byte slots lands 12 of the 16 first-pass rows, the rest comes from caller memory)
         x = rng.integers(0, q, size=(batch, n), dtype=np.uint64)
         x[1, :7] = rng.integers(q, 2**64, size=7, dtype=np.uint64)  # unreduced words are reduced on load
+        x[batch - 2, -5:] = rng.integers(q, 2**64, size=5, dtype=np.uint64)  # (N = 16384: in the rows that are NOT landed)
         check = sorted(set([0, 1, batch // 2, batch - 2, batch - 1]))
         xd = dev(torch, x)
         f = host(ntt.forward_ntt(xd))
