@@ -113,6 +113,7 @@ static int plan_finish(NttPlan* p) {
         FHEB_TRY(upload_heap(build_heap_table_u32(p->inv_table.data(), p->logn, q), &p->d_inv32));
         const uint64_t ni = p->inv_n % q;
         p->ninv32 = Tw{ni, (ni << 32) / q};
+        if (p->logn == 14) FHEB_TRY(upload_heap(build_heap_table_u32(p->fwd_table.data(), p->logn, q, PLAN_KEY_ALT14), &p->d_fwd32_alt));
     }
     if (p->mod.dp) {  // FP64 mode: one double per twiddle
         FHEB_TRY(upload_heap(build_heap_table_dp(p->fwd_table.data(), p->logn, q), &p->d_fwd));
@@ -120,6 +121,7 @@ static int plan_finish(NttPlan* p) {
     } else {
         FHEB_TRY(upload_heap(build_heap_table(p->fwd_table.data(), p->logn, q), &p->d_fwd));
         FHEB_TRY(upload_heap(build_heap_table(p->inv_table.data(), p->logn, q), &p->d_inv));
+        if (p->logn == 14) FHEB_TRY(upload_heap(build_heap_table(p->fwd_table.data(), p->logn, q, PLAN_KEY_ALT14), &p->d_fwd_alt));
     }
     return FHEB_OK;
 }
@@ -133,6 +135,8 @@ static void plan_free(NttPlan* p) {
     if (p->d_top_inv) cudaFree(p->d_top_inv);
     if (p->d_fwd32) cudaFree(p->d_fwd32);
     if (p->d_inv32) cudaFree(p->d_inv32);
+    if (p->d_fwd_alt) cudaFree(p->d_fwd_alt);
+    if (p->d_fwd32_alt) cudaFree(p->d_fwd32_alt);
     delete p;
 }
 
@@ -268,6 +272,17 @@ static int launch_transform(const NttPlan* p, int dir, const uint64_t* in, uint6
         FHEB_TRY(configure(k, G::SMEM, G::THREADS, &bps));
         k<<<persistent_grid(groups, bps), G::THREADS, G::SMEM, s>>>(in, out, batch, d_inv, ninv, p->mod);
     } else if (dir == DIR_FWD) {
+        if constexpr (L == 14 && (DP == MODE_INT || DP == MODE_U32)) {  // three passes of 5 + 5 + 4 stages (plan key 78) from the table built for them
+            const Tw* alt = (DP == MODE_U32) ? p->d_fwd32_alt : p->d_fwd_alt;
+            if (alt != nullptr && !getenv("FHEB_NO_ALT_PLAN")) {
+                auto k = ntt_forward_kernel<L, DP, G::THREADS, G::PPC, false, false, PLAN_KEY_ALT14>;
+                FHEB_TRY(configure(k, G::SMEM, G::THREADS, &bps));
+                k<<<persistent_grid(groups, bps), G::THREADS, G::SMEM, s>>>(in, out, batch, alt, ninv, p->mod);
+                FHEB_CHECK_LAUNCH();
+                count_launch();
+                return FHEB_OK;
+            }
+        }
         auto k = ntt_forward_kernel<L, DP, G::THREADS, G::PPC, false>;
         FHEB_TRY(configure(k, G::SMEM, G::THREADS, &bps));
         k<<<persistent_grid(groups, bps), G::THREADS, G::SMEM, s>>>(in, out, batch, d_fwd, ninv, p->mod);

@@ -586,7 +586,7 @@ FHEB_HD uint64_t scale_word(uint64_t x, const Tw& ninv, const ModQ& m) {
 }
 
 // ---- pass plans: how the L stages are split into register passes ----------------------
-// plan<L>::R[p] = stages in pass p (forward order); at most 5 passes, each of 1..4 stages.
+// plan<L>::R[p] = stages in pass p (forward order); at most 5 passes, each of 1..4 stages (5 in the FHEB_EXP_R5 experiment).
 template <int L> struct Plan;
 #define FHEB_PLAN(L_, P_, ...)                         \
     template <> struct Plan<L_> {                      \
@@ -607,10 +607,21 @@ FHEB_PLAN(12, 3, 4, 4, 4, 0, 0)
 #if defined(FHEB_EXP_R3)  // experiment: 8-value passes only (fewer registers, more warps)
 FHEB_PLAN(13, 5, 3, 3, 3, 2, 2)
 FHEB_PLAN(14, 5, 3, 3, 3, 3, 2)
+#elif defined(FHEB_EXP_R5)  // experiment: 32-value passes at N = 16384 (three passes instead of four) in EVERY kernel
+FHEB_PLAN(13, 4, 4, 3, 3, 3, 0)
+FHEB_PLAN(14, 3, 5, 5, 4, 0, 0)
 #else
 FHEB_PLAN(13, 4, 4, 3, 3, 3, 0)
 FHEB_PLAN(14, 4, 4, 4, 3, 3, 0)
 #endif
+// Plan KEYS above 64 are alternative splits of degree 2^(key - 64), used by single kernels through their `PK` template
+// parameter with a twiddle table of their own (NttPlan::d_fwd_alt).  78 = N = 16384 in THREE passes of 5 + 5 + 4 stages
+// (32 register-resident values per thread): one shared-memory round trip and one block barrier less than 4 + 4 + 3 + 3.
+// Measured per kernel (all bit-exact): plain forward over a 62-bit prime 0.1701 -> 0.1600 ms (no spills at 128
+// registers) and in 32-bit mode 0.0809 -> 0.0794 ms: used there; inverse 0.1810 -> 0.1810 (64 B of spills), fused product
+// 0.578 -> 0.678 ms (716 B of spills), FP64 mode 0.1050 -> 0.1060: those keep the four-pass plan.
+constexpr int PLAN_KEY_ALT14 = 78;
+FHEB_PLAN(78, 3, 5, 5, 4, 0, 0)
 #undef FHEB_PLAN
 
 template <int L, int PASS>
@@ -640,7 +651,7 @@ inline void plan_runtime(int L, int& P, int (&R)[5]) {
         for (int i = 0; i < 5; ++i) R[i] = Plan<L_>::R[i];        \
         break;
         FHEB_PLAN_RT(2) FHEB_PLAN_RT(3) FHEB_PLAN_RT(4) FHEB_PLAN_RT(5) FHEB_PLAN_RT(6) FHEB_PLAN_RT(7) FHEB_PLAN_RT(8)
-        FHEB_PLAN_RT(9) FHEB_PLAN_RT(10) FHEB_PLAN_RT(11) FHEB_PLAN_RT(12) FHEB_PLAN_RT(13) FHEB_PLAN_RT(14)
+        FHEB_PLAN_RT(9) FHEB_PLAN_RT(10) FHEB_PLAN_RT(11) FHEB_PLAN_RT(12) FHEB_PLAN_RT(13) FHEB_PLAN_RT(14) FHEB_PLAN_RT(78)
 #undef FHEB_PLAN_RT
     }
 }
@@ -680,18 +691,18 @@ constexpr int plan_inv_kin() {  // bound entering inverse pass PASS (run order P
 //   SCALE      : multiply the outputs by `ninv` (fast_ntt_inverse semantics)
 // OUT == IO_STASH_*: the finished transform is parked (position order, no bit reversal) in
 // `gout` for the fused polynomial product; canonical words in integer mode, lazy doubles (|v| < KOUT*q) in DP mode.
-template <int L, int DP, int PASS, int IN, int OUT, bool BITREV_OUT = true, bool SCALE = false, int IPT = 0, bool SUB = false, bool PIPE = false>
+template <int L, int DP, int PASS, int IN, int OUT, bool BITREV_OUT = true, bool SCALE = false, int IPT = 0, bool SUB = false, bool PIPE = false, int PK = L>
 FHEB_HD void fwd_pass(uint32_t tid, uint32_t nthreads, uint32_t polys, const uint64_t* gin, uint64_t* gout,
                       uint64_t* smem, const Tw* __restrict__ tw, const ModQ& m, const Tw ninv = Tw{0, 0},
                       const GlobalMap map = GlobalMap{0, 0}, const uint64_t* gin_rest = nullptr) {
-    constexpr int R = Plan<L>::R[PASS];
+    constexpr int R = Plan<PK>::R[PASS];
     constexpr int E = 1 << R;
-    constexpr int S0 = plan_s0<L, PASS>();
+    constexpr int S0 = plan_s0<PK, PASS>();
     constexpr int EB = L - S0 - R;  // lowest position bit handled by this pass
     constexpr bool UNIT = (PASS == 0 && !SUB);
-    constexpr int KIN = plan_fwd_kin<L, DP, PASS, SUB>();
+    constexpr int KIN = plan_fwd_kin<PK, DP, PASS, SUB>();
     constexpr int KOUT = fwd_pass_k(KIN, R, UNIT, DP);
-    constexpr bool LAST = (PASS == Plan<L>::P - 1);
+    constexpr bool LAST = (PASS == Plan<PK>::P - 1);
     constexpr uint32_t N = 1u << L;
     constexpr uint32_t ITEMS = N >> R;  // per polynomial
     const uint32_t units = units_of<DP>(polys);  // work-buffer units: polynomials, or pairs of them (MODE_U32P)
@@ -717,7 +728,7 @@ FHEB_HD void fwd_pass(uint32_t tid, uint32_t nthreads, uint32_t polys, const uin
                 uint32_t u = t0;
                 if (OUT == IO_GLOBAL && BITREV_OUT) u = bitrev_rt(u, L - R);
                 const uint32_t base = ((u >> EB) << (EB + R)) | (u & ((1u << EB) - 1u));
-                load_item_tw<R, S0, DP>(tw, BRTW ? (N + t0) : plan_tw_offset<L, PASS>() + (S0 ? (base >> (L - S0)) : 0u), wall[k]);
+                load_item_tw<R, S0, DP>(tw, BRTW ? (N + t0) : plan_tw_offset<PK, PASS>() + (S0 ? (base >> (L - S0)) : 0u), wall[k]);
             }
         }
     }
@@ -775,7 +786,7 @@ FHEB_HD void fwd_pass(uint32_t tid, uint32_t nthreads, uint32_t polys, const uin
 #pragma unroll
             for (int c = 0; c < E; ++c) x[c] = slot_load<DP>(sr, swzm<DP>((uint32_t)c << EB));
         }
-        const uint32_t TB = BRTW ? (N + t) : plan_tw_offset<L, PASS>() + (S0 ? (base >> (L - S0)) : 0u);
+        const uint32_t TB = BRTW ? (N + t) : plan_tw_offset<PK, PASS>() + (S0 ? (base >> (L - S0)) : 0u);
         if constexpr (IPT > 0) fwd_stages<R, S0, KIN, DP, UNIT, 0, true>(x, wall[k], 0u, m);
         else fwd_stages<R, S0, KIN, DP, UNIT>(x, tw, TB, m);
         if (OUT == IO_GLOBAL) {

@@ -53,13 +53,13 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
         : "memory");
 }
 
-template <int L, int DP, int PASS, bool SUB = false>
+template <int L, int DP, int PASS, bool SUB = false, int PK = L>
 __device__ __forceinline__ void fwd_middle(uint32_t tid, uint32_t nthreads, uint32_t polys, uint64_t* smem,
                                            const Tw* __restrict__ tw, const ModQ& m) {
-    if constexpr (PASS < Plan<L>::P - 1) {
-        fwd_pass<L, DP, PASS, IO_SMEM, IO_SMEM, true, false, 0, SUB>(tid, nthreads, polys, nullptr, nullptr, smem, tw, m);
+    if constexpr (PASS < Plan<PK>::P - 1) {
+        fwd_pass<L, DP, PASS, IO_SMEM, IO_SMEM, true, false, 0, SUB, false, PK>(tid, nthreads, polys, nullptr, nullptr, smem, tw, m);
         __syncthreads();
-        fwd_middle<L, DP, PASS + 1, SUB>(tid, nthreads, polys, smem, tw, m);
+        fwd_middle<L, DP, PASS + 1, SUB, PK>(tid, nthreads, polys, smem, tw, m);
     }
 }
 
@@ -77,11 +77,13 @@ __device__ __forceinline__ void inv_middle(uint32_t tid, uint32_t nthreads, uint
 // SCALE = true gives fast_ntt_inverse semantics when `tw` is the inverse table.
 // TMA = true (multi-pass plans, degrees up to 4096): shared memory = work buffer | landing buffer | mbarrier; the
 // next group's words are bulk-copied into the landing buffer while this group's later passes run.
-template <int L, int DP, int THREADS, int PPC, bool SCALE, bool TMA = false>
+// PK: plan key (ntt_core.cuh): the pass split this kernel runs, with the matching table in `tw`.
+template <int L, int DP, int THREADS, int PPC, bool SCALE, bool TMA = false, int PK = L>
 __global__ void __launch_bounds__(THREADS) ntt_forward_kernel(const uint64_t* in, uint64_t* out, size_t batch,
                                                               const Tw* __restrict__ tw, const Tw ninv, const ModQ m) {
     extern __shared__ __align__(128) uint64_t smem[];
-    constexpr int P = Plan<L>::P;
+    constexpr int P = Plan<PK>::P;
+    static_assert(PK == L || !TMA, "alternative plans run the plain-load form");
     constexpr size_t N = (size_t)1 << L;
     const uint32_t tid = threadIdx.x;
     const size_t groups = (batch + PPC - 1) / PPC;
@@ -138,10 +140,10 @@ __global__ void __launch_bounds__(THREADS) ntt_forward_kernel(const uint64_t* in
         if constexpr (P == 1) {
             fwd_pass<L, DP, 0, IO_GLOBAL, IO_GLOBAL, true, SCALE>(tid, THREADS, polys, gin, gout, smem, tw, m, ninv);
         } else {
-            fwd_pass<L, DP, 0, IO_GLOBAL, IO_SMEM, true, false, 0, false, (L >= 13 && FHEB_PIPE_MODE(DP))>(tid, THREADS, polys, gin, gout, smem, tw, m);
+            fwd_pass<L, DP, 0, IO_GLOBAL, IO_SMEM, true, false, 0, false, (L >= 13 && FHEB_PIPE_MODE(DP)), PK>(tid, THREADS, polys, gin, gout, smem, tw, m);
             __syncthreads();
-            fwd_middle<L, DP, 1>(tid, THREADS, polys, smem, tw, m);
-            fwd_pass<L, DP, P - 1, IO_SMEM, IO_GLOBAL, true, SCALE>(tid, THREADS, polys, gin, gout, smem, tw, m, ninv);
+            fwd_middle<L, DP, 1, false, PK>(tid, THREADS, polys, smem, tw, m);
+            fwd_pass<L, DP, P - 1, IO_SMEM, IO_GLOBAL, true, SCALE, 0, false, false, PK>(tid, THREADS, polys, gin, gout, smem, tw, m, ninv);
             __syncthreads();  // the next group's first pass overwrites the work buffer
         }
     }

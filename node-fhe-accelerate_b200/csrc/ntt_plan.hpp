@@ -23,10 +23,11 @@ inline uint32_t log2_exact(uint32_t n) {
 
 // Entry order (see tw_index in ntt_core.cuh): pass by pass, [a][g][blk]; the twiddle of block
 // b = (blk << a) + g at stage s = S0 + a is table[bitrev_s(b) << (L-1-s)].  N - 1 entries, padded to N.
+// key: plan key (ntt_core.cuh; the degree's own split unless an alternative one is asked for)
 template <class Put>
-inline void for_each_twiddle(uint32_t L, Put put) {
+inline void for_each_twiddle(uint32_t L, Put put, int key = 0) {
     int P, R[5];
-    plan_runtime((int)L, P, R);
+    plan_runtime(key ? key : (int)L, P, R);
     uint32_t idx = 0;
     int s0 = 0;
     for (int p = 0; p < P; ++p) {
@@ -49,9 +50,9 @@ inline void for_each_twiddle(uint32_t L, Put put) {
 // consecutive lanes read consecutive twiddles there too, instead of one 32-byte sector per lane (ntt_core.cuh:
 // fwd_pass / inv_pass, BRTW).  The first N entries are unchanged (fused product and bootstrap kernels use them).
 template <class T>
-inline void append_bitrev_last_pass(std::vector<T>& out, uint32_t L) {
+inline void append_bitrev_last_pass(std::vector<T>& out, uint32_t L, int key = 0) {
     int P, R[5];
-    plan_runtime((int)L, P, R);
+    plan_runtime(key ? key : (int)L, P, R);
     const size_t N = (size_t)1 << L;
     out.resize(2 * N, T{});
     uint32_t off = 0;
@@ -86,13 +87,13 @@ inline void append_bitrev_last_pass_words(uint64_t* words, uint32_t L, size_t ep
                 words[(N + ((size_t)slot << s0) + bitrev_c(blk, s0)) * epw + w] = words[(off + ((size_t)slot << s0) + blk) * epw + w];
 }
 
-inline std::vector<Tw> build_heap_table(const uint64_t* table, uint32_t L, uint64_t q) {
+inline std::vector<Tw> build_heap_table(const uint64_t* table, uint32_t L, uint64_t q, int key = 0) {
     std::vector<Tw> out((size_t)1 << L, Tw{0, 0});
     for_each_twiddle(L, [&](uint32_t at, uint32_t e) {
         const uint64_t w = table[e] % q;
         out[at] = Tw{w, shoup_companion(w, q)};
-    });
-    append_bitrev_last_pass(out, L);
+    }, key);
+    append_bitrev_last_pass(out, L, key);
     return out;
 }
 
@@ -106,13 +107,13 @@ inline std::vector<uint64_t> build_heap_table_dp(const uint64_t* table, uint32_t
 
 // U32 mode (q < 2^27): value and floor(w * 2^32 / q) packed into one 8-byte entry (low half: w)
 constexpr int U32_QBITS = 27;
-inline std::vector<uint64_t> build_heap_table_u32(const uint64_t* table, uint32_t L, uint64_t q) {
+inline std::vector<uint64_t> build_heap_table_u32(const uint64_t* table, uint32_t L, uint64_t q, int key = 0) {
     std::vector<uint64_t> out((size_t)1 << L, 0);
     for_each_twiddle(L, [&](uint32_t at, uint32_t e) {
         const uint64_t w = table[e] % q;
         out[at] = w | (((w << 32) / q) << 32);
-    });
-    append_bitrev_last_pass(out, L);
+    }, key);
+    append_bitrev_last_pass(out, L, key);
     return out;
 }
 
