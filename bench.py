@@ -241,7 +241,10 @@ def run_ours(args):
 
         fheb200.launch_count(reset=True)
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        fwd_ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+        # the forward kernel's own duration (for the roofline) is sampled on every eighth step of the timed region: an
+        # event pair around EVERY launch costs 1.3 % of the step (0.3465 vs 0.3422 ms measured)
+        sampled = list(range(0, args.steps, 8))
+        fwd_ev = {i: (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for i in sampled}
         barrier()
         # The K steps are queued BEHIND a spin kernel (torch.cuda._sleep, ~20 ms), so the device runs them back to back no
         # matter how fast this Python process issues them: with eight ranks, eight clock samplers and NCCL's threads on one
@@ -250,9 +253,11 @@ def run_ours(args):
         torch.cuda._sleep(int(20e-3 * 1.9e9))
         ev0.record()
         for i in range(args.steps):
-            fwd_ev[i][0].record()
+            if i in fwd_ev:
+                fwd_ev[i][0].record()
             ntt.forward_ntt(xs[i % NSETS], out=y)
-            fwd_ev[i][1].record()
+            if i in fwd_ev:
+                fwd_ev[i][1].record()
             ntt.inverse_ntt(y, out=z)
         ev1.record()
         barrier()
@@ -260,7 +265,7 @@ def run_ours(args):
     ms_total = max_over_ranks(ev0.elapsed_time(ev1))
     ms_step = ms_total / args.steps
     value = world * 2.0 * BATCH * N_DEG * args.steps / (ms_total * 1e-3)
-    fwd_ms = statistics.mean(a.elapsed_time(b) for a, b in fwd_ev)
+    fwd_ms = statistics.mean(a.elapsed_time(b) for a, b in fwd_ev.values())
     peak, peak_src = measured_peaks()
     algo_bytes = 16.0 * BATCH * N_DEG
     achieved = algo_bytes / (fwd_ms * 1e-3) / 1e9

@@ -114,6 +114,7 @@ static int plan_finish(NttPlan* p) {
         const uint64_t ni = p->inv_n % q;
         p->ninv32 = Tw{ni, (ni << 32) / q};
         if (p->logn == 14) FHEB_TRY(upload_heap(build_heap_table_u32(p->fwd_table.data(), p->logn, q, PLAN_KEY_ALT14), &p->d_fwd32_alt));
+        if (p->logn == 14) FHEB_TRY(upload_heap(build_heap_table_u32(p->inv_table.data(), p->logn, q, PLAN_KEY_ALT14_INV), &p->d_inv32_alt));
     }
     if (p->mod.dp) {  // FP64 mode: one double per twiddle
         FHEB_TRY(upload_heap(build_heap_table_dp(p->fwd_table.data(), p->logn, q), &p->d_fwd));
@@ -122,6 +123,7 @@ static int plan_finish(NttPlan* p) {
         FHEB_TRY(upload_heap(build_heap_table(p->fwd_table.data(), p->logn, q), &p->d_fwd));
         FHEB_TRY(upload_heap(build_heap_table(p->inv_table.data(), p->logn, q), &p->d_inv));
         if (p->logn == 14) FHEB_TRY(upload_heap(build_heap_table(p->fwd_table.data(), p->logn, q, PLAN_KEY_ALT14), &p->d_fwd_alt));
+        if (p->logn == 14) FHEB_TRY(upload_heap(build_heap_table(p->inv_table.data(), p->logn, q, PLAN_KEY_ALT14_INV), &p->d_inv_alt));
     }
     return FHEB_OK;
 }
@@ -137,6 +139,8 @@ static void plan_free(NttPlan* p) {
     if (p->d_inv32) cudaFree(p->d_inv32);
     if (p->d_fwd_alt) cudaFree(p->d_fwd_alt);
     if (p->d_fwd32_alt) cudaFree(p->d_fwd32_alt);
+    if (p->d_inv_alt) cudaFree(p->d_inv_alt);
+    if (p->d_inv32_alt) cudaFree(p->d_inv32_alt);
     delete p;
 }
 
@@ -268,6 +272,18 @@ static int launch_transform(const NttPlan* p, int dir, const uint64_t* in, uint6
         }
     }
     if (dir == DIR_INV) {
+        if constexpr (L == 14 && (DP == MODE_INT || DP == MODE_U32)) {  // three passes of 4 + 5 + 5 stages (plan key 79)
+            const Tw* alt = (DP == MODE_U32) ? p->d_inv32_alt : p->d_inv_alt;
+            const bool want = (DP == MODE_INT) ? !getenv("FHEB_NO_ALT_PLAN") : (getenv("FHEB_U32_INV_ALT") != nullptr);  // 32-bit inverse: experiment switch
+            if (alt != nullptr && want) {
+                auto k = ntt_inverse_kernel<L, DP, G::THREADS, G::PPC, false, PLAN_KEY_ALT14_INV>;
+                FHEB_TRY(configure(k, G::SMEM, G::THREADS, &bps));
+                k<<<persistent_grid(groups, bps), G::THREADS, G::SMEM, s>>>(in, out, batch, alt, ninv, p->mod);
+                FHEB_CHECK_LAUNCH();
+                count_launch();
+                return FHEB_OK;
+            }
+        }
         auto k = ntt_inverse_kernel<L, DP, G::THREADS, G::PPC>;
         FHEB_TRY(configure(k, G::SMEM, G::THREADS, &bps));
         k<<<persistent_grid(groups, bps), G::THREADS, G::SMEM, s>>>(in, out, batch, d_inv, ninv, p->mod);

@@ -620,8 +620,12 @@ FHEB_PLAN(14, 4, 4, 4, 3, 3, 0)
 // Measured per kernel (all bit-exact): plain forward over a 62-bit prime 0.1701 -> 0.1600 ms (no spills at 128
 // registers) and in 32-bit mode 0.0809 -> 0.0794 ms: used there; inverse 0.1810 -> 0.1810 (64 B of spills), fused product
 // 0.578 -> 0.678 ms (716 B of spills), FP64 mode 0.1050 -> 0.1060: those keep the four-pass plan.
+// 79 = 4 + 5 + 5: the INVERSE runs its passes last to first, so this split gives it the 32-value pass on the caller's
+// words and the 16-value pass on the scaled output: 0.1815 -> 0.1717 ms (5 + 4 + 5: 0.1753; no spills in either).
 constexpr int PLAN_KEY_ALT14 = 78;
+constexpr int PLAN_KEY_ALT14_INV = 79;
 FHEB_PLAN(78, 3, 5, 5, 4, 0, 0)
+FHEB_PLAN(79, 3, 4, 5, 5, 0, 0)
 #undef FHEB_PLAN
 
 template <int L, int PASS>
@@ -651,7 +655,7 @@ inline void plan_runtime(int L, int& P, int (&R)[5]) {
         for (int i = 0; i < 5; ++i) R[i] = Plan<L_>::R[i];        \
         break;
         FHEB_PLAN_RT(2) FHEB_PLAN_RT(3) FHEB_PLAN_RT(4) FHEB_PLAN_RT(5) FHEB_PLAN_RT(6) FHEB_PLAN_RT(7) FHEB_PLAN_RT(8)
-        FHEB_PLAN_RT(9) FHEB_PLAN_RT(10) FHEB_PLAN_RT(11) FHEB_PLAN_RT(12) FHEB_PLAN_RT(13) FHEB_PLAN_RT(14) FHEB_PLAN_RT(78)
+        FHEB_PLAN_RT(9) FHEB_PLAN_RT(10) FHEB_PLAN_RT(11) FHEB_PLAN_RT(12) FHEB_PLAN_RT(13) FHEB_PLAN_RT(14) FHEB_PLAN_RT(78) FHEB_PLAN_RT(79)
 #undef FHEB_PLAN_RT
     }
 }
@@ -884,16 +888,16 @@ FHEB_HD void polymul_mid_pass(uint32_t tid, uint32_t nthreads, uint32_t polys, c
 // may read the reference's input order (bit-reversed positions) from global memory; the
 // last one executed (PASS == 0) multiplies by N^-1 (`ninv`, Shoup pair) and stores canonical
 // values in natural order.
-template <int L, int DP, int PASS, int IN, int OUT, bool BITREV_IN = true, int IPT = 0, int KSTART = 1, bool SUB = false, bool PIPE = false>
+template <int L, int DP, int PASS, int IN, int OUT, bool BITREV_IN = true, int IPT = 0, int KSTART = 1, bool SUB = false, bool PIPE = false, int PK = L>
 FHEB_HD void inv_pass(uint32_t tid, uint32_t nthreads, uint32_t polys, const uint64_t* gin, uint64_t* gout,
                       uint64_t* smem, const Tw* __restrict__ tw, const Tw ninv, const ModQ& m,
                       const GlobalMap map = GlobalMap{0, 0}, const uint64_t* gin_rest = nullptr) {
-    constexpr int R = Plan<L>::R[PASS];
+    constexpr int R = Plan<PK>::R[PASS];
     constexpr int E = 1 << R;
-    constexpr int S0 = plan_s0<L, PASS>();
+    constexpr int S0 = plan_s0<PK, PASS>();
     constexpr int EB = L - S0 - R;
-    constexpr int KIN = plan_inv_kin<L, DP, PASS, KSTART>();
-    constexpr bool FIRST = (PASS == Plan<L>::P - 1);
+    constexpr int KIN = plan_inv_kin<PK, DP, PASS, KSTART>();
+    constexpr bool FIRST = (PASS == Plan<PK>::P - 1);
     constexpr uint32_t N = 1u << L;
     constexpr uint32_t ITEMS = N >> R;
     const uint32_t units = units_of<DP>(polys);
@@ -915,7 +919,7 @@ FHEB_HD void inv_pass(uint32_t tid, uint32_t nthreads, uint32_t polys, const uin
                 uint32_t u = t0;
                 if (FIRST && EXT_IN && BITREV_IN) u = bitrev_rt(u, L - R);
                 const uint32_t base = ((u >> EB) << (EB + R)) | (u & ((1u << EB) - 1u));
-                load_item_tw<R, S0, DP>(tw, BRTW ? (N + t0) : plan_tw_offset<L, PASS>() + (S0 ? (base >> (L - S0)) : 0u), wall[k]);
+                load_item_tw<R, S0, DP>(tw, BRTW ? (N + t0) : plan_tw_offset<PK, PASS>() + (S0 ? (base >> (L - S0)) : 0u), wall[k]);
             }
         }
     }
@@ -966,7 +970,7 @@ FHEB_HD void inv_pass(uint32_t tid, uint32_t nthreads, uint32_t polys, const uin
 #pragma unroll
             for (int c = 0; c < E; ++c) x[c] = slot_load<DP>(sr, swzm<DP>((uint32_t)c << EB));
         }
-        const uint32_t TB = BRTW ? (N + t) : plan_tw_offset<L, PASS>() + (S0 ? (base >> (L - S0)) : 0u);
+        const uint32_t TB = BRTW ? (N + t) : plan_tw_offset<PK, PASS>() + (S0 ? (base >> (L - S0)) : 0u);
         if constexpr (IPT > 0) inv_stages<R, S0, KIN, DP, (PASS == 0 && !SUB), R - 1, true>(x, wall[k], 0u, m);
         else inv_stages<R, S0, KIN, DP, (PASS == 0 && !SUB)>(x, tw, TB, m);
         if (OUT == IO_GLOBAL) {

@@ -63,13 +63,13 @@ __device__ __forceinline__ void fwd_middle(uint32_t tid, uint32_t nthreads, uint
     }
 }
 
-template <int L, int DP, int PASS, bool SUB = false>
+template <int L, int DP, int PASS, bool SUB = false, int PK = L>
 __device__ __forceinline__ void inv_middle(uint32_t tid, uint32_t nthreads, uint32_t polys, uint64_t* smem,
                                            const Tw* __restrict__ tw, const Tw ninv, const ModQ& m) {
     if constexpr (PASS > 0) {
-        inv_pass<L, DP, PASS, IO_SMEM, IO_SMEM, true, 0, 1, SUB>(tid, nthreads, polys, nullptr, nullptr, smem, tw, ninv, m);
+        inv_pass<L, DP, PASS, IO_SMEM, IO_SMEM, true, 0, 1, SUB, false, PK>(tid, nthreads, polys, nullptr, nullptr, smem, tw, ninv, m);
         __syncthreads();
-        inv_middle<L, DP, PASS - 1, SUB>(tid, nthreads, polys, smem, tw, ninv, m);
+        inv_middle<L, DP, PASS - 1, SUB, PK>(tid, nthreads, polys, smem, tw, ninv, m);
     }
 }
 
@@ -151,11 +151,12 @@ __global__ void __launch_bounds__(THREADS) ntt_forward_kernel(const uint64_t* in
 
 // Inverse transform (Gentleman-Sande network, bit-reversal folded into the loads, N^-1 folded
 // into the last pass).
-template <int L, int DP, int THREADS, int PPC, bool TMA = false>
+template <int L, int DP, int THREADS, int PPC, bool TMA = false, int PK = L>
 __global__ void __launch_bounds__(THREADS) ntt_inverse_kernel(const uint64_t* in, uint64_t* out, size_t batch,
                                                               const Tw* __restrict__ tw, const Tw ninv, const ModQ m) {
     extern __shared__ __align__(128) uint64_t smem[];
-    constexpr int P = Plan<L>::P;
+    constexpr int P = Plan<PK>::P;
+    static_assert(PK == L || !TMA, "alternative plans run the plain-load form");
     constexpr size_t N = (size_t)1 << L;
     const uint32_t tid = threadIdx.x;
     const size_t groups = (batch + PPC - 1) / PPC;
@@ -208,10 +209,10 @@ __global__ void __launch_bounds__(THREADS) ntt_inverse_kernel(const uint64_t* in
         if constexpr (P == 1) {
             inv_pass<L, DP, 0, IO_GLOBAL, IO_GLOBAL>(tid, THREADS, polys, gin, gout, smem, tw, ninv, m);
         } else {
-            inv_pass<L, DP, P - 1, IO_GLOBAL, IO_SMEM, true, 0, 1, false, (L >= 14 && FHEB_PIPE_MODE_INV(DP))>(tid, THREADS, polys, gin, gout, smem, tw, ninv, m);
+            inv_pass<L, DP, P - 1, IO_GLOBAL, IO_SMEM, true, 0, 1, false, (L >= 14 && FHEB_PIPE_MODE_INV(DP)), PK>(tid, THREADS, polys, gin, gout, smem, tw, ninv, m);
             __syncthreads();
-            inv_middle<L, DP, P - 2>(tid, THREADS, polys, smem, tw, ninv, m);
-            inv_pass<L, DP, 0, IO_SMEM, IO_GLOBAL>(tid, THREADS, polys, gin, gout, smem, tw, ninv, m);
+            inv_middle<L, DP, P - 2, false, PK>(tid, THREADS, polys, smem, tw, ninv, m);
+            inv_pass<L, DP, 0, IO_SMEM, IO_GLOBAL, true, 0, 1, false, false, PK>(tid, THREADS, polys, gin, gout, smem, tw, ninv, m);
             __syncthreads();
         }
     }

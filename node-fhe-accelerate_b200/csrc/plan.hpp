@@ -34,9 +34,11 @@ struct NttPlan {
     Tw* d_fwd32 = nullptr;
     Tw* d_inv32 = nullptr;
     Tw ninv32{};
-    // N = 16384: the plain forward kernels run the three-pass split (plan key 78, ntt_core.cuh) from a table of their own
+    // N = 16384: the plain forward / inverse kernels run three-pass splits (plan keys 78 / 79, ntt_core.cuh) from tables of their own
     Tw* d_fwd_alt = nullptr;    // integer mode
     Tw* d_fwd32_alt = nullptr;  // 32-bit mode
+    Tw* d_inv_alt = nullptr;    // inverse: 4 + 5 + 5 (plan key 79), integer mode
+    Tw* d_inv32_alt = nullptr;  // 32-bit mode
     // the device whose memory holds the tables above, and copies of the plan on other devices (made on first use when
     // a host batch is spread over several GPUs; owned by this plan)
     int device = 0;
