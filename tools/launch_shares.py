@@ -1,6 +1,6 @@
 """Aggregate an `ncu --metrics gpu__time_duration.sum --csv` launch list per kernel: python tools/launch_shares.py <csv> [--exclude-microbench].
 --exclude-microbench drops the kernels of tools/microbench/pipes (`k<MODE>`), which bench.py runs in a child process BEFORE the
-timed region to measure the pipe rates of its roofline and which ncu lists with everything else."""
+timed region to measure the pipe rates of its roofline and which ncu lists with everything else, and the spin kernel (torch.cuda._sleep) the timed steps are queued behind."""
 import csv
 import re
 import sys
@@ -20,7 +20,7 @@ for r in rows:
         continue
     scale = {"ns": 1e-3, "us": 1.0, "ms": 1e3, "s": 1e6}.get(r[ui], 1.0)
     name = re.sub(r"\(.*", "", r[ki]).strip()
-    if skip_mb and re.match(r"void k<\d+>", name):
+    if skip_mb and (re.match(r"void k<\d+>", name) or "spin_kernel" in name):
         continue
     tot[name][0] += 1
     tot[name][1] += v * scale
