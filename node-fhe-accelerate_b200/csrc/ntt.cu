@@ -113,7 +113,7 @@ static int plan_finish(NttPlan* p) {
         FHEB_TRY(upload_heap(build_heap_table_u32(p->inv_table.data(), p->logn, q), &p->d_inv32));
         const uint64_t ni = p->inv_n % q;
         p->ninv32 = Tw{ni, (ni << 32) / q};
-        if (p->logn == 14) FHEB_TRY(upload_heap(build_heap_table_u32(p->fwd_table.data(), p->logn, q, PLAN_KEY_ALT14), &p->d_fwd32_alt));
+        if (p->logn == 14) FHEB_TRY(upload_heap(build_heap_table_u32(p->fwd_table.data(), p->logn, q, PLAN_KEY_ALT14_U32), &p->d_fwd32_alt));
         if (p->logn == 14) FHEB_TRY(upload_heap(build_heap_table_u32(p->inv_table.data(), p->logn, q, PLAN_KEY_ALT14_INV), &p->d_inv32_alt));
     }
     if (p->mod.dp) {  // FP64 mode: one double per twiddle
@@ -291,7 +291,7 @@ static int launch_transform(const NttPlan* p, int dir, const uint64_t* in, uint6
         if constexpr (L == 14 && (DP == MODE_INT || DP == MODE_U32)) {  // three passes of 5 + 5 + 4 stages (plan key 78) from the table built for them
             const Tw* alt = (DP == MODE_U32) ? p->d_fwd32_alt : p->d_fwd_alt;
             if (alt != nullptr && !getenv("FHEB_NO_ALT_PLAN")) {
-                auto k = ntt_forward_kernel<L, DP, G::THREADS, G::PPC, false, false, PLAN_KEY_ALT14>;
+                auto k = ntt_forward_kernel<L, DP, G::THREADS, G::PPC, false, false, (DP == MODE_U32 ? PLAN_KEY_ALT14_U32 : PLAN_KEY_ALT14)>;
                 FHEB_TRY(configure(k, G::SMEM, G::THREADS, &bps));
                 k<<<persistent_grid(groups, bps), G::THREADS, G::SMEM, s>>>(in, out, batch, alt, ninv, p->mod);
                 FHEB_CHECK_LAUNCH();

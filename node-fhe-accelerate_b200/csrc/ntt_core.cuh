@@ -615,17 +615,20 @@ FHEB_PLAN(13, 4, 4, 3, 3, 3, 0)
 FHEB_PLAN(14, 4, 4, 4, 3, 3, 0)
 #endif
 // Plan KEYS above 64 are alternative splits of degree 2^(key - 64), used by single kernels through their `PK` template
-// parameter with a twiddle table of their own (NttPlan::d_fwd_alt).  78 = N = 16384 in THREE passes of 5 + 5 + 4 stages
+// parameter with a twiddle table of their own (NttPlan::d_fwd_alt / d_inv_alt).  78 = N = 16384 in THREE passes of 5 + 5 + 4 stages
 // (32 register-resident values per thread): one shared-memory round trip and one block barrier less than 4 + 4 + 3 + 3.
 // Measured per kernel (all bit-exact): plain forward over a 62-bit prime 0.1701 -> 0.1600 ms (no spills at 128
-// registers) and in 32-bit mode 0.0809 -> 0.0794 ms: used there; inverse 0.1810 -> 0.1810 (64 B of spills), fused product
+// registers) and in 32-bit mode 0.0809 -> 0.0794 ms (superseded by key 80 below); inverse 0.1810 -> 0.1810 (64 B of spills), fused product
 // 0.578 -> 0.678 ms (716 B of spills), FP64 mode 0.1050 -> 0.1060: those keep the four-pass plan.
 // 79 = 4 + 5 + 5: the INVERSE runs its passes last to first, so this split gives it the 32-value pass on the caller's
 // words and the 16-value pass on the scaled output: 0.1815 -> 0.1717 ms (5 + 4 + 5: 0.1753; no spills in either).
-constexpr int PLAN_KEY_ALT14 = 78;
-constexpr int PLAN_KEY_ALT14_INV = 79;
+// 80 = 5 + 4 + 5: forward over a 62-bit prime 0.1605 -> 0.1569 ms (4 + 5 + 5: 0.1733), 32-bit mode 0.0790 -> 0.0779 ms.
+constexpr int PLAN_KEY_ALT14 = 80;      // plain forward, integer mode
+constexpr int PLAN_KEY_ALT14_U32 = 80;  // plain forward, 32-bit mode
+constexpr int PLAN_KEY_ALT14_INV = 79;  // plain inverse, integer mode (32-bit mode: 188 registers, one block per SM, 0.0913 -> 0.0929 ms: experiment switch only)
 FHEB_PLAN(78, 3, 5, 5, 4, 0, 0)
 FHEB_PLAN(79, 3, 4, 5, 5, 0, 0)
+FHEB_PLAN(80, 3, 5, 4, 5, 0, 0)
 #undef FHEB_PLAN
 
 template <int L, int PASS>
@@ -655,7 +658,7 @@ inline void plan_runtime(int L, int& P, int (&R)[5]) {
         for (int i = 0; i < 5; ++i) R[i] = Plan<L_>::R[i];        \
         break;
         FHEB_PLAN_RT(2) FHEB_PLAN_RT(3) FHEB_PLAN_RT(4) FHEB_PLAN_RT(5) FHEB_PLAN_RT(6) FHEB_PLAN_RT(7) FHEB_PLAN_RT(8)
-        FHEB_PLAN_RT(9) FHEB_PLAN_RT(10) FHEB_PLAN_RT(11) FHEB_PLAN_RT(12) FHEB_PLAN_RT(13) FHEB_PLAN_RT(14) FHEB_PLAN_RT(78) FHEB_PLAN_RT(79)
+        FHEB_PLAN_RT(9) FHEB_PLAN_RT(10) FHEB_PLAN_RT(11) FHEB_PLAN_RT(12) FHEB_PLAN_RT(13) FHEB_PLAN_RT(14) FHEB_PLAN_RT(78) FHEB_PLAN_RT(79) FHEB_PLAN_RT(80)
 #undef FHEB_PLAN_RT
     }
 }
