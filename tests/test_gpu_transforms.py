@@ -142,6 +142,33 @@ def test_transforms_match_oracle_all_degrees(fhe, torch, oracle, logn, lazy, mon
     eq(ring.multiply(a[:2], a[:2]), oracle.multiply(a[:2], a[:2], q, fwd, inv, inv_n))  # aliased operands
 
 
+@pytest.mark.parametrize("four_pass", [False, True], ids=["three-passes", "four-passes"])
+def test_pass_plans_of_n16384_match_oracle(fhe, torch, oracle, four_pass, monkeypatch):
+    """N = 16384: the plain forward / inverse kernels run three passes of 5+4+5 / 4+5+5 stages from twiddle tables of their
+    own (plan keys 80 / 79, ntt_core.cuh); FHEB_NO_ALT_PLAN=1 puts them back on the 4+4+3+3 split every other kernel uses.
+    Both against the oracle, in the integer and the 32-bit mode, ragged batch (more polynomials than resident blocks)."""
+    if four_pass:
+        monkeypatch.setenv("FHEB_NO_ALT_PLAN", "1")
+    else:
+        monkeypatch.delenv("FHEB_NO_ALT_PLAN", raising=False)
+    n = 16384
+    for q in (Q62, Q27):
+        ntt = fhe.NTTProcessor(n, q)
+        fwd, inv, _, _, inv_n = oracle.twiddles(n, q)
+        rng = np.random.default_rng(n + q % 97)
+        batch = 148 * 3 + 5
+        x = rng.integers(0, q, size=(batch, n), dtype=np.uint64)
+        x[2, 5000:5009] = rng.integers(q, 2**64, size=9, dtype=np.uint64)  # unreduced words are reduced on load
+        check = [0, 2, 147, 148, batch - 1]
+        xd = dev(torch, x)
+        f = ntt.forward_ntt(xd)
+        eq(host(f[check]), oracle.forward(x[check], q, fwd))
+        eq(host(ntt.inverse_ntt(xd)[check]), oracle.inverse(x[check], q, inv, inv_n))
+        xr = x.copy()
+        xr[2] %= np.uint64(q)
+        eq(host(ntt.inverse_ntt(f)), xr)  # round trip on the whole batch
+
+
 @pytest.mark.parametrize("tma", ["1", "0"], ids=["tma-landing-buffer", "plain-loads"])
 @pytest.mark.parametrize("logn", range(5, 15))
 def test_first_pass_input_paths_match_oracle(fhe, torch, oracle, logn, tma, monkeypatch):
