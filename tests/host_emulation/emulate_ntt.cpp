@@ -22,41 +22,42 @@
 
 using namespace fheb;
 
-template <int L, int DP, int PASS>
+// PK: plan key (the degree's own pass split, or an alternative one with its own table - ntt_core.cuh)
+template <int L, int DP, int PASS, int PK = L>
 static void run_fwd(uint32_t threads, uint32_t polys, const uint64_t* gin, uint64_t* gout, uint64_t* smem,
                     const Tw* tw, const ModQ& m) {
-    constexpr int P = Plan<L>::P;
+    constexpr int P = Plan<PK>::P;
     if constexpr (PASS < P) {
         for (uint32_t tid = 0; tid < threads; ++tid) {
-            if constexpr (P == 1) fwd_pass<L, DP, PASS, IO_GLOBAL, IO_GLOBAL>(tid, threads, polys, gin, gout, smem, tw, m);
-            else if constexpr (PASS == 0) fwd_pass<L, DP, PASS, IO_GLOBAL, IO_SMEM>(tid, threads, polys, gin, gout, smem, tw, m);
-            else if constexpr (PASS == P - 1) fwd_pass<L, DP, PASS, IO_SMEM, IO_GLOBAL>(tid, threads, polys, gin, gout, smem, tw, m);
-            else fwd_pass<L, DP, PASS, IO_SMEM, IO_SMEM>(tid, threads, polys, gin, gout, smem, tw, m);
+            if constexpr (P == 1) fwd_pass<L, DP, PASS, IO_GLOBAL, IO_GLOBAL, true, false, 0, false, false, PK>(tid, threads, polys, gin, gout, smem, tw, m);
+            else if constexpr (PASS == 0) fwd_pass<L, DP, PASS, IO_GLOBAL, IO_SMEM, true, false, 0, false, false, PK>(tid, threads, polys, gin, gout, smem, tw, m);
+            else if constexpr (PASS == P - 1) fwd_pass<L, DP, PASS, IO_SMEM, IO_GLOBAL, true, false, 0, false, false, PK>(tid, threads, polys, gin, gout, smem, tw, m);
+            else fwd_pass<L, DP, PASS, IO_SMEM, IO_SMEM, true, false, 0, false, false, PK>(tid, threads, polys, gin, gout, smem, tw, m);
         }
-        run_fwd<L, DP, PASS + 1>(threads, polys, gin, gout, smem, tw, m);
+        run_fwd<L, DP, PASS + 1, PK>(threads, polys, gin, gout, smem, tw, m);
     }
 }
 
-template <int L, int DP, int PASS>
+template <int L, int DP, int PASS, int PK = L>
 static void run_inv(uint32_t threads, uint32_t polys, const uint64_t* gin, uint64_t* gout, uint64_t* smem,
                     const Tw* tw, const Tw& ninv, const ModQ& m) {
-    constexpr int P = Plan<L>::P;
+    constexpr int P = Plan<PK>::P;
     if constexpr (PASS >= 0) {
         for (uint32_t tid = 0; tid < threads; ++tid) {
-            if constexpr (P == 1) inv_pass<L, DP, PASS, IO_GLOBAL, IO_GLOBAL>(tid, threads, polys, gin, gout, smem, tw, ninv, m);
-            else if constexpr (PASS == P - 1) inv_pass<L, DP, PASS, IO_GLOBAL, IO_SMEM>(tid, threads, polys, gin, gout, smem, tw, ninv, m);
-            else if constexpr (PASS == 0) inv_pass<L, DP, PASS, IO_SMEM, IO_GLOBAL>(tid, threads, polys, gin, gout, smem, tw, ninv, m);
-            else inv_pass<L, DP, PASS, IO_SMEM, IO_SMEM>(tid, threads, polys, gin, gout, smem, tw, ninv, m);
+            if constexpr (P == 1) inv_pass<L, DP, PASS, IO_GLOBAL, IO_GLOBAL, true, 0, 1, false, false, PK>(tid, threads, polys, gin, gout, smem, tw, ninv, m);
+            else if constexpr (PASS == P - 1) inv_pass<L, DP, PASS, IO_GLOBAL, IO_SMEM, true, 0, 1, false, false, PK>(tid, threads, polys, gin, gout, smem, tw, ninv, m);
+            else if constexpr (PASS == 0) inv_pass<L, DP, PASS, IO_SMEM, IO_GLOBAL, true, 0, 1, false, false, PK>(tid, threads, polys, gin, gout, smem, tw, ninv, m);
+            else inv_pass<L, DP, PASS, IO_SMEM, IO_SMEM, true, 0, 1, false, false, PK>(tid, threads, polys, gin, gout, smem, tw, ninv, m);
         }
-        run_inv<L, DP, PASS - 1>(threads, polys, gin, gout, smem, tw, ninv, m);
+        run_inv<L, DP, PASS - 1, PK>(threads, polys, gin, gout, smem, tw, ninv, m);
     }
 }
 
 // the device twiddle heap as raw words: (w, w') pairs, or one double per entry in DP mode
-static std::vector<uint64_t> heap_words(const uint64_t* table, uint32_t L, uint64_t q, int mode) {
-    if (is_u32(mode)) return build_heap_table_u32(table, L, q);
+static std::vector<uint64_t> heap_words(const uint64_t* table, uint32_t L, uint64_t q, int mode, int key = 0) {
+    if (is_u32(mode)) return build_heap_table_u32(table, L, q, key);
     if (mode == MODE_DP) return build_heap_table_dp(table, L, q);
-    const std::vector<Tw> h = build_heap_table(table, L, q);
+    const std::vector<Tw> h = build_heap_table(table, L, q, key);
     std::vector<uint64_t> w(h.size() * 2);
     std::memcpy(w.data(), h.data(), w.size() * 8);
     return w;
@@ -70,7 +71,7 @@ static uint64_t pick_prime(int L, int mode) {
     return 4611686018326724609ULL;  // 62 bit
 }
 
-template <int L, int DP>
+template <int L, int DP, int PKF = L, int PKI = L>
 static int check(uint32_t threads, uint32_t polys, uint64_t q_override = 0) {
     const uint32_t N = 1u << L;
     uint64_t q = q_override ? q_override : pick_prime(L, DP);
@@ -90,7 +91,7 @@ static int check(uint32_t threads, uint32_t polys, uint64_t q_override = 0) {
         std::printf("L=%d: prime %llu too large for the 32-bit mode\n", L, (unsigned long long)q);
         return 1;
     }
-    const std::vector<uint64_t> hfw = heap_words(fwd.data(), L, q, DP), hiw = heap_words(inv.data(), L, q, DP);
+    const std::vector<uint64_t> hfw = heap_words(fwd.data(), L, q, DP, PKF == L ? 0 : PKF), hiw = heap_words(inv.data(), L, q, DP, PKI == L ? 0 : PKI);
     const Tw* hf = reinterpret_cast<const Tw*>(hfw.data());
     const Tw* hi = reinterpret_cast<const Tw*>(hiw.data());
     const Tw ninv = is_u32(DP) ? Tw{sc[2], (sc[2] << 32) / q}
@@ -103,14 +104,14 @@ static int check(uint32_t threads, uint32_t polys, uint64_t q_override = 0) {
         ref = x;
         orc_forward_ntt_batch(ref.data(), polys, N, q, fwd.data());
         std::fill(smem.begin(), smem.end(), 0xDEADBEEFDEADBEEFULL);
-        run_fwd<L, DP, 0>(threads, polys, x.data(), got.data(), smem.data(), hf, m);
+        run_fwd<L, DP, 0, PKF>(threads, polys, x.data(), got.data(), smem.data(), hf, m);
         if (std::memcmp(ref.data(), got.data(), got.size() * 8) != 0) {
             std::printf("L=%d dp=%d variant=%d threads=%u polys=%u: FORWARD mismatch\n", L, DP, variant, threads, polys);
             ++bad;
         }
         ref = x;
         orc_inverse_ntt_batch(ref.data(), polys, N, q, inv.data(), sc[2]);
-        run_inv<L, DP, Plan<L>::P - 1>(threads, polys, x.data(), got.data(), smem.data(), hi, ninv, m);
+        run_inv<L, DP, Plan<PKI>::P - 1, PKI>(threads, polys, x.data(), got.data(), smem.data(), hi, ninv, m);
         if (std::memcmp(ref.data(), got.data(), got.size() * 8) != 0) {
             std::printf("L=%d dp=%d variant=%d threads=%u polys=%u: INVERSE mismatch\n", L, DP, variant, threads, polys);
             ++bad;
@@ -135,6 +136,11 @@ static int check_all() {
         bad += check<L, MODE_U32P>(64, 4, 132120577ULL);
         bad += check<L, MODE_U32P>(96, 3, 133857281ULL);
         bad += check<L, MODE_U32P>(32, 1, 132120577ULL);
+    }
+    if constexpr (L == 14) {  // the three-pass splits of the plain kernels: forward 5+4+5 (key 80), inverse 4+5+5 (key 79), and 5+5+4 (key 78)
+        bad += check<L, MODE_INT, PLAN_KEY_ALT14, PLAN_KEY_ALT14_INV>(96, 2);
+        bad += check<L, MODE_U32, PLAN_KEY_ALT14_U32, PLAN_KEY_ALT14_INV>(64, 1, 133857281ULL);
+        bad += check<L, MODE_INT, 78, 78>(64, 1);
     }
     if constexpr (L < 14) bad += check_all<L + 1>();
     return bad;
