@@ -884,8 +884,13 @@ int fheb_tensor_multiply_batch(const fheb_ntt_plan* plan, const uint64_t* ct1, c
     FHEB_TRY(s1.bind(ct1, batch * 2 * N * 8, true, false, s));
     FHEB_TRY(s2.bind(ct2, batch * 2 * N * 8, true, false, s));
     FHEB_TRY(so.bind(out, batch * 3 * N * 8, false, true, s));
-    if (!getenv("FHEB_TENSOR_UNFUSED") && s1.ptr<uint64_t>() != so.ptr<uint64_t>() && s2.ptr<uint64_t>() != so.ptr<uint64_t>()) {
-        // one launch (tensor_fused.cu); the output must not alias an operand: a block writes 3 N words per 4 N it reads
+    auto overlaps = [&](const uint64_t* in) {  // [in, in + 2 N batch) against [out, out + 3 N batch)
+        const uint64_t* o0 = so.ptr<const uint64_t>();
+        return in < o0 + batch * 3 * N && o0 < in + batch * 2 * N;
+    };
+    if (!getenv("FHEB_TENSOR_UNFUSED") && !overlaps(s1.ptr<const uint64_t>()) && !overlaps(s2.ptr<const uint64_t>())) {
+        // one launch (tensor_fused.cu); an output that overlaps an operand takes the unfused path below, which has
+        // transformed both operands into its scratch before the first output word is written
         const int frc = tensor_fused_launch(p, s1.ptr<const uint64_t>(), s2.ptr<const uint64_t>(), so.ptr<uint64_t>(), batch, s);
         if (frc != TENSOR_FUSED_UNSUPPORTED) {
             FHEB_TRY(frc);

@@ -523,6 +523,12 @@ def test_tensor_multiply_batch_matches_oracle(fhe, torch, oracle):
         exp = np.stack([oracle.tensor_multiply(ct1[i], ct2[i], q, fwd, inv, inv_n) for i in range(9)])
         eq(got, exp)
         eq(ring.tensor_multiply(ct1[:2], ct2[:2]), exp[:2])  # host buffers
+        # output overlapping an operand (the first operand sits inside the output buffer): same words (the library takes
+        # the path that has read both operands before it writes)
+        buf = torch.zeros((9 * 3 * n,), dtype=torch.int64, device="cuda")
+        a_in = buf[n:n + 9 * 2 * n].view(9, 2, n)
+        a_in.copy_(dev(torch, ct1))
+        eq(host(ring.tensor_multiply(a_in, dev(torch, ct2), out=buf.view(9, 3, n))), exp)
 
 
 def test_streaming_tally_accumulator(fhe, torch, oracle):
