@@ -341,7 +341,8 @@ FHEB_API uint32_t fheb_relin_key_levels(const fheb_relin_key* key); /* levels ac
 /* replaces EncryptionEngine::relinearize / relinearize_inplace on degree-2 ciphertexts: cpp/src/encryption.cpp:
  * 904-1003.  cts = [batch][3][N] (c0, c1, c2), coefficient form, e.g. the output of fheb_tensor_multiply_batch;
  * out = [batch][2][N].  ct_key_id must equal the key's id (FHEB_ERR_KEY_MISMATCH, the reference's message).
- * With no key pairs c0 and c1 are returned untouched, as the reference does (:980-989). */
+ * With no key pairs c0 and c1 are returned untouched, as the reference does (:980-989).  out must not overlap cts
+ * (FHEB_ERR_INVALID_PARAMETERS). */
 FHEB_API int fheb_relinearize_batch(const fheb_relin_key* key, const uint64_t* cts, uint64_t ct_key_id, uint64_t* out,
                                     size_t batch, void* stream);
 

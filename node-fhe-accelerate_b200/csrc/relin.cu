@@ -247,11 +247,15 @@ int fheb_relinearize_batch(const fheb_relin_key* key, const uint64_t* cts, uint6
     FHEB_REQUIRE(cts != nullptr && out != nullptr, "ciphertext pointers must not be null");
     const size_t N = k->plan->degree;
     if (all_host({cts, out})) {
+        FHEB_REQUIRE(!(cts < out + batch * 2 * N && out < cts + batch * 3 * N), "out must not overlap cts");
         return run_host_pipeline(batch, {{cts, 3 * N * 8, 0, true, false}, {out, 2 * N * 8, 0, false, true}},
                                  [&](void* const* dev, size_t, size_t n, cudaStream_t s) {
                                      return relinearize_device(k, (const uint64_t*)dev[0], (uint64_t*)dev[1], n, s);
                                  });
     }
+    // ciphertexts are 3 N words in and 2 N words out: no overlap of the two buffers leaves every input word readable
+    // until it is needed (the reference's relinearize_inplace works on ONE ciphertext object, :995-1003)
+    FHEB_REQUIRE(!(cts < out + batch * 2 * N && out < cts + batch * 3 * N), "out must not overlap cts");
     cudaStream_t s = (cudaStream_t)stream;
     Staged si, so;
     FHEB_TRY(si.bind(cts, batch * 3 * N * 8, true, false, s));

@@ -401,6 +401,10 @@ def test_golden_relinearize(fhe, torch, name):
     assert e.value.code == 2 and "Evaluation key does not match ciphertext key" in str(e.value)
     with pytest.raises(fhe.FheError):
         fhe.RelinearizationKey(ring, g["keys"], 40, 3)  # third shift would reach 80 bits
+    ctd = dev(torch, g["ct"])
+    with pytest.raises(fhe.FheError) as e2:   # 3 N words in, 2 N words out: the buffers must not overlap
+        key.relinearize(ctd, out=ctd.view(-1)[: ctd.shape[0] * 2 * ctd.shape[-1]].view(ctd.shape[0], 2, ctd.shape[-1]))
+    assert "overlap" in str(e2.value)
 
 
 @pytest.mark.parametrize("n,q,key_count,bl,lv,batch", [(256, Q27, 16, 0, 0, 5), (2048, 1125899906826241, 3, 17, 3, 9),
