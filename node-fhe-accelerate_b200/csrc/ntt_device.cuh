@@ -9,13 +9,13 @@
 // else to hide the load latency behind.  The 32-bit kernel with 4-byte slots is the opposite case: without the pipeline's
 // 32 staging registers it needs 64 registers instead of 100, so THREE 256-thread blocks share an SM (64 KB of work buffer
 // each) and cover each other's loads - forward N = 16384, q = 132120577: 0.0916 -> 0.0815 ms (3.30 TB/s, 0.50 of the HBM peak).
-// The inverse already fits 64 registers with the pipeline (0.0901 ms with it, 0.0894 without: kept).
+// The inverse fits 64 registers either way; without the pipeline it measured 0.0890-0.0894 ms against 0.0901-0.0910 with it.
 #if defined(FHEB_EXP_U32_PIPE)
 #define FHEB_PIPE_MODE(DP) true
 #else
 #define FHEB_PIPE_MODE(DP) ((DP) != MODE_U32)
 #endif
-#define FHEB_PIPE_MODE_INV(DP) true
+#define FHEB_PIPE_MODE_INV(DP) ((DP) != MODE_U32)
 
 namespace fheb {
 
