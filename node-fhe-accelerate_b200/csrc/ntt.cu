@@ -230,10 +230,13 @@ enum { DIR_FWD = 0, DIR_INV = 1, DIR_INV_FWDNET = 2 };
 template <int L, int DP>
 constexpr bool TMA_DEFAULT(bool inverse) {
     if (L == 6) return true;
-    if (L == 8) return !inverse;
+    if (L == 8) return !inverse || DP == MODE_U32;  // 32-bit inverse: +1.2 / +2.7 / +5.0 % in three runs
     if (L == 10) return !inverse || DP != MODE_INT;
     if (L == 12) return inverse ? true : DP == MODE_INT;
-    if (L == 13) return DP == MODE_INT || (!inverse && DP == MODE_U32);  // 32-bit forward +15 %, 64-bit integer +3.5 / +4.4 % (profiles/r02_u32_tma_big.txt); 32-bit N = 16384: no difference
+    // N = 8192: 32-bit forward +15 % when measured first, 64-bit integer +3.5 / +4.4 %; re-measured with the leaner Shoup product
+    // (profiles/r02_tma_vs_plain.txt, third table): the 64-bit forward now LOSES 6.4 % with the landing buffer (0.1579 vs 0.1480 ms
+    // per 2^24 coefficients) and runs plain loads, the 64-bit inverse still gains 4.3 %.  32-bit N = 16384: no difference
+    if (L == 13) return (DP == MODE_INT && inverse) || (!inverse && DP == MODE_U32);
     return false;
 }
 

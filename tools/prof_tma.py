@@ -1,5 +1,5 @@
 """Bulk-async (TMA) landing buffer against plain global loads in the first pass of the transform kernels: forward and
-inverse, degrees 2^5..2^12, the three arithmetic modes.  Bit-exactness of the TMA path is checked against the plain path on
+inverse, degrees 2^6..2^13, the three arithmetic modes.  Bit-exactness of the TMA path is checked against the plain path on
 every case (and the plain path is what the parity suite pins to the oracle).  One process per setting (the switch is read
 once): python tools/prof_tma.py  ->  table."""
 import os
@@ -15,7 +15,7 @@ if len(sys.argv) > 1 and sys.argv[1] == "--worker":
 
     torch.manual_seed(1234)  # the same inputs in both runs: the checksums must agree
     res = {}
-    for logn in (6, 8, 10, 11, 12):
+    for logn in (6, 8, 10, 11, 12, 13):
         n = 1 << logn
         for q, tag in ((4611686018326724609, "int64"), (1099511678977, "fp64"), (132120577, "u32")):
             if (q - 1) % (2 * n):
